@@ -1,0 +1,11 @@
+"""ampnet_b200: B200-native (sm_100a) implementation of the AMP-Net data-parallel hot path.
+
+Directory name follows the repo convention (`3d-semantic-segmentation-amp-net_b200`); import it with
+`importlib.import_module("3d-semantic-segmentation-amp-net_b200")` or through the root-level
+shim `ampnet_b200.py`. Every op calls hand-written CUDA through the C ABI in
+include/ampnet_b200.h; there is no CPU / PyTorch fallback.
+"""
+from . import _lib  # noqa: F401
+from .sampling import fps, fps_batch, fps_indices, gather_rows  # noqa: F401
+from .clustering import (kmeans_clustering, split_kmeans, split_kmeans_array, kmeans_assign,  # noqa: F401
+                         kmeans_constrained_windows, regroup_windows, gather_feats, get_cluster_centroid)
