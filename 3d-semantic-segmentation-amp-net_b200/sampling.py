@@ -69,6 +69,25 @@ def fps_batch(pc, n_samples, start_idx=0):
     return gather_rows(pc, idx), idx
 
 
+def fps_host_batch(pc_host, n_samples, out=None, device=None):
+    """Host-buffer batch form of the sample_fps.py loop (data_proc/sample_fps.py:12-34): pc_host is a CPU
+    tensor / ndarray [B, P, D] float32 (pinned memory makes the copies asynchronous); returns the sampled
+    rows [B, S, D] on the host (written into `out` when given). One H2D copy, one FPS launch, one gather,
+    one D2H copy, one stream synchronise."""
+    t = torch.from_numpy(pc_host) if isinstance(pc_host, np.ndarray) else pc_host
+    if t.dim() != 3 or t.dtype not in (torch.float32, torch.float64):
+        raise ValueError("pc_host must be [B, P, D] float32/float64")
+    dev = _device(device)
+    d = t.to(dev, non_blocking=True)
+    idx = fps_indices(d, n_samples, check_finite=False)
+    rows = gather_rows(d, idx)
+    if out is None:
+        out = torch.empty(rows.shape, dtype=rows.dtype, pin_memory=True)
+    out.copy_(rows, non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    return out
+
+
 def fps(pc, n_samples, device=None):
     """Drop-in for the reference `fps(pc, n_samples)` (utils/utils.py:889).
 

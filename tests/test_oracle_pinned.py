@@ -80,3 +80,90 @@ def test_kmeans_oracle_invariants():
     groups = kmeans_oracle.regroup(np.arange(len(x2)), lab2, 3)
     assert sorted(np.concatenate(groups).tolist()) == list(range(len(x2)))
     assert all((np.diff(g) > 0).all() for g in groups)
+
+
+# ---------------------------------------------------------------------------------------------
+# NN oracle (oracle/nn_oracle.py) pinned to the reference modules
+# ---------------------------------------------------------------------------------------------
+import torch  # noqa: E402
+
+from oracle import make_golden_nn, nn_oracle, nn_params  # noqa: E402
+
+
+def _nn_golden():
+    return np.load(os.path.join(GOLDEN, "nn_reference.npz"))
+
+
+def _case_inputs(name):
+    B, N, W, seed, masked = make_golden_nn.CASES[name]
+    sd_e = nn_params.synthetic_state_dict(nn_params.encoder_shapes(), seed)
+    sd_s = nn_params.synthetic_state_dict(nn_params.seg_shapes(), seed + 1)
+    xs, cent = nn_params.synthetic_blocks(B, N, W, seed)
+    mask = None
+    if masked:
+        mask = torch.zeros(B, W, dtype=torch.bool); mask[0, W - 1] = True
+    return sd_e, sd_s, xs, cent, mask
+
+
+def _rel(a, b):
+    a = torch.as_tensor(a, dtype=torch.float64); b = torch.as_tensor(b, dtype=torch.float64)
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("name", sorted(make_golden_nn.CASES))
+def test_nn_oracle_eval_matches_golden(name):
+    z = _nn_golden()
+    sd_e, sd_s, xs, cent, mask = _case_inputs(name)
+    logits, ft = nn_oracle.forward_windows(sd_e, sd_s, xs, cent, mask, training=False)
+    assert _rel(logits, z[name + "__eval_logits"]) < 2e-5
+    assert _rel(ft, z[name + "__eval_ft"]) < 2e-5
+    out, _ = nn_oracle.base_pointnet(sd_e, xs[-1])
+    assert _rel(out[:, ::37, :], z[name + "__eval_enc_out_last"]) < 2e-5
+
+
+@pytest.mark.parametrize("name", sorted(make_golden_nn.CASES))
+def test_nn_oracle_train_matches_golden(name):
+    z = _nn_golden()
+    sd_e, sd_s, xs, cent, mask = _case_inputs(name)
+    for sd in (sd_e, sd_s):
+        for k, v in sd.items():
+            if v.is_floating_point() and "running" not in k:
+                v.requires_grad_(True)
+    st_e, st_s = {}, {}
+    logits, ft = nn_oracle.forward_windows(sd_e, sd_s, xs, cent, mask, training=True, stats_enc=st_e, stats_seg=st_s)
+    loss, _, _ = nn_oracle.train_step_loss(logits, torch.from_numpy(z[name + "__targets"]), ft)
+    loss.backward()
+    assert _rel(logits.detach(), z[name + "__train_logits"]) < 5e-5
+    assert abs(float(loss.detach()) - float(z[name + "__train_loss"])) < 1e-5 * abs(float(z[name + "__train_loss"]))
+    for key in z.files:
+        if key.startswith(name + "__grad_"):
+            tag, k = key[len(name) + 7:].split("_", 1)
+            g = (sd_e if tag == "enc" else sd_s)[k].grad
+            assert g is not None, key
+            # fp32 train-mode gradients of this net carry ~1e-3 relative noise (both implementations are
+            # that far from a float64 run), so the pin is 1e-2 of the largest entry
+            assert _rel(make_golden_nn.subsample(g.numpy()), z[key]) < 1e-2, key
+    assert _rel(sd_e["bn_6.running_mean"], z[name + "__train_rm_bn_6"]) < 1e-5
+    assert _rel(sd_e["bn_1.running_var"], z[name + "__train_rv_bn_1"]) < 1e-5
+    assert _rel(sd_s["bn_2.running_var"], z[name + "__train_rv_seg_bn_2"]) < 1e-5
+    assert int(sd_e["bn_1.num_batches_tracked"]) == 7 + len(xs)
+
+
+@pytest.mark.needs_reference
+def test_nn_param_tables_match_reference(reference):
+    model, _, _ = reference
+    enc = model.BasePointNet(point_dimension=3, return_local_features=True, global_feat_dim=256, device="cpu")
+    seg = model.SegmentationWithAttention(256, 8, num_classes=5, local_dim=64, device="cpu")
+    assert [(k, tuple(v.shape)) for k, v in enc.state_dict().items()] == nn_params.encoder_shapes()
+    assert [(k, tuple(v.shape)) for k, v in seg.state_dict().items()] == nn_params.seg_shapes()
+
+
+@pytest.mark.needs_reference
+def test_nn_oracle_matches_reference_live(reference):
+    model, _, _ = reference
+    enc, seg, sd_e, sd_s = make_golden_nn.build_reference(model, 5)
+    xs, cent = nn_params.synthetic_blocks(2, 96, 2, 5)
+    with torch.no_grad():
+        r = make_golden_nn.run_reference(enc, seg, xs, cent, None, train=False)
+    logits, ft = nn_oracle.forward_windows(sd_e, sd_s, xs, cent, None, training=False)
+    assert _rel(logits, r["logits"]) < 2e-5 and _rel(ft, r["ft"]) < 2e-5
