@@ -138,7 +138,7 @@ def test_nn_oracle_train_matches_golden(name):
     logits, ft = nn_oracle.forward_windows(sd_e, sd_s, xs, cent, mask, training=True, stats_enc=st_e, stats_seg=st_s)
     loss, _, _ = nn_oracle.train_step_loss(logits, torch.from_numpy(z[name + "__targets"]), ft)
     loss.backward()
-    assert _rel(logits.detach(), z[name + "__train_logits"]) < 5e-5
+    assert _rel(logits.detach(), z[name + "__train_logits"]) < 2e-4
     assert abs(float(loss.detach()) - float(z[name + "__train_loss"])) < 1e-5 * abs(float(z[name + "__train_loss"]))
     for key in z.files:
         if key.startswith(name + "__grad_"):
