@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libampnet_b200.so")
 
 _c = ctypes
 _vp, _i64, _i32, _sz, _dbl = _c.c_void_p, _c.c_int64, _c.c_int32, _c.c_size_t, _c.c_double
+_f32, _u64 = _c.c_float, _c.c_uint64
 
 # name -> (restype, argtypes); must list every symbol declared in include/ampnet_b200.h
 SIGNATURES = {
@@ -26,6 +27,20 @@ SIGNATURES = {
     "amp_kmeans_constrained_f32": (_c.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32,
                                               _dbl, _vp, _vp, _vp, _vp, _sz, _vp]),
     "amp_kmeans_regroup": (_c.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "amp_encoder_param_count": (_c.c_int, []),
+    "amp_encoder_param_name": (_c.c_char_p, [_c.c_int]),
+    "amp_encoder_saved_bytes": (_sz, [_i64, _i64, _i32]),
+    "amp_encoder_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "amp_encoder_fwd": (_c.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
+    "amp_encoder_bwd": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _sz, _vp, _sz, _vp]),
+    "amp_seg_param_count": (_c.c_int, []),
+    "amp_seg_param_name": (_c.c_char_p, [_c.c_int]),
+    "amp_seg_saved_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32]),
+    "amp_seg_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32]),
+    "amp_seg_fwd": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _u64,
+                               _vp, _vp, _sz, _vp, _sz, _vp]),
+    "amp_seg_bwd": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _f32, _u64,
+                               _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
 }
 
 _lib = None

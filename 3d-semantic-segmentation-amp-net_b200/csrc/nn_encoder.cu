@@ -1,0 +1,397 @@
+// PointNet encoder: forward and backward host orchestration behind amp_encoder_fwd / amp_encoder_bwd.
+//
+// Replaces BasePointNet.forward (pointNet/model/pointnetAtt.py:80-112) with its two TransformationNets
+// (:28-47) and, for training, the autograd backward that loss.backward() runs through it
+// (pointNet/self-attention/train_pointnet-attention.py:467).
+//
+// Forward = 21 fused point-wise layers (nn_linear.cu). Eval: BatchNorm folded to scale/shift in the GEMM
+// epilogue, activations stored once as final values, max-pools taken in the epilogue (pooled layers are
+// never stored). Training: raw layer outputs are kept for backward, the batch statistics come out of the
+// producing GEMM's epilogue and BatchNorm + ReLU are applied in the consumer's prologue.
+// The 3x3 input transform is folded into per-cloud conv_1 weights (bmm + cat of :85-86 never materialise).
+#include <limits>
+
+#include "nn_layout.cuh"
+
+namespace amp {
+namespace {
+
+constexpr float kBnEps = 1e-5f, kBnMomentum = 0.1f;
+
+struct EncCtx {
+    const void* const* P;       // parameter pointers, state_dict order
+    void* const* Gd;            // gradient pointers, same order (backward only)
+    cudaStream_t st;
+    int B, N;
+    bool train;
+    EncSaved S;
+    float *part_sum, *part_sq;
+    unsigned long long *pmax, *pmin;
+    // backward-only
+    float *k1, *k2, *k3;        // BatchNorm-backward coefficient tables [kEncBnTotal]
+    float* wg; size_t wg_floats;
+    const float* pf(int i) const { return reinterpret_cast<const float*>(P[i]); }
+    float* gf(int i) const { return reinterpret_cast<float*>(Gd[i]); }
+};
+
+#define AMP_TRY(expr) do { int rc_ = (expr); if (rc_ != AMP_OK) return rc_; } while (0)
+#define AMP_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fail(AMP_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); } while (0)
+
+// one Conv1d / Linear (+ BatchNorm + ReLU) (+ max-pool over the rows of each cloud)
+int fwd_layer(EncCtx& c, const float* X, long long ldx, int K, int in_bn, const float* W, long long ldw,
+              long long wstride, int w_kn, const float* bias, float* Y, long long ldy, int Nout, int out_bn,
+              float* pooled, int* arg, int clouds, int rows) {
+    PwParams p{};
+    p.X = X; p.ldx = ldx; p.K = K;
+    if (c.train && in_bn >= 0) {
+        const int o = enc_bn_offset(in_bn);
+        p.in_a = c.S.scale + o; p.in_b = c.pf(kEncBnParam[in_bn] + BN_B); p.in_m = c.S.mean + o; p.in_relu = 1;
+    }
+    p.W = W; p.ldw = ldw; p.w_cloud_stride = wstride; p.w_kn = w_kn;
+    p.bias = bias; p.n_groups = 1;
+    p.Y = Y; p.ldy = ldy; p.n_clouds = clouds; p.rows_per_cloud = rows; p.Nout = Nout;
+    const int o = out_bn >= 0 ? enc_bn_offset(out_bn) : 0;
+    if (out_bn >= 0) {
+        if (c.train) {
+            p.part_sum = c.part_sum; p.part_sq = c.part_sq;
+            if (pooled) {
+                p.pool_mode = 2; p.pool_max = c.pmax; p.pool_min = c.pmin;
+                AMP_CUDA(cudaMemsetAsync(c.pmax, 0, sizeof(unsigned long long) * clouds * Nout, c.st));
+                AMP_CUDA(cudaMemsetAsync(c.pmin, 0, sizeof(unsigned long long) * clouds * Nout, c.st));
+            }
+        } else {
+            p.out_scale = c.S.scale + o; p.out_shift = c.S.shift + o; p.out_relu = 1;
+            if (pooled) {
+                p.pool_mode = 1; p.pool_max = c.pmax; p.Y = nullptr;
+                AMP_CUDA(cudaMemsetAsync(c.pmax, 0, sizeof(unsigned long long) * clouds * Nout, c.st));
+            }
+        }
+    }
+    AMP_TRY(pw_linear(p, c.st));
+    if (out_bn >= 0 && c.train) {
+        const int pb = kEncBnParam[out_bn];
+        AMP_TRY(bn_finalize_train(c.part_sum, c.part_sq, clouds, rows, Nout, c.pf(pb + BN_W),
+                                  const_cast<float*>(c.pf(pb + BN_RM)), const_cast<float*>(c.pf(pb + BN_RV)),
+                                  reinterpret_cast<long long*>(const_cast<void*>(c.P[pb + BN_NBT])), kBnMomentum, kBnEps,
+                                  c.S.scale + o, c.S.mean + o, c.S.invstd + o, c.st));
+    }
+    if (pooled) {
+        if (c.train)
+            AMP_TRY(pool_decode(c.pmax, c.pmin, 2, c.S.scale + o, c.pf(kEncBnParam[out_bn] + BN_B), c.S.mean + o, clouds, Nout,
+                                pooled, arg, c.st));
+        else
+            AMP_TRY(pool_decode(c.pmax, c.pmin, 1, nullptr, nullptr, nullptr, clouds, Nout, pooled, arg, c.st));
+    }
+    return AMP_OK;
+}
+
+// TransformationNet.forward (pointnetAtt.py:28-47): A = input rows (with the BatchNorm+ReLU of layer a_bn pending
+// in training mode), out = [B, d*d] transform (+ identity)
+int tnet_fwd(EncCtx& c, int pbase, int L1, int d, const float* A, long long lda, int K, int a_bn, float* y1, float* y2,
+             float* y3, float* pool, int* arg, float* f1, float* f2, float* out) {
+    const int B = c.B, N = c.N;
+    AMP_TRY(fwd_layer(c, A, lda, K, a_bn, c.pf(pbase + T_CONV1), K, 0, 0, nullptr, y1, 64, 64, L1, nullptr, nullptr, B, N));
+    AMP_TRY(fwd_layer(c, y1, 64, 64, L1, c.pf(pbase + T_CONV2), 64, 0, 0, nullptr, y2, 128, 128, L1 + 1, nullptr, nullptr, B, N));
+    AMP_TRY(fwd_layer(c, y2, 128, 128, L1 + 1, c.pf(pbase + T_CONV3), 128, 0, 0, nullptr, y3, 256, 256, L1 + 2, pool, arg, B, N));
+    AMP_TRY(fwd_layer(c, pool, 256, 256, -1, c.pf(pbase + T_FC1), 256, 0, 0, nullptr, f1, 256, 256, L1 + 3, nullptr, nullptr, 1, B));
+    AMP_TRY(fwd_layer(c, f1, 256, 256, L1 + 3, c.pf(pbase + T_FC2), 256, 0, 0, nullptr, f2, 128, 128, L1 + 4, nullptr, nullptr, 1, B));
+    AMP_TRY(fwd_layer(c, f2, 128, 128, L1 + 4, c.pf(pbase + T_FC3W), 128, 0, 0, c.pf(pbase + T_FC3B), out, d * d, d * d, -1,
+                      nullptr, nullptr, 1, B));
+    return add_identity(out, B, d, c.st);
+}
+
+size_t fwd_ws_bytes(long long B, long long N, bool training) {
+    Arena a(nullptr, std::numeric_limits<size_t>::max());
+    const size_t tiles = (size_t)pw_tiles((int)B, (int)N);
+    a.take<float>(tiles * 256); a.take<float>(tiles * 256);
+    a.take<unsigned long long>(B * 256); a.take<unsigned long long>(B * 256);
+    if (!training) enc_carve(a, B, N, false);
+    return a.off + 256;
+}
+
+struct BwdWs {
+    float *gA, *gB, *g64, *dG, *dF, *dT, *dW1eff, *d_f2, *d_f1, *dpool, *colsum;
+};
+
+size_t wg_floats_needed(long long B, long long N) {
+    size_t m = wgrad_workspace_floats((int)B, (int)N, 256, 128);
+    const size_t fc3 = wgrad_workspace_floats(1, (int)B, 4096, 128);
+    const size_t w1 = wgrad_workspace_floats((int)B, (int)N, 64, 64);
+    if (fc3 > m) m = fc3;
+    if (w1 > m) m = w1;
+    return m;
+}
+
+BwdWs bwd_carve(Arena& a, EncCtx* c, long long B, long long N) {
+    BwdWs w{};
+    const size_t M = (size_t)B * N;
+    const size_t tiles = (size_t)pw_tiles((int)B, (int)N);
+    float* ps = a.take<float>(tiles * 256); float* pq = a.take<float>(tiles * 256);
+    float* k1 = a.take<float>(kEncBnTotal); float* k2 = a.take<float>(kEncBnTotal); float* k3 = a.take<float>(kEncBnTotal);
+    const size_t wgf = wg_floats_needed(B, N);
+    float* wg = a.take<float>(wgf);
+    if (c) { c->part_sum = ps; c->part_sq = pq; c->k1 = k1; c->k2 = k2; c->k3 = k3; c->wg = wg; c->wg_floats = wgf; }
+    w.gA = a.take<float>(M * 256); w.gB = a.take<float>(M * 256); w.g64 = a.take<float>(M * 64);
+    w.dG = a.take<float>(B * 256); w.dF = a.take<float>(B * 4096); w.dT = a.take<float>(B * 9 + 7);
+    w.dW1eff = a.take<float>(B * 576); w.d_f2 = a.take<float>(B * 128); w.d_f1 = a.take<float>(B * 256);
+    w.dpool = a.take<float>(B * 256);
+    w.colsum = a.take<float>(colsum_scratch_floats((int)B, (int)N, 256));
+    return w;
+}
+
+// BatchNorm-backward sums -> dgamma / dbeta of layer L and the coefficients its consumers apply
+int bwd_finalize(EncCtx& c, int L, int tiles, long long count) {
+    const int o = enc_bn_offset(L), pb = kEncBnParam[L];
+    return bn_backward_finalize(c.part_sum, c.part_sq, tiles, count, kEncBnChannels[L], c.pf(pb + BN_W), c.S.mean + o,
+                                c.S.invstd + o, c.gf(pb + BN_W), c.gf(pb + BN_B), 0, c.k1 + o, c.k2 + o, c.k3 + o, c.st);
+}
+
+// Backward through  y_out = act_in(A) @ W^T (+ b)  given dz (gradient w.r.t. the BatchNorm OUTPUT of layer L_out
+// after its ReLU mask; L_out < 0: dz is the plain gradient of y_out):
+//   dW (+ db) = dy^T act_in(A),   dA = mask_in(dy @ W)   with dy = bn_backward(dz) applied on the fly.
+// act_in = ReLU(BatchNorm_{L_in}(.)) when L_in >= 0. dA gets the ReLU mask and the BatchNorm-backward sums of L_in
+// unless defer (the tensor has another gradient contribution still to come).
+int bwd_step(EncCtx& c, const float* dz, int Nout, int L_out, const float* y_out, const float* A, long long lda, int K,
+             int L_in, const float* W, float* dW, float* db, float* dA, long long ldda, int accumulate, bool defer,
+             int clouds, int rows) {
+    const int oo = L_out >= 0 ? enc_bn_offset(L_out) : 0, oi = L_in >= 0 ? enc_bn_offset(L_in) : 0;
+    WgParams g{};
+    g.dY = dz; g.lddy = Nout; g.Nout = Nout;
+    if (L_out >= 0) { g.y_a = c.k1 + oo; g.y_b = c.k3 + oo; g.y_c = c.k2 + oo; g.y_m = c.S.mean + oo; g.Y2 = y_out; }
+    g.A = A; g.lda = lda; g.K = K;
+    if (L_in >= 0) { g.a_a = c.S.scale + oi; g.a_b = c.pf(kEncBnParam[L_in] + BN_B); g.a_m = c.S.mean + oi; g.a_relu = 1; }
+    g.n_clouds = clouds; g.rows_per_cloud = rows;
+    g.dW = dW; g.ldw = K; g.db = db;
+    g.partials = c.wg; g.partial_floats = c.wg_floats;
+    AMP_TRY(wgrad(g, c.st));
+    if (!dA) return AMP_OK;
+    PwParams p{};
+    p.X = dz; p.ldx = Nout; p.K = Nout;
+    if (L_out >= 0) { p.in_a = c.k1 + oo; p.in_b = c.k3 + oo; p.in_c = c.k2 + oo; p.in_m = c.S.mean + oo; p.X2 = y_out; }
+    p.W = W; p.ldw = K; p.w_kn = 1;
+    p.n_groups = 1;
+    p.accumulate = accumulate;
+    p.Y = dA; p.ldy = ldda; p.n_clouds = clouds; p.rows_per_cloud = rows; p.Nout = K;
+    const bool mask = L_in >= 0 && !defer;
+    if (mask) {
+        p.mask_y = A; p.ld_mask = lda; p.mask_scale = c.S.scale + oi; p.mask_shift = c.pf(kEncBnParam[L_in] + BN_B);
+        p.mask_mean = c.S.mean + oi; p.mask_invstd = c.S.invstd + oi;
+        p.part_sum = c.part_sum; p.part_sq = c.part_sq;
+    }
+    AMP_TRY(pw_linear(p, c.st));
+    if (mask) AMP_TRY(bwd_finalize(c, L_in, pw_tiles(clouds, rows), (long long)clouds * rows));
+    return AMP_OK;
+}
+
+// backward of max-pool over the rows + ReLU + BatchNorm of the pooled layer L (raw output y [M, 256])
+int bwd_pool(EncCtx& c, const float* dpool, const int* arg, const float* y, int L, float* dz) {
+    const int o = enc_bn_offset(L);
+    const size_t M = (size_t)c.B * c.N;
+    AMP_CUDA(cudaMemsetAsync(dz, 0, M * 256 * sizeof(float), c.st));
+    AMP_TRY(pool_scatter_bwd(dpool, arg, y, c.S.scale + o, c.pf(kEncBnParam[L] + BN_B), c.S.mean + o, c.S.invstd + o, c.B, c.N, 256, dz,
+                             c.part_sum, c.part_sq, c.st));
+    return bwd_finalize(c, L, 1, (long long)M);
+}
+
+// backward of TransformationNet given dM [B, d*d]; gS [M,256] and gT [M,128] are scratch
+int tnet_bwd(EncCtx& c, BwdWs& w, int pbase, int L1, int d, const float* dM, const float* y1, const float* y2,
+             const float* y3, const float* pool, const int* arg, const float* f1, const float* f2, const float* A,
+             long long lda, int K, int a_bn, float* dX, long long lddx, float* gS, float* gT) {
+    const int B = c.B, N = c.N;
+    AMP_TRY(bwd_step(c, dM, d * d, -1, nullptr, f2, 128, 128, L1 + 4, c.pf(pbase + T_FC3W), c.gf(pbase + T_FC3W),
+                     c.gf(pbase + T_FC3B), w.d_f2, 128, 0, false, 1, B));
+    AMP_TRY(bwd_step(c, w.d_f2, 128, L1 + 4, f2, f1, 256, 256, L1 + 3, c.pf(pbase + T_FC2), c.gf(pbase + T_FC2), nullptr,
+                     w.d_f1, 256, 0, false, 1, B));
+    AMP_TRY(bwd_step(c, w.d_f1, 256, L1 + 3, f1, pool, 256, 256, -1, c.pf(pbase + T_FC1), c.gf(pbase + T_FC1), nullptr,
+                     w.dpool, 256, 0, false, 1, B));
+    AMP_TRY(bwd_pool(c, w.dpool, arg, y3, L1 + 2, gS));
+    AMP_TRY(bwd_step(c, gS, 256, L1 + 2, y3, y2, 128, 128, L1 + 1, c.pf(pbase + T_CONV3), c.gf(pbase + T_CONV3), nullptr,
+                     gT, 128, 0, false, B, N));
+    AMP_TRY(bwd_step(c, gT, 128, L1 + 1, y2, y1, 64, 64, L1, c.pf(pbase + T_CONV2), c.gf(pbase + T_CONV2), nullptr,
+                     gS, 64, 0, false, B, N));
+    // conv_1: the input gradient (if any) accumulates onto dX and closes the fan-in of its BatchNorm layer
+    AMP_TRY(bwd_step(c, gS, 64, L1, y1, A, lda, K, a_bn, c.pf(pbase + T_CONV1), c.gf(pbase + T_CONV1), nullptr,
+                     dX, lddx, 1, false, B, N));
+    return AMP_OK;
+}
+
+int check_sizes(int64_t B, int64_t N, const char* who) {
+    if (B < 1 || N < 1 || B > 65535 || B * N > (1LL << 31) / 320)
+        return fail(AMP_E_BADARG, "%s: unsupported shape B=%lld N=%lld", who, (long long)B, (long long)N);
+    return AMP_OK;
+}
+
+const char* kTnetNames[T_COUNT] = {
+    "conv_1.weight", "conv_2.weight", "conv_3.weight",
+    "bn_1.weight", "bn_1.bias", "bn_1.running_mean", "bn_1.running_var", "bn_1.num_batches_tracked",
+    "bn_2.weight", "bn_2.bias", "bn_2.running_mean", "bn_2.running_var", "bn_2.num_batches_tracked",
+    "bn_3.weight", "bn_3.bias", "bn_3.running_mean", "bn_3.running_var", "bn_3.num_batches_tracked",
+    "bn_4.weight", "bn_4.bias", "bn_4.running_mean", "bn_4.running_var", "bn_4.num_batches_tracked",
+    "bn_5.weight", "bn_5.bias", "bn_5.running_mean", "bn_5.running_var", "bn_5.num_batches_tracked",
+    "fc_1.weight", "fc_2.weight", "fc_3.weight", "fc_3.bias"};
+const char* kBnSuffix[BN_STRIDE] = {"weight", "bias", "running_mean", "running_var", "num_batches_tracked"};
+
+}  // namespace
+}  // namespace amp
+
+extern "C" {
+
+int amp_encoder_param_count(void) { return amp::E_COUNT; }
+
+const char* amp_encoder_param_name(int i) {
+    using namespace amp;
+    static thread_local char buf[96];
+    if (i < 0 || i >= E_COUNT) return nullptr;
+    if (i < E_FT) { snprintf(buf, sizeof buf, "input_transform.%s", kTnetNames[i]); return buf; }
+    if (i < E_CONV1) { snprintf(buf, sizeof buf, "feature_transform.%s", kTnetNames[i - E_FT]); return buf; }
+    if (i < E_BN1) { snprintf(buf, sizeof buf, "conv_%d.weight", i - E_CONV1 + 1); return buf; }
+    snprintf(buf, sizeof buf, "bn_%d.%s", (i - E_BN1) / BN_STRIDE + 1, kBnSuffix[(i - E_BN1) % BN_STRIDE]);
+    return buf;
+}
+
+size_t amp_encoder_saved_bytes(int64_t B, int64_t N, int32_t training) {
+    if (!training) return 0;
+    amp::Arena a(nullptr, std::numeric_limits<size_t>::max());
+    amp::enc_carve(a, B, N, true);
+    return a.off + 256;
+}
+
+size_t amp_encoder_workspace_bytes(int64_t B, int64_t N, int32_t training) {
+    size_t f = amp::fwd_ws_bytes(B, N, training != 0);
+    if (training) {
+        amp::Arena a(nullptr, std::numeric_limits<size_t>::max());
+        amp::bwd_carve(a, nullptr, B, N);
+        if (a.off + 256 > f) f = a.off + 256;
+    }
+    return f;
+}
+
+int amp_encoder_fwd(const void* const* params, const float* x, int64_t B, int64_t N, int32_t training,
+                    float* out, float* feat_t, void* saved, size_t saved_bytes, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+    using namespace amp;
+    if (!params || !x || !out || !feat_t || !workspace) return fail(AMP_E_BADARG, "encoder_fwd: null pointer");
+    AMP_TRY(check_sizes(B, N, "encoder_fwd"));
+    if (training && B * N < 2) return fail(AMP_E_BADARG, "encoder_fwd: BatchNorm in training mode needs more than 1 row");
+    if (training && B < 2) return fail(AMP_E_BADARG, "encoder_fwd: training mode needs B >= 2 (BatchNorm over the T-Net FC rows)");
+    for (int i = 0; i < E_COUNT; ++i)
+        if (!params[i]) return fail(AMP_E_BADARG, "encoder_fwd: parameter %d (%s) is null", i, amp_encoder_param_name(i));
+    if (workspace_bytes < fwd_ws_bytes(B, N, training != 0)) return fail(AMP_E_WORKSPACE, "encoder_fwd: workspace too small");
+    if (training && (!saved || saved_bytes < amp_encoder_saved_bytes(B, N, 1)))
+        return fail(AMP_E_WORKSPACE, "encoder_fwd: saved-for-backward buffer too small");
+    EncCtx c{};
+    c.P = params; c.st = (cudaStream_t)stream; c.B = (int)B; c.N = (int)N; c.train = training != 0;
+    Arena wa(workspace, workspace_bytes);
+    const size_t tiles = (size_t)pw_tiles(c.B, c.N);
+    c.part_sum = wa.take<float>(tiles * 256); c.part_sq = wa.take<float>(tiles * 256);
+    c.pmax = wa.take<unsigned long long>(B * 256); c.pmin = wa.take<unsigned long long>(B * 256);
+    if (c.train) { Arena sa(saved, saved_bytes); c.S = enc_carve(sa, B, N, true); }
+    else c.S = enc_carve(wa, B, N, false);
+    EncSaved& S = c.S;
+    if (!c.train) {
+        BnDesc t[L_ENC_BN];
+        for (int L = 0; L < L_ENC_BN; ++L) {
+            const int pb = kEncBnParam[L], o = enc_bn_offset(L);
+            t[L] = BnDesc{c.pf(pb + BN_W), c.pf(pb + BN_B), c.pf(pb + BN_RM), c.pf(pb + BN_RV), S.scale + o, S.shift + o,
+                          kEncBnChannels[L]};
+        }
+        AMP_TRY(bn_fold_eval(t, L_ENC_BN, kBnEps, c.st));
+    }
+    const int Bi = c.B, Ni = c.N;
+    // input T-Net on xyz (:83-84)
+    AMP_TRY(tnet_fwd(c, E_IT, L_IT1, 3, x, 9, 3, -1, S.it_y1, S.it_y2, S.it_y3, S.it_pool, S.it_arg, S.it_f1, S.it_f2, S.T));
+    // bmm + cat + conv_1 (:85-90) as per-cloud conv_1 weights
+    AMP_TRY(fold_input_transform(c.pf(E_CONV1), S.T, Bi, S.W1eff, c.st));
+    AMP_TRY(fwd_layer(c, x, 9, 9, -1, S.W1eff, 9, 576, 0, nullptr, S.c1, 64, 64, L_C1, nullptr, nullptr, Bi, Ni));
+    AMP_TRY(fwd_layer(c, S.c1, 64, 64, L_C1, c.pf(E_CONV2), 64, 0, 0, nullptr, S.c2, 64, 64, L_C2, nullptr, nullptr, Bi, Ni));
+    // feature T-Net (:94); its output is the second module output
+    AMP_TRY(tnet_fwd(c, E_FT, L_FT1, 64, S.c2, 64, 64, L_C2, S.ft_y1, S.ft_y2, S.ft_y3, S.ft_pool, S.ft_arg, S.ft_f1, S.ft_f2, feat_t));
+    // local features = x @ F (:96-97), written straight into out[:, :, 256:320]
+    float* local = out + 256;
+    AMP_TRY(fwd_layer(c, S.c2, 64, 64, L_C2, feat_t, 64, 4096, 1, nullptr, local, 320, 64, -1, nullptr, nullptr, Bi, Ni));
+    // conv_3 .. conv_6 + global max-pool (:100-106)
+    AMP_TRY(fwd_layer(c, local, 320, 64, -1, c.pf(E_CONV3), 64, 0, 0, nullptr, S.c3, 64, 64, L_C3, nullptr, nullptr, Bi, Ni));
+    AMP_TRY(fwd_layer(c, S.c3, 64, 64, L_C3, c.pf(E_CONV4), 64, 0, 0, nullptr, S.c4, 128, 128, L_C4, nullptr, nullptr, Bi, Ni));
+    AMP_TRY(fwd_layer(c, S.c4, 128, 128, L_C4, c.pf(E_CONV5), 128, 0, 0, nullptr, S.c5, 128, 128, L_C5, nullptr, nullptr, Bi, Ni));
+    AMP_TRY(fwd_layer(c, S.c5, 128, 128, L_C5, c.pf(E_CONV6), 128, 0, 0, nullptr, S.c6, 256, 256, L_C6, S.G, S.g_arg, Bi, Ni));
+    // repeat + cat (:109-110)
+    return broadcast_rows(S.G, Bi, Ni, 256, out, 320, c.st);
+}
+
+int amp_encoder_bwd(const void* const* params, void* const* grads, const float* x, const float* out,
+                    const float* feat_t, const float* d_out, const float* d_feat_t, int64_t B, int64_t N,
+                    void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace amp;
+    if (!params || !grads || !x || !out || !feat_t || !d_out || !saved || !workspace)
+        return fail(AMP_E_BADARG, "encoder_bwd: null pointer");
+    AMP_TRY(check_sizes(B, N, "encoder_bwd"));
+    if (saved_bytes < amp_encoder_saved_bytes(B, N, 1)) return fail(AMP_E_WORKSPACE, "encoder_bwd: saved buffer too small");
+    if (workspace_bytes < amp_encoder_workspace_bytes(B, N, 1)) return fail(AMP_E_WORKSPACE, "encoder_bwd: workspace too small");
+    for (int i = 0; i < E_COUNT; ++i) {
+        const bool is_buf = i >= E_BN1 ? (i - E_BN1) % BN_STRIDE >= BN_RM
+                          : i < E_CONV1 ? ((i % T_COUNT) >= T_BN1 && (i % T_COUNT) < T_FC1 && ((i % T_COUNT) - T_BN1) % BN_STRIDE >= BN_RM)
+                                        : false;
+        if (!params[i] || (!is_buf && !grads[i]))
+            return fail(AMP_E_BADARG, "encoder_bwd: parameter / gradient %d (%s) is null", i, amp_encoder_param_name(i));
+    }
+    EncCtx c{};
+    c.P = params; c.Gd = grads; c.st = (cudaStream_t)stream; c.B = (int)B; c.N = (int)N; c.train = true;
+    Arena sa(saved, saved_bytes);
+    c.S = enc_carve(sa, B, N, true);
+    Arena wa(workspace, workspace_bytes);
+    BwdWs w = bwd_carve(wa, &c, B, N);
+    EncSaved& S = c.S;
+    const int Bi = c.B, Ni = c.N;
+    const size_t M = (size_t)B * N;
+    const float* local = out + 256;
+
+    // out = [G broadcast | local]: dG = column sums of d_out[:, :, :256]
+    AMP_TRY(colsum_rows(d_out, 320, Bi, Ni, 256, w.dG, w.colsum, c.st));
+    AMP_TRY(bwd_pool(c, w.dG, S.g_arg, S.c6, L_C6, w.gA));
+    AMP_TRY(bwd_step(c, w.gA, 256, L_C6, S.c6, S.c5, 128, 128, L_C5, c.pf(E_CONV6), c.gf(E_CONV6), nullptr, w.gB, 128, 0, false, Bi, Ni));
+    AMP_TRY(bwd_step(c, w.gB, 128, L_C5, S.c5, S.c4, 128, 128, L_C4, c.pf(E_CONV5), c.gf(E_CONV5), nullptr, w.gA, 128, 0, false, Bi, Ni));
+    AMP_TRY(bwd_step(c, w.gA, 128, L_C4, S.c4, S.c3, 64, 64, L_C3, c.pf(E_CONV4), c.gf(E_CONV4), nullptr, w.gB, 64, 0, false, Bi, Ni));
+    // d local = d_out[:, :, 256:] + conv_3 input gradient
+    AMP_CUDA(cudaMemcpy2DAsync(w.gA, 64 * sizeof(float), d_out + 256, 320 * sizeof(float), 64 * sizeof(float), M,
+                               cudaMemcpyDeviceToDevice, c.st));
+    AMP_TRY(bwd_step(c, w.gB, 64, L_C3, S.c3, local, 320, 64, -1, c.pf(E_CONV3), c.gf(E_CONV3), nullptr, w.gA, 64, 1, false, Bi, Ni));
+    // local = relu(bn_2(c2)) @ F[b]:  dF[b] = a2^T dlocal (+ d_feat_t),  d a2 = dlocal @ F[b]^T
+    if (d_feat_t) AMP_CUDA(cudaMemcpyAsync(w.dF, d_feat_t, sizeof(float) * B * 4096, cudaMemcpyDeviceToDevice, c.st));
+    else AMP_CUDA(cudaMemsetAsync(w.dF, 0, sizeof(float) * B * 4096, c.st));
+    {
+        const int o2 = enc_bn_offset(L_C2);
+        WgParams g{};
+        g.dY = w.gA; g.lddy = 64; g.Nout = 64;
+        g.A = S.c2; g.lda = 64; g.K = 64; g.a_a = S.scale + o2; g.a_b = c.pf(E_BN2 + BN_B); g.a_m = S.mean + o2; g.a_relu = 1;
+        g.n_clouds = Bi; g.rows_per_cloud = Ni; g.per_cloud = 1; g.w_kn = 1;
+        g.dW = w.dF; g.ldw = 64; g.w_cloud_stride = 4096; g.accumulate = 1;
+        g.partials = c.wg; g.partial_floats = c.wg_floats;
+        AMP_TRY(wgrad(g, c.st));
+        PwParams p{};
+        p.X = w.gA; p.ldx = 64; p.K = 64;
+        p.W = feat_t; p.ldw = 64; p.w_cloud_stride = 4096; p.w_kn = 0; p.n_groups = 1;
+        p.Y = w.g64; p.ldy = 64; p.n_clouds = Bi; p.rows_per_cloud = Ni; p.Nout = 64;
+        AMP_TRY(pw_linear(p, c.st));
+    }
+    // feature T-Net; closes the fan-in of bn_2 (its conv_1 input gradient accumulates onto g64)
+    AMP_TRY(tnet_bwd(c, w, E_FT, L_FT1, 64, w.dF, S.ft_y1, S.ft_y2, S.ft_y3, S.ft_pool, S.ft_arg, S.ft_f1, S.ft_f2, S.c2, 64, 64,
+                     L_C2, w.g64, 64, w.gA, w.gB));
+    AMP_TRY(bwd_step(c, w.g64, 64, L_C2, S.c2, S.c1, 64, 64, L_C1, c.pf(E_CONV2), c.gf(E_CONV2), nullptr, w.gA, 64, 0, false, Bi, Ni));
+    // conv_1 with per-cloud folded weights: dW1eff[b] = dy1[b]^T x[b], then unfold into conv_1.weight and dT
+    {
+        const int o1 = enc_bn_offset(L_C1);
+        WgParams g{};
+        g.dY = w.gA; g.lddy = 64; g.Nout = 64; g.y_a = c.k1 + o1; g.y_b = c.k3 + o1; g.y_c = c.k2 + o1; g.y_m = S.mean + o1; g.Y2 = S.c1;
+        g.A = x; g.lda = 9; g.K = 9;
+        g.n_clouds = Bi; g.rows_per_cloud = Ni; g.per_cloud = 1;
+        g.dW = w.dW1eff; g.ldw = 9; g.w_cloud_stride = 576;
+        g.partials = c.wg; g.partial_floats = c.wg_floats;
+        AMP_TRY(wgrad(g, c.st));
+        AMP_TRY(fold_input_transform_bwd(w.dW1eff, c.pf(E_CONV1), S.T, Bi, c.gf(E_CONV1), w.dT, c.st));
+    }
+    // input T-Net (no input gradient: x is data)
+    return tnet_bwd(c, w, E_IT, L_IT1, 3, w.dT, S.it_y1, S.it_y2, S.it_y3, S.it_pool, S.it_arg, S.it_f1, S.it_f2, x, 9, 3, -1,
+                    nullptr, 0, w.gB, w.gA);
+}
+
+}  // extern "C"

@@ -1,0 +1,342 @@
+// Attention + segmentation head: forward and backward host orchestration behind amp_seg_fwd / amp_seg_bwd.
+//
+// Replaces SegmentationWithAttention.forward (pointNet/model/pointnetAtt.py:176-209): positional encoding
+// (:183-185), nn.MultiheadAttention over the W block tokens of each window (:187-190), the repeat/cat loop
+// (:192-200) and conv_2/bn_2/relu/dropout, conv_3/bn_3/relu/dropout, conv_4 (:203-207); and the autograd
+// backward through them (pointNet/self-attention/train_pointnet-attention.py:467).
+//
+// The [B, sumN, 320] concatenation is never built: conv_2 is split as
+//   conv_2(cat(local, g_w)) = W2[:, :64] local + (W2[:, 64:] g_w + b2)
+// and the second term is a per-(window, block) bias [B, W, 128] computed once per token.
+#include <limits>
+
+#include "nn_layout.cuh"
+
+namespace amp {
+namespace {
+
+constexpr float kBnEps = 1e-5f, kBnMomentum = 0.1f;
+constexpr int kSegBn2 = 0, kSegBn3 = 128, kSegBnTotal = 192;   // offsets into the scale/shift tables
+
+#define AMP_TRY(expr) do { int rc_ = (expr); if (rc_ != AMP_OK) return rc_; } while (0)
+#define AMP_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fail(AMP_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); } while (0)
+
+struct SegSaved {
+    float *tokens, *h_pre, *qkv, *probs, *attn_o, *g_w, *cb;      // per token
+    float *y2, *y3;                                               // per point (raw in training, final in eval)
+    float *scale, *shift, *mean, *invstd;                         // [kSegBnTotal]
+};
+
+SegSaved seg_carve(Arena& a, long long B, long long W, long long R, int E, int heads, int hid) {
+    SegSaved s{};
+    const size_t T = (size_t)B * W, M = (size_t)B * R;
+    s.tokens = a.take<float>(T * E); s.h_pre = a.take<float>(T * 16); s.qkv = a.take<float>(T * 3 * E);
+    s.probs = a.take<float>((size_t)B * heads * W * W); s.attn_o = a.take<float>(T * E); s.g_w = a.take<float>(T * E);
+    s.cb = a.take<float>(T * hid);
+    s.y2 = a.take<float>(M * hid); s.y3 = a.take<float>(M * 64);
+    s.scale = a.take<float>(kSegBnTotal); s.shift = a.take<float>(kSegBnTotal);
+    s.mean = a.take<float>(kSegBnTotal); s.invstd = a.take<float>(kSegBnTotal);
+    return s;
+}
+
+struct SegWs {
+    float *part_sum, *part_sq, *k1, *k2, *k3, *wg; size_t wg_floats;
+    float *dz3, *dz2, *dcb, *dg_w, *dattn_o, *dqkv, *dtokens, *dpre;
+};
+
+constexpr int kMinGroupSlab = 64;
+size_t seg_wg_floats(long long B, long long W, long long R, int E, int hid) {
+    size_t m = wgrad_workspace_floats((int)B, (int)R, hid, 64, R < kMinGroupSlab ? (int)R : kMinGroupSlab);
+    size_t o = wgrad_workspace_floats((int)B, (int)R, 64, hid);
+    if (o > m) m = o;
+    o = wgrad_workspace_floats(1, (int)(B * W), 3 * E, E);
+    if (o > m) m = o;
+    return m;
+}
+
+SegWs seg_ws_carve(Arena& a, long long B, long long W, long long R, int E, int hid, bool backward) {
+    SegWs w{};
+    const size_t T = (size_t)B * W, M = (size_t)B * R;
+    const size_t tiles = (size_t)pw_tiles((int)B, (int)R);
+    w.part_sum = a.take<float>(tiles * 128); w.part_sq = a.take<float>(tiles * 128);
+    if (!backward) return w;
+    w.k1 = a.take<float>(kSegBnTotal); w.k2 = a.take<float>(kSegBnTotal); w.k3 = a.take<float>(kSegBnTotal);
+    w.wg_floats = seg_wg_floats(B, W, R, E, hid);
+    w.wg = a.take<float>(w.wg_floats);
+    w.dz3 = a.take<float>(M * 64); w.dz2 = a.take<float>(M * hid);
+    w.dcb = a.take<float>(T * hid); w.dg_w = a.take<float>(T * E); w.dattn_o = a.take<float>(T * E);
+    w.dqkv = a.take<float>(T * 3 * E); w.dtokens = a.take<float>(T * E); w.dpre = a.take<float>(T * 16);
+    return w;
+}
+
+struct SegShape { int64_t B, W, R; int E, heads, C, hid; };
+
+int seg_check(const SegShape& s, const int32_t* np_cluster, const char* who) {
+    if (s.B < 1 || s.W < 1 || s.W > 1024 || s.R < 1 || s.B > 65535 || s.B * s.R > (1LL << 31) / 320)
+        return fail(AMP_E_BADARG, "%s: unsupported shape B=%lld W=%lld rows=%lld", who, (long long)s.B, (long long)s.W, (long long)s.R);
+    if (s.E != 256 || s.heads < 1 || s.E % s.heads || s.hid != s.E / 2 || s.C < 1 || s.C > 64)
+        return fail(AMP_E_BADARG, "%s: unsupported head E=%d heads=%d classes=%d", who, s.E, s.heads, s.C);
+    long long sum = 0;
+    for (int i = 0; i < s.W; ++i) {
+        if (np_cluster[i] < 1) return fail(AMP_E_BADARG, "%s: empty block %d", who, i);
+        sum += np_cluster[i];
+    }
+    if (sum != s.R) return fail(AMP_E_BADARG, "%s: sum(np_cluster)=%lld != rows=%lld", who, sum, (long long)s.R);
+    return AMP_OK;
+}
+
+const char* kSegNames[S_COUNT] = {
+    "fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "attention.in_proj_weight", "attention.in_proj_bias",
+    "attention.out_proj.weight", "attention.out_proj.bias", "conv_2.weight", "conv_2.bias", "conv_3.weight", "conv_3.bias",
+    "conv_4.weight", "conv_4.bias",
+    "bn_2.weight", "bn_2.bias", "bn_2.running_mean", "bn_2.running_var", "bn_2.num_batches_tracked",
+    "bn_3.weight", "bn_3.bias", "bn_3.running_mean", "bn_3.running_var", "bn_3.num_batches_tracked"};
+
+inline const float* pf(const void* const* P, int i) { return reinterpret_cast<const float*>(P[i]); }
+inline float* gf(void* const* G, int i) { return reinterpret_cast<float*>(G[i]); }
+
+}  // namespace
+}  // namespace amp
+
+extern "C" {
+
+int amp_seg_param_count(void) { return amp::S_COUNT; }
+const char* amp_seg_param_name(int i) { return (i < 0 || i >= amp::S_COUNT) ? nullptr : amp::kSegNames[i]; }
+
+size_t amp_seg_saved_bytes(int64_t B, int64_t W, int64_t rows, int32_t embed_dim, int32_t heads) {
+    amp::Arena a(nullptr, std::numeric_limits<size_t>::max());
+    amp::seg_carve(a, B, W, rows, embed_dim, heads, embed_dim / 2);
+    return a.off + 256;
+}
+
+size_t amp_seg_workspace_bytes(int64_t B, int64_t W, int64_t rows, int32_t embed_dim, int32_t training) {
+    amp::Arena a(nullptr, std::numeric_limits<size_t>::max());
+    amp::seg_ws_carve(a, B, W, rows, embed_dim, embed_dim / 2, training != 0);
+    return a.off + 256;
+}
+
+int amp_seg_fwd(const void* const* params, const float* gl_feats, const float* lo_feats, const float* centroids,
+                const int32_t* np_cluster, const int32_t* group_rows, const uint8_t* key_padding_mask, int64_t B,
+                int64_t W, int64_t rows, int32_t embed_dim, int32_t heads, int32_t num_classes, int32_t training,
+                float dropout_p, uint64_t seed, float* logits, void* saved, size_t saved_bytes, void* workspace,
+                size_t workspace_bytes, void* stream) {
+    using namespace amp;
+    if (!params || !gl_feats || !lo_feats || !centroids || !np_cluster || !group_rows || !logits || !saved || !workspace)
+        return fail(AMP_E_BADARG, "seg_fwd: null pointer");
+    const SegShape sh{B, W, rows, embed_dim, heads, num_classes, embed_dim / 2};
+    AMP_TRY(seg_check(sh, np_cluster, "seg_fwd"));
+    if (dropout_p < 0.f || dropout_p >= 1.f) return fail(AMP_E_BADARG, "seg_fwd: dropout p must be in [0, 1)");
+    for (int i = 0; i < S_COUNT; ++i)
+        if (!params[i]) return fail(AMP_E_BADARG, "seg_fwd: parameter %d (%s) is null", i, kSegNames[i]);
+    if (saved_bytes < amp_seg_saved_bytes(B, W, rows, embed_dim, heads)) return fail(AMP_E_WORKSPACE, "seg_fwd: saved buffer too small");
+    if (workspace_bytes < amp_seg_workspace_bytes(B, W, rows, embed_dim, 0)) return fail(AMP_E_WORKSPACE, "seg_fwd: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool train = training != 0;
+    const float dp = train ? dropout_p : 0.f;
+    const int E = embed_dim, hid = sh.hid, Bi = (int)B, Wi = (int)W, Ri = (int)rows, T = Bi * Wi;
+    Arena sa(saved, saved_bytes);
+    SegSaved S = seg_carve(sa, B, W, rows, E, heads, hid);
+    Arena wa(workspace, workspace_bytes);
+    SegWs ws = seg_ws_carve(wa, B, W, rows, E, hid, false);
+
+    // positional encoding + token-major layout (:183-185)
+    AMP_TRY(posenc_add(gl_feats, centroids, pf(params, S_FC1W), pf(params, S_FC1B), pf(params, S_FC2W), pf(params, S_FC2B), Bi, Wi, E,
+                       S.tokens, S.h_pre, st));
+    // nn.MultiheadAttention (:187-190): in_proj, per-head softmax(QK^T)V, out_proj
+    {
+        PwParams p{};
+        p.X = S.tokens; p.ldx = E; p.K = E; p.W = pf(params, S_INW); p.ldw = E; p.bias = pf(params, S_INB); p.n_groups = 1;
+        p.Y = S.qkv; p.ldy = 3 * E; p.n_clouds = 1; p.rows_per_cloud = T; p.Nout = 3 * E;
+        AMP_TRY(pw_linear(p, st));
+    }
+    AMP_TRY(attention_core(S.qkv, key_padding_mask, dp, seed + 1, Bi, Wi, E, heads, S.attn_o, S.probs, st));
+    {
+        PwParams p{};
+        p.X = S.attn_o; p.ldx = E; p.K = E; p.W = pf(params, S_OUTW); p.ldw = E; p.bias = pf(params, S_OUTB); p.n_groups = 1;
+        p.Y = S.g_w; p.ldy = E; p.n_clouds = 1; p.rows_per_cloud = T; p.Nout = E;
+        AMP_TRY(pw_linear(p, st));
+    }
+    // per-block bias of conv_2: cb[b, w, :] = W2[:, 64:] g_w[b, w] + b2   (the repeat/cat of :192-200 folded away)
+    {
+        PwParams p{};
+        p.X = S.g_w; p.ldx = E; p.K = E; p.W = pf(params, S_C2W) + 64; p.ldw = 64 + E; p.bias = pf(params, S_C2B); p.n_groups = 1;
+        p.Y = S.cb; p.ldy = hid; p.n_clouds = 1; p.rows_per_cloud = T; p.Nout = hid;
+        AMP_TRY(pw_linear(p, st));
+    }
+    if (!train) {
+        BnDesc t[2] = {
+            {pf(params, S_BN2 + BN_W), pf(params, S_BN2 + BN_B), pf(params, S_BN2 + BN_RM), pf(params, S_BN2 + BN_RV), S.scale + kSegBn2, S.shift + kSegBn2, hid},
+            {pf(params, S_BN3 + BN_W), pf(params, S_BN3 + BN_B), pf(params, S_BN3 + BN_RM), pf(params, S_BN3 + BN_RV), S.scale + kSegBn3, S.shift + kSegBn3, 64}};
+        AMP_TRY(bn_fold_eval(t, 2, kBnEps, st));
+    }
+    auto finalize = [&](int bn, int off, int C) {
+        return bn_finalize_train(ws.part_sum, ws.part_sq, Bi, Ri, C, pf(params, bn + BN_W),
+                                 const_cast<float*>(pf(params, bn + BN_RM)), const_cast<float*>(pf(params, bn + BN_RV)),
+                                 reinterpret_cast<long long*>(const_cast<void*>(params[bn + BN_NBT])), kBnMomentum, kBnEps,
+                                 S.scale + off, S.mean + off, S.invstd + off, st);
+    };
+    // conv_2 on the local half + per-block bias, bn_2, relu (:203)
+    {
+        PwParams p{};
+        p.X = lo_feats; p.ldx = 64; p.K = 64; p.W = pf(params, S_C2W); p.ldw = 64 + E;
+        p.bias = S.cb; p.bias_group_stride = hid; p.group_rows = group_rows; p.n_groups = Wi;
+        p.Y = S.y2; p.ldy = hid; p.n_clouds = Bi; p.rows_per_cloud = Ri; p.Nout = hid;
+        if (train) { p.part_sum = ws.part_sum; p.part_sq = ws.part_sq; }
+        else { p.out_scale = S.scale + kSegBn2; p.out_shift = S.shift + kSegBn2; p.out_relu = 1; }
+        AMP_TRY(pw_linear(p, st));
+        if (train) AMP_TRY(finalize(S_BN2, kSegBn2, hid));
+    }
+    // dropout, conv_3, bn_3, relu (:204-205)
+    {
+        PwParams p{};
+        p.X = S.y2; p.ldx = hid; p.K = hid;
+        if (train) { p.in_a = S.scale + kSegBn2; p.in_b = pf(params, S_BN2 + BN_B); p.in_m = S.mean + kSegBn2; p.in_relu = 1; p.in_drop_p = dp; p.in_drop_seed = seed + 2; }
+        p.W = pf(params, S_C3W); p.ldw = hid; p.bias = pf(params, S_C3B); p.n_groups = 1;
+        p.Y = S.y3; p.ldy = 64; p.n_clouds = Bi; p.rows_per_cloud = Ri; p.Nout = 64;
+        if (train) { p.part_sum = ws.part_sum; p.part_sq = ws.part_sq; }
+        else { p.out_scale = S.scale + kSegBn3; p.out_shift = S.shift + kSegBn3; p.out_relu = 1; }
+        AMP_TRY(pw_linear(p, st));
+        if (train) AMP_TRY(finalize(S_BN3, kSegBn3, 64));
+    }
+    // dropout, conv_4 -> logits [B, C, rows] (:206-207)
+    {
+        PwParams p{};
+        p.X = S.y3; p.ldx = 64; p.K = 64;
+        if (train) { p.in_a = S.scale + kSegBn3; p.in_b = pf(params, S_BN3 + BN_B); p.in_m = S.mean + kSegBn3; p.in_relu = 1; p.in_drop_p = dp; p.in_drop_seed = seed + 3; }
+        p.W = pf(params, S_C4W); p.ldw = 64; p.bias = pf(params, S_C4B); p.n_groups = 1;
+        p.Y = logits; p.y_transposed = 1; p.n_clouds = Bi; p.rows_per_cloud = Ri; p.Nout = num_classes;
+        AMP_TRY(pw_linear(p, st));
+    }
+    return AMP_OK;
+}
+
+int amp_seg_bwd(const void* const* params, void* const* grads, const float* lo_feats, const float* centroids,
+                const int32_t* np_cluster, const int32_t* group_rows, const float* d_logits, int64_t B, int64_t W,
+                int64_t rows, int32_t embed_dim, int32_t heads, int32_t num_classes, float dropout_p, uint64_t seed,
+                float* d_gl_feats, float* d_lo_feats, void* saved, size_t saved_bytes, void* workspace,
+                size_t workspace_bytes, void* stream) {
+    using namespace amp;
+    if (!params || !grads || !lo_feats || !centroids || !np_cluster || !group_rows || !d_logits || !d_gl_feats || !d_lo_feats ||
+        !saved || !workspace)
+        return fail(AMP_E_BADARG, "seg_bwd: null pointer");
+    const SegShape sh{B, W, rows, embed_dim, heads, num_classes, embed_dim / 2};
+    AMP_TRY(seg_check(sh, np_cluster, "seg_bwd"));
+    if (W > 64) return fail(AMP_E_BADARG, "seg_bwd: more than 64 blocks per window");
+    const int gslab = wgrad_group_slab(np_cluster, (int)W);
+    if (gslab < kMinGroupSlab && gslab != rows)
+        return fail(AMP_E_BADARG, "seg_bwd: block sizes must share a factor >= %d points (training blocks are equal-sized)", kMinGroupSlab);
+    for (int i = 0; i < S_COUNT; ++i) {
+        const bool is_buf = i >= S_BN2 && (i - S_BN2) % BN_STRIDE >= BN_RM;
+        if (!params[i] || (!is_buf && !grads[i])) return fail(AMP_E_BADARG, "seg_bwd: parameter / gradient %d (%s) is null", i, kSegNames[i]);
+    }
+    if (saved_bytes < amp_seg_saved_bytes(B, W, rows, embed_dim, heads)) return fail(AMP_E_WORKSPACE, "seg_bwd: saved buffer too small");
+    if (workspace_bytes < amp_seg_workspace_bytes(B, W, rows, embed_dim, 1)) return fail(AMP_E_WORKSPACE, "seg_bwd: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const float dp = dropout_p;
+    const int E = embed_dim, hid = sh.hid, Bi = (int)B, Wi = (int)W, Ri = (int)rows, T = Bi * Wi, C = num_classes;
+    Arena sa(saved, saved_bytes);
+    SegSaved S = seg_carve(sa, B, W, rows, E, heads, hid);
+    Arena wa(workspace, workspace_bytes);
+    SegWs ws = seg_ws_carve(wa, B, W, rows, E, hid, true);
+    const int tiles = pw_tiles(Bi, Ri);
+    const long long count = (long long)Bi * Ri;
+
+    // conv_4: dW4 / db4 from the [B, C, rows] logit gradients; d a3 -> dropout, relu mask, bn_3 sums
+    {
+        WgParams g{};
+        g.dY = d_logits; g.Nout = C; g.dy_transposed = 1;
+        g.A = S.y3; g.lda = 64; g.K = 64; g.a_a = S.scale + kSegBn3; g.a_b = pf(params, S_BN3 + BN_B); g.a_m = S.mean + kSegBn3; g.a_relu = 1;
+        g.a_drop_p = dp; g.a_drop_seed = seed + 3;
+        g.n_clouds = Bi; g.rows_per_cloud = Ri; g.dW = gf(grads, S_C4W); g.ldw = 64; g.db = gf(grads, S_C4B);
+        g.partials = ws.wg; g.partial_floats = ws.wg_floats;
+        AMP_TRY(wgrad(g, st));
+        PwParams p{};
+        p.X = d_logits; p.K = C; p.x_transposed = 1; p.W = pf(params, S_C4W); p.ldw = 64; p.w_kn = 1; p.n_groups = 1;
+        p.mask_y = S.y3; p.ld_mask = 64; p.mask_scale = S.scale + kSegBn3; p.mask_shift = pf(params, S_BN3 + BN_B);
+        p.mask_mean = S.mean + kSegBn3; p.mask_invstd = S.invstd + kSegBn3; p.out_drop_p = dp; p.out_drop_seed = seed + 3;
+        p.part_sum = ws.part_sum; p.part_sq = ws.part_sq;
+        p.Y = ws.dz3; p.ldy = 64; p.n_clouds = Bi; p.rows_per_cloud = Ri; p.Nout = 64;
+        AMP_TRY(pw_linear(p, st));
+        AMP_TRY(bn_backward_finalize(ws.part_sum, ws.part_sq, tiles, count, 64, pf(params, S_BN3 + BN_W), S.mean + kSegBn3,
+                                     S.invstd + kSegBn3, gf(grads, S_BN3 + BN_W), gf(grads, S_BN3 + BN_B), 0, ws.k1 + kSegBn3,
+                                     ws.k2 + kSegBn3, ws.k3 + kSegBn3, st));
+    }
+    // conv_3
+    {
+        WgParams g{};
+        g.dY = ws.dz3; g.lddy = 64; g.Nout = 64; g.y_a = ws.k1 + kSegBn3; g.y_b = ws.k3 + kSegBn3; g.y_c = ws.k2 + kSegBn3; g.y_m = S.mean + kSegBn3; g.Y2 = S.y3;
+        g.A = S.y2; g.lda = hid; g.K = hid; g.a_a = S.scale + kSegBn2; g.a_b = pf(params, S_BN2 + BN_B); g.a_m = S.mean + kSegBn2; g.a_relu = 1;
+        g.a_drop_p = dp; g.a_drop_seed = seed + 2;
+        g.n_clouds = Bi; g.rows_per_cloud = Ri; g.dW = gf(grads, S_C3W); g.ldw = hid; g.db = gf(grads, S_C3B);
+        g.partials = ws.wg; g.partial_floats = ws.wg_floats;
+        AMP_TRY(wgrad(g, st));
+        PwParams p{};
+        p.X = ws.dz3; p.ldx = 64; p.K = 64; p.in_a = ws.k1 + kSegBn3; p.in_b = ws.k3 + kSegBn3; p.in_c = ws.k2 + kSegBn3; p.in_m = S.mean + kSegBn3; p.X2 = S.y3;
+        p.W = pf(params, S_C3W); p.ldw = hid; p.w_kn = 1; p.n_groups = 1;
+        p.mask_y = S.y2; p.ld_mask = hid; p.mask_scale = S.scale + kSegBn2; p.mask_shift = pf(params, S_BN2 + BN_B);
+        p.mask_mean = S.mean + kSegBn2; p.mask_invstd = S.invstd + kSegBn2; p.out_drop_p = dp; p.out_drop_seed = seed + 2;
+        p.part_sum = ws.part_sum; p.part_sq = ws.part_sq;
+        p.Y = ws.dz2; p.ldy = hid; p.n_clouds = Bi; p.rows_per_cloud = Ri; p.Nout = hid;
+        AMP_TRY(pw_linear(p, st));
+        AMP_TRY(bn_backward_finalize(ws.part_sum, ws.part_sq, tiles, count, hid, pf(params, S_BN2 + BN_W), S.mean + kSegBn2,
+                                     S.invstd + kSegBn2, gf(grads, S_BN2 + BN_W), gf(grads, S_BN2 + BN_B), 0, ws.k1 + kSegBn2,
+                                     ws.k2 + kSegBn2, ws.k3 + kSegBn2, st));
+    }
+    // conv_2, local half: dW2[:, :64], per-block bias gradient dcb, d lo_feats
+    {
+        WgParams g{};
+        g.dY = ws.dz2; g.lddy = hid; g.Nout = hid; g.y_a = ws.k1 + kSegBn2; g.y_b = ws.k3 + kSegBn2; g.y_c = ws.k2 + kSegBn2; g.y_m = S.mean + kSegBn2; g.Y2 = S.y2;
+        g.A = lo_feats; g.lda = 64; g.K = 64;
+        g.n_clouds = Bi; g.rows_per_cloud = Ri; g.dW = gf(grads, S_C2W); g.ldw = 64 + E;
+        g.group_rows = group_rows; g.n_groups = Wi; g.dbg = ws.dcb; g.slab_rows = gslab;
+        g.partials = ws.wg; g.partial_floats = ws.wg_floats;
+        AMP_TRY(wgrad(g, st));
+        PwParams p{};
+        p.X = ws.dz2; p.ldx = hid; p.K = hid; p.in_a = ws.k1 + kSegBn2; p.in_b = ws.k3 + kSegBn2; p.in_c = ws.k2 + kSegBn2; p.in_m = S.mean + kSegBn2; p.X2 = S.y2;
+        p.W = pf(params, S_C2W); p.ldw = 64 + E; p.w_kn = 1; p.n_groups = 1;
+        p.Y = d_lo_feats; p.ldy = 64; p.n_clouds = Bi; p.rows_per_cloud = Ri; p.Nout = 64;
+        AMP_TRY(pw_linear(p, st));
+    }
+    // conv_2, global half through the per-block bias: dW2[:, 64:], db2, d g_w
+    {
+        WgParams g{};
+        g.dY = ws.dcb; g.lddy = hid; g.Nout = hid; g.A = S.g_w; g.lda = E; g.K = E;
+        g.n_clouds = 1; g.rows_per_cloud = T; g.dW = gf(grads, S_C2W) + 64; g.ldw = 64 + E; g.db = gf(grads, S_C2B);
+        g.partials = ws.wg; g.partial_floats = ws.wg_floats;
+        AMP_TRY(wgrad(g, st));
+        PwParams p{};
+        p.X = ws.dcb; p.ldx = hid; p.K = hid; p.W = pf(params, S_C2W) + 64; p.ldw = 64 + E; p.w_kn = 1; p.n_groups = 1;
+        p.Y = ws.dg_w; p.ldy = E; p.n_clouds = 1; p.rows_per_cloud = T; p.Nout = E;
+        AMP_TRY(pw_linear(p, st));
+    }
+    // out_proj
+    {
+        WgParams g{};
+        g.dY = ws.dg_w; g.lddy = E; g.Nout = E; g.A = S.attn_o; g.lda = E; g.K = E;
+        g.n_clouds = 1; g.rows_per_cloud = T; g.dW = gf(grads, S_OUTW); g.ldw = E; g.db = gf(grads, S_OUTB);
+        g.partials = ws.wg; g.partial_floats = ws.wg_floats;
+        AMP_TRY(wgrad(g, st));
+        PwParams p{};
+        p.X = ws.dg_w; p.ldx = E; p.K = E; p.W = pf(params, S_OUTW); p.ldw = E; p.w_kn = 1; p.n_groups = 1;
+        p.Y = ws.dattn_o; p.ldy = E; p.n_clouds = 1; p.rows_per_cloud = T; p.Nout = E;
+        AMP_TRY(pw_linear(p, st));
+    }
+    AMP_TRY(attention_core_bwd(ws.dattn_o, S.qkv, S.probs, dp, seed + 1, Bi, Wi, E, heads, ws.dqkv, st));
+    // in_proj
+    {
+        WgParams g{};
+        g.dY = ws.dqkv; g.lddy = 3 * E; g.Nout = 3 * E; g.A = S.tokens; g.lda = E; g.K = E;
+        g.n_clouds = 1; g.rows_per_cloud = T; g.dW = gf(grads, S_INW); g.ldw = E; g.db = gf(grads, S_INB);
+        g.partials = ws.wg; g.partial_floats = ws.wg_floats;
+        AMP_TRY(wgrad(g, st));
+        PwParams p{};
+        p.X = ws.dqkv; p.ldx = 3 * E; p.K = 3 * E; p.W = pf(params, S_INW); p.ldw = E; p.w_kn = 1; p.n_groups = 1;
+        p.Y = ws.dtokens; p.ldy = E; p.n_clouds = 1; p.rows_per_cloud = T; p.Nout = E;
+        AMP_TRY(pw_linear(p, st));
+    }
+    // positional encoding
+    return posenc_bwd(ws.dtokens, centroids, S.h_pre, pf(params, S_FC2W), Bi, Wi, E, d_gl_feats, ws.dpre, gf(grads, S_FC1W),
+                      gf(grads, S_FC1B), gf(grads, S_FC2W), gf(grads, S_FC2B), st);
+}
+
+}  // extern "C"

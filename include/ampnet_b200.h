@@ -89,6 +89,65 @@ int amp_kmeans_regroup(const int32_t* labels, const int64_t* offsets, const int3
                        int32_t kmax, const float* pc, int64_t row_stride,
                        int64_t* order, int32_t* counts, float* xy_mean, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * PointNet encoder.  Replaces BasePointNet.forward (pointNet/model/pointnetAtt.py:80-112, with its two
+ * TransformationNets :28-47) as called by train_pointnet-attention.py:410 / test_pointnet_att_segmen.py:164,
+ * and the autograd backward loss.backward() runs through it (train_pointnet-attention.py:467).
+ *   params      host array of amp_encoder_param_count() DEVICE pointers, one per state_dict entry of
+ *               BasePointNet(point_dimension=3, global_feat_dim=256) in state_dict order
+ *               (amp_encoder_param_name(i) names entry i); float32, num_batches_tracked int64
+ *   x           [B, N, 9] f32        out [B, N, 320] f32 = [global 256 (repeated) | local 64] (:109-110)
+ *   feat_t      [B, 64, 64] f32 feature transform (second module output, :94)
+ *   training    0: eval (BatchNorm running statistics);  1: train (batch statistics; running_mean /
+ *               running_var / num_batches_tracked updated in place; `saved` filled for backward)
+ *   saved       amp_encoder_saved_bytes() bytes, kept by the caller between fwd and bwd (training only)
+ *   workspace   amp_encoder_workspace_bytes() bytes of scratch (may be reused after the call's work completes)
+ * amp_encoder_bwd: grads = host array of DEVICE pointers like params (NULL for the BatchNorm buffers), every
+ * gradient is overwritten (not accumulated); d_out [B, N, 320]; d_feat_t [B, 64, 64] or NULL.
+ * ------------------------------------------------------------------------------------------ */
+int amp_encoder_param_count(void);
+const char* amp_encoder_param_name(int i);
+size_t amp_encoder_saved_bytes(int64_t B, int64_t N, int32_t training);
+size_t amp_encoder_workspace_bytes(int64_t B, int64_t N, int32_t training);
+int amp_encoder_fwd(const void* const* params, const float* x, int64_t B, int64_t N, int32_t training,
+                    float* out, float* feat_t, void* saved, size_t saved_bytes, void* workspace,
+                    size_t workspace_bytes, void* stream);
+int amp_encoder_bwd(const void* const* params, void* const* grads, const float* x, const float* out,
+                    const float* feat_t, const float* d_out, const float* d_feat_t, int64_t B, int64_t N,
+                    void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Attention + segmentation head.  Replaces SegmentationWithAttention.forward
+ * (pointNet/model/pointnetAtt.py:176-209) as called by train_pointnet-attention.py:435 /
+ * test_pointnet_att_segmen.py:176-177, and its autograd backward.
+ *   params      host array of amp_seg_param_count() DEVICE pointers in state_dict order of
+ *               SegmentationWithAttention(256, heads, num_classes, local_dim=64)
+ *   gl_feats    [W, B, E] f32 (sequence first, as the script passes it)      lo_feats [B, rows, 64] f32
+ *   centroids   [B, W, 2] f32      np_cluster HOST int32 [W] points per block, sum = rows
+ *   group_rows  DEVICE int32 [W]: first row of each block (exclusive prefix sum of np_cluster)
+ *   key_padding_mask  DEVICE uint8 [B, W] (1 = ignore key) or NULL
+ *   logits      [B, num_classes, rows] f32
+ *   training    1: batch-statistics BatchNorm + dropout(dropout_p) driven by the counter-based generator
+ *               seeded with `seed` (pass the same seed to amp_seg_bwd)
+ *   saved       amp_seg_saved_bytes() bytes (needed in both modes; kept for backward in training)
+ * amp_seg_bwd: d_logits [B, num_classes, rows]; writes d_gl_feats [W, B, E], d_lo_feats [B, rows, 64] and every
+ * parameter gradient (overwritten). Needs block sizes sharing a factor >= 64 points and W <= 64.
+ * ------------------------------------------------------------------------------------------ */
+int amp_seg_param_count(void);
+const char* amp_seg_param_name(int i);
+size_t amp_seg_saved_bytes(int64_t B, int64_t W, int64_t rows, int32_t embed_dim, int32_t heads);
+size_t amp_seg_workspace_bytes(int64_t B, int64_t W, int64_t rows, int32_t embed_dim, int32_t training);
+int amp_seg_fwd(const void* const* params, const float* gl_feats, const float* lo_feats, const float* centroids,
+                const int32_t* np_cluster, const int32_t* group_rows, const uint8_t* key_padding_mask, int64_t B,
+                int64_t W, int64_t rows, int32_t embed_dim, int32_t heads, int32_t num_classes, int32_t training,
+                float dropout_p, uint64_t seed, float* logits, void* saved, size_t saved_bytes, void* workspace,
+                size_t workspace_bytes, void* stream);
+int amp_seg_bwd(const void* const* params, void* const* grads, const float* lo_feats, const float* centroids,
+                const int32_t* np_cluster, const int32_t* group_rows, const float* d_logits, int64_t B, int64_t W,
+                int64_t rows, int32_t embed_dim, int32_t heads, int32_t num_classes, float dropout_p, uint64_t seed,
+                float* d_gl_feats, float* d_lo_feats, void* saved, size_t saved_bytes, void* workspace,
+                size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
