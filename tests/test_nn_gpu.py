@@ -90,15 +90,30 @@ def test_train_step_matches_reference_golden(amp, cuda, name):
     loss.backward()
     assert _rel(logits, z[name + "__train_logits"]) < TOL_LOGITS
     assert abs(float(loss.detach()) - float(z[name + "__train_loss"])) < 1e-4 * abs(float(z[name + "__train_loss"]))
+    # Exact (float64) gradients from the oracle: the reference's own fp32 gradients (the golden vectors) are up to a
+    # few 1e-2 away from them on these tiny batches (BatchNorm over 3-4 near-identical clouds, near-tied max-pool
+    # winners), so the bound is "as close to the exact gradient as the unmodified reference is".
+    sd_e64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in nn_params.synthetic_state_dict(nn_params.encoder_shapes(), seed).items()}
+    sd_s64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in nn_params.synthetic_state_dict(nn_params.seg_shapes(), seed + 1).items()}
+    for sd in (sd_e64, sd_s64):
+        for k, v in sd.items():
+            if v.is_floating_point() and "running" not in k:
+                v.requires_grad_(True)
+    t_logits, t_ft = nn_oracle.forward_windows(sd_e64, sd_s64, [x.double() for x in xs], cent.double(), mask, training=True)
+    nn_oracle.train_step_loss(t_logits, tg.cpu(), t_ft)[0].backward()
     checked = 0
     for key in z.files:
         if key.startswith(name + "__grad_"):
             tag, k = key[len(name) + 7:].split("_", 1)
             g = dict((enc if tag == "enc" else seg).named_parameters())[k].grad
             assert g is not None, key
-            # same bound the oracle itself is pinned with (tests/test_oracle_pinned.py): fp32 train-mode gradients of
-            # this net carry ~1e-3..1e-2 relative noise in the reference itself (near-tied max-pool winners)
-            assert _relnorm(make_golden_nn.subsample(g.cpu().numpy()), z[key]) < 3e-2, key
+            truth = make_golden_nn.subsample((sd_e64 if tag == "enc" else sd_s64)[k].grad.numpy())
+            ours = _relnorm(make_golden_nn.subsample(g.cpu().numpy()), truth)
+            ref32 = _relnorm(z[key], truth)
+            # (a 1e-4 wobble of the feature transform flips ~1 % of the near-tied global max-pool winners, which moves
+            # a gradient by ~1e-2 of its norm; test_all_gradients_match_oracle is the tight, well-conditioned check)
+            assert ours < max(10 * ref32, 3e-2), (key, ours, ref32)
+            assert _relnorm(make_golden_nn.subsample(g.cpu().numpy()), z[key]) < 6e-2, key
             checked += 1
     assert checked >= 10
     assert _rel(enc.bn_6.running_mean, z[name + "__train_rm_bn_6"]) < 1e-4
@@ -110,9 +125,16 @@ def test_train_step_matches_reference_golden(amp, cuda, name):
 
 def test_all_gradients_match_oracle(amp, cuda):
     """Every parameter gradient of both modules against autograd through the CPU oracle (dropout off)."""
-    B, N, W, seed = 3, 192, 2, 31
+    B, N, W, seed = 8, 192, 2, 31
     enc, seg, sd_e, sd_s = _build(amp, seed, cuda)
     xs, cent = nn_params.synthetic_blocks(B, N, W, seed)
+    # clouds that differ from each other (per-cloud channel scales / offsets): with the i.i.d. uniform blocks of
+    # synthetic_blocks the T-Net BatchNorms over the B pooled rows divide by a near-zero spread and every fp32
+    # implementation, the reference included, is only good to ~1e-2; here the problem is well conditioned and the
+    # bound can be tight
+    g = torch.Generator().manual_seed(9)
+    xs = [x * (0.15 + 0.85 * torch.rand(B, 1, 9, generator=g)) + 0.3 * torch.randn(B, 1, 9, generator=g) for x in xs]
+    cent = torch.stack([x[:, :, :2].mean(1) for x in xs], 1)
     enc.train(); seg.train()
     logits, ft, _ = _run(enc, seg, xs, cent, None, cuda)
     tg = torch.randint(-1, 5, (B, N * W), generator=torch.Generator().manual_seed(3))
@@ -149,8 +171,8 @@ def test_all_gradients_match_oracle(amp, cuda):
                 assert float(p.grad.norm()) < 1e-4, k
                 continue
             ours, ref32 = _relnorm(p.grad, tg64), _relnorm(sd[k].grad, tg64)
-            assert ours < 2.5 * ref32 + 2e-3, (k, ours, ref32)
-            assert ours < 3e-2, (k, ours)
+            assert ours < 2.5 * ref32 + 1e-4, (k, ours, ref32)
+            assert ours < 1e-3, (k, ours)
     for mod, sd in ((enc, sd_e), (seg, sd_s)):
         for k, b in mod.named_buffers():
             if "running" in k:

@@ -55,6 +55,10 @@ def main():
     seed = 21
     enc, seg, sd_e, sd_s = build(seed, dev)
     xs, cent = nn_params.synthetic_blocks(B, N, W, seed)
+    if "--hetero" in sys.argv:      # clouds that differ from each other: BatchNorm over the B rows is well conditioned
+        g = torch.Generator().manual_seed(9)
+        xs = [x * (0.15 + 0.85 * torch.rand(B, 1, 9, generator=g)) + 0.3 * torch.randn(B, 1, 9, generator=g) for x in xs]
+        cent = torch.stack([x[:, :, :2].mean(1) for x in xs], 1)
     mask = None
     enc.train(train); seg.train(train)
     if not train:
