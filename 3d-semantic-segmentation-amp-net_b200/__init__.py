@@ -10,3 +10,9 @@ from .sampling import fps, fps_batch, fps_indices, gather_rows, fps_host_batch  
 from .clustering import (kmeans_clustering, split_kmeans, split_kmeans_array, kmeans_assign,  # noqa: F401
                          kmeans_constrained_windows, regroup_windows, gather_feats, get_cluster_centroid)
 from .modules import BasePointNet, TransformationNet, SegmentationWithAttention  # noqa: F401
+from .parallel import shard_windows, GradAllReduce  # noqa: F401
+
+
+def bench_hooks():
+    from . import nn_bench
+    return nn_bench.hooks()

@@ -1,0 +1,85 @@
+"""CPU baseline legs of bench.py for the PointNet-attention workloads -- TEST / BENCH INFRASTRUCTURE ONLY.
+
+Times the oracle restatement (oracle/nn_oracle.py, pinned to the unmodified reference modules) of the
+reference's CPU path on the box's host cores: the forward of pointNet/model/pointnetAtt.py:80-112,176-209 and
+the training step of train_pointnet-attention.py:445-470 (autograd through the same ops + 2 x Adam), fp32,
+all host threads. /root/reference does not exist on the GPU box, so the unmodified modules cannot be timed there.
+"""
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import nn_oracle, nn_params
+
+B, N = 32, 2048
+
+
+def _inputs():
+    xs, cent = nn_params.synthetic_blocks(B, N, 1, 2000)
+    sd_e = nn_params.synthetic_state_dict(nn_params.encoder_shapes(), 0, trained_bn=False)
+    sd_s = nn_params.synthetic_state_dict(nn_params.seg_shapes(), 1, trained_bn=False)
+    return xs, cent, sd_e, sd_s
+
+
+def cpu_forward(sample_steps=3):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    xs, cent, sd_e, sd_s = _inputs()
+    with torch.no_grad():
+        nn_oracle.forward_windows(sd_e, sd_s, xs, cent)
+        ts = []
+        for _ in range(sample_steps):
+            t = time.perf_counter()
+            nn_oracle.forward_windows(sd_e, sd_s, xs, cent)
+            ts.append(time.perf_counter() - t)
+    best = min(ts)
+    return {"value": B * N / best, "unit": "points/s", "cores": cores, "kind": "port",
+            "sample": "%d forward passes of the full 32 x 2048 batch (oracle port of pointnetAtt.py on torch CPU fp32, %d threads), "
+                      "best %.3f s" % (sample_steps, cores, best), "seconds": ts}
+
+
+def cpu_train(sample_steps=2):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    xs, cent, sd_e, sd_s = _inputs()
+    tg = torch.from_numpy(np.random.default_rng(0).integers(0, 5, (B, N)).astype(np.int64))
+    leaves = []
+    for sd in (sd_e, sd_s):
+        for k, v in sd.items():
+            if v.is_floating_point() and "running" not in k:
+                v.requires_grad_(True)
+                leaves.append(v)
+    opt = torch.optim.Adam(leaves, lr=1e-3)
+    ts = []
+    for i in range(sample_steps + 1):
+        t = time.perf_counter()
+        opt.zero_grad()
+        logits, ft = nn_oracle.forward_windows(sd_e, sd_s, xs, cent, training=True, stats_enc={}, stats_seg={})
+        loss, _, _ = nn_oracle.train_step_loss(logits, tg, ft)
+        loss.backward()
+        opt.step()
+        if i:
+            ts.append(time.perf_counter() - t)
+    best = min(ts)
+    return {"value": B * N / best, "unit": "points/s", "cores": cores, "kind": "port",
+            "sample": "%d training steps of the full 32 x 2048 batch (oracle port on torch CPU fp32 autograd + Adam, %d threads), "
+                      "best %.3f s" % (sample_steps, cores, best), "seconds": ts}
+
+
+def reference_line(workload, args):
+    fn = cpu_forward if workload == "fwd" else cpu_train
+    for _ in range(min(args.warmup, 1)):
+        fn(1)
+    r = fn(max(1, args.steps))
+    secs = r.pop("seconds")
+    v = B * N * len(secs) / sum(secs)
+    metric = "segmented points/sec (fwd)" if workload == "fwd" else "train pts/sec"
+    cfg = ("configs[0]: segmentation forward, batch 32 x 2048 points, 9 channels, eval, random-init weights" if workload == "fwd"
+           else "configs[2]: training step fwd+loss+bwd+2xAdam, batch 32 x 2048 points per GPU")
+    r["value"] = v
+    return {"impl": "reference", "metric": metric, "value": v, "unit": "points/s", "n_gpus": args.gpus, "steps": len(secs),
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": cfg}, "cpu_baseline": r,
+            "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
