@@ -148,6 +148,20 @@ int amp_seg_bwd(const void* const* params, void* const* grads, const float* lo_f
                 float* d_gl_feats, float* d_lo_feats, void* saved, size_t saved_bytes, void* workspace,
                 size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * One point-wise linear layer (Conv1d kernel 1 / Linear of pointnetAtt.py) on the tcgen05 tensor cores, the
+ * building block of the fused bf16 chains used by amp_encoder_fwd / amp_seg_fwd with precision AMP_PREC_BF16:
+ *   y[c, r, :] = act(x[c, r, :K] @ w[N, K]^T + bias)      operands rounded to bf16, fp32 accumulate
+ *   x [n_clouds, rows_per_cloud, K] f32, w [N, K] f32, bias [N] f32 | NULL, y [n_clouds, rows_per_cloud, N] f32 | NULL
+ *   pool_max   [n_clouds, N] uint32 | NULL: bit patterns of max over the rows of each cloud (needs relu, N % 128 == 0;
+ *              zero-initialised by the caller; the layer then runs channels x points and y is not written)
+ * K multiple of 16 in [16, 128], N multiple of 16 in [16, 256].
+ * ------------------------------------------------------------------------------------------ */
+size_t amp_tc_linear_workspace_bytes(int32_t K, int32_t N);
+int amp_tc_linear_bf16(const float* x, int64_t n_clouds, int64_t rows_per_cloud, int32_t K, const float* w,
+                       const float* bias, int32_t N, int32_t relu, float* y, uint32_t* pool_max, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
