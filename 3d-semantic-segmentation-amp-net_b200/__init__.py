@@ -9,7 +9,7 @@ from . import _lib  # noqa: F401
 from .sampling import fps, fps_batch, fps_indices, gather_rows, fps_host_batch  # noqa: F401
 from .clustering import (kmeans_clustering, split_kmeans, split_kmeans_array, kmeans_assign,  # noqa: F401
                          kmeans_constrained_windows, regroup_windows, gather_feats, get_cluster_centroid)
-from .modules import BasePointNet, TransformationNet, SegmentationWithAttention  # noqa: F401
+from .modules import BasePointNet, TransformationNet, SegmentationWithAttention, set_default_precision  # noqa: F401
 from .parallel import shard_windows, GradAllReduce  # noqa: F401
 from .tensorcore import tc_linear  # noqa: F401
 

@@ -12,6 +12,7 @@
 #include <limits>
 
 #include "nn_layout.cuh"
+#include "tc_chain.cuh"
 
 namespace amp {
 namespace {
@@ -100,12 +101,34 @@ int tnet_fwd(EncCtx& c, int pbase, int L1, int d, const float* A, long long lda,
     return add_identity(out, B, d, c.st);
 }
 
+constexpr int kBlob1 = 2048 + 16384 + 65536;               // it.conv_1 (64 x 16 split), it.conv_2 (128 x 64), it.conv_3 (256 x 128)
+constexpr int kBlob2 = 8192 + 8192 + 16384 + 65536;        // conv_2, ft.conv_1, ft.conv_2, ft.conv_3
+constexpr int kBlob3 = 8192 + 8192 + 16384 + 32768 + 65536;// conv_2, conv_3, conv_4, conv_5, conv_6
+constexpr int kWcW1 = 4096, kWcF = 8192, kWcStride = kWcW1 + kWcF;   // per cloud: W1eff (64 x 32 split), F^T (64 x 64)
+
+struct EncTc {
+    float *scale, *shift;
+    unsigned char *blobs, *wcloud;
+    float *pools;                       // it_pool | ft_pool | G, [B, 256] each
+    float *f1, *f2, *T, *W1eff;
+};
+
+EncTc enc_tc_carve(Arena& a, long long B) {
+    EncTc t{};
+    t.scale = a.take<float>(kEncBnTotal); t.shift = a.take<float>(kEncBnTotal);
+    t.blobs = a.take<unsigned char>(kBlob1 + kBlob2 + kBlob3);
+    t.wcloud = a.take<unsigned char>((size_t)B * kWcStride);
+    t.pools = a.take<float>((size_t)B * 256 * 3);
+    t.f1 = a.take<float>(B * 256); t.f2 = a.take<float>(B * 128); t.T = a.take<float>(B * 9 + 7); t.W1eff = a.take<float>(B * 576);
+    return t;
+}
+
 size_t fwd_ws_bytes(long long B, long long N, bool training) {
     Arena a(nullptr, std::numeric_limits<size_t>::max());
     const size_t tiles = (size_t)pw_tiles((int)B, (int)N);
     a.take<float>(tiles * 256); a.take<float>(tiles * 256);
     a.take<unsigned long long>(B * 256); a.take<unsigned long long>(B * 256);
-    if (!training) enc_carve(a, B, N, false);
+    if (!training) { enc_carve(a, B, N, false); enc_tc_carve(a, B); }
     return a.off + 256;
 }
 
@@ -215,6 +238,133 @@ int tnet_bwd(EncCtx& c, BwdWs& w, int pbase, int L1, int d, const float* dM, con
     return AMP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// bf16 tensor-core eval path (AMP_PREC_BF16): three fused tcgen05 chains split at the cloud-wide max-pools
+//   chain 1: xyz -> input T-Net convs -> max          chain 2: x -> conv_1, conv_2 -> feature T-Net convs -> max
+//   chain 3: x -> conv_1, conv_2 -> bmm(F) = local features (stored) -> conv_3 .. conv_6 -> max
+// conv_1 / conv_2 are recomputed in chain 3 instead of storing their activations (4.7 kMAC per point against a
+// 128 B/point round trip); the T-Net FC stacks run on the CUDA cores in fp32 (B rows only).
+// ---------------------------------------------------------------------------------------------------------------
+inline TcOp tc_op(int K, int N, int w_off, int w_cloud, int bias_off, int relu) {
+    TcOp o{}; o.K = K; o.N = N; o.w_off = w_off; o.w_cloud = w_cloud; o.bias_off = bias_off; o.relu = relu; o.write_act = 1;
+    return o;
+}
+
+int tnet_fc_fwd(EncCtx& c, int pbase, int L1, int d, const float* pool, float* f1, float* f2, float* out) {
+    const int B = c.B;
+    AMP_TRY(fwd_layer(c, pool, 256, 256, -1, c.pf(pbase + T_FC1), 256, 0, 0, nullptr, f1, 256, 256, L1 + 3, nullptr, nullptr, 1, B));
+    AMP_TRY(fwd_layer(c, f1, 256, 256, L1 + 3, c.pf(pbase + T_FC2), 256, 0, 0, nullptr, f2, 128, 128, L1 + 4, nullptr, nullptr, 1, B));
+    AMP_TRY(fwd_layer(c, f2, 128, 128, L1 + 4, c.pf(pbase + T_FC3W), 128, 0, 0, c.pf(pbase + T_FC3B), out, d * d, d * d, -1,
+                      nullptr, nullptr, 1, B));
+    return add_identity(out, B, d, c.st);
+}
+
+int encoder_fwd_bf16(EncCtx& c, const float* x, float* out, float* feat_t, Arena& wa) {
+    const int B = c.B, N = c.N;
+    EncTc t = enc_tc_carve(wa, B);
+    if (!wa.ok()) return fail(AMP_E_WORKSPACE, "encoder_fwd: workspace too small");
+    c.S.scale = t.scale; c.S.shift = t.shift;
+    {
+        BnDesc d[L_ENC_BN];
+        for (int L = 0; L < L_ENC_BN; ++L) {
+            const int pb = kEncBnParam[L], o = enc_bn_offset(L);
+            d[L] = BnDesc{c.pf(pb + BN_W), c.pf(pb + BN_B), c.pf(pb + BN_RM), c.pf(pb + BN_RV), t.scale + o, t.shift + o, kEncBnChannels[L]};
+        }
+        AMP_TRY(bn_fold_eval(d, L_ENC_BN, kBnEps, c.st));
+    }
+    auto sc = [&](int L) { return t.scale + enc_bn_offset(L); };
+    // shared weights of the three chains, BatchNorm scale folded in
+    const int b1 = 0, b2 = kBlob1, b3 = kBlob1 + kBlob2;
+    {
+        TcPackTable pt{};
+        pt.n = 12; pt.n_clouds = 1;
+        pt.job[0] = TcPackJob{c.pf(E_IT + T_CONV1), 3, 0, sc(L_IT1), 64, 3, 64, 16, 0, 3, b1, 0};
+        pt.job[1] = TcPackJob{c.pf(E_IT + T_CONV2), 64, 0, sc(L_IT2), 128, 64, 128, 64, 0, 0, b1 + 2048, 0};
+        pt.job[2] = TcPackJob{c.pf(E_IT + T_CONV3), 128, 0, sc(L_IT3), 256, 128, 256, 128, 0, 0, b1 + 2048 + 16384, 0};
+        pt.job[3] = TcPackJob{c.pf(E_CONV2), 64, 0, sc(L_C2), 64, 64, 64, 64, 0, 0, b2, 0};
+        pt.job[4] = TcPackJob{c.pf(E_FT + T_CONV1), 64, 0, sc(L_FT1), 64, 64, 64, 64, 0, 0, b2 + 8192, 0};
+        pt.job[5] = TcPackJob{c.pf(E_FT + T_CONV2), 64, 0, sc(L_FT2), 128, 64, 128, 64, 0, 0, b2 + 16384, 0};
+        pt.job[6] = TcPackJob{c.pf(E_FT + T_CONV3), 128, 0, sc(L_FT3), 256, 128, 256, 128, 0, 0, b2 + 32768, 0};
+        pt.job[7] = TcPackJob{c.pf(E_CONV2), 64, 0, sc(L_C2), 64, 64, 64, 64, 0, 0, b3, 0};
+        pt.job[8] = TcPackJob{c.pf(E_CONV3), 64, 0, sc(L_C3), 64, 64, 64, 64, 0, 0, b3 + 8192, 0};
+        pt.job[9] = TcPackJob{c.pf(E_CONV4), 64, 0, sc(L_C4), 128, 64, 128, 64, 0, 0, b3 + 16384, 0};
+        pt.job[10] = TcPackJob{c.pf(E_CONV5), 128, 0, sc(L_C5), 128, 128, 128, 128, 0, 0, b3 + 32768, 0};
+        pt.job[11] = TcPackJob{c.pf(E_CONV6), 128, 0, sc(L_C6), 256, 128, 256, 128, 0, 0, b3 + 65536, 0};
+        AMP_TRY(tc_pack_weights(pt, t.blobs, c.st));
+    }
+    AMP_CUDA(cudaMemsetAsync(t.pools, 0, sizeof(float) * B * 256 * 3, c.st));
+    float* it_pool = t.pools; float* ft_pool = t.pools + (size_t)B * 256; float* G = t.pools + (size_t)B * 512;
+    TcChainParams base{};
+    base.in_mode = 0; base.in_x = x; base.in_ld = 9; base.n_groups = 1; base.n_clouds = B; base.rows_per_cloud = N;
+    // chain 1: input T-Net convs on xyz + max-pool (:31-35)
+    {
+        TcChainParams p = base;
+        p.in_k = 3; p.n_ops = 3;
+        p.tables = t.shift + enc_bn_offset(L_IT1); p.n_table_floats = 64 + 128 + 256;
+        p.wblob = t.blobs + b1; p.wblob_bytes = kBlob1;
+        p.op[0] = tc_op(16, 64, 0, 0, 0, 1);
+        p.op[1] = tc_op(64, 128, 2048, 0, 64, 1);
+        p.op[2] = tc_op(128, 256, 2048 + 16384, 0, 192, 1); p.op[2].write_act = 0; p.op[2].pool = 1;
+        p.pool = reinterpret_cast<unsigned int*>(it_pool);
+        AMP_TRY(tc_chain_launch(p, c.st));
+    }
+    AMP_TRY(tnet_fc_fwd(c, E_IT, L_IT1, 3, it_pool, t.f1, t.f2, t.T));
+    // bmm + cat + conv_1 (:85-90) as per-cloud conv_1 weights, packed with the bn_1 scale
+    AMP_TRY(fold_input_transform(c.pf(E_CONV1), t.T, B, t.W1eff, c.st));
+    {
+        TcPackTable pt{};
+        pt.n = 1; pt.n_clouds = B;
+        pt.job[0] = TcPackJob{t.W1eff, 9, 576, sc(L_C1), 64, 9, 64, 32, 0, 9, 0, kWcStride};
+        AMP_TRY(tc_pack_weights(pt, t.wcloud, c.st));
+    }
+    // chain 2: conv_1, conv_2, feature T-Net convs + max-pool (:90-94)
+    {
+        const int o0 = enc_bn_offset(L_FT1);
+        auto bo = [&](int L) { return enc_bn_offset(L) - o0; };
+        TcChainParams p = base;
+        p.in_k = 9; p.n_ops = 5;
+        p.tables = t.shift + o0; p.n_table_floats = enc_bn_offset(L_C2) + 64 - o0;
+        p.wblob = t.blobs + b2; p.wblob_bytes = kBlob2;
+        p.wcloud = t.wcloud; p.wcloud_stride = kWcStride; p.wcloud_bytes = kWcW1;
+        p.op[0] = tc_op(32, 64, 0, 1, bo(L_C1), 1);
+        p.op[1] = tc_op(64, 64, 0, 0, bo(L_C2), 1);
+        p.op[2] = tc_op(64, 64, 8192, 0, bo(L_FT1), 1);
+        p.op[3] = tc_op(64, 128, 16384, 0, bo(L_FT2), 1);
+        p.op[4] = tc_op(128, 256, 32768, 0, bo(L_FT3), 1); p.op[4].write_act = 0; p.op[4].pool = 1;
+        p.pool = reinterpret_cast<unsigned int*>(ft_pool);
+        AMP_TRY(tc_chain_launch(p, c.st));
+    }
+    AMP_TRY(tnet_fc_fwd(c, E_FT, L_FT1, 64, ft_pool, t.f1, t.f2, feat_t));
+    {
+        TcPackTable pt{};
+        pt.n = 1; pt.n_clouds = B;
+        pt.job[0] = TcPackJob{feat_t, 64, 4096, nullptr, 64, 64, 64, 64, 1, 0, kWcW1, kWcStride};
+        AMP_TRY(tc_pack_weights(pt, t.wcloud, c.st));
+    }
+    // chain 3: conv_1, conv_2, bmm with the feature transform (= local features, :96-97), conv_3 .. conv_6 + max-pool
+    {
+        const int o0 = enc_bn_offset(L_C1);
+        auto bo = [&](int L) { return enc_bn_offset(L) - o0; };
+        TcChainParams p = base;
+        p.in_k = 9; p.n_ops = 7;
+        p.tables = t.shift + o0; p.n_table_floats = 704;
+        p.wblob = t.blobs + b3; p.wblob_bytes = kBlob3;
+        p.wcloud = t.wcloud; p.wcloud_stride = kWcStride; p.wcloud_bytes = kWcStride;
+        p.op[0] = tc_op(32, 64, 0, 1, bo(L_C1), 1);
+        p.op[1] = tc_op(64, 64, 0, 0, bo(L_C2), 1);
+        p.op[2] = tc_op(64, 64, kWcW1, 1, -1, 0); p.op[2].store_f32 = 1;
+        p.op[3] = tc_op(64, 64, 8192, 0, bo(L_C3), 1);
+        p.op[4] = tc_op(64, 128, 16384, 0, bo(L_C4), 1);
+        p.op[5] = tc_op(128, 128, 32768, 0, bo(L_C5), 1);
+        p.op[6] = tc_op(128, 256, 65536, 0, bo(L_C6), 1); p.op[6].write_act = 0; p.op[6].pool = 1;
+        p.out_f32 = out; p.out_ld = 320; p.out_col0 = 256;
+        p.pool = reinterpret_cast<unsigned int*>(G);
+        AMP_TRY(tc_chain_launch(p, c.st));
+    }
+    // repeat + cat (:109-110)
+    return broadcast_rows(G, B, N, 256, out, 320, c.st);
+}
+
 int check_sizes(int64_t B, int64_t N, const char* who) {
     if (B < 1 || N < 1 || B > 65535 || B * N > (1LL << 31) / 320)
         return fail(AMP_E_BADARG, "%s: unsupported shape B=%lld N=%lld", who, (long long)B, (long long)N);
@@ -266,12 +416,15 @@ size_t amp_encoder_workspace_bytes(int64_t B, int64_t N, int32_t training) {
     return f;
 }
 
-int amp_encoder_fwd(const void* const* params, const float* x, int64_t B, int64_t N, int32_t training,
+int amp_encoder_fwd(const void* const* params, const float* x, int64_t B, int64_t N, int32_t training, int32_t precision,
                     float* out, float* feat_t, void* saved, size_t saved_bytes, void* workspace,
                     size_t workspace_bytes, void* stream) {
     using namespace amp;
     if (!params || !x || !out || !feat_t || !workspace) return fail(AMP_E_BADARG, "encoder_fwd: null pointer");
     AMP_TRY(check_sizes(B, N, "encoder_fwd"));
+    if (precision != AMP_PREC_FP32 && precision != AMP_PREC_BF16) return fail(AMP_E_BADARG, "encoder_fwd: unknown precision %d", precision);
+    if (training && precision != AMP_PREC_FP32)
+        return fail(AMP_E_BADARG, "encoder_fwd: the bf16 tensor-core path is eval-only; training runs in AMP_PREC_FP32");
     if (training && B * N < 2) return fail(AMP_E_BADARG, "encoder_fwd: BatchNorm in training mode needs more than 1 row");
     if (training && B < 2) return fail(AMP_E_BADARG, "encoder_fwd: training mode needs B >= 2 (BatchNorm over the T-Net FC rows)");
     for (int i = 0; i < E_COUNT; ++i)
@@ -282,6 +435,7 @@ int amp_encoder_fwd(const void* const* params, const float* x, int64_t B, int64_
     EncCtx c{};
     c.P = params; c.st = (cudaStream_t)stream; c.B = (int)B; c.N = (int)N; c.train = training != 0;
     Arena wa(workspace, workspace_bytes);
+    if (precision == AMP_PREC_BF16) return encoder_fwd_bf16(c, x, out, feat_t, wa);
     const size_t tiles = (size_t)pw_tiles(c.B, c.N);
     c.part_sum = wa.take<float>(tiles * 256); c.part_sq = wa.take<float>(tiles * 256);
     c.pmax = wa.take<unsigned long long>(B * 256); c.pmin = wa.take<unsigned long long>(B * 256);

@@ -11,12 +11,15 @@
 #include <limits>
 
 #include "nn_layout.cuh"
+#include "tc_chain.cuh"
 
 namespace amp {
 namespace {
 
 constexpr float kBnEps = 1e-5f, kBnMomentum = 0.1f;
 constexpr int kSegBn2 = 0, kSegBn3 = 128, kSegBnTotal = 192;   // offsets into the scale/shift tables
+// bf16 tensor-core head: conv_2 local half (128 x 64), conv_3 (64 x 128), conv_4 (<= 32 x 64) packed; biases of conv_3 / conv_4
+constexpr int kSegTcBlob = 16384 + 16384 + 4096, kSegTcTab = 64 + 32;
 
 #define AMP_TRY(expr) do { int rc_ = (expr); if (rc_ != AMP_OK) return rc_; } while (0)
 #define AMP_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fail(AMP_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); } while (0)
@@ -40,6 +43,7 @@ SegSaved seg_carve(Arena& a, long long B, long long W, long long R, int E, int h
 }
 
 struct SegWs {
+    unsigned char* tc_blob; float* tc_tab;                      // bf16 tensor-core path: packed head weights, bias tables
     float *part_sum, *part_sq, *k1, *k2, *k3, *wg; size_t wg_floats;
     float *dz3, *dz2, *dcb, *dg_w, *dattn_o, *dqkv, *dtokens, *dpre;
 };
@@ -59,7 +63,10 @@ SegWs seg_ws_carve(Arena& a, long long B, long long W, long long R, int E, int h
     const size_t T = (size_t)B * W, M = (size_t)B * R;
     const size_t tiles = (size_t)pw_tiles((int)B, (int)R);
     w.part_sum = a.take<float>(tiles * 128); w.part_sq = a.take<float>(tiles * 128);
-    if (!backward) return w;
+    if (!backward) {
+        w.tc_blob = a.take<unsigned char>(kSegTcBlob); w.tc_tab = a.take<float>(kSegTcTab);
+        return w;
+    }
     w.k1 = a.take<float>(kSegBnTotal); w.k2 = a.take<float>(kSegBnTotal); w.k3 = a.take<float>(kSegBnTotal);
     w.wg_floats = seg_wg_floats(B, W, R, E, hid);
     w.wg = a.take<float>(w.wg_floats);
@@ -118,9 +125,13 @@ size_t amp_seg_workspace_bytes(int64_t B, int64_t W, int64_t rows, int32_t embed
 int amp_seg_fwd(const void* const* params, const float* gl_feats, const float* lo_feats, const float* centroids,
                 const int32_t* np_cluster, const int32_t* group_rows, const uint8_t* key_padding_mask, int64_t B,
                 int64_t W, int64_t rows, int32_t embed_dim, int32_t heads, int32_t num_classes, int32_t training,
-                float dropout_p, uint64_t seed, float* logits, void* saved, size_t saved_bytes, void* workspace,
-                size_t workspace_bytes, void* stream) {
+                int32_t precision, float dropout_p, uint64_t seed, float* logits, void* saved, size_t saved_bytes,
+                void* workspace, size_t workspace_bytes, void* stream) {
     using namespace amp;
+    if (precision != AMP_PREC_FP32 && precision != AMP_PREC_BF16) return fail(AMP_E_BADARG, "seg_fwd: unknown precision %d", precision);
+    if (precision == AMP_PREC_BF16 && training)
+        return fail(AMP_E_BADARG, "seg_fwd: the bf16 tensor-core path is eval-only; training runs in AMP_PREC_FP32");
+    if (precision == AMP_PREC_BF16 && num_classes > 32) return fail(AMP_E_BADARG, "seg_fwd: the bf16 head supports up to 32 classes");
     if (!params || !gl_feats || !lo_feats || !centroids || !np_cluster || !group_rows || !logits || !saved || !workspace)
         return fail(AMP_E_BADARG, "seg_fwd: null pointer");
     const SegShape sh{B, W, rows, embed_dim, heads, num_classes, embed_dim / 2};
@@ -161,7 +172,46 @@ int amp_seg_fwd(const void* const* params, const float* gl_feats, const float* l
         PwParams p{};
         p.X = S.g_w; p.ldx = E; p.K = E; p.W = pf(params, S_C2W) + 64; p.ldw = 64 + E; p.bias = pf(params, S_C2B); p.n_groups = 1;
         p.Y = S.cb; p.ldy = hid; p.n_clouds = 1; p.rows_per_cloud = T; p.Nout = hid;
-        AMP_TRY(pw_linear(p, st));
+        if (precision != AMP_PREC_BF16) AMP_TRY(pw_linear(p, st));
+    }
+    if (precision == AMP_PREC_BF16) {
+        // fused head on the tensor cores: bn_2 / bn_3 folded into the packed weights and the biases; the per-block bias
+        // becomes cb' = scale2 * (W2[:, 64:] g_w + b2) + shift2
+        BnDesc t[2] = {
+            {pf(params, S_BN2 + BN_W), pf(params, S_BN2 + BN_B), pf(params, S_BN2 + BN_RM), pf(params, S_BN2 + BN_RV), S.scale + kSegBn2, S.shift + kSegBn2, hid},
+            {pf(params, S_BN3 + BN_W), pf(params, S_BN3 + BN_B), pf(params, S_BN3 + BN_RM), pf(params, S_BN3 + BN_RV), S.scale + kSegBn3, S.shift + kSegBn3, 64}};
+        AMP_TRY(bn_fold_eval(t, 2, kBnEps, st));
+        {
+            PwParams p{};
+            p.X = S.g_w; p.ldx = E; p.K = E; p.W = pf(params, S_C2W) + 64; p.ldw = 64 + E; p.bias = pf(params, S_C2B); p.n_groups = 1;
+            p.out_scale = S.scale + kSegBn2; p.out_shift = S.shift + kSegBn2;
+            p.Y = S.cb; p.ldy = hid; p.n_clouds = 1; p.rows_per_cloud = T; p.Nout = hid;
+            AMP_TRY(pw_linear(p, st));
+        }
+        const int Cp = (num_classes + 15) / 16 * 16;
+        TcPackTable pt{};
+        pt.n = 3; pt.n_clouds = 1;
+        pt.job[0] = TcPackJob{pf(params, S_C2W), 64 + E, 0, S.scale + kSegBn2, hid, 64, hid, 64, 0, 0, 0, 0};
+        pt.job[1] = TcPackJob{pf(params, S_C3W), hid, 0, S.scale + kSegBn3, 64, hid, 64, hid, 0, 0, 16384, 0};
+        pt.job[2] = TcPackJob{pf(params, S_C4W), 64, 0, nullptr, num_classes, 64, Cp, 64, 0, 0, 32768, 0};
+        AMP_TRY(tc_pack_weights(pt, ws.tc_blob, st));
+        TcBiasTable bt{};
+        bt.n = 2;
+        bt.job[0] = TcBiasJob{pf(params, S_C3B), S.scale + kSegBn3, S.shift + kSegBn3, 64, 64, 0};
+        bt.job[1] = TcBiasJob{pf(params, S_C4B), nullptr, nullptr, num_classes, Cp, 64};
+        AMP_TRY(tc_bias_tables(bt, ws.tc_tab, st));
+        TcChainParams p{};
+        p.n_ops = 3;
+        p.op[0] = TcOp{64, hid, 0, 0, -1, 1, 1, 1, 0, 0, 0};
+        p.op[1] = TcOp{hid, 64, 16384, 0, 0, 1, 0, 1, 0, 0, 0};
+        p.op[2] = TcOp{64, Cp, 32768, 0, 64, 0, 0, 0, 0, 0, 1};
+        p.in_mode = 1; p.in_x = lo_feats; p.in_ld = 64; p.in_k = 64;
+        p.tables = ws.tc_tab; p.n_table_floats = 64 + Cp;
+        p.wblob = ws.tc_blob; p.wblob_bytes = 32768 + Cp * 128;
+        p.gbias = S.cb; p.group_rows = group_rows; p.n_groups = Wi;
+        p.logits = logits; p.n_classes = num_classes;
+        p.n_clouds = Bi; p.rows_per_cloud = Ri;
+        return tc_chain_launch(p, st);
     }
     if (!train) {
         BnDesc t[2] = {

@@ -19,6 +19,19 @@ import torch.nn as nn
 from . import _lib
 
 
+PRECISIONS = {"fp32": 0, "bf16": 1}          # AMP_PREC_* of include/ampnet_b200.h
+_default_precision = "fp32"
+
+
+def set_default_precision(name):
+    """Arithmetic of the eval forward for modules that do not set `.precision` themselves:
+    "fp32" (CUDA cores, the parity path) or "bf16" (fused tcgen05 chains). Training always runs in fp32."""
+    global _default_precision
+    if name not in PRECISIONS:
+        raise ValueError("precision must be one of %s" % sorted(PRECISIONS))
+    _default_precision = name
+
+
 def _ptr_array(tensors):
     arr = (ctypes.c_void_p * len(tensors))()
     for i, t in enumerate(tensors):
@@ -34,6 +47,13 @@ class _NativeModule(nn.Module):
     """Caches the state_dict-ordered tensor list the C ABI takes and checks it against the library's names."""
     _abi_count = None
     _abi_name = None
+    precision = None        # None: follow set_default_precision(); "fp32" | "bf16" (eval only; training is fp32)
+
+    def _precision(self):
+        name = self.precision or _default_precision
+        if name not in PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(PRECISIONS))
+        return 0 if self.training else PRECISIONS[name]
 
     def _native_tensors(self):
         ts = self.__dict__.get("_amp_tensors")
@@ -105,7 +125,7 @@ class TransformationNet(nn.Module):
 
 class _EncoderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, training, *tensors):
+    def forward(ctx, x, training, precision, *tensors):
         lib = _lib.lib()
         B, N, _ = x.shape
         dev = x.device
@@ -117,7 +137,7 @@ class _EncoderFn(torch.autograd.Function):
         ws_bytes = lib.amp_encoder_workspace_bytes(B, N, 0)
         ws = _bytes(ws_bytes, dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.amp_encoder_fwd(_ptr_array(tensors), x.data_ptr(), B, N, tr, out.data_ptr(), ft.data_ptr(),
+            _lib.check(lib.amp_encoder_fwd(_ptr_array(tensors), x.data_ptr(), B, N, tr, precision, out.data_ptr(), ft.data_ptr(),
                                            saved.data_ptr() if training else None, saved_bytes, ws.data_ptr(), ws_bytes,
                                            _lib.stream_ptr()))
         if training:
@@ -150,7 +170,7 @@ class _EncoderFn(torch.autograd.Function):
                                            B, N, saved.data_ptr(), saved.numel(), ws.data_ptr(), ws_bytes,
                                            _lib.stream_ptr()))
         ctx.saved = None
-        return (None, None) + tuple(grads)
+        return (None, None, None) + tuple(grads)
 
 
 class BasePointNet(_NativeModule):
@@ -190,7 +210,7 @@ class BasePointNet(_NativeModule):
         x = _input(x, "x", tensors[0].device)
         if x.dim() != 3 or x.shape[2] != 9:
             raise ValueError("x must be [B, N, 9], got %s" % (tuple(x.shape),))
-        out, ft = _EncoderFn.apply(x, self.training, *tensors)
+        out, ft = _EncoderFn.apply(x, self.training, self._precision(), *tensors)
         if self.return_local_features:
             return out, ft
         return out[:, 0, :256], ft
@@ -200,7 +220,7 @@ class _SegFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, gl, lo, cent, training, meta, *tensors):
         lib = _lib.lib()
-        npc, group_rows, mask, E, heads, C, p, seed = meta
+        npc, group_rows, mask, E, heads, C, p, seed, precision = meta
         W, B, _ = gl.shape
         R = lo.shape[1]
         dev = lo.device
@@ -212,7 +232,7 @@ class _SegFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(lib.amp_seg_fwd(_ptr_array(tensors), gl.data_ptr(), lo.data_ptr(), cent.data_ptr(), npc,
                                        group_rows.data_ptr(), mask.data_ptr() if mask is not None else None, B, W, R, E,
-                                       heads, C, 1 if training else 0, p, seed, logits.data_ptr(), saved.data_ptr(),
+                                       heads, C, 1 if training else 0, precision, p, seed, logits.data_ptr(), saved.data_ptr(),
                                        saved_bytes, ws.data_ptr(), ws_bytes, _lib.stream_ptr()))
         if training:
             ctx.tensors = tensors
@@ -227,7 +247,7 @@ class _SegFn(torch.autograd.Function):
     def backward(ctx, d_logits):
         lib = _lib.lib()
         gl, lo, cent = ctx.saved_tensors
-        npc, group_rows, mask, E, heads, C, p, seed = ctx.meta
+        npc, group_rows, mask, E, heads, C, p, seed, _ = ctx.meta
         tensors = ctx.tensors
         W, B, _ = gl.shape
         R = lo.shape[1]
@@ -316,6 +336,6 @@ class SegmentationWithAttention(_NativeModule):
                 raise ValueError("attn_mask must be [B, W]")
         p = self.dropout_p if self.training else 0.0
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0.0 else 0
-        meta = (npc, group_rows, mask, E, self.num_heads, self.num_classes, p, seed)
+        meta = (npc, group_rows, mask, E, self.num_heads, self.num_classes, p, seed, self._precision())
         logits = _SegFn.apply(gl, lo, cent, self.training, meta, *tensors)
         return logits, 0

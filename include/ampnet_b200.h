@@ -29,6 +29,12 @@ extern "C" {
 #define AMP_E_CUDA       -3   /* launch failed (cudaGetLastError) */
 #define AMP_E_ARCH       -4   /* device is not sm_100             */
 
+/* arithmetic of the PointNet-attention forward (amp_encoder_fwd / amp_seg_fwd `precision`):
+ *   AMP_PREC_FP32  fp32 on the CUDA cores: the parity path (logits within 1e-3 relative of the reference), train + eval
+ *   AMP_PREC_BF16  eval only: fused tcgen05 chains, bf16 operands (BatchNorm folded into the weights), fp32 accumulate */
+#define AMP_PREC_FP32     0
+#define AMP_PREC_BF16     1
+
 const char* amp_last_error(void);
 /* ABI version of this header: major*1000 + minor. */
 int amp_abi_version(void);
@@ -100,6 +106,7 @@ int amp_kmeans_regroup(const int32_t* labels, const int64_t* offsets, const int3
  *   feat_t      [B, 64, 64] f32 feature transform (second module output, :94)
  *   training    0: eval (BatchNorm running statistics);  1: train (batch statistics; running_mean /
  *               running_var / num_batches_tracked updated in place; `saved` filled for backward)
+ *   precision   AMP_PREC_FP32 | AMP_PREC_BF16 (eval only)
  *   saved       amp_encoder_saved_bytes() bytes, kept by the caller between fwd and bwd (training only)
  *   workspace   amp_encoder_workspace_bytes() bytes of scratch (may be reused after the call's work completes)
  * amp_encoder_bwd: grads = host array of DEVICE pointers like params (NULL for the BatchNorm buffers), every
@@ -109,7 +116,7 @@ int amp_encoder_param_count(void);
 const char* amp_encoder_param_name(int i);
 size_t amp_encoder_saved_bytes(int64_t B, int64_t N, int32_t training);
 size_t amp_encoder_workspace_bytes(int64_t B, int64_t N, int32_t training);
-int amp_encoder_fwd(const void* const* params, const float* x, int64_t B, int64_t N, int32_t training,
+int amp_encoder_fwd(const void* const* params, const float* x, int64_t B, int64_t N, int32_t training, int32_t precision,
                     float* out, float* feat_t, void* saved, size_t saved_bytes, void* workspace,
                     size_t workspace_bytes, void* stream);
 int amp_encoder_bwd(const void* const* params, void* const* grads, const float* x, const float* out,
@@ -129,6 +136,7 @@ int amp_encoder_bwd(const void* const* params, void* const* grads, const float* 
  *   logits      [B, num_classes, rows] f32
  *   training    1: batch-statistics BatchNorm + dropout(dropout_p) driven by the counter-based generator
  *               seeded with `seed` (pass the same seed to amp_seg_bwd)
+ *   precision   AMP_PREC_FP32 | AMP_PREC_BF16 (eval only, num_classes <= 32)
  *   saved       amp_seg_saved_bytes() bytes (needed in both modes; kept for backward in training)
  * amp_seg_bwd: d_logits [B, num_classes, rows]; writes d_gl_feats [W, B, E], d_lo_feats [B, rows, 64] and every
  * parameter gradient (overwritten). Needs block sizes sharing a factor >= 64 points and W <= 64.
@@ -140,8 +148,8 @@ size_t amp_seg_workspace_bytes(int64_t B, int64_t W, int64_t rows, int32_t embed
 int amp_seg_fwd(const void* const* params, const float* gl_feats, const float* lo_feats, const float* centroids,
                 const int32_t* np_cluster, const int32_t* group_rows, const uint8_t* key_padding_mask, int64_t B,
                 int64_t W, int64_t rows, int32_t embed_dim, int32_t heads, int32_t num_classes, int32_t training,
-                float dropout_p, uint64_t seed, float* logits, void* saved, size_t saved_bytes, void* workspace,
-                size_t workspace_bytes, void* stream);
+                int32_t precision, float dropout_p, uint64_t seed, float* logits, void* saved, size_t saved_bytes,
+                void* workspace, size_t workspace_bytes, void* stream);
 int amp_seg_bwd(const void* const* params, void* const* grads, const float* lo_feats, const float* centroids,
                 const int32_t* np_cluster, const int32_t* group_rows, const float* d_logits, int64_t B, int64_t W,
                 int64_t rows, int32_t embed_dim, int32_t heads, int32_t num_classes, float dropout_p, uint64_t seed,
