@@ -77,10 +77,11 @@ class _Flush:
         self.buf.fill_(1)
 
 
-def bench_fwd(dist, amp, steps, warmup, with_cpu):
+def bench_fwd(dist, amp, steps, warmup, with_cpu, precision="fp32"):
     dev = dist.device
     enc, seg = build_modules(amp, dev)
     enc.eval(); seg.eval()
+    enc.precision = seg.precision = precision
     x_np, c_np, _ = synthetic_blocks(dist.rank)
     x_host = torch.from_numpy(x_np).pin_memory()
     c_host = torch.from_numpy(c_np).pin_memory()
@@ -111,12 +112,14 @@ def bench_fwd(dist, amp, steps, warmup, with_cpu):
         "value": pts / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms / steps, "gpu_launches": int(launches),
         "e2e": {"value": pts / (e_ms * 1e-3), "unit": "points/s",
                 "h2d_bytes_per_step": int(x_host.numel() * 4 + c_host.numel() * 4), "d2h_bytes_per_step": int(logits_host.numel() * 4)},
-        "roofline": {"bound": "tensor", "kernel": "whole forward (pw_linear_kernel chain, fp32 CUDA cores)", "achieved": ach, "peak": peak,
+        "roofline": {"bound": "tensor", "kernel": "whole forward (pw_linear_kernel chain, fp32 CUDA cores)" if precision == "fp32"
+                     else "whole forward (tc_chain_kernel x 4: tcgen05 bf16 chains + fp32 per-cloud FC / attention kernels)",
+                     "achieved": ach, "peak": peak,
                      "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": src,
                      "model": "413 143 algorithmic FLOP per point (SURVEY 8d) x 65 536 points / step time"},
         "config": {"workload": "configs[0]: segmentation forward, batch %d x %d points, 9 channels, eval, random-init weights"
-                               % (NN_BATCH, NN_POINTS), "l2": "flushed between steps (256 MiB write)", "precision": "fp32"},
-        "dtype": "f32",
+                               % (NN_BATCH, NN_POINTS), "l2": "flushed between steps (256 MiB write)", "precision": precision},
+        "dtype": "f32" if precision == "fp32" else "bf16",
     }
     if with_cpu:
         from oracle import nn_bench as onb
@@ -188,5 +191,9 @@ def bench_train(dist, amp, steps, warmup, with_cpu):
     return res
 
 
+def bench_fwd_bf16(dist, amp, steps, warmup, with_cpu):
+    return bench_fwd(dist, amp, steps, warmup, with_cpu, precision="bf16")
+
+
 def hooks():
-    return {"fwd": bench_fwd, "train": bench_train}
+    return {"fwd": bench_fwd, "fwd_bf16": bench_fwd_bf16, "train": bench_train}

@@ -271,7 +271,7 @@ def run_reference(args):
                 "e2e": {"value": v, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     else:
         from oracle import nn_bench
-        line = nn_bench.reference_line(wl, args)
+        line = nn_bench.reference_line("fwd" if wl.startswith("fwd") else wl, args)
     print(json.dumps(line), flush=True)
 
 
@@ -281,7 +281,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="fps", choices=["fps", "fwd", "train"])
+    ap.add_argument("--workload", default="fps", choices=["fps", "fwd", "fwd_bf16", "train"])
     ap.add_argument("--only", action="store_true", help="measure only the headline workload")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
@@ -303,7 +303,8 @@ def main():
         raise SystemExit("workload %s is not available in this build" % args.workload)
     with ClockSampler(dist.local_rank) as clk:
         head = table[args.workload](dist, amp, args.steps, args.warmup, with_cpu)
-    line = {"metric": {"fps": "FPS clouds/sec", "fwd": "segmented points/sec (fwd)", "train": "train pts/sec"}[args.workload],
+    line = {"metric": {"fps": "FPS clouds/sec", "fwd": "segmented points/sec (fwd)", "fwd_bf16": "segmented points/sec (fwd)",
+                       "train": "train pts/sec"}[args.workload],
             "value": head.pop("value"), "unit": head.pop("unit"), "n_gpus": dist.world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": head.pop("ms_per_step"), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "data": "synthetic"}
