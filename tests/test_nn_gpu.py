@@ -238,3 +238,60 @@ def test_no_cpu_fallback(amp):
     enc = amp.BasePointNet(point_dimension=3, return_local_features=True)
     with pytest.raises(RuntimeError):
         enc(torch.zeros(2, 16, 9))
+
+
+# ---- bf16 tensor-core eval path (AMP_PREC_BF16): stated separately from the fp32 parity bound --------------------
+TOL_BF16_LOGITS = 2e-2      # max-norm relative; measured 2.7e-3 .. 6.6e-3 on the golden cases
+TOL_BF16_FT = 1e-3
+
+
+@pytest.mark.parametrize("name", sorted(make_golden_nn.CASES))
+def test_bf16_tensor_core_forward_vs_reference_golden(amp, cuda, name):
+    z = np.load(GOLDEN)
+    seed, xs, cent, mask = _case(name)
+    enc, seg, _, _ = _build(amp, seed, cuda)
+    enc.eval(); seg.eval()
+    enc.precision = seg.precision = "bf16"
+    logits, ft, out = _run(enc, seg, xs, cent, mask, cuda)
+    ref = torch.from_numpy(z[name + "__eval_logits"])
+    assert _rel(logits, ref) < TOL_BF16_LOGITS
+    assert _relnorm(logits, ref) < TOL_BF16_LOGITS / 2
+    assert (logits.argmax(1).cpu() == ref.argmax(1)).float().mean().item() >= 0.97
+    assert _rel(ft, z[name + "__eval_ft"]) < TOL_BF16_FT
+    assert _rel(out[:, ::37, :], z[name + "__eval_enc_out_last"]) < TOL_BF16_LOGITS
+
+
+def test_bf16_forward_ragged_blocks_and_training_refusal(amp, cuda):
+    """Variable block sizes (test script shape, batch 1, rows not a multiple of the 128-point tile) on the tensor-core
+    path against the fp32 path; the bf16 path is eval-only."""
+    enc, seg, _, _ = _build(amp, 5, cuda)
+    enc.eval(); seg.eval()
+    g = torch.Generator().manual_seed(3)
+    sizes = [2048, 2500, 2177]
+    xs = [torch.rand(1, n, 9, generator=g) for n in sizes]
+    cent = torch.rand(1, len(sizes), 2, generator=g)
+    res = {}
+    for prec in ("fp32", "bf16"):
+        enc.precision = seg.precision = prec
+        res[prec], _, _ = _run(enc, seg, xs, cent, None, cuda)
+    assert res["bf16"].shape == (1, 5, sum(sizes))
+    assert _rel(res["bf16"], res["fp32"]) < TOL_BF16_LOGITS
+    enc.train(); seg.train()       # training ignores the precision switch and runs the fp32 path
+    out, ft = enc(torch.rand(2, 256, 9, generator=g).to(cuda))
+    assert out.requires_grad
+
+
+def test_tc_linear_matches_bf16_rounded_matmul(amp, cuda):
+    torch.manual_seed(0)
+    for (C, R, K, N, relu, pool) in [(1, 128, 16, 16, False, False), (3, 200, 128, 128, True, False), (2, 256, 128, 256, True, True),
+                                     (3, 77, 64, 128, True, True), (4, 1000, 32, 64, False, False)]:
+        x = torch.randn(C, R, K, device=cuda); w = torch.randn(N, K, device=cuda) / K ** 0.5; b = torch.randn(N, device=cuda)
+        got = amp.tc_linear(x, w, b, relu=relu, pool=pool)
+        exp = x.bfloat16().float() @ w.bfloat16().float().t() + b
+        if relu:
+            exp = torch.relu(exp)
+        if pool:
+            exp = exp.max(dim=1).values
+        assert (got - exp).abs().max().item() < 1e-4
+    with pytest.raises(RuntimeError, match="multiple of 16"):
+        amp.tc_linear(torch.zeros(1, 8, 24, device=cuda), torch.zeros(16, 24, device=cuda))

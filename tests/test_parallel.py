@@ -1,0 +1,62 @@
+"""Host-side multi-GPU plumbing on CPU: window sharding and the flat gradient all-reduce (gloo, world size 2)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _shards(amp, blocks, world):
+    b = amp.shard_windows(blocks, world)
+    assert len(b) == world
+    assert b[0][0] == 0 and b[-1][1] == len(blocks)
+    for (a0, a1), (b0, b1) in zip(b, b[1:]):
+        assert a1 == b0 and a0 <= a1 and b0 <= b1
+    return b
+
+
+def test_shard_windows_partitions_and_balances(amp):
+    assert _shards(amp, [1] * 8, 4) == [(0, 2), (2, 4), (4, 6), (6, 8)]
+    b = _shards(amp, [9, 1, 1, 1, 9, 1, 1, 1], 2)
+    loads = [sum([9, 1, 1, 1, 9, 1, 1, 1][s:e]) for s, e in b]
+    assert max(loads) - min(loads) <= 9
+    _shards(amp, [3], 4)                   # fewer windows than ranks: trailing ranks get empty ranges
+    _shards(amp, [], 2)
+    for world in (1, 2, 3, 8):
+        _shards(amp, [((7 * i) % 18) + 1 for i in range(53)], world)
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import importlib
+    amp = importlib.import_module("3d-semantic-segmentation-amp-net_b200")
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2, 2))]
+    params[2].requires_grad_(False)
+    params[0].grad = torch.full((5, 3), float(rank + 1))
+    params[1].grad = None                                   # a parameter that got no gradient on this rank
+    red = amp.GradAllReduce(params, world)
+    red.all_reduce()
+    ok = torch.allclose(params[0].grad, torch.full((5, 3), (1 + world) / 2.0)) and torch.count_nonzero(params[1].grad) == 0 \
+        and params[2].grad is None
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_grad_all_reduce_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
