@@ -30,6 +30,7 @@ struct PwParams {
     // optional bias[(cloud * n_groups + g) * bias_group_stride + n]; g = group of row r by group_rows
     // (group_rows[g] = first row of group g; the per-cluster bias of the segmentation head)
     const float* bias; long long bias_group_stride; const int* group_rows; int n_groups;
+    int groups_tile_aligned;            // host hint: every group starts on a multiple of 128 rows (tensor-core path)
     // accumulate: acc += Y (previous content) before the rest of the epilogue (gradient fan-in)
     int accumulate;
     // forward epilogue per output channel: y = y * out_scale[n] + out_shift[n]; then ReLU if out_relu
@@ -52,6 +53,7 @@ struct PwParams {
 };
 
 int pw_linear(const PwParams& p, cudaStream_t st);
+int tc_layer_try(const PwParams& p, cudaStream_t st);   // nn_tc_layer.cu: 1 = launched, 0 = not eligible, < 0 = error
 int pw_tiles(int n_clouds, int rows_per_cloud);      // number of row tiles (= rows of part_sum)
 
 // ---------------------------------------------------------------------------------------------

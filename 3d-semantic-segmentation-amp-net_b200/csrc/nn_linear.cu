@@ -424,6 +424,11 @@ int pw_linear(const PwParams& p, cudaStream_t st) {
         count_launch();
         return check_launch("small_linear");
     }
+    // many rows, tensor-core friendly K: split-bf16 tcgen05 path (nn_tc_layer.cu)
+    {
+        const int rc = tc_layer_try(p, st);
+        if (rc != 0) return rc < 0 ? rc : AMP_OK;
+    }
     PwParams q = p;
     if (q.n_groups < 1) q.n_groups = 1;
     const bool wide = p.Nout > 64;

@@ -230,6 +230,8 @@ int amp_seg_fwd(const void* const* params, const float* gl_feats, const float* l
         PwParams p{};
         p.X = lo_feats; p.ldx = 64; p.K = 64; p.W = pf(params, S_C2W); p.ldw = 64 + E;
         p.bias = S.cb; p.bias_group_stride = hid; p.group_rows = group_rows; p.n_groups = Wi;
+        p.groups_tile_aligned = 1;
+        for (int i = 0; i < Wi; ++i) if (np_cluster[i] % 128) p.groups_tile_aligned = 0;
         p.Y = S.y2; p.ldy = hid; p.n_clouds = Bi; p.rows_per_cloud = Ri; p.Nout = hid;
         if (train) { p.part_sum = ws.part_sum; p.part_sq = ws.part_sq; }
         else { p.out_scale = S.scale + kSegBn2; p.out_shift = S.shift + kSegBn2; p.out_relu = 1; }
