@@ -11,7 +11,7 @@ from .clustering import (kmeans_clustering, split_kmeans, split_kmeans_array, km
                          kmeans_constrained_windows, regroup_windows, gather_feats, get_cluster_centroid)
 from .modules import BasePointNet, TransformationNet, SegmentationWithAttention, set_default_precision  # noqa: F401
 from .parallel import shard_windows, GradAllReduce  # noqa: F401
-from .tensorcore import tc_linear  # noqa: F401
+from .tensorcore import tc_linear, linear_wgrad  # noqa: F401
 
 
 def bench_hooks():

@@ -43,6 +43,8 @@ SIGNATURES = {
                                _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     "amp_tc_linear_workspace_bytes": (_sz, [_i32, _i32]),
     "amp_tc_linear_bf16": (_c.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "amp_wgrad_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
+    "amp_wgrad_f32": (_c.c_int, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None

@@ -81,6 +81,7 @@ struct WgParams {
 size_t wgrad_workspace_floats(int n_clouds, int rows_per_cloud, int Nout, int K, int slab_rows = 0);
 int wgrad_group_slab(const int* group_sizes, int n_groups);
 int wgrad(const WgParams& p, cudaStream_t st);
+int tc_wgrad_try(const WgParams& p, int slabs, int SLAB, cudaStream_t st);   // nn_tc_wgrad.cu: 1 launched, 0 not eligible, < 0 error
 
 // packed (value, row) keys for the pooling atomics: larger key = larger value, then lower row
 __host__ __device__ inline unsigned int ordered_bits(float v) {

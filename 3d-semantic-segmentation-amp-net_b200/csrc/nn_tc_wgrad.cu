@@ -1,0 +1,328 @@
+// Weight gradients of the point-wise linear layers on the tcgen05 tensor cores at fp32-class accuracy (split bf16,
+// see nn_tc_layer.cu):   dW[n, k] = sum_r dy'[r, n] * a'[r, k]   with the prologues of WgParams applied on the fly
+// (dy' = BatchNorm-backward of dY, a' = BatchNorm + ReLU + Dropout of the saved raw activation), i.e. the autograd
+// backward of nn.Conv1d(k=1) / torch.bmm of pointNet/model/pointnetAtt.py driven by train_pointnet-attention.py:467.
+//
+// The reduction runs over the ROWS, which is the slow dimension of both operands in memory, so both UMMA operands are
+// MN-major: element (mn, r) of an operand lives at  (mn / 8) * 128 + (r / 8) * LBO + (r % 8) * 16 + (mn % 8) * 2  bytes
+// (8 x 8 core matrices, 16-byte rows along MN; SBO = 128 B between MN groups, LBO between groups of 8 rows). A staging
+// thread owns one row r and writes 16-byte pieces (8 consecutive channels) -- conflict-free, no transpose.
+//
+// Work unit = one (cloud, slab of SLAB rows) = one partial of wgrad_reduce_kernel (fixed-order, deterministic sum).
+// One CTA per unit; its two warpgroups split the 64-row blocks of the slab and accumulate into separate TMEM
+// regions (D[n, k], lanes = n, columns = k), which the epilogue adds in a fixed order. The bias gradient
+// db[n] = sum_r dy'[r, n] is one more accumulator column: the B operand carries a constant column of ones.
+#include "nn_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace amp {
+namespace {
+using namespace tcx;
+
+constexpr int TW_THREADS = 256, TW_RB = 64;
+constexpr int TW_MAX_SMEM = 232448, TW_MIN_SMEM = 120 * 1024;
+
+struct TwPlan { int a_lo, b_hi, b_lo, slot, tab, bar, total; };
+__host__ __device__ inline TwPlan tw_plan(int Mpad, int Kext, int Nout, int K) {
+    TwPlan s;
+    const int abytes = TW_RB * Mpad * 2, bbytes = TW_RB * Kext * 2;
+    s.a_lo = abytes; s.b_hi = 2 * abytes; s.b_lo = 2 * abytes + bbytes;
+    s.slot = 2 * abytes + 2 * bbytes;
+    s.tab = 2 * s.slot;
+    s.bar = s.tab + 16 * (Nout + K) + 64;
+    s.bar = (s.bar + 15) / 16 * 16;
+    s.total = s.bar + 64;
+    return s;
+}
+
+__device__ __forceinline__ void split_pair_w(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16x2(a, b);
+    lo = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+}
+__device__ __forceinline__ void split_store8_w(const float (&v)[8], uint4* hi_dst, uint4* lo_dst) {
+    uint4 h, l;
+    split_pair_w(v[0], v[1], h.x, l.x); split_pair_w(v[2], v[3], h.y, l.y);
+    split_pair_w(v[4], v[5], h.z, l.z); split_pair_w(v[6], v[7], h.w, l.w);
+    *hi_dst = h; *lo_dst = l;
+}
+// instruction descriptor with both operands MN-major
+__device__ __forceinline__ uint32_t umma_idesc_mn(int M, int N) { return umma_idesc(M, N) | (1u << 15) | (1u << 16); }
+
+__global__ void __launch_bounds__(TW_THREADS, 1)
+tc_wgrad_kernel(const __grid_constant__ WgParams p, const int Mpad, const int Kext, const int slabs, const int SLAB) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = warp >> 2, wtid = tid & 127;
+    const int K = p.K, Nout = p.Nout, rows = p.rows_per_cloud;
+    const TwPlan sp = tw_plan(Mpad, Kext, Nout, K);
+    unsigned char* s_slot = smem + wg * sp.slot;
+    uint4* s_ahi = reinterpret_cast<uint4*>(s_slot);
+    uint4* s_alo = reinterpret_cast<uint4*>(s_slot + sp.a_lo);
+    uint4* s_bhi = reinterpret_cast<uint4*>(s_slot + sp.b_hi);
+    uint4* s_blo = reinterpret_cast<uint4*>(s_slot + sp.b_lo);
+    float* s_ya = reinterpret_cast<float*>(smem + sp.tab);      // [Nout] x 4: y_a, y_b, y_c, y_m ; [K] x 3: a_a, a_b, a_m
+    float* s_yb = s_ya + Nout; float* s_yc = s_yb + Nout; float* s_ym = s_yc + Nout;
+    float* s_aa = s_ym + Nout; float* s_ab = s_aa + K; float* s_am = s_ab + K;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + sp.bar);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + sp.bar + 32);
+    const uint32_t mbar = smem_u32(&s_bar[wg]);
+
+    if (tid == 0) {
+        mbar_init(smem_u32(&s_bar[0]), 1);
+        mbar_init(smem_u32(&s_bar[1]), 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(s_tmem), 512);
+    for (int n = tid; n < Nout; n += TW_THREADS) {
+        s_ya[n] = p.y_a ? __ldg(p.y_a + n) : 1.f; s_yb[n] = p.y_b ? __ldg(p.y_b + n) : 0.f;
+        s_yc[n] = p.y_c ? __ldg(p.y_c + n) : 0.f; s_ym[n] = p.y_m ? __ldg(p.y_m + n) : 0.f;
+    }
+    for (int k = tid; k < K; k += TW_THREADS) {
+        s_aa[k] = p.a_a ? __ldg(p.a_a + k) : 1.f; s_ab[k] = p.a_b ? __ldg(p.a_b + k) : 0.f; s_am[k] = p.a_m ? __ldg(p.a_m + k) : 0.f;
+    }
+    const int a_groups = Mpad >> 3, b_groups = Kext >> 3;       // 16-byte pieces per row
+    // constant part of the B operand: columns K .. Kext-1 (a column of ones for the bias gradient, then zeros)
+    if (Kext > K) {
+        const int r = wtid & 63, half = wtid >> 6;
+        const int g = (K >> 3) + half;                          // two extra groups of 8 columns
+        s_bhi[g * 8 + (r >> 3) * (b_groups * 8) + (r & 7)] = make_uint4(half == 0 ? 0x00003f80u : 0u, 0u, 0u, 0u);   // bf16 1.0 at column K
+        s_blo[g * 8 + (r >> 3) * (b_groups * 8) + (r & 7)] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    const int n_mt = Mpad >> 7;
+    const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t slot_col = tmem_base + (uint32_t)(wg * 256);
+    const uint32_t ahi_addr = smem_u32(s_ahi), alo_addr = smem_u32(s_alo), bhi_addr = smem_u32(s_bhi), blo_addr = smem_u32(s_blo);
+    const uint32_t a_lbo = (uint32_t)a_groups * 128u, b_lbo = (uint32_t)b_groups * 128u;
+    const uint32_t idesc = umma_idesc_mn(128, Kext);
+    const bool y_pro = p.y_a != nullptr, a_pro = p.a_a != nullptr;
+    uint32_t phase = 0;
+    const int sr = wtid & 63, shalf = wtid >> 6;                // staging: row within the block, which half of the channels
+    const int n_units = p.n_clouds * slabs;
+
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int cloud = unit / slabs, slab = unit - cloud * slabs;
+        const int r_begin = slab * SLAB, r_end = min(rows, r_begin + SLAB);
+        const long long cloud_row = (long long)cloud * rows;
+        const int nb = (r_end - r_begin + TW_RB - 1) / TW_RB;
+        const int nb0 = (nb + 1) >> 1;
+        const int blk_lo = wg == 0 ? 0 : nb0, blk_hi = wg == 0 ? nb0 : nb;
+        for (int blk = blk_lo; blk < blk_hi; ++blk) {
+            const int r = r_begin + blk * TW_RB + sr;
+            const bool row_ok = r < r_end;
+            const long long grow = cloud_row + r;
+            // ---- A operand: dy'[r, n] for this thread's half of the channels ----
+            {
+                const float* __restrict__ yrow = p.dY + grow * p.lddy;
+                const float* __restrict__ y2row = p.Y2 ? p.Y2 + grow * p.lddy : nullptr;
+                const int g0 = shalf * (a_groups >> 1), g1 = g0 + (a_groups >> 1);
+                for (int gb = g0; gb < g1; gb += 4) {           // batches of 32 channels
+                    float4 xa[8], ya[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int n = gb * 8 + i * 4;
+                        xa[i] = (row_ok && n < Nout) ? __ldg(reinterpret_cast<const float4*>(yrow + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (y2row) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int n = gb * 8 + i * 4;
+                            ya[i] = (row_ok && n < Nout) ? __ldg(reinterpret_cast<const float4*>(y2row + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int g = gb + c, n = g * 8;
+                        float v[8] = {xa[2 * c].x, xa[2 * c].y, xa[2 * c].z, xa[2 * c].w, xa[2 * c + 1].x, xa[2 * c + 1].y, xa[2 * c + 1].z, xa[2 * c + 1].w};
+                        if (row_ok && n < Nout) {
+                            if (y_pro) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], s_ya[n + i], s_yb[n + i]);
+                            }
+                            if (y2row) {
+                                const float y2[8] = {ya[2 * c].x, ya[2 * c].y, ya[2 * c].z, ya[2 * c].w, ya[2 * c + 1].x, ya[2 * c + 1].y, ya[2 * c + 1].z, ya[2 * c + 1].w};
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] = fmaf(y2[i] - s_ym[n + i], s_yc[n + i], v[i]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                        }
+                        const int off = g * 8 + (sr >> 3) * (a_groups * 8) + (sr & 7);
+                        split_store8_w(v, s_ahi + off, s_alo + off);
+                    }
+                }
+            }
+            // ---- B operand: a'[r, k] for this thread's half of the input channels ----
+            {
+                const float* __restrict__ arow = p.A + grow * p.lda;
+                const int kg = K >> 3;                          // groups with data (K % 16 == 0 -> even)
+                const int g0 = shalf * (kg >> 1), g1 = g0 + (kg >> 1);
+                for (int gb = g0; gb < g1; gb += 4) {
+                    float4 xa[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int g = gb + (i >> 1);
+                        xa[i] = (row_ok && g < g1) ? __ldg(reinterpret_cast<const float4*>(arow + gb * 8) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int g = gb + c, k = g * 8;
+                        if (g < g1) {
+                            float v[8] = {xa[2 * c].x, xa[2 * c].y, xa[2 * c].z, xa[2 * c].w, xa[2 * c + 1].x, xa[2 * c + 1].y, xa[2 * c + 1].z, xa[2 * c + 1].w};
+                            if (row_ok) {
+                                if (a_pro) {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i] - s_am[k + i], s_aa[k + i], s_ab[k + i]);
+                                }
+                                if (p.a_relu) {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                                }
+                                if (p.a_drop_p > 0.f) {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i)
+                                        v[i] *= dropout_keep(p.a_drop_seed, (unsigned long long)grow * K + k + i, p.a_drop_p);
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                            }
+                            const int off = g * 8 + (sr >> 3) * (b_groups * 8) + (sr & 7);
+                            split_store8_w(v, s_bhi + off, s_blo + off);
+                        }
+                    }
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            wg_bar_sync(wg);
+            if (wtid == 0) {
+                tc_fence_after();
+                for (int mt = 0; mt < n_mt; ++mt) {
+                    const uint32_t d = slot_col + (uint32_t)(mt * Kext);
+#pragma unroll
+                    for (int ks = 0; ks < TW_RB / 16; ++ks) {
+                        const uint32_t aoff = (uint32_t)mt * 2048u + (uint32_t)ks * 2u * a_lbo, boff = (uint32_t)ks * 2u * b_lbo;
+                        const uint64_t a_hi = umma_desc(ahi_addr + aoff, a_lbo, 128u), a_lo = umma_desc(alo_addr + aoff, a_lbo, 128u);
+                        const uint64_t b_hi = umma_desc(bhi_addr + boff, b_lbo, 128u), b_lo = umma_desc(blo_addr + boff, b_lbo, 128u);
+                        umma_bf16(d, a_lo, b_hi, idesc, (blk != blk_lo || ks != 0) ? 1u : 0u);
+                        umma_bf16(d, a_hi, b_lo, idesc, 1u);
+                        umma_bf16(d, a_hi, b_hi, idesc, 1u);
+                    }
+                }
+                umma_commit(mbar);
+            }
+            __syncwarp();
+            mbar_wait(mbar, phase);
+            phase ^= 1u;
+            tc_fence_after();
+        }
+        // ---- both halves of the slab are accumulated: add them (slot 0 + slot 1) and write the partial ----
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        {
+            const bool two = nb - nb0 > 0;
+            float* __restrict__ part = p.partials + (long long)unit * ((long long)Nout * K + Nout);
+            const int lrow = (warp & 3) * 32 + lane;
+            for (int mt = 0; mt < n_mt; ++mt) {
+                const int n = mt * 128 + lrow;
+                const uint32_t c_base = tmem_base + lane_addr + (uint32_t)(mt * Kext);
+                int ci = 0;
+                for (int c0 = 0; c0 < Kext; c0 += 32, ++ci) {
+                    if ((ci & 1) != wg) continue;
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(c_base + (uint32_t)c0, v0);
+                    if (two) tmem_ld32(c_base + 256u + (uint32_t)c0, v1);
+                    tmem_wait_ld();
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v0[j]) + (two ? __uint_as_float(v1[j]) : 0.f);
+                    if (n < Nout) {
+                        const int nc = min(32, Kext - c0);           // 16 or 32 accumulator columns in this chunk
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int k = c0 + q * 4;
+                            if (q * 4 < nc && k < K)
+                                *reinterpret_cast<float4*>(part + (long long)n * K + k) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                        }
+                        if (Kext > K && K >= c0 && K < c0 + nc) {
+                            float b = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) b = (c0 + j == K) ? f[j] : b;
+                            part[(long long)Nout * K + n] = b;
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();                 // accumulators are free for the next unit
+        tc_fence_after();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+// Tensor-core partial pass of wgrad(): 1 = launched (the caller still runs wgrad_reduce), 0 = not eligible, < 0 = error.
+int tc_wgrad_try(const WgParams& p, int slabs, int SLAB, cudaStream_t st) {
+    const bool need_bias = p.db != nullptr || p.dbg != nullptr;
+    const int Mpad = (p.Nout + 127) / 128 * 128, Kext = p.K + (need_bias ? 16 : 0);
+    if ((long long)p.n_clouds * p.rows_per_cloud < 2048 || p.dy_transposed) return 0;
+    if (p.K % 16 || p.K < 16 || p.K > 256 || p.Nout > 256 || Kext > 256 || (Mpad >> 7) * Kext > 256) return 0;
+    if (SLAB % TW_RB) return 0;
+    if (p.lddy % 4 || p.lda % 4 || p.Nout % 8 || (reinterpret_cast<uintptr_t>(p.dY) & 15) || (reinterpret_cast<uintptr_t>(p.A) & 15) ||
+        (p.Y2 && (reinterpret_cast<uintptr_t>(p.Y2) & 15)))
+        return 0;
+    if ((((long long)p.Nout * p.K + p.Nout) % 4) || (p.K % 4) || (reinterpret_cast<uintptr_t>(p.partials) & 15)) return 0;
+    const TwPlan sp = tw_plan(Mpad, Kext, p.Nout, p.K);
+    if (sp.total > TW_MAX_SMEM) return 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_MAX_SMEM);
+        if (e != cudaSuccess) return fail(AMP_E_CUDA, "tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    long long grid = (long long)p.n_clouds * slabs;
+    if (grid > kNumSMs) grid = kNumSMs;
+    const int smem_bytes = sp.total < TW_MIN_SMEM ? TW_MIN_SMEM : sp.total;
+    tc_wgrad_kernel<<<(int)grid, TW_THREADS, smem_bytes, st>>>(p, Mpad, Kext, slabs, SLAB);
+    count_launch();
+    const int rc = check_launch("tc_wgrad_kernel");
+    return rc == AMP_OK ? 1 : rc;
+}
+
+}  // namespace amp
+
+// ---------------------------------------------------------------------------------------------------------------
+// C ABI: plain weight gradient (no prologues), the unit the backward is built from; used by the tests
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+size_t amp_wgrad_workspace_bytes(int64_t n_clouds, int64_t rows_per_cloud, int32_t N, int32_t K) {
+    return amp::wgrad_workspace_floats((int)n_clouds, (int)rows_per_cloud, N, K) * sizeof(float) + 256;
+}
+
+int amp_wgrad_f32(const float* dy, const float* a, int64_t n_clouds, int64_t rows_per_cloud, int32_t N, int32_t K, float* dw,
+                  float* db, void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace amp;
+    if (!dy || !a || !dw || !workspace) return fail(AMP_E_BADARG, "wgrad: null pointer");
+    if (n_clouds < 1 || rows_per_cloud < 1 || N < 1 || K < 1 || n_clouds > 65535) return fail(AMP_E_BADARG, "wgrad: bad shape");
+    if (workspace_bytes < amp_wgrad_workspace_bytes(n_clouds, rows_per_cloud, N, K)) return fail(AMP_E_WORKSPACE, "wgrad: workspace too small");
+    WgParams g{};
+    g.dY = dy; g.lddy = N; g.Nout = N; g.A = a; g.lda = K; g.K = K;
+    g.n_clouds = (int)n_clouds; g.rows_per_cloud = (int)rows_per_cloud;
+    g.dW = dw; g.ldw = K; g.db = db;
+    g.partials = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    g.partial_floats = wgrad_workspace_floats((int)n_clouds, (int)rows_per_cloud, N, K);
+    return wgrad(g, (cudaStream_t)stream);
+}
+
+}  // extern "C"

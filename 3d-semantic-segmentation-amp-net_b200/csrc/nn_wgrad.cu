@@ -174,11 +174,15 @@ int wgrad(const WgParams& p, cudaStream_t st) {
     if (p.dbg && (!p.group_rows || p.n_groups < 1)) return fail(AMP_E_BADARG, "wgrad: dbg needs group_rows");
     const int slabs = (p.rows_per_cloud + SLAB - 1) / SLAB;
     const int n_tiles = (p.Nout + TNo - 1) / TNo, k_tiles = (p.K + TKo - 1) / TKo;
-    dim3 grid(slabs, n_tiles * k_tiles, p.n_clouds);
-    wgrad_partial_kernel<<<grid, NT, 0, st>>>(p, n_tiles, k_tiles, slabs, SLAB);
-    count_launch();
-    int rc = check_launch("wgrad_partial");
-    if (rc) return rc;
+    int rc = tc_wgrad_try(p, slabs, SLAB, st);           // tensor-core partial pass when the shape allows (nn_tc_wgrad.cu)
+    if (rc < 0) return rc;
+    if (rc == 0) {
+        dim3 grid(slabs, n_tiles * k_tiles, p.n_clouds);
+        wgrad_partial_kernel<<<grid, NT, 0, st>>>(p, n_tiles, k_tiles, slabs, SLAB);
+        count_launch();
+        rc = check_launch("wgrad_partial");
+        if (rc) return rc;
+    }
     const long long total = (long long)(p.per_cloud ? p.n_clouds : 1) * p.Nout * (p.K + 1) +
                             (p.dbg ? (long long)p.n_clouds * p.n_groups * p.Nout : 0);
     long long blocks = (total + 255) / 256;

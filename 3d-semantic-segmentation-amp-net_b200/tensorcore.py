@@ -28,3 +28,24 @@ def tc_linear(x, weight, bias=None, relu=False, pool=False):
                                           1 if relu else 0, y.data_ptr() if y is not None else None,
                                           pm.data_ptr() if pm is not None else None, ws.data_ptr(), ws_bytes, _lib.stream_ptr()))
     return pm.view(torch.float32) if pool else y
+
+
+def linear_wgrad(dy, a, bias=False):
+    """dy [clouds, rows, N] f32, a [clouds, rows, K] f32 -> dw [N, K] (and db [N] when bias=True): the weight gradient of a
+    point-wise linear layer summed over all rows (amp_wgrad_f32; tensor cores when the shape allows)."""
+    lib = _lib.lib()
+    dy = _lib.require_cuda(dy, "dy", torch.float32)
+    a = _lib.require_cuda(a, "a", torch.float32)
+    if dy.dim() != 3 or a.dim() != 3 or dy.shape[:2] != a.shape[:2]:
+        raise ValueError("dy must be [clouds, rows, N] and a [clouds, rows, K]")
+    C, R, N = dy.shape
+    K = a.shape[2]
+    dev = dy.device
+    dw = torch.empty((N, K), dtype=torch.float32, device=dev)
+    db = torch.empty((N,), dtype=torch.float32, device=dev) if bias else None
+    ws_bytes = lib.amp_wgrad_workspace_bytes(C, R, N, K)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.amp_wgrad_f32(dy.data_ptr(), a.data_ptr(), C, R, N, K, dw.data_ptr(), db.data_ptr() if bias else None,
+                                     ws.data_ptr(), ws_bytes, _lib.stream_ptr()))
+    return (dw, db) if bias else dw

@@ -170,6 +170,16 @@ int amp_tc_linear_bf16(const float* x, int64_t n_clouds, int64_t rows_per_cloud,
                        const float* bias, int32_t N, int32_t relu, float* y, uint32_t* pool_max, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* Weight / bias gradient of one point-wise linear layer, the unit amp_encoder_bwd / amp_seg_bwd are built from
+ * (autograd backward of nn.Conv1d(k=1), pointnetAtt.py; driven by train_pointnet-attention.py:467):
+ *   dw[n, k] = sum over all rows of dy[r, n] * a[r, k]        db[n] = sum dy[r, n]   (db may be NULL)
+ *   dy [n_clouds, rows_per_cloud, N] f32, a [n_clouds, rows_per_cloud, K] f32, dw [N, K], deterministic summation.
+ * Runs on the tcgen05 tensor cores (split bf16, fp32-class accuracy) when K % 16 == 0, N % 8 == 0, K, N <= 256 and there
+ * are at least 2048 rows; on the CUDA cores otherwise. */
+size_t amp_wgrad_workspace_bytes(int64_t n_clouds, int64_t rows_per_cloud, int32_t N, int32_t K);
+int amp_wgrad_f32(const float* dy, const float* a, int64_t n_clouds, int64_t rows_per_cloud, int32_t N, int32_t K, float* dw,
+                  float* db, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
