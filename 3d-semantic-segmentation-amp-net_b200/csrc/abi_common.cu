@@ -1,4 +1,7 @@
 // Error state, version and launch counter of the C ABI (include/ampnet_b200.h).
+#include <stdlib.h>
+#include <string.h>
+
 #include "amp_common.cuh"
 
 namespace amp {
@@ -7,6 +10,11 @@ std::atomic<long long> g_launches{0};
 char* last_error_buf() {
     static thread_local char buf[512] = "";
     return buf;
+}
+
+bool path_disabled(const char* name) {
+    static const char* env = getenv("AMP_DISABLE");
+    return env && strstr(env, name) != nullptr;
 }
 
 int fail(int code, const char* fmt, ...) {

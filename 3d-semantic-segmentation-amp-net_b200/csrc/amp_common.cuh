@@ -27,4 +27,7 @@ inline int check_launch(const char* what) {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// debugging aid: AMP_DISABLE=name1,name2 switches optional fast paths off (they fall back to the generic kernels)
+bool path_disabled(const char* name);
+
 }  // namespace amp

@@ -53,6 +53,7 @@ struct PwParams {
 };
 
 int pw_linear(const PwParams& p, cudaStream_t st);
+int small_linear_try(const PwParams& p, cudaStream_t st);   // nn_small.cu: few-row layers; 1 launched, 0 not eligible, < 0 error
 int tc_layer_try(const PwParams& p, cudaStream_t st);   // nn_tc_layer.cu: 1 = launched, 0 = not eligible, < 0 = error
 int pw_tiles(int n_clouds, int rows_per_cloud);      // number of row tiles (= rows of part_sum)
 
@@ -81,6 +82,8 @@ struct WgParams {
 size_t wgrad_workspace_floats(int n_clouds, int rows_per_cloud, int Nout, int K, int slab_rows = 0);
 int wgrad_group_slab(const int* group_sizes, int n_groups);
 int wgrad(const WgParams& p, cudaStream_t st);
+int small_wgrad_try(const WgParams& p, cudaStream_t st);   // nn_small.cu
+int narrow_wgrad_try(const WgParams& p, int slabs, int SLAB, cudaStream_t st);   // nn_small.cu
 int tc_wgrad_try(const WgParams& p, int slabs, int SLAB, cudaStream_t st);   // nn_tc_wgrad.cu: 1 launched, 0 not eligible, < 0 error
 
 // packed (value, row) keys for the pooling atomics: larger key = larger value, then lower row

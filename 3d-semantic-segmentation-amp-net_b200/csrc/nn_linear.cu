@@ -338,58 +338,6 @@ pw_linear_kernel(const PwParams p) {
 }
 
 
-// ---------------------------------------------------------------------------------------------------------------
-// Few-row variant (the per-cloud T-Net FC stacks :38-40 and the per-token attention projections :187-190 in eval
-// mode: 32 .. 300 rows): weight-read bound, so every warp streams whole rows of W (coalesced 128-byte requests) against
-// a 32-row tile of X held in shared memory; lane <-> k, 32 row accumulators per lane, one butterfly transpose-reduce
-// (31 shuffles) per output column. y = act((x . w + bias) * scale + shift).
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int SM_ROWS = 32, SM_COLS = 16, SM_MAXK = 512;
-
-__global__ void __launch_bounds__(256)
-small_linear_kernel(const float* __restrict__ X, long long ldx, int M, int K, const float* __restrict__ W, long long ldw,
-                    const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
-                    float* __restrict__ Y, long long ldy, int N) {
-    extern __shared__ float xs[];                 // [SM_ROWS][K]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int r0 = blockIdx.y * SM_ROWS;
-    for (int e = tid; e < SM_ROWS * K; e += 256) {
-        const int r = e / K, k = e - r * K;
-        xs[e] = (r0 + r < M) ? __ldg(X + (long long)(r0 + r) * ldx + k) : 0.f;
-    }
-    __syncthreads();
-    for (int c = warp; c < SM_COLS; c += 8) {
-        const int n = blockIdx.x * SM_COLS + c;
-        if (n >= N) break;
-        float acc[SM_ROWS];
-#pragma unroll
-        for (int r = 0; r < SM_ROWS; ++r) acc[r] = 0.f;
-        const float* __restrict__ w = W + (long long)n * ldw;
-        for (int k = lane; k < K; k += 32) {
-            const float wv = __ldg(w + k);
-#pragma unroll
-            for (int r = 0; r < SM_ROWS; ++r) acc[r] = fmaf(xs[r * K + k], wv, acc[r]);
-        }
-        // butterfly: after the five steps lane L holds the full sum of row L
-#pragma unroll
-        for (int o = 16, n2 = 16; o >= 1; o >>= 1, n2 >>= 1) {
-            const bool up = (lane & o) != 0;
-#pragma unroll
-            for (int i = 0; i < n2; ++i) {
-                const float send = up ? acc[i] : acc[i + n2];
-                const float keep = up ? acc[i + n2] : acc[i];
-                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-            }
-        }
-        if (r0 + lane < M) {
-            float v = acc[0] + (bias ? __ldg(bias + n) : 0.f);
-            if (scale) v = fmaf(v, __ldg(scale + n), __ldg(shift + n));
-            if (relu) v = fmaxf(v, 0.f);
-            Y[(long long)(r0 + lane) * ldy + n] = v;
-        }
-    }
-}
-
 }  // namespace
 
 int pw_tiles(int n_clouds, int rows_per_cloud) { return n_clouds * ((rows_per_cloud + BM - 1) / BM); }
@@ -408,21 +356,10 @@ int pw_linear(const PwParams& p, cudaStream_t st) {
     if (p.mask_y && p.part_sum && !p.mask_invstd) return fail(AMP_E_BADARG, "pw_linear: backward sums need invstd");
     if (p.y_transposed && p.accumulate) return fail(AMP_E_BADARG, "pw_linear: accumulate into a transposed output");
     if (p.group_rows && p.n_groups > 1024) return fail(AMP_E_BADARG, "pw_linear: more than 1024 row groups");
-    // few rows, plain epilogue: the weight-streaming variant
-    if (p.n_clouds == 1 && p.rows_per_cloud <= 1024 && p.K <= SM_MAXK && !p.in_a && !p.X2 && !p.x_transposed && !p.w_kn &&
-        !p.w_cloud_stride && !p.group_rows && !p.accumulate && !p.mask_y && !p.y_transposed && !p.pool_mode && !p.part_sum &&
-        p.in_drop_p == 0.f && p.out_drop_p == 0.f && p.Y) {
-        dim3 grid((p.Nout + SM_COLS - 1) / SM_COLS, (p.rows_per_cloud + SM_ROWS - 1) / SM_ROWS);
-        const size_t smem = sizeof(float) * SM_ROWS * p.K;
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(small_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * SM_ROWS * SM_MAXK));
-            attr_set = true;
-        }
-        small_linear_kernel<<<grid, 256, smem, st>>>(p.X, p.ldx, p.rows_per_cloud, p.K, p.W, p.ldw, p.bias, p.out_scale, p.out_shift,
-                                                     p.out_relu, p.Y, p.ldy, p.Nout);
-        count_launch();
-        return check_launch("small_linear");
+    // few rows (per-cloud FC stacks, per-token projections): weight-streaming kernels (nn_small.cu)
+    {
+        const int rc = small_linear_try(p, st);
+        if (rc != 0) return rc < 0 ? rc : AMP_OK;
     }
     // many rows, tensor-core friendly K: split-bf16 tcgen05 path (nn_tc_layer.cu)
     {

@@ -1,0 +1,312 @@
+// Few-row linear layers in fp32: the per-cloud T-Net FC stacks (pointNet/model/pointnetAtt.py:38-40, rows = batch size)
+// and the per-token projections of the attention layer (:183-190, rows = batch x blocks), forward and backward.
+// With 32 .. 300 rows these GEMMs are a few MFLOP: the tiled kernels (128-row tiles, one CTA per 128 output channels)
+// leave the chip idle and serialise on K, so they are weight-read / latency bound problems and get their own kernels:
+//
+//   small_fwd_kernel    y = epi(pro(x) . W^T)        warp streams rows of W (coalesced), X tile in shared memory,
+//                                                     butterfly transpose-reduce -> lane == row
+//   small_dgrad_kernel  dx = epi(pro(dy) . W)        lane == row, warps split the reduction range, W rows broadcast,
+//                                                     fixed-order cross-warp sum in shared memory
+//   small_wgrad_kernel  dW = pro(dy)^T . pro(a)      thread == input channel k, 8 output channels per CTA, rows walked in
+//                                                     order (deterministic, no partial buffers)
+// Prologues / epilogues are those of PwParams / WgParams (BatchNorm apply or backward, ReLU mask, batch statistics).
+// Because a warp holds a whole column of <= 32 rows, the BatchNorm sums are warp shuffles in a fixed order.
+#include "nn_common.cuh"
+
+namespace amp {
+namespace {
+
+constexpr int SM_ROWS = 32, SM_COLS = 16, SM_MAXK = 512;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// shared epilogue for one output element held by lane == row (valid when row < M); returns the value to store
+struct SmallEpi {
+    const PwParams& p; int M; int r0;
+    __device__ __forceinline__ void run(float v, int lane, int n) const {
+        const int r = r0 + lane;
+        const bool ok = r < M;
+        if (p.bias) v += __ldg(p.bias + n);
+        if (p.accumulate && ok) v += p.Y[(long long)r * p.ldy + n];
+        if (p.part_sum && !p.mask_y) {                       // forward batch statistics (rows <= 32: one tile)
+            const float s = warp_sum(ok ? v : 0.f);
+            const float d = ok ? v - s / (float)M : 0.f;
+            const float q = warp_sum(d * d);
+            if (lane == 0) { p.part_sum[n] = s; p.part_sq[n] = q; }
+        }
+        if (p.out_scale) v = fmaf(v, __ldg(p.out_scale + n), __ldg(p.out_shift + n));
+        if (p.out_relu) v = fmaxf(v, 0.f);
+        if (p.mask_y) {
+            const float y = ok ? __ldg(p.mask_y + (long long)r * p.ld_mask + n) : 0.f;
+            const float mu = __ldg(p.mask_mean + n);
+            const float dz = (ok && fmaf(y - mu, __ldg(p.mask_scale + n), __ldg(p.mask_shift + n)) > 0.f) ? v : 0.f;
+            if (p.part_sum) {
+                const float is = p.mask_invstd ? __ldg(p.mask_invstd + n) : 0.f;
+                const float s = warp_sum(dz), q = warp_sum(dz * (y - mu) * is);
+                if (lane == 0) { p.part_sum[n] = s; p.part_sq[n] = q; }
+            }
+            v = dz;
+        }
+        if (ok && p.Y) p.Y[(long long)r * p.ldy + n] = v;
+    }
+};
+
+__device__ __forceinline__ float small_pro(const PwParams& p, const float* X, const float* X2, long long off, int k) {
+    float v = __ldg(X + off);
+    const float m = p.in_m ? __ldg(p.in_m + k) : 0.f;
+    if (X2) v = fmaf(__ldg(X2 + off) - m, __ldg(p.in_c + k), fmaf(v, __ldg(p.in_a + k), __ldg(p.in_b + k)));
+    else if (p.in_a) v = fmaf(v - m, __ldg(p.in_a + k), __ldg(p.in_b + k));
+    if (p.in_relu) v = fmaxf(v, 0.f);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) small_fwd_kernel(const PwParams p) {
+    extern __shared__ float xs[];                 // [SM_ROWS][K]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int M = p.rows_per_cloud, K = p.K, N = p.Nout;
+    const int r0 = blockIdx.y * SM_ROWS;
+    for (int e = tid; e < SM_ROWS * K; e += 256) {
+        const int r = e / K, k = e - r * K;
+        xs[e] = (r0 + r < M) ? small_pro(p, p.X, p.X2, (long long)(r0 + r) * p.ldx + k, k) : 0.f;
+    }
+    __syncthreads();
+    const SmallEpi epi{p, M, r0};
+    for (int c = warp; c < SM_COLS; c += 8) {
+        const int n = blockIdx.x * SM_COLS + c;
+        if (n >= N) break;
+        float acc[SM_ROWS];
+#pragma unroll
+        for (int r = 0; r < SM_ROWS; ++r) acc[r] = 0.f;
+        const float* __restrict__ w = p.W + (long long)n * p.ldw;
+        for (int k = lane; k < K; k += 32) {
+            const float wv = __ldg(w + k);
+#pragma unroll
+            for (int r = 0; r < SM_ROWS; ++r) acc[r] = fmaf(xs[r * K + k], wv, acc[r]);
+        }
+        // butterfly: after the five steps lane L holds the full sum of row L
+#pragma unroll
+        for (int o = 16, n2 = 16; o >= 1; o >>= 1, n2 >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int i = 0; i < n2; ++i) {
+                const float send = up ? acc[i] : acc[i + n2];
+                const float keep = up ? acc[i + n2] : acc[i];
+                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+        }
+        epi.run(acc[0], lane, n);
+    }
+}
+
+// dx[r, c] = sum_n pro(dy)[r, n] * W[n * ldw + c]   (w_kn == 1): lane == row, 16 output columns per CTA, the 8 warps take
+// interleaved reduction indices n = warp, warp + 8, ... and their partials are added in warp order
+constexpr int SD_COLS = 16;
+__global__ void __launch_bounds__(256) small_dgrad_kernel(const PwParams p) {
+    __shared__ float red[8][SM_ROWS][SD_COLS + 1];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int M = p.rows_per_cloud, K = p.K, N = p.Nout;
+    const int r0 = blockIdx.y * SM_ROWS, c0 = blockIdx.x * SD_COLS;
+    const int r = r0 + lane;
+    const bool ok = r < M;
+    float acc[SD_COLS];
+#pragma unroll
+    for (int j = 0; j < SD_COLS; ++j) acc[j] = 0.f;
+    const bool vec = (c0 + SD_COLS <= N) && (p.ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.W) & 15) == 0);
+    for (int n = warp; n < K; n += 8) {
+        const float x = ok ? small_pro(p, p.X, p.X2, (long long)r * p.ldx + n, n) : 0.f;
+        const float* __restrict__ w = p.W + (long long)n * p.ldw + c0;
+        if (vec) {
+#pragma unroll
+            for (int q = 0; q < SD_COLS / 4; ++q) {
+                const float4 wv = __ldg(reinterpret_cast<const float4*>(w) + q);
+                acc[4 * q] = fmaf(x, wv.x, acc[4 * q]); acc[4 * q + 1] = fmaf(x, wv.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(x, wv.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(x, wv.w, acc[4 * q + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < SD_COLS; ++j) acc[j] = fmaf(x, (c0 + j < N) ? __ldg(w + j) : 0.f, acc[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < SD_COLS; ++j) red[warp][lane][j] = acc[j];
+    __syncthreads();
+    const SmallEpi epi{p, M, r0};
+    for (int j = warp; j < SD_COLS; j += 8) {
+        const int c = c0 + j;
+        if (c >= N) break;
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w][lane][j];
+        epi.run(v, lane, c);
+    }
+}
+
+// dW[n, k] = sum_r dy'[r, n] * a'[r, k], db[n] = sum_r dy'[r, n]: thread == k, 8 output channels n per CTA
+constexpr int SW_N = 8;
+__global__ void __launch_bounds__(256) small_wgrad_kernel(const WgParams p) {
+    __shared__ float ys[SM_ROWS][SW_N];
+    const int tid = threadIdx.x;
+    const int M = p.rows_per_cloud, K = p.K, N = p.Nout;
+    const int n0 = blockIdx.x * SW_N;
+    float acc[SW_N];
+#pragma unroll
+    for (int j = 0; j < SW_N; ++j) acc[j] = 0.f;
+    float bsum = 0.f;
+    const bool has_k = tid < K;
+    const float aa = (p.a_a && has_k) ? __ldg(p.a_a + tid) : 1.f, ab = (p.a_b && has_k) ? __ldg(p.a_b + tid) : 0.f;
+    const float am = (p.a_m && has_k) ? __ldg(p.a_m + tid) : 0.f;
+    for (int rb = 0; rb < M; rb += SM_ROWS) {
+        float a[SM_ROWS];
+#pragma unroll
+        for (int r = 0; r < SM_ROWS; ++r) {
+            float v = 0.f;
+            if (has_k && rb + r < M) {
+                v = __ldg(p.A + (long long)(rb + r) * p.lda + tid);
+                if (p.a_a) v = fmaf(v - am, aa, ab);
+                if (p.a_relu) v = fmaxf(v, 0.f);
+            }
+            a[r] = v;
+        }
+        {
+            const int r = tid / SW_N, j = tid % SW_N, n = n0 + j;      // 256 threads == 32 rows x 8 channels
+            float v = 0.f;
+            if (rb + r < M && n < N) {
+                const long long off = (long long)(rb + r) * p.lddy + n;
+                v = __ldg(p.dY + off);
+                if (p.y_a) v = fmaf(v, __ldg(p.y_a + n), __ldg(p.y_b + n));
+                if (p.Y2) v = fmaf(__ldg(p.Y2 + off) - (p.y_m ? __ldg(p.y_m + n) : 0.f), __ldg(p.y_c + n), v);
+            }
+            __syncthreads();                                           // previous tile fully consumed
+            ys[r][j] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < SM_ROWS; ++r) {
+#pragma unroll
+            for (int j = 0; j < SW_N; ++j) acc[j] = fmaf(ys[r][j], a[r], acc[j]);
+        }
+        if (tid < SW_N) {
+#pragma unroll
+            for (int r = 0; r < SM_ROWS; ++r) bsum += ys[r][tid];
+        }
+    }
+    if (has_k) {
+#pragma unroll
+        for (int j = 0; j < SW_N; ++j) {
+            const int n = n0 + j;
+            if (n < N) {
+                float* dst = p.dW + (p.w_kn ? (long long)tid * p.ldw + n : (long long)n * p.ldw + tid);
+                *dst = p.accumulate ? *dst + acc[j] : acc[j];
+            }
+        }
+    }
+    if (p.db && tid < SW_N && n0 + tid < N) p.db[n0 + tid] = p.accumulate ? p.db[n0 + tid] + bsum : bsum;
+}
+
+// Narrow input (K <= 16: the 3 xyz / 9 raw feature columns, per-cloud or shared weights) over many rows, exact fp32:
+// memory bound on dy'. One CTA per (cloud, slab) partial of wgrad_reduce_kernel; thread == (output channel n, row phase),
+// the slab's input rows sit in shared memory, the row phases are added in a fixed order.
+constexpr int NW_MAXK = 16, NW_SLAB_MAX = 512;
+__global__ void __launch_bounds__(256) narrow_wgrad_kernel(const WgParams p, int slabs, int SLAB) {
+    __shared__ float as[NW_SLAB_MAX * NW_MAXK];                  // input rows of the slab; reused for the phase partials
+    float* red = as;
+    const int tid = threadIdx.x;
+    const int K = p.K, N = p.Nout, rows = p.rows_per_cloud;
+    const int unit = blockIdx.x, cloud = unit / slabs, slab = unit - cloud * slabs;
+    const int r_begin = slab * SLAB, r_end = min(rows, r_begin + SLAB);
+    const long long cloud_row = (long long)cloud * rows;
+    for (int e = tid; e < (r_end - r_begin) * K; e += 256) {
+        const int r = e / K, k = e - r * K;
+        float v = __ldg(p.A + (cloud_row + r_begin + r) * p.lda + k);
+        if (p.a_a) v = fmaf(v - (p.a_m ? __ldg(p.a_m + k) : 0.f), __ldg(p.a_a + k), __ldg(p.a_b + k));
+        if (p.a_relu) v = fmaxf(v, 0.f);
+        as[e] = v;
+    }
+    __syncthreads();
+    const int phases = 256 / N, n = tid % N, ph = tid / N;       // N in {64, 128, 256}
+    float acc[NW_MAXK], bsum = 0.f;
+#pragma unroll
+    for (int k = 0; k < NW_MAXK; ++k) acc[k] = 0.f;
+    const float ya = p.y_a ? __ldg(p.y_a + n) : 1.f, yb = p.y_b ? __ldg(p.y_b + n) : 0.f;
+    const float yc = p.Y2 ? __ldg(p.y_c + n) : 0.f, ym = (p.Y2 && p.y_m) ? __ldg(p.y_m + n) : 0.f;
+    for (int r = r_begin + ph; r < r_end; r += phases) {
+        const long long off = (cloud_row + r) * p.lddy + n;
+        float v = __ldg(p.dY + off);
+        if (p.y_a) v = fmaf(v, ya, yb);
+        if (p.Y2) v = fmaf(__ldg(p.Y2 + off) - ym, yc, v);
+        bsum += v;
+        const float* a = as + (r - r_begin) * K;
+#pragma unroll
+        for (int k = 0; k < NW_MAXK; ++k)
+            if (k < K) acc[k] = fmaf(v, a[k], acc[k]);
+    }
+    __syncthreads();                                             // everybody is done reading the input rows
+#pragma unroll
+    for (int k = 0; k < NW_MAXK; ++k) red[tid * (NW_MAXK + 1) + k] = acc[k];
+    red[tid * (NW_MAXK + 1) + NW_MAXK] = bsum;
+    __syncthreads();
+    float* part = p.partials + (long long)unit * ((long long)N * K + N);
+    for (int e = tid; e < N * (K + 1); e += 256) {
+        const int nn = e / (K + 1), k = e - nn * (K + 1);
+        float s = 0.f;
+        for (int q = 0; q < phases; ++q) s += red[(q * N + nn) * (NW_MAXK + 1) + (k < K ? k : NW_MAXK)];
+        if (k < K) part[(long long)nn * K + k] = s;
+        else part[(long long)N * K + nn] = s;
+    }
+}
+
+}  // namespace
+
+// partial pass of wgrad() for narrow inputs: 1 = launched (the caller still runs wgrad_reduce), 0 = not eligible
+int narrow_wgrad_try(const WgParams& p, int slabs, int SLAB, cudaStream_t st) {
+    if (path_disabled("narrow_wgrad")) return 0;
+    if (p.K > NW_MAXK || SLAB > NW_SLAB_MAX || p.dy_transposed || p.a_drop_p != 0.f) return 0;
+    if (p.Nout != 64 && p.Nout != 128 && p.Nout != 256) return 0;
+    narrow_wgrad_kernel<<<p.n_clouds * slabs, 256, 0, st>>>(p, slabs, SLAB);
+    count_launch();
+    const int rc = check_launch("narrow_wgrad");
+    return rc == AMP_OK ? 1 : rc;
+}
+
+int small_linear_try(const PwParams& p, cudaStream_t st) {
+    if (path_disabled(p.w_kn ? "small_dgrad" : "small_fwd")) return 0;
+    if (p.n_clouds != 1 || p.rows_per_cloud > 1024 || p.x_transposed || p.y_transposed || p.w_cloud_stride || p.group_rows ||
+        p.pool_mode || p.in_drop_p != 0.f || p.out_drop_p != 0.f || !p.Y)
+        return 0;
+    const bool stats = p.part_sum != nullptr;
+    if ((stats || p.mask_y) && p.rows_per_cloud > SM_ROWS) return 0;      // the warp-level sums cover one 32-row tile
+    const dim3 grid_rows((p.rows_per_cloud + SM_ROWS - 1) / SM_ROWS);
+    if (p.w_kn == 0) {
+        if (p.K > SM_MAXK) return 0;
+        dim3 grid((p.Nout + SM_COLS - 1) / SM_COLS, grid_rows.x);
+        const size_t smem = sizeof(float) * SM_ROWS * p.K;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * SM_ROWS * SM_MAXK));
+            attr_set = true;
+        }
+        small_fwd_kernel<<<grid, 256, smem, st>>>(p);
+    } else {
+        if (p.bias) return 0;
+        dim3 grid((p.Nout + SD_COLS - 1) / SD_COLS, grid_rows.x);
+        small_dgrad_kernel<<<grid, 256, 0, st>>>(p);
+    }
+    count_launch();
+    const int rc = check_launch("small_linear");
+    return rc == AMP_OK ? 1 : rc;
+}
+
+int small_wgrad_try(const WgParams& p, cudaStream_t st) {
+    if (path_disabled("small_wgrad")) return 0;
+    if (p.n_clouds != 1 || p.rows_per_cloud > 1024 || p.dy_transposed || p.per_cloud || p.dbg || p.K > 256 || p.a_drop_p != 0.f) return 0;
+    small_wgrad_kernel<<<(p.Nout + SW_N - 1) / SW_N, 256, 0, st>>>(p);
+    count_launch();
+    const int rc = check_launch("small_wgrad");
+    return rc == AMP_OK ? 1 : rc;
+}
+
+}  // namespace amp

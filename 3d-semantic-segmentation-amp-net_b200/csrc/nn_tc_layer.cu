@@ -343,6 +343,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
 
 // Large-row path of pw_linear(): returns 1 when the launch was taken, 0 when the shape is not eligible, < 0 on error.
 int tc_layer_try(const PwParams& p, cudaStream_t st) {
+    if (path_disabled("tc_layer")) return 0;
     const long long total_rows = (long long)p.n_clouds * p.rows_per_cloud;
     const int Mpad = (p.Nout + 127) / 128 * 128;
     if (total_rows < 2048 || p.K % 16 || p.K < 16 || p.K > 256 || p.Nout > 256 || (long long)Mpad * p.K > TL_MAX_WELEMS) return 0;

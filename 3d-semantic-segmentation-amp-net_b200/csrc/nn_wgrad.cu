@@ -174,7 +174,10 @@ int wgrad(const WgParams& p, cudaStream_t st) {
     if (p.dbg && (!p.group_rows || p.n_groups < 1)) return fail(AMP_E_BADARG, "wgrad: dbg needs group_rows");
     const int slabs = (p.rows_per_cloud + SLAB - 1) / SLAB;
     const int n_tiles = (p.Nout + TNo - 1) / TNo, k_tiles = (p.K + TKo - 1) / TKo;
-    int rc = tc_wgrad_try(p, slabs, SLAB, st);           // tensor-core partial pass when the shape allows (nn_tc_wgrad.cu)
+    int rc = small_wgrad_try(p, st);                     // few rows: direct deterministic kernel, no partials (nn_small.cu)
+    if (rc != 0) return rc < 0 ? rc : AMP_OK;
+    rc = narrow_wgrad_try(p, slabs, SLAB, st);           // K <= 16 over many rows: memory-bound exact fp32 partial pass
+    if (rc == 0) rc = tc_wgrad_try(p, slabs, SLAB, st);  // tensor-core partial pass when the shape allows (nn_tc_wgrad.cu)
     if (rc < 0) return rc;
     if (rc == 0) {
         dim3 grid(slabs, n_tiles * k_tiles, p.n_clouds);

@@ -7,7 +7,7 @@ amp = importlib.import_module("3d-semantic-segmentation-amp-net_b200")
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 for (C, R, N, K, bias) in [(1, 2048, 64, 64, False), (1, 2048, 64, 64, True), (4, 2048, 128, 64, True), (32, 2048, 256, 128, False),
-                           (32, 2048, 128, 256, False), (3, 1000, 64, 128, True), (8, 300, 128, 128, False), (2, 100, 64, 64, True)]:
+                           (32, 2048, 128, 256, False), (3, 1000, 64, 128, True), (8, 300, 128, 128, False), (2, 100, 64, 64, True), (32, 2048, 64, 9, False), (4, 2048, 64, 3, True), (1, 32, 4096, 128, True), (1, 288, 768, 256, True)]:
     dy = torch.randn(C, R, N, device=dev); a = torch.randn(C, R, K, device=dev)
     out = amp.linear_wgrad(dy, a, bias=bias)
     torch.cuda.synchronize()
