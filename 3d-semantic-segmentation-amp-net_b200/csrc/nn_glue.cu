@@ -26,14 +26,34 @@ __global__ void bn_finalize_train_kernel(const float* __restrict__ part_sum, con
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (c < C) {
+        // up to 16 tiles per lane are kept in registers: one pass over global memory, all loads in flight together
+        constexpr int kReg = 16;
+        float ps[kReg], pq[kReg];
+#pragma unroll
+        for (int i = 0; i < kReg; ++i) {
+            const int t = lane + 32 * i;
+            ps[i] = t < tiles ? part_sum[(long long)t * C + c] : 0.f;
+            pq[i] = t < tiles ? part_m2[(long long)t * C + c] : 0.f;
+        }
         double s = 0.0;
-        for (int t = lane; t < tiles; t += 32) s += (double)part_sum[(long long)t * C + c];
+#pragma unroll
+        for (int i = 0; i < kReg; ++i) s += (double)ps[i];
+        for (int t = lane + 32 * kReg; t < tiles; t += 32) s += (double)part_sum[(long long)t * C + c];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         const double n = (double)count;
         const double mean = s / n;
         double m2 = 0.0;
-        for (int t = lane; t < tiles; t += 32) {
+#pragma unroll
+        for (int i = 0; i < kReg; ++i) {
+            const int t = lane + 32 * i;
+            if (t < tiles) {
+                const int nt = min(128, rows_per_cloud - (t % tiles_per_cloud) * 128);
+                const double d = (double)ps[i] / nt - mean;
+                m2 += (double)pq[i] + nt * d * d;
+            }
+        }
+        for (int t = lane + 32 * kReg; t < tiles; t += 32) {
             const int nt = min(128, rows_per_cloud - (t % tiles_per_cloud) * 128);
             const double d = (double)part_sum[(long long)t * C + c] / nt - mean;
             m2 += (double)part_m2[(long long)t * C + c] + nt * d * d;

@@ -69,9 +69,24 @@ __global__ void __launch_bounds__(256) small_fwd_kernel(const PwParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int M = p.rows_per_cloud, K = p.K, N = p.Nout;
     const int r0 = blockIdx.y * SM_ROWS;
-    for (int e = tid; e < SM_ROWS * K; e += 256) {
-        const int r = e / K, k = e - r * K;
-        xs[e] = (r0 + r < M) ? small_pro(p, p.X, p.X2, (long long)(r0 + r) * p.ldx + k, k) : 0.f;
+    for (int k = tid; k < K; k += 256) {          // thread == input channel: prologue constants once, 32 independent row loads
+        const float m = p.in_m ? __ldg(p.in_m + k) : 0.f, a = p.in_a ? __ldg(p.in_a + k) : 1.f, b = p.in_b ? __ldg(p.in_b + k) : 0.f;
+        const float cc = p.X2 ? __ldg(p.in_c + k) : 0.f;
+        float x[SM_ROWS], x2[SM_ROWS];
+#pragma unroll
+        for (int r = 0; r < SM_ROWS; ++r) x[r] = (r0 + r < M) ? __ldg(p.X + (long long)(r0 + r) * p.ldx + k) : 0.f;
+        if (p.X2) {
+#pragma unroll
+            for (int r = 0; r < SM_ROWS; ++r) x2[r] = (r0 + r < M) ? __ldg(p.X2 + (long long)(r0 + r) * p.ldx + k) : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < SM_ROWS; ++r) {
+            float v = x[r];
+            if (p.X2) v = fmaf(x2[r] - m, cc, fmaf(v, a, b));
+            else if (p.in_a) v = fmaf(v - m, a, b);
+            if (p.in_relu) v = fmaxf(v, 0.f);
+            xs[r * K + k] = (r0 + r < M) ? v : 0.f;
+        }
     }
     __syncthreads();
     const SmallEpi epi{p, M, r0};
@@ -116,6 +131,7 @@ __global__ void __launch_bounds__(256) small_dgrad_kernel(const PwParams p) {
 #pragma unroll
     for (int j = 0; j < SD_COLS; ++j) acc[j] = 0.f;
     const bool vec = (c0 + SD_COLS <= N) && (p.ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.W) & 15) == 0);
+#pragma unroll 4
     for (int n = warp; n < K; n += 8) {
         const float x = ok ? small_pro(p, p.X, p.X2, (long long)r * p.ldx + n, n) : 0.f;
         const float* __restrict__ w = p.W + (long long)n * p.ldw + c0;
@@ -233,16 +249,29 @@ __global__ void __launch_bounds__(256) narrow_wgrad_kernel(const WgParams p, int
     for (int k = 0; k < NW_MAXK; ++k) acc[k] = 0.f;
     const float ya = p.y_a ? __ldg(p.y_a + n) : 1.f, yb = p.y_b ? __ldg(p.y_b + n) : 0.f;
     const float yc = p.Y2 ? __ldg(p.y_c + n) : 0.f, ym = (p.Y2 && p.y_m) ? __ldg(p.y_m + n) : 0.f;
-    for (int r = r_begin + ph; r < r_end; r += phases) {
-        const long long off = (cloud_row + r) * p.lddy + n;
-        float v = __ldg(p.dY + off);
-        if (p.y_a) v = fmaf(v, ya, yb);
-        if (p.Y2) v = fmaf(__ldg(p.Y2 + off) - ym, yc, v);
-        bsum += v;
-        const float* a = as + (r - r_begin) * K;
+    for (int rb = r_begin + ph; rb < r_end; rb += 8 * phases) {      // 8 rows per step: their loads are issued together
+        float dv[8], y2[8];
 #pragma unroll
-        for (int k = 0; k < NW_MAXK; ++k)
-            if (k < K) acc[k] = fmaf(v, a[k], acc[k]);
+        for (int u = 0; u < 8; ++u) {
+            const int r = rb + u * phases;
+            const long long off = (cloud_row + r) * p.lddy + n;
+            dv[u] = r < r_end ? __ldg(p.dY + off) : 0.f;
+            y2[u] = (p.Y2 && r < r_end) ? __ldg(p.Y2 + off) : ym;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int r = rb + u * phases;
+            if (r < r_end) {
+                float v = dv[u];
+                if (p.y_a) v = fmaf(v, ya, yb);
+                if (p.Y2) v = fmaf(y2[u] - ym, yc, v);
+                bsum += v;
+                const float* a = as + (r - r_begin) * K;
+#pragma unroll
+                for (int k = 0; k < NW_MAXK; ++k)
+                    if (k < K) acc[k] = fmaf(v, a[k], acc[k]);
+            }
+        }
     }
     __syncthreads();                                             // everybody is done reading the input rows
 #pragma unroll

@@ -117,6 +117,21 @@ wgrad_partial_kernel(const WgParams p, int n_tiles, int k_tiles, int slabs, int 
 }
 
 // one thread per dW element (and per db / dbg element): fixed-order sum over the chunks
+// fixed-order sum of `count` floats spaced `stride` apart; the loads of 8 terms are issued before they are added
+__device__ __forceinline__ float chunk_sum(const float* __restrict__ src, long long stride, long long count) {
+    float s = 0.f;
+    long long ch = 0;
+    for (; ch + 8 <= count; ch += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (ch + u) * stride);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; ch < count; ++ch) s += __ldg(src + ch * stride);
+    return s;
+}
+
 __global__ void wgrad_reduce_kernel(const WgParams p, int slabs, int SLAB) {
     const long long per = (long long)p.Nout * p.K + p.Nout;
     const int out_clouds = p.per_cloud ? p.n_clouds : 1;
@@ -128,18 +143,14 @@ __global__ void wgrad_reduce_kernel(const WgParams p, int slabs, int SLAB) {
         if (i < n_w) {
             const int k = (int)(i % p.K), n = (int)((i / p.K) % p.Nout), c = (int)(i / ((long long)p.K * p.Nout));
             const int c_lo = p.per_cloud ? c : 0, c_hi = p.per_cloud ? c + 1 : p.n_clouds;
-            float s = 0.f;
-            for (long long ch = (long long)c_lo * slabs; ch < (long long)c_hi * slabs; ++ch)
-                s += p.partials[ch * per + (long long)n * p.K + k];
+            const float s = chunk_sum(p.partials + (long long)c_lo * slabs * per + (long long)n * p.K + k, per, (long long)(c_hi - c_lo) * slabs);
             float* dst = p.dW + (long long)c * p.w_cloud_stride + (p.w_kn ? (long long)k * p.ldw + n : (long long)n * p.ldw + k);
             *dst = p.accumulate ? *dst + s : s;
         } else if (i < n_w + n_b) {
             const long long e = i - n_w;
             const int n = (int)(e % p.Nout), c = (int)(e / p.Nout);
             const int c_lo = p.per_cloud ? c : 0, c_hi = p.per_cloud ? c + 1 : p.n_clouds;
-            float s = 0.f;
-            for (long long ch = (long long)c_lo * slabs; ch < (long long)c_hi * slabs; ++ch)
-                s += p.partials[ch * per + (long long)p.Nout * p.K + n];
+            const float s = chunk_sum(p.partials + (long long)c_lo * slabs * per + (long long)p.Nout * p.K + n, per, (long long)(c_hi - c_lo) * slabs);
             p.db[e] = p.accumulate ? p.db[e] + s : s;
         } else {
             const long long e = i - n_w - n_b;
