@@ -112,7 +112,7 @@ def bench_fwd(dist, amp, steps, warmup, with_cpu, precision="fp32"):
         "value": pts / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms / steps, "gpu_launches": int(launches),
         "e2e": {"value": pts / (e_ms * 1e-3), "unit": "points/s",
                 "h2d_bytes_per_step": int(x_host.numel() * 4 + c_host.numel() * 4), "d2h_bytes_per_step": int(logits_host.numel() * 4)},
-        "roofline": {"bound": "tensor", "kernel": "whole forward (pw_linear_kernel chain, fp32 CUDA cores)" if precision == "fp32"
+        "roofline": {"bound": "tensor", "kernel": "whole forward (tc_layer_kernel: split-bf16 3-MMA tcgen05 layers at fp32-class accuracy, + few-row fp32 kernels)" if precision == "fp32"
                      else "whole forward (tc_chain_kernel x 4: tcgen05 bf16 chains + fp32 per-cloud FC / attention kernels)",
                      "achieved": ach, "peak": peak,
                      "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": src,
@@ -177,7 +177,7 @@ def bench_train(dist, amp, steps, warmup, with_cpu):
         "value": pts / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms / steps, "gpu_launches": int(launches),
         "e2e": {"value": pts / (e_ms * 1e-3), "unit": "points/s",
                 "h2d_bytes_per_step": int(x_host.numel() * 4 + c_host.numel() * 4 + t_host.numel() * 8), "d2h_bytes_per_step": 4},
-        "roofline": {"bound": "tensor", "kernel": "whole step (pw_linear / wgrad chains, fp32 CUDA cores)", "achieved": ach, "peak": peak,
+        "roofline": {"bound": "tensor", "kernel": "whole step (tc_layer_kernel / tc_wgrad_kernel: split-bf16 3-MMA tcgen05 GEMMs at fp32-class accuracy, few-row fp32 kernels, torch Adam)", "achieved": ach, "peak": peak,
                      "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": src,
                      "model": "3 x 413 143 algorithmic FLOP per point (SURVEY 8d) x 65 536 points / step time"},
         "config": {"workload": "configs[2]: training step fwd+loss+bwd+2xAdam, batch %d x %d points per GPU, dropout 0.3%s"
@@ -195,5 +195,125 @@ def bench_fwd_bf16(dist, amp, steps, warmup, with_cpu):
     return bench_fwd(dist, amp, steps, warmup, with_cpu, precision="bf16")
 
 
+# ------------------------------------------------------------------------------------------------
+# configs[3]: arbitrary-scale inference of one 1M-point tile (k-means split into 2048-point blocks, blocks sharded)
+# ------------------------------------------------------------------------------------------------
+TILE_POINTS, TILE_SIDE, TILE_GRID, TILE_DIMS = 1_000_000, 1000.0, 10, 13
+
+
+def synthetic_tile(seed=3000):
+    """1 km^2 tile, 1M points: x, y in metres, z (HAG), 10 feature columns in [0, 1) (13-column rows as written by
+    data_proc/2_preprocessing_filter_norm.py:76-104); cut into a 10 x 10 grid of 100 m windows (1_get_windows_split.py:57-80),
+    every window filled with random duplicates to k * 2048 points (3_kmeans.py:54-69), coordinates normalised per window."""
+    rng = np.random.default_rng(seed)
+    pts = rng.random((TILE_POINTS, TILE_DIMS), dtype=np.float32)
+    xy = pts[:, :2] * TILE_SIDE
+    cell = (np.minimum((xy[:, 0] // (TILE_SIDE / TILE_GRID)).astype(np.int64), TILE_GRID - 1) * TILE_GRID +
+            np.minimum((xy[:, 1] // (TILE_SIDE / TILE_GRID)).astype(np.int64), TILE_GRID - 1))
+    order = np.argsort(cell, kind="stable")
+    counts = np.bincount(cell, minlength=TILE_GRID * TILE_GRID)
+    wins, ks, real = [], [], []
+    o = 0
+    for c in counts:
+        w = pts[order[o:o + c]].copy()
+        o += c
+        side = TILE_SIDE / TILE_GRID
+        w[:, 0] = (w[:, 0] * TILE_SIDE % side) / side
+        w[:, 1] = (w[:, 1] * TILE_SIDE % side) / side
+        w[:, 2] *= 0.3
+        k = min(int(np.ceil(len(w) / NN_POINTS)), 9)
+        need = k * NN_POINTS
+        if len(w) < need:
+            w = np.concatenate([w, w[rng.integers(0, len(w), need - len(w))]], 0)
+        else:
+            w = w[rng.permutation(len(w))[:need]]
+        wins.append(w); ks.append(k); real.append(int(min(c, need)))
+    return wins, ks, real
+
+
+def bench_tile(dist, amp, steps, warmup, with_cpu, precision="fp32"):
+    """One step = the whole tile: per rank, k-means block split of its windows (one launch for all windows), regroup,
+    encoder over all blocks, attention + head per window (batched over windows of equal block count)."""
+    dev = dist.device
+    enc, seg = build_modules(amp, dev)
+    enc.eval(); seg.eval()
+    enc.precision = seg.precision = precision
+    wins, ks, real = synthetic_tile()
+    lo_w, hi_w = amp.shard_windows(ks, dist.world)[dist.rank]
+    wins, ks, real = wins[lo_w:hi_w], ks[lo_w:hi_w], real[lo_w:hi_w]
+    flush = _Flush(dev)
+    out = {}
+    if len(wins):
+        host = torch.from_numpy(np.concatenate(wins, 0)).pin_memory()
+        offsets = np.concatenate([[0], np.cumsum([len(w) for w in wins])]).astype(np.int64)
+        pc = host.to(dev)
+        by_k = {}
+        for i, k in enumerate(ks):
+            by_k.setdefault(k, []).append(i)
+    ev = {}
+
+    def step(pc_dev):
+        if not len(wins):
+            return
+        ev["a"] = torch.cuda.Event(enable_timing=True); ev["b"] = torch.cuda.Event(enable_timing=True)
+        ev["a"].record()
+        feats = amp.gather_feats(pc_dev, (0, 1, 9))                                   # 3_kmeans.py:81
+        labels, _, _ = amp.kmeans_constrained_windows(feats, offsets, ks, NN_POINTS, NN_POINTS)
+        order, _, xy = amp.regroup_windows(labels, offsets, ks, pc_dev)
+        ev["b"].record()
+        grouped = pc_dev.index_select(0, order)                                       # rows sorted by (window, block)
+        x9 = torch.cat((grouped[:, 0:3], grouped[:, 4:10]), 1)                        # datasets.py:342 keeps cols 0:3, 4:10
+        x9[:, :2] = x9[:, :2] * 2 - 1                                                 # datasets.py:378-379
+        blocks = x9.view(-1, NN_POINTS, NN_DIMS)
+        feats_out = []
+        for b0 in range(0, blocks.shape[0], 64):                                      # encoder over all blocks, 64 per call
+            o, _ = enc(blocks[b0:b0 + 64])
+            feats_out.append(o)
+        enc_out = torch.cat(feats_out, 0)
+        blk0 = np.concatenate([[0], np.cumsum(ks)])
+        preds = {}
+        for k, idx in by_k.items():                                                   # windows of equal block count together
+            sel = torch.as_tensor(np.concatenate([np.arange(blk0[i], blk0[i] + k) for i in idx]), device=dev)
+            e = enc_out.index_select(0, sel).view(len(idx), k, NN_POINTS, 320)
+            gl = e[:, :, 0, :256].permute(1, 0, 2).contiguous()                       # [k, B, 256]
+            lo = e[:, :, :, 256:].reshape(len(idx), k * NN_POINTS, 64)
+            cent = xy[torch.as_tensor(idx, device=dev), :k, :]
+            logits, _ = seg(gl, lo, cent, [NN_POINTS] * k, None)
+            preds[k] = logits.argmax(1)
+        out["preds"] = preds
+
+    ms = _timed(dist, lambda: step(pc if len(wins) else None), steps, warmup, flush)
+    km_ms = ev["a"].elapsed_time(ev["b"]) if ev else 0.0
+
+    def step_e2e():
+        if not len(wins):
+            return
+        step(host.to(dev, non_blocking=True))
+        for k, pr in out["preds"].items():
+            out.setdefault("host", {})[k] = pr.to("cpu", non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e_ms = _timed(dist, step_e2e, max(2, steps // 2), 1, flush)
+    es = max(2, steps // 2)
+    n_pts = TILE_POINTS
+    n_rows = int(sum(len(w) for w in wins))
+    res = {
+        "value": n_pts * steps / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms / steps, "scaling": "strong",
+        "e2e": {"value": n_pts * es / (e_ms * 1e-3), "unit": "points/s",
+                "h2d_bytes_per_step": n_rows * TILE_DIMS * 4, "d2h_bytes_per_step": n_rows * 8},
+        "stages": {"kmeans_split_ms_rank0_last_step": km_ms, "blocks_this_rank": int(sum(ks)), "windows_this_rank": len(ks),
+                   "rows_with_duplicate_fill_this_rank": n_rows},
+        "config": {"workload": "configs[3]: 1M-point synthetic tile, 10 x 10 windows, constrained k-means into 2048-point blocks, "
+                               "blocks sharded by window over %d GPU(s), eval forward" % dist.world,
+                   "l2": "flushed between steps (256 MiB write)", "precision": precision},
+        "dtype": "f32" if precision == "fp32" else "bf16",
+    }
+    return res
+
+
+def bench_tile_bf16(dist, amp, steps, warmup, with_cpu):
+    return bench_tile(dist, amp, steps, warmup, with_cpu, precision="bf16")
+
+
 def hooks():
-    return {"fwd": bench_fwd, "fwd_bf16": bench_fwd_bf16, "train": bench_train}
+    return {"fwd": bench_fwd, "fwd_bf16": bench_fwd_bf16, "train": bench_train, "tile": bench_tile, "tile_bf16": bench_tile_bf16}

@@ -281,7 +281,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="fps", choices=["fps", "fwd", "fwd_bf16", "train"])
+    ap.add_argument("--workload", default="fps", choices=["fps", "fwd", "fwd_bf16", "train", "tile", "tile_bf16"])
     ap.add_argument("--only", action="store_true", help="measure only the headline workload")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
@@ -304,11 +304,11 @@ def main():
     with ClockSampler(dist.local_rank) as clk:
         head = table[args.workload](dist, amp, args.steps, args.warmup, with_cpu)
     line = {"metric": {"fps": "FPS clouds/sec", "fwd": "segmented points/sec (fwd)", "fwd_bf16": "segmented points/sec (fwd)",
-                       "train": "train pts/sec"}[args.workload],
+                       "train": "train pts/sec", "tile": "segmented points/sec (fwd)", "tile_bf16": "segmented points/sec (fwd)"}[args.workload],
             "value": head.pop("value"), "unit": head.pop("unit"), "n_gpus": dist.world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": head.pop("ms_per_step"), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "data": "synthetic"}
-    line.update(head)
+    line.update(head)          # a workload may override "scaling" (the tile workload shards one tile: strong)
     line["clocks"] = clk.summary()
     if not args.only:
         others = {}
@@ -317,7 +317,7 @@ def main():
                 continue
             try:
                 r = fn(dist, amp, max(3, args.steps // 2), 3, False)
-                others[name] = {k: r[k] for k in ("value", "unit", "ms_per_step", "e2e", "roofline", "config", "dtype")
+                others[name] = {k: r[k] for k in ("value", "unit", "ms_per_step", "scaling", "e2e", "roofline", "stages", "config", "dtype")
                                 if k in r}
             except Exception as e:  # a secondary workload must not take the headline down
                 others[name] = {"error": repr(e)[:200]}
