@@ -129,6 +129,19 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
         fence_proxy_async();
     };
 
+    // pull this thread's row of a later tile into L2 while the current tile is being worked on (no registers held)
+    auto prefetch_tile = [&](int cloud, int t) {
+        const long long r = (long long)cloud * rows + t * TL_ROWS + lrow;
+        if (t * TL_ROWS + lrow < rows) {
+            const char* x = reinterpret_cast<const char*>(p.X + r * p.ldx);
+            for (int b = 0; b < K * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + b));
+            if (p.X2) {
+                const char* x2 = reinterpret_cast<const char*>(p.X2 + r * p.ldx);
+                for (int b = 0; b < K * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(x2 + b));
+            }
+        }
+    };
+
     auto process = [&](int cloud, int t) {
         const int row0 = t * TL_ROWS;
         const int valid = min(TL_ROWS, rows - row0);
@@ -136,6 +149,16 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
         const long long tile = (long long)cloud * tpc + t;
         // ---------------- K chunks: stage B operand (hi, lo), MMA ----------------
         const bool row_ok = lrow < valid;
+        if (row_ok && (MODE & (TL_MASK | TL_ACC))) {          // rows the epilogue of THIS tile will read: start them towards L2 now
+            if (MODE & TL_MASK) {
+                const char* m = reinterpret_cast<const char*>(p.mask_y + (row_base + lrow) * p.ld_mask);
+                for (int b = 0; b < Nout * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(m + b));
+            }
+            if (MODE & TL_ACC) {
+                const char* y = reinterpret_cast<const char*>(p.Y + (row_base + lrow) * p.ldy);
+                for (int b = 0; b < Nout * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + b));
+            }
+        }
         const float* __restrict__ xrow = p.X + (row_base + lrow) * p.ldx;
         const float* __restrict__ x2row = p.X2 ? p.X2 + (row_base + lrow) * p.ldx : nullptr;
         for (int kc = 0; kc * TL_KC < K; ++kc) {
@@ -325,13 +348,20 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
         stage_weights(0);
         __syncthreads();
         const int n_tiles = p.n_clouds * tpc;
-        for (int tile = blockIdx.x * 2 + wg; tile < n_tiles; tile += gridDim.x * 2) process(tile / tpc, tile % tpc);
+        for (int tile = blockIdx.x * 2 + wg; tile < n_tiles; tile += gridDim.x * 2) {
+            const int nxt = tile + gridDim.x * 2;
+            if (nxt < n_tiles) prefetch_tile(nxt / tpc, nxt % tpc);
+            process(tile / tpc, tile % tpc);
+        }
     } else {
         for (int cloud = blockIdx.x; cloud < p.n_clouds; cloud += gridDim.x) {
             __syncthreads();                  // every MMA that read the previous cloud's weights has been waited for
             stage_weights(cloud);
             __syncthreads();
-            for (int t = wg; t < tpc; t += 2) process(cloud, t);
+            for (int t = wg; t < tpc; t += 2) {
+                if (t + 2 < tpc) prefetch_tile(cloud, t + 2);
+                process(cloud, t);
+            }
         }
     }
     tc_fence_before();

@@ -115,6 +115,18 @@ tc_wgrad_kernel(const __grid_constant__ WgParams p, const int Mpad, const int Kp
             const int r = r_begin + blk * TW_RB + sr;
             const bool row_ok = r < r_end;
             const long long grow = cloud_row + r;
+            if (blk + 1 < blk_hi && r + TW_RB < r_end) {        // this thread's share of the next block's rows -> L2
+                const long long gn = grow + TW_RB;
+                const int nb_y = (Nout * 4) >> 1, nb_a = (K * 4) >> 1;
+                const char* y = reinterpret_cast<const char*>(p.dY + gn * p.lddy) + shalf * nb_y;
+                for (int b = 0; b < nb_y; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + b));
+                if (p.Y2) {
+                    const char* y2 = reinterpret_cast<const char*>(p.Y2 + gn * p.lddy) + shalf * nb_y;
+                    for (int b = 0; b < nb_y; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(y2 + b));
+                }
+                const char* a = reinterpret_cast<const char*>(p.A + gn * p.lda) + shalf * nb_a;
+                for (int b = 0; b < nb_a; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + b));
+            }
             // ---- A operand: dy'[r, n] for this thread's half of the channels ----
             {
                 const float* __restrict__ yrow = p.dY + grow * p.lddy;

@@ -135,8 +135,9 @@ def bench_train(dist, amp, steps, warmup, with_cpu):
     if dist.pg:
         for p in params:
             torch.distributed.broadcast(p.data, 0)
-    opt_e = torch.optim.Adam(enc.parameters(), lr=1e-3)
-    opt_s = torch.optim.Adam(seg.parameters(), lr=1e-3)
+    # the script's two Adam optimizers (train_pointnet-attention.py:141-142), torch's fused multi-tensor implementation
+    opt_e = torch.optim.Adam(enc.parameters(), lr=1e-3, fused=True)
+    opt_s = torch.optim.Adam(seg.parameters(), lr=1e-3, fused=True)
     ce = torch.nn.CrossEntropyLoss(weight=torch.tensor([1., 2., 2., 1., 1.], device=dev), reduction="mean", ignore_index=-1)
     x_np, c_np, t_np = synthetic_blocks(dist.rank)
     x_host, c_host, t_host = (torch.from_numpy(a).pin_memory() for a in (x_np, c_np, t_np))
@@ -180,7 +181,7 @@ def bench_train(dist, amp, steps, warmup, with_cpu):
         "roofline": {"bound": "tensor", "kernel": "whole step (tc_layer_kernel / tc_wgrad_kernel: split-bf16 3-MMA tcgen05 GEMMs at fp32-class accuracy, few-row fp32 kernels, torch Adam)", "achieved": ach, "peak": peak,
                      "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": src,
                      "model": "3 x 413 143 algorithmic FLOP per point (SURVEY 8d) x 65 536 points / step time"},
-        "config": {"workload": "configs[2]: training step fwd+loss+bwd+2xAdam, batch %d x %d points per GPU, dropout 0.3%s"
+        "config": {"workload": "configs[2]: training step fwd+loss+bwd+2xAdam(fused), batch %d x %d points per GPU, dropout 0.3%s"
                                % (NN_BATCH, NN_POINTS, ", NCCL gradient all-reduce" if dist.pg else ""),
                    "l2": "flushed between steps (256 MiB write)", "precision": "fp32"},
         "dtype": "f32", "final_loss": float(keep["loss"]),
