@@ -44,12 +44,15 @@ __global__ void bn_finalize_train_kernel(const float* __restrict__ part_sum, con
         const double n = (double)count;
         const double mean = s / n;
         double m2 = 0.0;
+        const int nt_last = rows_per_cloud - (tiles_per_cloud - 1) * 128;        // rows of the last tile of a cloud
+        const double inv_full = 1.0 / 128.0, inv_last = 1.0 / (double)nt_last;     // (no fp64 divide per tile)
 #pragma unroll
         for (int i = 0; i < kReg; ++i) {
             const int t = lane + 32 * i;
             if (t < tiles) {
-                const int nt = min(128, rows_per_cloud - (t % tiles_per_cloud) * 128);
-                const double d = (double)ps[i] / nt - mean;
+                const bool last = (t % tiles_per_cloud) == tiles_per_cloud - 1;
+                const int nt = last ? nt_last : 128;
+                const double d = (double)ps[i] * (last ? inv_last : inv_full) - mean;
                 m2 += (double)pq[i] + nt * d * d;
             }
         }
@@ -214,9 +217,21 @@ __global__ void bn_backward_finalize_kernel(const float* __restrict__ part_sum, 
     const int lane = threadIdx.x & 31;
     if (c >= C) return;
     double s = 0.0, q = 0.0;
-    for (int t = lane; t < tiles; t += 32) {
-        s += (double)part_sum[(long long)t * C + c];
-        q += (double)part_sq[(long long)t * C + c];
+    {
+        constexpr int kReg = 16;                  // all loads of the first 512 tiles in flight together
+        float ps[kReg], pq[kReg];
+#pragma unroll
+        for (int i = 0; i < kReg; ++i) {
+            const int t = lane + 32 * i;
+            ps[i] = t < tiles ? part_sum[(long long)t * C + c] : 0.f;
+            pq[i] = t < tiles ? part_sq[(long long)t * C + c] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < kReg; ++i) { s += (double)ps[i]; q += (double)pq[i]; }
+        for (int t = lane + 32 * kReg; t < tiles; t += 32) {
+            s += (double)part_sum[(long long)t * C + c];
+            q += (double)part_sq[(long long)t * C + c];
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

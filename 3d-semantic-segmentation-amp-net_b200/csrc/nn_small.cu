@@ -3,10 +3,9 @@
 // With 32 .. 300 rows these GEMMs are a few MFLOP: the tiled kernels (128-row tiles, one CTA per 128 output channels)
 // leave the chip idle and serialise on K, so they are weight-read / latency bound problems and get their own kernels:
 //
-//   small_fwd_kernel    y = epi(pro(x) . W^T)        warp streams rows of W (coalesced), X tile in shared memory,
-//                                                     butterfly transpose-reduce -> lane == row
-//   small_dgrad_kernel  dx = epi(pro(dy) . W)        lane == row, warps split the reduction range, W rows broadcast,
-//                                                     fixed-order cross-warp sum in shared memory
+//   small_fwd_kernel    y = epi(pro(x) . W^T) and dx = epi(pro(dy) . W) (transposed weights): a warp streams W for its
+//                                                     output column against a chunk of the input rows held in shared
+//                                                     memory (lane == reduction index), butterfly transpose-reduce -> lane == row
 //   small_wgrad_kernel  dW = pro(dy)^T . pro(a)      thread == input channel k, 8 output channels per CTA, rows walked in
 //                                                     order (deterministic, no partial buffers)
 // Prologues / epilogues are those of PwParams / WgParams (BatchNorm apply or backward, ReLU mask, batch statistics).
@@ -55,109 +54,74 @@ struct SmallEpi {
     }
 };
 
-__device__ __forceinline__ float small_pro(const PwParams& p, const float* X, const float* X2, long long off, int k) {
-    float v = __ldg(X + off);
-    const float m = p.in_m ? __ldg(p.in_m + k) : 0.f;
-    if (X2) v = fmaf(__ldg(X2 + off) - m, __ldg(p.in_c + k), fmaf(v, __ldg(p.in_a + k), __ldg(p.in_b + k)));
-    else if (p.in_a) v = fmaf(v - m, __ldg(p.in_a + k), __ldg(p.in_b + k));
-    if (p.in_relu) v = fmaxf(v, 0.f);
-    return v;
-}
-
 __global__ void __launch_bounds__(256) small_fwd_kernel(const PwParams p) {
-    extern __shared__ float xs[];                 // [SM_ROWS][K]
+    extern __shared__ float xs[];                 // [SM_ROWS][kc] chunk of the (prologue-applied) input rows
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int M = p.rows_per_cloud, K = p.K, N = p.Nout;
     const int r0 = blockIdx.y * SM_ROWS;
-    for (int k = tid; k < K; k += 256) {          // thread == input channel: prologue constants once, 32 independent row loads
-        const float m = p.in_m ? __ldg(p.in_m + k) : 0.f, a = p.in_a ? __ldg(p.in_a + k) : 1.f, b = p.in_b ? __ldg(p.in_b + k) : 0.f;
-        const float cc = p.X2 ? __ldg(p.in_c + k) : 0.f;
-        float x[SM_ROWS], x2[SM_ROWS];
+    const int KC = K < SM_MAXK ? K : SM_MAXK;
+    float acc[2][SM_ROWS];                        // this warp's two output columns: c = warp, warp + 8
 #pragma unroll
-        for (int r = 0; r < SM_ROWS; ++r) x[r] = (r0 + r < M) ? __ldg(p.X + (long long)(r0 + r) * p.ldx + k) : 0.f;
-        if (p.X2) {
+    for (int j = 0; j < 2; ++j)
 #pragma unroll
-            for (int r = 0; r < SM_ROWS; ++r) x2[r] = (r0 + r < M) ? __ldg(p.X2 + (long long)(r0 + r) * p.ldx + k) : 0.f;
+        for (int r = 0; r < SM_ROWS; ++r) acc[j][r] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += KC) {
+        const int kc = min(KC, K - k0);
+        if (k0) __syncthreads();
+        for (int kk = tid; kk < kc; kk += 256) {  // thread == input channel: prologue constants once, 32 independent row loads
+            const int k = k0 + kk;
+            const float m = p.in_m ? __ldg(p.in_m + k) : 0.f, a = p.in_a ? __ldg(p.in_a + k) : 1.f, b = p.in_b ? __ldg(p.in_b + k) : 0.f;
+            const float cc = p.X2 ? __ldg(p.in_c + k) : 0.f;
+            float x[SM_ROWS], x2[SM_ROWS];
+#pragma unroll
+            for (int r = 0; r < SM_ROWS; ++r) x[r] = (r0 + r < M) ? __ldg(p.X + (long long)(r0 + r) * p.ldx + k) : 0.f;
+            if (p.X2) {
+#pragma unroll
+                for (int r = 0; r < SM_ROWS; ++r) x2[r] = (r0 + r < M) ? __ldg(p.X2 + (long long)(r0 + r) * p.ldx + k) : 0.f;
+            }
+#pragma unroll
+            for (int r = 0; r < SM_ROWS; ++r) {
+                float v = x[r];
+                if (p.X2) v = fmaf(x2[r] - m, cc, fmaf(v, a, b));
+                else if (p.in_a) v = fmaf(v - m, a, b);
+                if (p.in_relu) v = fmaxf(v, 0.f);
+                xs[r * kc + kk] = (r0 + r < M) ? v : 0.f;
+            }
         }
+        __syncthreads();
 #pragma unroll
-        for (int r = 0; r < SM_ROWS; ++r) {
-            float v = x[r];
-            if (p.X2) v = fmaf(x2[r] - m, cc, fmaf(v, a, b));
-            else if (p.in_a) v = fmaf(v - m, a, b);
-            if (p.in_relu) v = fmaxf(v, 0.f);
-            xs[r * K + k] = (r0 + r < M) ? v : 0.f;
+        for (int j = 0; j < 2; ++j) {
+            const int n = blockIdx.x * SM_COLS + warp + 8 * j;
+            if (n < N) {
+                // w_kn == 0: W[n][k] (a contiguous row per output); w_kn == 1: W[k][n] (transposed weights of the backward)
+                const float* __restrict__ w = p.w_kn ? p.W + (long long)k0 * p.ldw + n : p.W + (long long)n * p.ldw + k0;
+                const long long ws = p.w_kn ? p.ldw : 1;
+#pragma unroll 4
+                for (int kk = lane; kk < kc; kk += 32) {
+                    const float wv = __ldg(w + kk * ws);
+#pragma unroll
+                    for (int r = 0; r < SM_ROWS; ++r) acc[j][r] = fmaf(xs[r * kc + kk], wv, acc[j][r]);
+                }
+            }
         }
     }
-    __syncthreads();
     const SmallEpi epi{p, M, r0};
-    for (int c = warp; c < SM_COLS; c += 8) {
-        const int n = blockIdx.x * SM_COLS + c;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int n = blockIdx.x * SM_COLS + warp + 8 * j;
         if (n >= N) break;
-        float acc[SM_ROWS];
-#pragma unroll
-        for (int r = 0; r < SM_ROWS; ++r) acc[r] = 0.f;
-        const float* __restrict__ w = p.W + (long long)n * p.ldw;
-        for (int k = lane; k < K; k += 32) {
-            const float wv = __ldg(w + k);
-#pragma unroll
-            for (int r = 0; r < SM_ROWS; ++r) acc[r] = fmaf(xs[r * K + k], wv, acc[r]);
-        }
         // butterfly: after the five steps lane L holds the full sum of row L
 #pragma unroll
         for (int o = 16, n2 = 16; o >= 1; o >>= 1, n2 >>= 1) {
             const bool up = (lane & o) != 0;
 #pragma unroll
             for (int i = 0; i < n2; ++i) {
-                const float send = up ? acc[i] : acc[i + n2];
-                const float keep = up ? acc[i + n2] : acc[i];
-                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                const float send = up ? acc[j][i] : acc[j][i + n2];
+                const float keep = up ? acc[j][i + n2] : acc[j][i];
+                acc[j][i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
             }
         }
-        epi.run(acc[0], lane, n);
-    }
-}
-
-// dx[r, c] = sum_n pro(dy)[r, n] * W[n * ldw + c]   (w_kn == 1): lane == row, 16 output columns per CTA, the 8 warps take
-// interleaved reduction indices n = warp, warp + 8, ... and their partials are added in warp order
-constexpr int SD_COLS = 16;
-__global__ void __launch_bounds__(256) small_dgrad_kernel(const PwParams p) {
-    __shared__ float red[8][SM_ROWS][SD_COLS + 1];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int M = p.rows_per_cloud, K = p.K, N = p.Nout;
-    const int r0 = blockIdx.y * SM_ROWS, c0 = blockIdx.x * SD_COLS;
-    const int r = r0 + lane;
-    const bool ok = r < M;
-    float acc[SD_COLS];
-#pragma unroll
-    for (int j = 0; j < SD_COLS; ++j) acc[j] = 0.f;
-    const bool vec = (c0 + SD_COLS <= N) && (p.ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.W) & 15) == 0);
-#pragma unroll 4
-    for (int n = warp; n < K; n += 8) {
-        const float x = ok ? small_pro(p, p.X, p.X2, (long long)r * p.ldx + n, n) : 0.f;
-        const float* __restrict__ w = p.W + (long long)n * p.ldw + c0;
-        if (vec) {
-#pragma unroll
-            for (int q = 0; q < SD_COLS / 4; ++q) {
-                const float4 wv = __ldg(reinterpret_cast<const float4*>(w) + q);
-                acc[4 * q] = fmaf(x, wv.x, acc[4 * q]); acc[4 * q + 1] = fmaf(x, wv.y, acc[4 * q + 1]);
-                acc[4 * q + 2] = fmaf(x, wv.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(x, wv.w, acc[4 * q + 3]);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < SD_COLS; ++j) acc[j] = fmaf(x, (c0 + j < N) ? __ldg(w + j) : 0.f, acc[j]);
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < SD_COLS; ++j) red[warp][lane][j] = acc[j];
-    __syncthreads();
-    const SmallEpi epi{p, M, r0};
-    for (int j = warp; j < SD_COLS; j += 8) {
-        const int c = c0 + j;
-        if (c >= N) break;
-        float v = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) v += red[w][lane][j];
-        epi.run(v, lane, c);
+        epi.run(acc[j][0], lane, n);
     }
 }
 
@@ -309,20 +273,16 @@ int small_linear_try(const PwParams& p, cudaStream_t st) {
     const bool stats = p.part_sum != nullptr;
     if ((stats || p.mask_y) && p.rows_per_cloud > SM_ROWS) return 0;      // the warp-level sums cover one 32-row tile
     const dim3 grid_rows((p.rows_per_cloud + SM_ROWS - 1) / SM_ROWS);
-    if (p.w_kn == 0) {
-        if (p.K > SM_MAXK) return 0;
+    {
+        if (p.w_kn && p.bias) return 0;
         dim3 grid((p.Nout + SM_COLS - 1) / SM_COLS, grid_rows.x);
-        const size_t smem = sizeof(float) * SM_ROWS * p.K;
+        const size_t smem = sizeof(float) * SM_ROWS * (p.K < SM_MAXK ? p.K : SM_MAXK);
         static bool attr_set = false;
         if (!attr_set) {
             cudaFuncSetAttribute(small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * SM_ROWS * SM_MAXK));
             attr_set = true;
         }
         small_fwd_kernel<<<grid, 256, smem, st>>>(p);
-    } else {
-        if (p.bias) return 0;
-        dim3 grid((p.Nout + SD_COLS - 1) / SD_COLS, grid_rows.x);
-        small_dgrad_kernel<<<grid, 256, 0, st>>>(p);
     }
     count_launch();
     const int rc = check_launch("small_linear");

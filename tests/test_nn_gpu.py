@@ -309,3 +309,52 @@ def test_tc_linear_matches_bf16_rounded_matmul(amp, cuda):
         assert (got - exp).abs().max().item() < 1e-4
     with pytest.raises(RuntimeError, match="multiple of 16"):
         amp.tc_linear(torch.zeros(1, 8, 24, device=cuda), torch.zeros(16, 24, device=cuda))
+
+
+def test_linear_wgrad_entry_point(amp, cuda):
+    """amp_wgrad_f32: tensor-core (split bf16) path for wide K, exact fp32 paths for narrow K and few rows."""
+    torch.manual_seed(1)
+    for (C, R, N, K, bias, tol) in [(4, 2048, 128, 64, True, 2e-5), (8, 2048, 256, 128, False, 2e-5), (3, 1000, 64, 128, True, 2e-5),
+                                    (8, 2048, 64, 9, False, 2e-6), (2, 2048, 64, 3, True, 2e-6), (1, 32, 4096, 128, True, 2e-6),
+                                    (1, 288, 768, 256, True, 3e-6), (2, 100, 64, 64, True, 2e-6)]:
+        dy = torch.randn(C, R, N, device=cuda); a = torch.randn(C, R, K, device=cuda)
+        out = amp.linear_wgrad(dy, a, bias=bias)
+        dw = out[0] if bias else out
+        ref = dy.double().reshape(-1, N).t() @ a.double().reshape(-1, K)
+        assert float((dw.double() - ref).abs().max() / ref.abs().max()) < tol, (C, R, N, K)
+        if bias:
+            rb = dy.double().reshape(-1, N).sum(0)
+            assert float((out[1].double() - rb).abs().max() / rb.abs().max()) < tol
+        again = amp.linear_wgrad(dy, a, bias=bias)                       # deterministic: bit-identical on a second run
+        assert torch.equal(dw, again[0] if bias else again)
+
+
+def test_tile_pipeline_blocks_and_logits(amp, cuda):
+    """configs[3] in miniature: windows -> constrained k-means (exactly 2048 per block) -> encoder over all blocks ->
+    attention + head per window; every point gets a label and the block split is a partition of each window."""
+    rng = np.random.default_rng(5)
+    ks = [2, 3, 2]
+    wins = [rng.random((k * 2048, 13), dtype=np.float32) for k in ks]
+    pc = torch.from_numpy(np.concatenate(wins, 0)).to(cuda)
+    offsets = np.concatenate([[0], np.cumsum([len(w) for w in wins])])
+    feats = amp.gather_feats(pc, (0, 1, 9))
+    labels, _, _ = amp.kmeans_constrained_windows(feats, offsets, ks, 2048, 2048)
+    order, counts, xy = amp.regroup_windows(labels, offsets, ks, pc)
+    counts = counts.cpu().numpy()
+    for w, k in enumerate(ks):
+        assert (counts[w, :k] == 2048).all()
+        seg_order = order[offsets[w]:offsets[w + 1]].cpu().numpy()
+        assert sorted(seg_order.tolist()) == list(range(offsets[w], offsets[w + 1]))       # partition of the window's rows
+    enc, seg, _, _ = _build(amp, 7, cuda)
+    enc.eval(); seg.eval()
+    grouped = pc.index_select(0, order)
+    x9 = torch.cat((grouped[:, 0:3], grouped[:, 4:10]), 1).view(-1, 2048, 9)
+    out, _ = enc(x9)
+    b0 = 0
+    for w, k in enumerate(ks):
+        e = out[b0:b0 + k]
+        gl = e[:, 0, :256].unsqueeze(1)                                   # [k, 1, 256]
+        lo = e[:, :, 256:].reshape(1, k * 2048, 64)
+        logits, _ = seg(gl, lo, xy[w:w + 1, :k, :], [2048] * k, None)
+        assert tuple(logits.shape) == (1, 5, k * 2048) and torch.isfinite(logits).all()
+        b0 += k
