@@ -101,10 +101,12 @@ int tnet_fwd(EncCtx& c, int pbase, int L1, int d, const float* A, long long lda,
     return add_identity(out, B, d, c.st);
 }
 
-constexpr int kBlob1 = 2048 + 16384 + 65536;               // it.conv_1 (64 x 16 split), it.conv_2 (128 x 64), it.conv_3 (256 x 128)
-constexpr int kBlob2 = 8192 + 8192 + 16384 + 65536;        // conv_2, ft.conv_1, ft.conv_2, ft.conv_3
-constexpr int kBlob3 = 8192 + 8192 + 16384 + 32768 + 65536;// conv_2, conv_3, conv_4, conv_5, conv_6
-constexpr int kWcW1 = 4096, kWcF = 8192, kWcStride = kWcW1 + kWcF;   // per cloud: W1eff (64 x 32 split), F^T (64 x 64)
+// packed chain blobs: weights [K/8][N][8] bf16, each followed (128-byte aligned) by its bias K group [N][8] where the
+// layer's bias goes through the tensor pipe (tc_chain.cuh)
+constexpr int kBlob1 = 2048 + (16384 + 2048) + 65536;                       // it.conv_1 (64 x 16 split, bias folded), it.conv_2 + bias, it.conv_3
+constexpr int kBlob2 = (8192 + 1024) * 2 + (16384 + 2048) + 65536;          // conv_2, ft.conv_1, ft.conv_2 (+ biases), ft.conv_3
+constexpr int kBlob3 = (8192 + 1024) * 2 + (16384 + 2048) + (32768 + 2048) + 65536;   // conv_2 .. conv_5 (+ biases), conv_6
+constexpr int kWcW1 = 4096, kWcF = 8192, kWcStride = kWcW1 + kWcF;   // per cloud: W1eff (64 x 32 split, bias folded), F^T (64 x 64)
 
 struct EncTc {
     float *scale, *shift;
@@ -245,9 +247,14 @@ int tnet_bwd(EncCtx& c, BwdWs& w, int pbase, int L1, int d, const float* dM, con
 // conv_1 / conv_2 are recomputed in chain 3 instead of storing their activations (4.7 kMAC per point against a
 // 128 B/point round trip); the T-Net FC stacks run on the CUDA cores in fp32 (B rows only).
 // ---------------------------------------------------------------------------------------------------------------
-inline TcOp tc_op(int K, int N, int w_off, int w_cloud, int bias_off, int relu) {
-    TcOp o{}; o.K = K; o.N = N; o.w_off = w_off; o.w_cloud = w_cloud; o.bias_off = bias_off; o.relu = relu; o.write_act = 1;
+inline TcOp tc_op(int K, int N, int w_off, int w_cloud, int b_off, int relu) {
+    TcOp o{}; o.K = K; o.N = N; o.w_off = w_off; o.w_cloud = w_cloud; o.b_off = b_off; o.relu = relu; o.write_act = 1;
     return o;
+}
+// pack job of a BatchNorm-folded layer: weights scaled by the BN scale, bias = BN shift
+inline TcPackJob tc_job(const float* w, int ld, const float* scale, const float* shift, int N, int K, int Kpad, int split_in_k,
+                        int bias_col, long long bias_dst_off, long long dst_off) {
+    return TcPackJob{w, ld, 0, scale, nullptr, nullptr, shift, bias_col, bias_dst_off, N, K, N, Kpad, 0, split_in_k, dst_off, 0};
 }
 
 int tnet_fc_fwd(EncCtx& c, int pbase, int L1, int d, const float* pool, float* f1, float* f2, float* out) {
@@ -273,92 +280,94 @@ int encoder_fwd_bf16(EncCtx& c, const float* x, float* out, float* feat_t, Arena
         AMP_TRY(bn_fold_eval(d, L_ENC_BN, kBnEps, c.st));
     }
     auto sc = [&](int L) { return t.scale + enc_bn_offset(L); };
-    // shared weights of the three chains, BatchNorm scale folded in
+    auto sh = [&](int L) { return t.shift + enc_bn_offset(L); };
+    // shared weights of the three chains, BatchNorm scale folded into the rows, BatchNorm shift as the bias K group
     const int b1 = 0, b2 = kBlob1, b3 = kBlob1 + kBlob2;
+    // chain 1 layout
+    const int c1_w1 = 0, c1_w2 = 2048, c1_b2 = c1_w2 + 16384, c1_w3 = c1_b2 + 2048;
+    // chain 2 layout
+    const int c2_w2 = 0, c2_b2 = 8192, c2_f1 = c2_b2 + 1024, c2_fb1 = c2_f1 + 8192, c2_f2 = c2_fb1 + 1024, c2_fb2 = c2_f2 + 16384,
+              c2_f3 = c2_fb2 + 2048;
+    // chain 3 layout
+    const int c3_w2 = 0, c3_b2 = 8192, c3_w3 = c3_b2 + 1024, c3_b3 = c3_w3 + 8192, c3_w4 = c3_b3 + 1024, c3_b4 = c3_w4 + 16384,
+              c3_w5 = c3_b4 + 2048, c3_b5 = c3_w5 + 32768, c3_w6 = c3_b5 + 2048;
     {
         TcPackTable pt{};
         pt.n = 12; pt.n_clouds = 1;
-        pt.job[0] = TcPackJob{c.pf(E_IT + T_CONV1), 3, 0, sc(L_IT1), 64, 3, 64, 16, 0, 3, b1, 0};
-        pt.job[1] = TcPackJob{c.pf(E_IT + T_CONV2), 64, 0, sc(L_IT2), 128, 64, 128, 64, 0, 0, b1 + 2048, 0};
-        pt.job[2] = TcPackJob{c.pf(E_IT + T_CONV3), 128, 0, sc(L_IT3), 256, 128, 256, 128, 0, 0, b1 + 2048 + 16384, 0};
-        pt.job[3] = TcPackJob{c.pf(E_CONV2), 64, 0, sc(L_C2), 64, 64, 64, 64, 0, 0, b2, 0};
-        pt.job[4] = TcPackJob{c.pf(E_FT + T_CONV1), 64, 0, sc(L_FT1), 64, 64, 64, 64, 0, 0, b2 + 8192, 0};
-        pt.job[5] = TcPackJob{c.pf(E_FT + T_CONV2), 64, 0, sc(L_FT2), 128, 64, 128, 64, 0, 0, b2 + 16384, 0};
-        pt.job[6] = TcPackJob{c.pf(E_FT + T_CONV3), 128, 0, sc(L_FT3), 256, 128, 256, 128, 0, 0, b2 + 32768, 0};
-        pt.job[7] = TcPackJob{c.pf(E_CONV2), 64, 0, sc(L_C2), 64, 64, 64, 64, 0, 0, b3, 0};
-        pt.job[8] = TcPackJob{c.pf(E_CONV3), 64, 0, sc(L_C3), 64, 64, 64, 64, 0, 0, b3 + 8192, 0};
-        pt.job[9] = TcPackJob{c.pf(E_CONV4), 64, 0, sc(L_C4), 128, 64, 128, 64, 0, 0, b3 + 16384, 0};
-        pt.job[10] = TcPackJob{c.pf(E_CONV5), 128, 0, sc(L_C5), 128, 128, 128, 128, 0, 0, b3 + 32768, 0};
-        pt.job[11] = TcPackJob{c.pf(E_CONV6), 128, 0, sc(L_C6), 256, 128, 256, 128, 0, 0, b3 + 65536, 0};
+        pt.job[0] = tc_job(c.pf(E_IT + T_CONV1), 3, sc(L_IT1), sh(L_IT1), 64, 3, 16, 3, 3, -1, b1 + c1_w1);
+        pt.job[1] = tc_job(c.pf(E_IT + T_CONV2), 64, sc(L_IT2), sh(L_IT2), 128, 64, 64, 0, -1, b1 + c1_b2, b1 + c1_w2);
+        pt.job[2] = tc_job(c.pf(E_IT + T_CONV3), 128, sc(L_IT3), nullptr, 256, 128, 128, 0, -1, -1, b1 + c1_w3);
+        pt.job[3] = tc_job(c.pf(E_CONV2), 64, sc(L_C2), sh(L_C2), 64, 64, 64, 0, -1, b2 + c2_b2, b2 + c2_w2);
+        pt.job[4] = tc_job(c.pf(E_FT + T_CONV1), 64, sc(L_FT1), sh(L_FT1), 64, 64, 64, 0, -1, b2 + c2_fb1, b2 + c2_f1);
+        pt.job[5] = tc_job(c.pf(E_FT + T_CONV2), 64, sc(L_FT2), sh(L_FT2), 128, 64, 64, 0, -1, b2 + c2_fb2, b2 + c2_f2);
+        pt.job[6] = tc_job(c.pf(E_FT + T_CONV3), 128, sc(L_FT3), nullptr, 256, 128, 128, 0, -1, -1, b2 + c2_f3);
+        pt.job[7] = tc_job(c.pf(E_CONV2), 64, sc(L_C2), sh(L_C2), 64, 64, 64, 0, -1, b3 + c3_b2, b3 + c3_w2);
+        pt.job[8] = tc_job(c.pf(E_CONV3), 64, sc(L_C3), sh(L_C3), 64, 64, 64, 0, -1, b3 + c3_b3, b3 + c3_w3);
+        pt.job[9] = tc_job(c.pf(E_CONV4), 64, sc(L_C4), sh(L_C4), 128, 64, 64, 0, -1, b3 + c3_b4, b3 + c3_w4);
+        pt.job[10] = tc_job(c.pf(E_CONV5), 128, sc(L_C5), sh(L_C5), 128, 128, 128, 0, -1, b3 + c3_b5, b3 + c3_w5);
+        pt.job[11] = tc_job(c.pf(E_CONV6), 128, sc(L_C6), nullptr, 256, 128, 128, 0, -1, -1, b3 + c3_w6);
         AMP_TRY(tc_pack_weights(pt, t.blobs, c.st));
     }
     AMP_CUDA(cudaMemsetAsync(t.pools, 0, sizeof(float) * B * 256 * 3, c.st));
     float* it_pool = t.pools; float* ft_pool = t.pools + (size_t)B * 256; float* G = t.pools + (size_t)B * 512;
     TcChainParams base{};
-    base.in_mode = 0; base.in_x = x; base.in_ld = 9; base.n_groups = 1; base.n_clouds = B; base.rows_per_cloud = N;
+    base.in_mode = 0; base.in_x = x; base.in_ld = 9; base.in_bias = 1; base.n_groups = 1; base.n_clouds = B; base.rows_per_cloud = N;
     // chain 1: input T-Net convs on xyz + max-pool (:31-35)
     {
         TcChainParams p = base;
         p.in_k = 3; p.n_ops = 3;
-        p.tables = t.shift + enc_bn_offset(L_IT1); p.n_table_floats = 64 + 128 + 256;
         p.wblob = t.blobs + b1; p.wblob_bytes = kBlob1;
-        p.op[0] = tc_op(16, 64, 0, 0, 0, 1);
-        p.op[1] = tc_op(64, 128, 2048, 0, 64, 1);
-        p.op[2] = tc_op(128, 256, 2048 + 16384, 0, 192, 1); p.op[2].write_act = 0; p.op[2].pool = 1;
-        p.pool = reinterpret_cast<unsigned int*>(it_pool);
+        p.op[0] = tc_op(16, 64, c1_w1, 0, -1, 1);
+        p.op[1] = tc_op(64, 128, c1_w2, 0, c1_b2, 1);
+        p.op[2] = tc_op(128, 256, c1_w3, 0, -1, 1); p.op[2].write_act = 0; p.op[2].pool = 1;
+        p.pool = reinterpret_cast<unsigned int*>(it_pool); p.pool_bias = sh(L_IT3);
         AMP_TRY(tc_chain_launch(p, c.st));
     }
     AMP_TRY(tnet_fc_fwd(c, E_IT, L_IT1, 3, it_pool, t.f1, t.f2, t.T));
-    // bmm + cat + conv_1 (:85-90) as per-cloud conv_1 weights, packed with the bn_1 scale
+    // bmm + cat + conv_1 (:85-90) as per-cloud conv_1 weights, packed with the bn_1 scale; bn_1 shift rides in two spare input columns
     AMP_TRY(fold_input_transform(c.pf(E_CONV1), t.T, B, t.W1eff, c.st));
     {
         TcPackTable pt{};
         pt.n = 1; pt.n_clouds = B;
-        pt.job[0] = TcPackJob{t.W1eff, 9, 576, sc(L_C1), 64, 9, 64, 32, 0, 9, 0, kWcStride};
+        pt.job[0] = TcPackJob{t.W1eff, 9, 576, sc(L_C1), nullptr, nullptr, sh(L_C1), 9, -1, 64, 9, 64, 32, 0, 9, 0, kWcStride};
         AMP_TRY(tc_pack_weights(pt, t.wcloud, c.st));
     }
     // chain 2: conv_1, conv_2, feature T-Net convs + max-pool (:90-94)
     {
-        const int o0 = enc_bn_offset(L_FT1);
-        auto bo = [&](int L) { return enc_bn_offset(L) - o0; };
         TcChainParams p = base;
         p.in_k = 9; p.n_ops = 5;
-        p.tables = t.shift + o0; p.n_table_floats = enc_bn_offset(L_C2) + 64 - o0;
         p.wblob = t.blobs + b2; p.wblob_bytes = kBlob2;
         p.wcloud = t.wcloud; p.wcloud_stride = kWcStride; p.wcloud_bytes = kWcW1;
-        p.op[0] = tc_op(32, 64, 0, 1, bo(L_C1), 1);
-        p.op[1] = tc_op(64, 64, 0, 0, bo(L_C2), 1);
-        p.op[2] = tc_op(64, 64, 8192, 0, bo(L_FT1), 1);
-        p.op[3] = tc_op(64, 128, 16384, 0, bo(L_FT2), 1);
-        p.op[4] = tc_op(128, 256, 32768, 0, bo(L_FT3), 1); p.op[4].write_act = 0; p.op[4].pool = 1;
-        p.pool = reinterpret_cast<unsigned int*>(ft_pool);
+        p.op[0] = tc_op(32, 64, 0, 1, -1, 1);
+        p.op[1] = tc_op(64, 64, c2_w2, 0, c2_b2, 1);
+        p.op[2] = tc_op(64, 64, c2_f1, 0, c2_fb1, 1);
+        p.op[3] = tc_op(64, 128, c2_f2, 0, c2_fb2, 1);
+        p.op[4] = tc_op(128, 256, c2_f3, 0, -1, 1); p.op[4].write_act = 0; p.op[4].pool = 1;
+        p.pool = reinterpret_cast<unsigned int*>(ft_pool); p.pool_bias = sh(L_FT3);
         AMP_TRY(tc_chain_launch(p, c.st));
     }
     AMP_TRY(tnet_fc_fwd(c, E_FT, L_FT1, 64, ft_pool, t.f1, t.f2, feat_t));
     {
         TcPackTable pt{};
         pt.n = 1; pt.n_clouds = B;
-        pt.job[0] = TcPackJob{feat_t, 64, 4096, nullptr, 64, 64, 64, 64, 1, 0, kWcW1, kWcStride};
+        pt.job[0] = TcPackJob{feat_t, 64, 4096, nullptr, nullptr, nullptr, nullptr, -1, -1, 64, 64, 64, 64, 1, 0, kWcW1, kWcStride};
         AMP_TRY(tc_pack_weights(pt, t.wcloud, c.st));
     }
     // chain 3: conv_1, conv_2, bmm with the feature transform (= local features, :96-97), conv_3 .. conv_6 + max-pool
     {
-        const int o0 = enc_bn_offset(L_C1);
-        auto bo = [&](int L) { return enc_bn_offset(L) - o0; };
         TcChainParams p = base;
         p.in_k = 9; p.n_ops = 7;
-        p.tables = t.shift + o0; p.n_table_floats = 704;
         p.wblob = t.blobs + b3; p.wblob_bytes = kBlob3;
         p.wcloud = t.wcloud; p.wcloud_stride = kWcStride; p.wcloud_bytes = kWcStride;
-        p.op[0] = tc_op(32, 64, 0, 1, bo(L_C1), 1);
-        p.op[1] = tc_op(64, 64, 0, 0, bo(L_C2), 1);
+        p.op[0] = tc_op(32, 64, 0, 1, -1, 1);
+        p.op[1] = tc_op(64, 64, c3_w2, 0, c3_b2, 1);
         p.op[2] = tc_op(64, 64, kWcW1, 1, -1, 0); p.op[2].store_f32 = 1;
-        p.op[3] = tc_op(64, 64, 8192, 0, bo(L_C3), 1);
-        p.op[4] = tc_op(64, 128, 16384, 0, bo(L_C4), 1);
-        p.op[5] = tc_op(128, 128, 32768, 0, bo(L_C5), 1);
-        p.op[6] = tc_op(128, 256, 65536, 0, bo(L_C6), 1); p.op[6].write_act = 0; p.op[6].pool = 1;
+        p.op[3] = tc_op(64, 64, c3_w3, 0, c3_b3, 1);
+        p.op[4] = tc_op(64, 128, c3_w4, 0, c3_b4, 1);
+        p.op[5] = tc_op(128, 128, c3_w5, 0, c3_b5, 1);
+        p.op[6] = tc_op(128, 256, c3_w6, 0, -1, 1); p.op[6].write_act = 0; p.op[6].pool = 1;
         p.out_f32 = out; p.out_ld = 320; p.out_col0 = 256;
-        p.pool = reinterpret_cast<unsigned int*>(G);
+        p.pool = reinterpret_cast<unsigned int*>(G); p.pool_bias = sh(L_C6);
         AMP_TRY(tc_chain_launch(p, c.st));
     }
     // repeat + cat (:109-110)

@@ -19,7 +19,7 @@ namespace {
 constexpr float kBnEps = 1e-5f, kBnMomentum = 0.1f;
 constexpr int kSegBn2 = 0, kSegBn3 = 128, kSegBnTotal = 192;   // offsets into the scale/shift tables
 // bf16 tensor-core head: conv_2 local half (128 x 64), conv_3 (64 x 128), conv_4 (<= 32 x 64) packed; biases of conv_3 / conv_4
-constexpr int kSegTcBlob = 16384 + 16384 + 4096, kSegTcTab = 64 + 32;
+constexpr int kSegTcBlob = 16384 + (16384 + 1024) + (4096 + 512), kSegTcTab = 64;
 
 #define AMP_TRY(expr) do { int rc_ = (expr); if (rc_ != AMP_OK) return rc_; } while (0)
 #define AMP_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fail(AMP_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); } while (0)
@@ -189,25 +189,21 @@ int amp_seg_fwd(const void* const* params, const float* gl_feats, const float* l
             AMP_TRY(pw_linear(p, st));
         }
         const int Cp = (num_classes + 15) / 16 * 16;
+        const int o_w2 = 0, o_w3 = 16384, o_b3 = o_w3 + 16384, o_w4 = o_b3 + 1024, o_b4 = o_w4 + 4096;
         TcPackTable pt{};
         pt.n = 3; pt.n_clouds = 1;
-        pt.job[0] = TcPackJob{pf(params, S_C2W), 64 + E, 0, S.scale + kSegBn2, hid, 64, hid, 64, 0, 0, 0, 0};
-        pt.job[1] = TcPackJob{pf(params, S_C3W), hid, 0, S.scale + kSegBn3, 64, hid, 64, hid, 0, 0, 16384, 0};
-        pt.job[2] = TcPackJob{pf(params, S_C4W), 64, 0, nullptr, num_classes, 64, Cp, 64, 0, 0, 32768, 0};
+        pt.job[0] = TcPackJob{pf(params, S_C2W), 64 + E, 0, S.scale + kSegBn2, nullptr, nullptr, nullptr, -1, -1, hid, 64, hid, 64, 0, 0, o_w2, 0};
+        pt.job[1] = TcPackJob{pf(params, S_C3W), hid, 0, S.scale + kSegBn3, pf(params, S_C3B), S.scale + kSegBn3, S.shift + kSegBn3, -1, o_b3,
+                              64, hid, 64, hid, 0, 0, o_w3, 0};
+        pt.job[2] = TcPackJob{pf(params, S_C4W), 64, 0, nullptr, pf(params, S_C4B), nullptr, nullptr, -1, o_b4, num_classes, 64, Cp, 64, 0, 0, o_w4, 0};
         AMP_TRY(tc_pack_weights(pt, ws.tc_blob, st));
-        TcBiasTable bt{};
-        bt.n = 2;
-        bt.job[0] = TcBiasJob{pf(params, S_C3B), S.scale + kSegBn3, S.shift + kSegBn3, 64, 64, 0};
-        bt.job[1] = TcBiasJob{pf(params, S_C4B), nullptr, nullptr, num_classes, Cp, 64};
-        AMP_TRY(tc_bias_tables(bt, ws.tc_tab, st));
         TcChainParams p{};
         p.n_ops = 3;
-        p.op[0] = TcOp{64, hid, 0, 0, -1, 1, 1, 1, 0, 0, 0};
-        p.op[1] = TcOp{hid, 64, 16384, 0, 0, 1, 0, 1, 0, 0, 0};
-        p.op[2] = TcOp{64, Cp, 32768, 0, 64, 0, 0, 0, 0, 0, 1};
+        p.op[0] = TcOp{64, hid, o_w2, 0, -1, 1, 1, 1, 0, 0, 0};
+        p.op[1] = TcOp{hid, 64, o_w3, 0, o_b3, 1, 0, 1, 0, 0, 0};
+        p.op[2] = TcOp{64, Cp, o_w4, 0, o_b4, 0, 0, 0, 0, 0, 1};
         p.in_mode = 1; p.in_x = lo_feats; p.in_ld = 64; p.in_k = 64;
-        p.tables = ws.tc_tab; p.n_table_floats = 64 + Cp;
-        p.wblob = ws.tc_blob; p.wblob_bytes = 32768 + Cp * 128;
+        p.wblob = ws.tc_blob; p.wblob_bytes = o_b4 + Cp * 16;
         p.gbias = S.cb; p.group_rows = group_rows; p.n_groups = Wi;
         p.logits = logits; p.n_classes = num_classes;
         p.n_clouds = Bi; p.rows_per_cloud = Ri;

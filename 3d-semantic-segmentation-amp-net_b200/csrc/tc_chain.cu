@@ -1,19 +1,23 @@
 // Fused shared-MLP chain kernel on tcgen05 tensor cores (see tc_chain.cuh for the contract).
 //
-// Layout of one CTA (256 threads = 2 independent warpgroups, 1 CTA per SM):
+// Layout of one CTA (512 threads, 1 CTA per SM):
 //   * the packed bf16 weights of the whole chain live in shared memory for the CTA's lifetime (TMA bulk copies
 //     global -> shared, completion on an mbarrier);
-//   * each warpgroup owns a "slot": a 32 KB activation buffer (the K-major A operand of the next layer), a region for
-//     per-cloud weights, 256 TMEM columns of fp32 accumulators and one mbarrier. It walks its own stream of 128-point
-//     tiles: stage input -> for every layer { one thread issues the tcgen05.mma K-steps and commits to the mbarrier;
-//     all 128 threads wait, read the accumulator with tcgen05.ld (thread == TMEM lane == point row), add bias, ReLU,
-//     write bf16 back as the next A operand } . While one warpgroup is in its epilogue the other one's MMAs run, so
-//     tensor pipe and CUDA cores overlap without any cross-warpgroup synchronisation.
+//   * two independent "slots", each served by 256 threads (two warpgroups): a 32 KB activation buffer (the K-major A
+//     operand of the next layer), a region for per-cloud weights, 256 TMEM columns of fp32 accumulators and one
+//     mbarrier. A slot walks its own stream of 128-point tiles: stage input -> for every layer { one thread issues the
+//     tcgen05.mma K-steps (+ one more against a constant block of ones, whose other operand is the layer's bias K group,
+//     read with a zero leading-dimension stride: the bias add costs no ALU work) and commits to the mbarrier; the 256 threads wait, read the accumulator with tcgen05.ld
+//     (thread == TMEM lane == point row; the two warpgroups take alternating 32-column chunks), pack to bf16,
+//     ReLU on the packed pairs, and write the next A operand }. While one slot is in its epilogue the other slot's
+//     MMAs run, so tensor pipe and CUDA cores overlap without cross-slot synchronisation.
 //   * pooled layers run TRANSPOSED: D^T[channel, point] = W[channel, :] . act[point, :], so that TMEM lanes are
 //     channels and the max over the points of the tile is a per-thread register reduction (no shuffles); one
-//     atomicMax per (cloud, channel, tile).
+//     atomicMax per (cloud, channel, half tile).
 // Operand layout in shared memory (both A and B): K-major, no swizzle, 8 x 16-byte core matrices:
 //   element (row r, k) at byte ((k / 8) * rows + r) * 16 + (k % 8) * 2      -> SBO = 128 B, LBO = rows * 16 B.
+#include <cuda_fp16.h>
+
 #include "tc_chain.cuh"
 #include "tc_ptx.cuh"
 
@@ -21,8 +25,9 @@ namespace amp {
 namespace {
 using namespace tcx;
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512, kSlotThreads = 256;
 constexpr int kActBytes = kTcTileRows * 128 * 2;          // 128 rows x up to 128 channels of bf16
+constexpr int kOnesBytes = kTcTileRows * 16 * 2;          // constant A / B operand of the bias MMA: [2][128][8] bf16
 constexpr int kTmemCols = 512;
 constexpr int kSlotCols = 256;
 constexpr int kMaxSmem = 232448;                          // 227 KB per CTA on sm_100
@@ -30,32 +35,38 @@ constexpr int kMinSmem = 120 * 1024;                      // more than half an S
 
 __host__ __device__ inline int align_i(int v, int a) { return (v + a - 1) / a * a; }
 
-// ---------------------------------------------------------------------------------------------------------------
-// the chain kernel
-// ---------------------------------------------------------------------------------------------------------------
-struct SmemPlan { int w, wc, act0, tab, bar, total; };
-__host__ __device__ inline SmemPlan smem_plan(int wblob_bytes, int wcloud_bytes, int n_table_floats) {
+struct SmemPlan { int w, wc, act0, ones, bar, total; };
+__host__ __device__ inline SmemPlan smem_plan(int wblob_bytes, int wcloud_bytes) {
     SmemPlan s;
     s.w = align_i(wblob_bytes, 128);
     s.wc = align_i(wcloud_bytes, 128);
     s.act0 = s.w + 2 * s.wc;
-    s.tab = s.act0 + 2 * kActBytes;
-    s.bar = s.tab + align_i(n_table_floats * 4, 16);
+    s.ones = s.act0 + 2 * kActBytes;
+    s.bar = s.ones + kOnesBytes;
     s.total = s.bar + 64;
     return s;
 }
 
+__device__ __forceinline__ void slot_bar_sync(int slot) { asm volatile("bar.sync %0, 256;" ::"r"(slot + 1) : "memory"); }
+// max(x, 0) on a packed bf16 pair
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t u) {
+    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+    v = __hmax2(v, __float2bfloat162_rn(0.f));
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
 __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_constant__ TcChainParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = warp >> 2, wtid = tid & 127;
-    const SmemPlan sp = smem_plan(p.wblob_bytes, p.wcloud_bytes, p.n_table_floats);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int slot = warp >> 3, sub = (warp >> 2) & 1, stid = tid & (kSlotThreads - 1);
+    const SmemPlan sp = smem_plan(p.wblob_bytes, p.wcloud_bytes);
     unsigned char* s_w = smem;
-    unsigned char* s_wc = smem + sp.w + wg * sp.wc;
-    unsigned char* s_act = smem + sp.act0 + wg * kActBytes;
-    float* s_tab = reinterpret_cast<float*>(smem + sp.tab);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + sp.bar);       // [0] weights, [1 + wg] MMA completion
+    unsigned char* s_wc = smem + sp.w + slot * sp.wc;
+    unsigned char* s_act = smem + sp.act0 + slot * kActBytes;
+    uint4* s_ones = reinterpret_cast<uint4*>(smem + sp.ones);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + sp.bar);       // [0] weights, [1 + slot] MMA completion
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + sp.bar + 32);
-    const uint32_t wbar = smem_u32(&s_bar[0]), mbar = smem_u32(&s_bar[1 + wg]);
+    const uint32_t wbar = smem_u32(&s_bar[0]), mbar = smem_u32(&s_bar[1 + slot]);
 
     if (tid == 0) {
         mbar_init(wbar, 1);
@@ -64,7 +75,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(s_tmem), kTmemCols);
-    for (int i = tid; i < p.n_table_floats; i += kThreads) s_tab[i] = __ldg(p.tables + i);
+    // ones block: K group 0 = [1, 1, 0, 0, 0, 0, 0, 0] per row (multiplies the bias hi and lo terms), K group 1 = 0
+    if (tid < 256) s_ones[tid] = tid < 128 ? make_uint4(0x3f803f80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -83,12 +96,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
     const int n_tiles = p.n_clouds * tiles_per_cloud;
     const int row = (warp & 3) * 32 + lane;                      // this thread's TMEM lane == tile row
     const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t slot_col = tmem_base + (uint32_t)(wg * kSlotCols);
-    const uint32_t act_addr = smem_u32(s_act);
+    const uint32_t slot_col = tmem_base + (uint32_t)(slot * kSlotCols);
+    const uint32_t act_addr = smem_u32(s_act), ones_addr = smem_u32(s_ones);
     uint32_t phase = 0;
     int cur_cloud = -1;
 
-    for (int tile = blockIdx.x * 2 + wg; tile < n_tiles; tile += gridDim.x * 2) {
+    for (int tile = blockIdx.x * 2 + slot; tile < n_tiles; tile += gridDim.x * 2) {
         const int cloud = tile / tiles_per_cloud;
         const int row0 = (tile - cloud * tiles_per_cloud) * kTcTileRows;
         const int valid = min(kTcTileRows, rows - row0);
@@ -99,41 +112,47 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
         if (p.wcloud_bytes > 0 && cloud != cur_cloud) {
             const uint4* src = reinterpret_cast<const uint4*>(p.wcloud + (long long)cloud * p.wcloud_stride);
             uint4* dst = reinterpret_cast<uint4*>(s_wc);
-            for (int i = wtid; i < p.wcloud_bytes / 16; i += 128) dst[i] = __ldg(src + i);
+            for (int i = stid; i < p.wcloud_bytes / 16; i += kSlotThreads) dst[i] = __ldg(src + i);
             cur_cloud = cloud;
         }
         // ---- input stage: fp32 rows -> bf16 A operand [K/8][128][8] ----
         if (p.in_mode == 0) {
-            const float* src = p.in_x + grow * p.in_ld;
-            float xv[9];
+            if (sub == 0) {
+                const float* src = p.in_x + grow * p.in_ld;
+                float xv[9];
 #pragma unroll
-            for (int j = 0; j < 9; ++j) xv[j] = (row_ok && j < p.in_k) ? __ldg(src + j) : 0.f;
-            float hi[9], lo[9];
+                for (int j = 0; j < 9; ++j) xv[j] = (row_ok && j < p.in_k) ? __ldg(src + j) : 0.f;
+                float hi[9], lo[9];
 #pragma unroll
-            for (int j = 0; j < 9; ++j) {
-                const __nv_bfloat16 h = __float2bfloat16_rn(xv[j]);
-                hi[j] = __bfloat162float(h);
-                lo[j] = xv[j] - hi[j];
-            }
-            uint4* dst = reinterpret_cast<uint4*>(s_act);
-            if (p.op[0].K == 16) {          // in_k <= 3 ... 8: k 0..7 = hi, k 8..15 = lo
-                dst[0 * 128 + row] = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]),
-                                                pack_bf16x2(hi[6], hi[7]));
-                dst[1 * 128 + row] = make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]),
-                                                pack_bf16x2(lo[6], lo[7]));
-            } else {                        // K == 32: k 0..15 = hi (9 used), k 16..31 = lo
-                dst[0 * 128 + row] = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]),
-                                                pack_bf16x2(hi[6], hi[7]));
-                dst[1 * 128 + row] = make_uint4(pack_bf16x2(hi[8], 0.f), 0u, 0u, 0u);
-                dst[2 * 128 + row] = make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]),
-                                                pack_bf16x2(lo[6], lo[7]));
-                dst[3 * 128 + row] = make_uint4(pack_bf16x2(lo[8], 0.f), 0u, 0u, 0u);
+                for (int j = 0; j < 9; ++j) {
+                    const __nv_bfloat16 h = __float2bfloat16_rn(xv[j]);
+                    hi[j] = __bfloat162float(h);
+                    lo[j] = xv[j] - hi[j];
+                }
+                const float one = p.in_bias ? 1.f : 0.f;        // constant columns in_k, in_k + 1 multiply the folded bias
+                uint4* dst = reinterpret_cast<uint4*>(s_act);
+                if (p.op[0].K == 16) {          // in_k <= 6: k 0..7 = hi (+ ones), k 8..15 = lo
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j == p.in_k || j == p.in_k + 1) hi[j] = one;
+                    dst[0 * 128 + row] = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]),
+                                                    pack_bf16x2(hi[6], hi[7]));
+                    dst[1 * 128 + row] = make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]),
+                                                    pack_bf16x2(lo[6], lo[7]));
+                } else {                        // K == 32: k 0..15 = hi (9 used), k 16..31 = lo
+                    dst[0 * 128 + row] = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]),
+                                                    pack_bf16x2(hi[6], hi[7]));
+                    dst[1 * 128 + row] = make_uint4(pack_bf16x2(hi[8], one), pack_bf16x2(one, 0.f), 0u, 0u);   // k 9, 10 = ones
+                    dst[2 * 128 + row] = make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]),
+                                                    pack_bf16x2(lo[6], lo[7]));
+                    dst[3 * 128 + row] = make_uint4(pack_bf16x2(lo[8], 0.f), 0u, 0u, 0u);
+                }
             }
         } else {
             const float4* src = reinterpret_cast<const float4*>(p.in_x + grow * p.in_ld);
             uint4* dst = reinterpret_cast<uint4*>(s_act);
             const int chunks = p.op[0].K >> 3;
-            for (int c = 0; c < chunks; ++c) {
+            for (int c = sub; c < chunks; c += 2) {        // the two warpgroups take alternating 8-channel groups
                 float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
                 if (row_ok) { a = __ldg(src + 2 * c); b = __ldg(src + 2 * c + 1); }
                 dst[c * 128 + row] = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
@@ -147,12 +166,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
         }
         fence_proxy_async();
         tc_fence_before();
-        wg_bar_sync(wg);
+        slot_bar_sync(slot);
 
         for (int l = 0; l < p.n_ops; ++l) {
             const TcOp& op = p.op[l];
-            // ---- MMA issue: one thread per warpgroup ----
-            if (wtid == 0) {
+            // ---- MMA issue: one thread per slot ----
+            if (stid == 0) {
                 if (!w_ready) { mbar_wait(wbar, 0); w_ready = true; }
                 tc_fence_after();
                 const uint32_t wbase = op.w_cloud ? smem_u32(s_wc) + (uint32_t)op.w_off : smem_u32(s_w) + (uint32_t)op.w_off;
@@ -163,13 +182,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
                     for (int k = 0; k < ksteps; ++k)
                         umma_bf16(slot_col, umma_desc(act_addr + (uint32_t)k * 4096u, 2048u, 128u),
                                   umma_desc(wbase + (uint32_t)k * 2u * w_lbo, w_lbo, 128u), idesc, k > 0);
+                    if (op.b_off >= 0)          // bias K group: both K halves alias the same 8 columns (LBO 0), ones half 1 is zero
+                        umma_bf16(slot_col, umma_desc(ones_addr, 2048u, 128u),
+                                  umma_desc((op.w_cloud ? smem_u32(s_wc) : smem_u32(s_w)) + (uint32_t)op.b_off, 0u, 128u), idesc, 1u);
                 } else {
                     const uint32_t idesc = umma_idesc(128, 128);
-                    for (int mt = 0; mt < (op.N >> 7); ++mt)
+                    for (int mt = 0; mt < (op.N >> 7); ++mt) {
                         for (int k = 0; k < ksteps; ++k)
                             umma_bf16(slot_col + (uint32_t)mt * 128u,
                                       umma_desc(wbase + (uint32_t)mt * 2048u + (uint32_t)k * 2u * w_lbo, w_lbo, 128u),
                                       umma_desc(act_addr + (uint32_t)k * 4096u, 2048u, 128u), idesc, k > 0);
+                    }
                 }
                 umma_commit(mbar);
             }
@@ -178,67 +201,68 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
             phase ^= 1u;
             tc_fence_after();
 
-            // ---- epilogue ----
+            // ---- epilogue: the two warpgroups of the slot take alternating 32-column chunks ----
             if (!op.pool) {
                 const float* gb = op.bias_grouped ? p.gbias + ((long long)cloud * p.n_groups + group) * op.N : nullptr;
-                for (int c0 = 0; c0 < op.N; c0 += 32) {
+                const bool plain = !gb && !op.store_f32 && !op.store_logits;
+                for (int c0 = sub * 32; c0 < op.N; c0 += 64) {
                     uint32_t v[32];
                     tmem_ld32(slot_col + lane_addr + (uint32_t)c0, v);
                     tmem_wait_ld();
-                    float f[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                     const int nc = min(32, op.N - c0);           // 16 or 32
-                    if (op.bias_off >= 0) {
-                        const float4* b4 = reinterpret_cast<const float4*>(s_tab + op.bias_off + c0);
+                    uint32_t u[16];
+                    if (plain) {                                  // hot path: pack, ReLU on the packed pairs
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            if (q * 4 < nc) {
-                                const float4 b = b4[q];
-                                f[4 * q] += b.x; f[4 * q + 1] += b.y; f[4 * q + 2] += b.z; f[4 * q + 3] += b.w;
+                        for (int q = 0; q < 16; ++q) u[q] = pack_bf16x2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+                        if (op.relu) {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) u[q] = relu_bf16x2(u[q]);
+                        }
+                    } else {
+                        float f[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                        if (gb) {
+                            const float4* g4 = reinterpret_cast<const float4*>(gb + c0);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                if (q * 4 < nc) {
+                                    const float4 b = __ldg(g4 + q);
+                                    f[4 * q] += b.x; f[4 * q + 1] += b.y; f[4 * q + 2] += b.z; f[4 * q + 3] += b.w;
+                                }
                             }
                         }
-                    }
-                    if (gb) {
-                        const float4* g4 = reinterpret_cast<const float4*>(gb + c0);
+                        if (op.relu) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            if (q * 4 < nc) {
-                                const float4 b = __ldg(g4 + q);
-                                f[4 * q] += b.x; f[4 * q + 1] += b.y; f[4 * q + 2] += b.z; f[4 * q + 3] += b.w;
-                            }
+                            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
                         }
-                    }
-                    if (op.relu) {
+                        if (op.store_f32 && row_ok) {
+                            float4* o = reinterpret_cast<float4*>(p.out_f32 + grow * p.out_ld + p.out_col0 + c0);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-                    }
-                    if (op.store_f32 && row_ok) {
-                        float4* o = reinterpret_cast<float4*>(p.out_f32 + grow * p.out_ld + p.out_col0 + c0);
+                            for (int q = 0; q < 8; ++q)
+                                if (q * 4 < nc) o[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                        }
+                        if (op.store_logits && c0 == 0 && row_ok) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            if (q * 4 < nc) o[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                            for (int n = 0; n < 32; ++n)
+                                if (n < p.n_classes)
+                                    p.logits[((long long)cloud * p.n_classes + n) * rows + row0 + row] = f[n];
+                        }
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) u[q] = pack_bf16x2(f[2 * q], f[2 * q + 1]);
                     }
                     if (op.write_act) {
                         uint4* dst = reinterpret_cast<uint4*>(s_act);
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
-                            if (q * 8 < nc)
-                                dst[((c0 >> 3) + q) * 128 + row] =
-                                    make_uint4(pack_bf16x2(f[8 * q], f[8 * q + 1]), pack_bf16x2(f[8 * q + 2], f[8 * q + 3]),
-                                               pack_bf16x2(f[8 * q + 4], f[8 * q + 5]), pack_bf16x2(f[8 * q + 6], f[8 * q + 7]));
-                    }
-                    if (op.store_logits && c0 == 0 && row_ok) {
-#pragma unroll
-                        for (int n = 0; n < 32; ++n)
-                            if (n < p.n_classes)
-                                p.logits[((long long)cloud * p.n_classes + n) * rows + row0 + row] = f[n];
+                            if (q * 8 < nc) dst[((c0 >> 3) + q) * 128 + row] = make_uint4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
                     }
                 }
             } else {
+                // lanes = channels; this warpgroup's half of the tile's points: columns [sub * 64, sub * 64 + 64)
                 for (int mt = 0; mt < (op.N >> 7); ++mt) {
                     float m = -3.0e38f;
-                    for (int c0 = 0; c0 < kTcTileRows; c0 += 32) {
+                    for (int c0 = sub * 64; c0 < sub * 64 + 64; c0 += 32) {
                         if (c0 >= valid) break;
                         uint32_t v[32];
                         tmem_ld32(slot_col + lane_addr + (uint32_t)(mt * 128 + c0), v);
@@ -252,16 +276,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
                                 if (c0 + j < valid) m = fmaxf(m, __uint_as_float(v[j]));
                         }
                     }
-                    const int ch = mt * 128 + row;
-                    float r = m + (op.bias_off >= 0 ? s_tab[op.bias_off + ch] : 0.f);
-                    r = fmaxf(r, 0.f);
-                    atomicMax(p.pool + (long long)cloud * op.N + ch, __float_as_uint(r));
+                    if (sub * 64 < valid) {
+                        const int ch = mt * 128 + row;
+                        const float r = fmaxf(m + (p.pool_bias ? __ldg(p.pool_bias + ch) : 0.f), 0.f);
+                        atomicMax(p.pool + (long long)cloud * op.N + ch, __float_as_uint(r));
+                    }
                 }
             }
             // accumulator reads and A-operand writes of this layer are done before the next MMA is issued
             tc_fence_before();
             fence_proxy_async();
-            wg_bar_sync(wg);
+            slot_bar_sync(slot);
         }
     }
     if (tid == 0 && !w_ready) mbar_wait(wbar, 0);        // never leave with a bulk copy in flight
@@ -276,30 +301,37 @@ __global__ void tc_pack_kernel(const TcPackTable t, unsigned char* __restrict__ 
     if (cloud > 0 && j.src_cloud_stride == 0) return;
     const float* src = j.src + (long long)cloud * j.src_cloud_stride;
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(dst + j.dst_off + (long long)cloud * j.dst_cloud_stride);
-    const int total = j.Npad * j.Kpad;
+    __nv_bfloat16* bout = j.bias_dst_off >= 0 ? reinterpret_cast<__nv_bfloat16*>(dst + j.bias_dst_off + (long long)cloud * j.dst_cloud_stride) : nullptr;
+    const bool has_bias = j.bias || j.bias_shift;
+    const int n_w = j.Npad * j.Kpad, total = n_w + (bout ? j.Npad * 8 : 0);
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-        const int k8 = e & 7, n = (e >> 3) % j.Npad, kc = (e >> 3) / j.Npad;
+        const int ee = e < n_w ? e : e - n_w;
+        const int k8 = ee & 7, n = (ee >> 3) % j.Npad, kc = (ee >> 3) / j.Npad;
         const int k = kc * 8 + k8;
+        float b = 0.f, bhi = 0.f;
+        if (has_bias && n < j.N) {
+            b = (j.bias_scale ? j.bias_scale[n] : 1.f) * (j.bias ? j.bias[n] : 0.f) + (j.bias_shift ? j.bias_shift[n] : 0.f);
+            bhi = __bfloat162float(__float2bfloat16_rn(b));
+        }
+        if (e >= n_w) {                                   // separate bias K group: hi at k8 = 0, lo at k8 = 1
+            bout[ee] = __float2bfloat16_rn(k8 == 0 ? bhi : (k8 == 1 ? b - bhi : 0.f));
+            continue;
+        }
+        float v = 0.f;
         int ks = k < j.K ? k : -1;
         if (j.split_in_k) {
             const int half = j.Kpad >> 1;
             ks = k < j.split_in_k ? k : ((k >= half && k < half + j.split_in_k) ? k - half : -1);
         }
-        float v = 0.f;
         if (n < j.N && ks >= 0) {
             v = j.transposed ? src[(long long)ks * j.ld + n] : src[(long long)n * j.ld + ks];
             if (j.scale) v *= j.scale[n];
         }
+        if (j.bias_col >= 0 && has_bias) {                // bias folded into two spare weight columns (input stage ones)
+            if (k == j.bias_col) v = bhi;
+            else if (k == j.bias_col + 1) v = b - bhi;
+        }
         out[e] = __float2bfloat16_rn(v);
-    }
-}
-
-__global__ void tc_bias_kernel(const TcBiasTable t, float* __restrict__ dst) {
-    const TcBiasJob& j = t.job[blockIdx.x];
-    for (int i = threadIdx.x; i < j.npad; i += blockDim.x) {
-        float v = 0.f;
-        if (i < j.n) v = (j.scale ? j.scale[i] : 1.f) * (j.bias ? j.bias[i] : 0.f) + (j.shift ? j.shift[i] : 0.f);
-        dst[j.dst_off + i] = v;
     }
 }
 
@@ -314,9 +346,8 @@ int tc_chain_launch(const TcChainParams& p, cudaStream_t st) {
         if (o.pool && (o.N % 128 || !o.relu || !p.pool)) return fail(AMP_E_BADARG, "tc_chain: op %d cannot pool", l);
         if (o.write_act && (o.N > 128 || l + 1 >= p.n_ops || p.op[l + 1].K != o.N))
             return fail(AMP_E_BADARG, "tc_chain: op %d does not feed op %d", l, l + 1);
-        if (o.bias_off >= 0 && (o.bias_off % 4 || o.bias_off + o.N > p.n_table_floats))
-            return fail(AMP_E_BADARG, "tc_chain: op %d bias table out of range", l);
-        if (o.w_off % 128) return fail(AMP_E_BADARG, "tc_chain: op %d weights are not 128-byte aligned", l);
+        if (o.w_off % 128 || (o.b_off >= 0 && o.b_off % 128)) return fail(AMP_E_BADARG, "tc_chain: op %d weights are not 128-byte aligned", l);
+        if (o.pool && o.b_off >= 0) return fail(AMP_E_BADARG, "tc_chain: op %d: pooled ops take pool_bias", l);
         if (o.store_logits && (!p.logits || p.n_classes < 1 || p.n_classes > o.N || p.n_classes > 32))
             return fail(AMP_E_BADARG, "tc_chain: op %d cannot store logits", l);
         if (o.store_f32 && (!p.out_f32 || p.out_ld % 4 || p.out_col0 % 4 || ((uintptr_t)p.out_f32 & 15)))
@@ -333,7 +364,7 @@ int tc_chain_launch(const TcChainParams& p, cudaStream_t st) {
     if (p.wblob_bytes % 16 || p.wcloud_bytes % 16 || p.wcloud_stride % 16 || ((uintptr_t)p.wblob & 15) || ((uintptr_t)p.wcloud & 15))
         return fail(AMP_E_BADARG, "tc_chain: packed weights are not 16-byte aligned");
     if (p.n_clouds < 1 || p.rows_per_cloud < 1) return fail(AMP_E_BADARG, "tc_chain: empty input");
-    const SmemPlan sp = smem_plan(p.wblob_bytes, p.wcloud_bytes, p.n_table_floats);
+    const SmemPlan sp = smem_plan(p.wblob_bytes, p.wcloud_bytes);
     if (sp.total > kMaxSmem) return fail(AMP_E_BADARG, "tc_chain: chain needs %d bytes of shared memory", sp.total);
     static bool attr_set = false;
     if (!attr_set) {
@@ -353,7 +384,7 @@ int tc_pack_weights(const TcPackTable& t, unsigned char* dst, cudaStream_t st) {
     if (t.n < 1 || t.n > TcPackTable::kMax) return fail(AMP_E_BADARG, "tc_pack_weights: bad job count");
     int mx = 0;
     for (int i = 0; i < t.n; ++i) {
-        const int e = t.job[i].Npad * t.job[i].Kpad;
+        const int e = t.job[i].Npad * (t.job[i].Kpad + 8);
         if (e > mx) mx = e;
         if (t.job[i].Npad % 16 || t.job[i].Kpad % 16 || t.job[i].dst_off % 128)
             return fail(AMP_E_BADARG, "tc_pack_weights: job %d is not tile aligned", i);
@@ -365,13 +396,6 @@ int tc_pack_weights(const TcPackTable& t, unsigned char* dst, cudaStream_t st) {
     return check_launch("tc_pack_kernel");
 }
 
-int tc_bias_tables(const TcBiasTable& t, float* dst, cudaStream_t st) {
-    if (t.n < 1 || t.n > TcBiasTable::kMax) return fail(AMP_E_BADARG, "tc_bias_tables: bad job count");
-    tc_bias_kernel<<<t.n, 128, 0, st>>>(t, dst);
-    count_launch();
-    return check_launch("tc_bias_kernel");
-}
-
 }  // namespace amp
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -381,7 +405,7 @@ extern "C" {
 
 size_t amp_tc_linear_workspace_bytes(int32_t K, int32_t N) {
     const int Kp = (K + 15) / 16 * 16, Np = (N + 15) / 16 * 16;
-    return (size_t)amp::tc_packed_bytes(Np, Kp) + (size_t)Np * 4 + 512;
+    return (size_t)amp::tc_packed_bytes(Np, Kp) + (size_t)amp::tc_bias_bytes(Np) + 512;
 }
 
 int amp_tc_linear_bf16(const float* x, int64_t n_clouds, int64_t rows_per_cloud, int32_t K, const float* w, const float* bias,
@@ -397,23 +421,19 @@ int amp_tc_linear_bf16(const float* x, int64_t n_clouds, int64_t rows_per_cloud,
     if (pool_max && (!relu || N % 128)) return fail(AMP_E_BADARG, "tc_linear: pooling needs relu and N % 128 == 0");
     cudaStream_t st = (cudaStream_t)stream;
     unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    const int wbytes = tc_packed_bytes(N, K);
-    float* tab = reinterpret_cast<float*>(base + wbytes);
     TcPackTable pt{};
     pt.n = 1; pt.n_clouds = 1;
-    pt.job[0] = TcPackJob{w, K, 0, nullptr, N, K, N, K, 0, 0, 0, 0};
+    const int wbytes = tc_packed_bytes(N, K);
+    const bool bias_group = bias && !pool_max;            // pooled layers add their bias in the epilogue
+    pt.job[0] = TcPackJob{w, K, 0, nullptr, bias, nullptr, nullptr, -1, bias_group ? wbytes : -1, N, K, N, K, 0, 0, 0, 0};
     int rc = tc_pack_weights(pt, base, st);
-    if (rc != AMP_OK) return rc;
-    TcBiasTable bt{};
-    bt.n = 1; bt.job[0] = TcBiasJob{bias, nullptr, nullptr, bias ? N : 0, N, 0};
-    rc = tc_bias_tables(bt, tab, st);
     if (rc != AMP_OK) return rc;
     TcChainParams p{};
     p.n_ops = 1;
-    p.op[0] = TcOp{K, N, 0, 0, 0, relu, 0, 0, pool_max ? 0 : 1, pool_max ? 1 : 0, 0};
+    p.op[0] = TcOp{K, N, 0, 0, bias_group ? wbytes : -1, relu, 0, 0, pool_max ? 0 : 1, pool_max ? 1 : 0, 0};
     p.in_mode = 1; p.in_x = x; p.in_ld = K; p.in_k = K;
-    p.tables = tab; p.n_table_floats = N;
-    p.wblob = base; p.wblob_bytes = wbytes;
+    p.wblob = base; p.wblob_bytes = wbytes + (bias_group ? tc_bias_bytes(N) : 0);
+    p.pool_bias = pool_max ? bias : nullptr;
     p.n_groups = 1;
     p.out_f32 = y; p.out_ld = N; p.out_col0 = 0;
     p.pool = pool_max;
