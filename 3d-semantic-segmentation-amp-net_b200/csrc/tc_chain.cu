@@ -17,6 +17,7 @@
 // Operand layout in shared memory (both A and B): K-major, no swizzle, 8 x 16-byte core matrices:
 //   element (row r, k) at byte ((k / 8) * rows + r) * 16 + (k % 8) * 2      -> SBO = 128 B, LBO = rows * 16 B.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "tc_chain.cuh"
 #include "tc_ptx.cuh"
@@ -53,6 +54,45 @@ __device__ __forceinline__ uint32_t relu_bf16x2(uint32_t u) {
     __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
     v = __hmax2(v, __float2bfloat162_rn(0.f));
     return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// Rare epilogue variants of one 32-column chunk (per-block bias of the head, fp32 store of the local features, logits):
+// kept out of line so that their address arithmetic is not hoisted in front of every layer's hot loop.
+__device__ __noinline__ void epilogue_slow(const TcChainParams& p, const TcOp& op, const uint32_t (&v)[32], uint32_t (&u)[16], const float* gb,
+                                           int c0, int nc, bool row_ok, long long grow, int cloud, int row_in_cloud) {
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    if (gb) {
+        const float4* g4 = reinterpret_cast<const float4*>(gb + c0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (q * 4 < nc) {
+                const float4 b = __ldg(g4 + q);
+                f[4 * q] += b.x; f[4 * q + 1] += b.y; f[4 * q + 2] += b.z; f[4 * q + 3] += b.w;
+            }
+        }
+    }
+    if (op.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (op.store_f32 && row_ok) {
+        float4* o = reinterpret_cast<float4*>(p.out_f32 + grow * p.out_ld + p.out_col0 + c0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (q * 4 < nc) o[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+    }
+    if (op.store_logits && c0 == 0 && row_ok) {
+        float* lp = p.logits + (long long)cloud * p.n_classes * p.rows_per_cloud + row_in_cloud;
+#pragma unroll
+        for (int n = 0; n < 32; ++n) {
+            if (n < p.n_classes) *lp = f[n];
+            lp += p.rows_per_cloud;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) u[q] = pack_bf16x2(f[2 * q], f[2 * q + 1]);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_constant__ TcChainParams p) {
@@ -100,6 +140,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
     const uint32_t act_addr = smem_u32(s_act), ones_addr = smem_u32(s_ones);
     uint32_t phase = 0;
     int cur_cloud = -1;
+    int pi = 0;
+    const bool prof = p.prof != nullptr && blockIdx.x == 0 && stid == 0 && slot == 0;
+#define AMP_PROF() do { if (prof && pi < 250) p.prof[pi++] = clock64(); } while (0)
+    AMP_PROF();
 
     for (int tile = blockIdx.x * 2 + slot; tile < n_tiles; tile += gridDim.x * 2) {
         const int cloud = tile / tiles_per_cloud;
@@ -149,13 +193,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
                 }
             }
         } else {
-            const float4* src = reinterpret_cast<const float4*>(p.in_x + grow * p.in_ld);
-            uint4* dst = reinterpret_cast<uint4*>(s_act);
-            const int chunks = p.op[0].K >> 3;
-            for (int c = sub; c < chunks; c += 2) {        // the two warpgroups take alternating 8-channel groups
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-                if (row_ok) { a = __ldg(src + 2 * c); b = __ldg(src + 2 * c + 1); }
-                dst[c * 128 + row] = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+            // coalesced: 8 consecutive lanes read 128 contiguous bytes of one row; a lane's float4 is half of a 16-byte
+            // K group of the operand, written as one 8-byte store
+            const int K0 = p.op[0].K, f4_per_row = K0 >> 2, total = kTcTileRows * f4_per_row;
+            const float* base = p.in_x + ((long long)cloud * rows + row0) * p.in_ld;
+            for (int i = stid; i < total; i += kSlotThreads) {
+                const int r = i / f4_per_row, q = i - r * f4_per_row;
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < valid) a = __ldg(reinterpret_cast<const float4*>(base + (long long)r * p.in_ld) + q);
+                uint2* dst = reinterpret_cast<uint2*>(s_act + ((q >> 1) * 128 + r) * 16 + (q & 1) * 8);
+                *dst = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
             }
         }
         // group of this row (per-block bias of the segmentation head)
@@ -164,9 +211,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
             const int r = row0 + (row_ok ? row : 0);
             for (int g = 1; g < p.n_groups; ++g) group += (r >= __ldg(p.group_rows + g)) ? 1 : 0;
         }
+        AMP_PROF();            // staged
         fence_proxy_async();
         tc_fence_before();
         slot_bar_sync(slot);
+        AMP_PROF();            // after barrier
 
         for (int l = 0; l < p.n_ops; ++l) {
             const TcOp& op = p.op[l];
@@ -174,37 +223,38 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
             if (stid == 0) {
                 if (!w_ready) { mbar_wait(wbar, 0); w_ready = true; }
                 tc_fence_after();
-                const uint32_t wbase = op.w_cloud ? smem_u32(s_wc) + (uint32_t)op.w_off : smem_u32(s_w) + (uint32_t)op.w_off;
+                // descriptors advance linearly with the K step: build them once, then one 64-bit add per MMA
+                const uint32_t wreg = op.w_cloud ? smem_u32(s_wc) : smem_u32(s_w);
                 const uint32_t w_lbo = (uint32_t)op.N * 16u;
                 const int ksteps = op.K >> 4;
+                const uint64_t act_d = umma_desc(act_addr, 2048u, 128u), act_step = 4096u >> 4;
+                const uint64_t w_d = umma_desc(wreg + (uint32_t)op.w_off, w_lbo, 128u), w_step = (2u * w_lbo) >> 4;
                 if (!op.pool) {
                     const uint32_t idesc = umma_idesc(128, op.N);
-                    for (int k = 0; k < ksteps; ++k)
-                        umma_bf16(slot_col, umma_desc(act_addr + (uint32_t)k * 4096u, 2048u, 128u),
-                                  umma_desc(wbase + (uint32_t)k * 2u * w_lbo, w_lbo, 128u), idesc, k > 0);
+                    for (int k = 0; k < ksteps; ++k) umma_bf16(slot_col, act_d + k * act_step, w_d + k * w_step, idesc, k > 0);
                     if (op.b_off >= 0)          // bias K group: both K halves alias the same 8 columns (LBO 0), ones half 1 is zero
-                        umma_bf16(slot_col, umma_desc(ones_addr, 2048u, 128u),
-                                  umma_desc((op.w_cloud ? smem_u32(s_wc) : smem_u32(s_w)) + (uint32_t)op.b_off, 0u, 128u), idesc, 1u);
+                        umma_bf16(slot_col, umma_desc(ones_addr, 2048u, 128u), umma_desc(wreg + (uint32_t)op.b_off, 0u, 128u), idesc, 1u);
                 } else {
                     const uint32_t idesc = umma_idesc(128, 128);
                     for (int mt = 0; mt < (op.N >> 7); ++mt) {
+                        const uint64_t w_m = w_d + (uint64_t)(mt * (2048 >> 4));
                         for (int k = 0; k < ksteps; ++k)
-                            umma_bf16(slot_col + (uint32_t)mt * 128u,
-                                      umma_desc(wbase + (uint32_t)mt * 2048u + (uint32_t)k * 2u * w_lbo, w_lbo, 128u),
-                                      umma_desc(act_addr + (uint32_t)k * 4096u, 2048u, 128u), idesc, k > 0);
+                            umma_bf16(slot_col + (uint32_t)mt * 128u, w_m + k * w_step, act_d + k * act_step, idesc, k > 0);
                     }
                 }
                 umma_commit(mbar);
             }
+            AMP_PROF();        // issued
             __syncwarp();
-            mbar_wait(mbar, phase);
+            mbar_spin(mbar, phase);                // every warp polls (a single polling warp + bar.sync measured 2x slower)
             phase ^= 1u;
             tc_fence_after();
+            AMP_PROF();        // MMA complete
 
             // ---- epilogue: the two warpgroups of the slot take alternating 32-column chunks ----
             if (!op.pool) {
                 const float* gb = op.bias_grouped ? p.gbias + ((long long)cloud * p.n_groups + group) * op.N : nullptr;
-                const bool plain = !gb && !op.store_f32 && !op.store_logits;
+                const bool plain = !op.store_logits || p.n_classes <= 16;
                 for (int c0 = sub * 32; c0 < op.N; c0 += 64) {
                     uint32_t v[32];
                     tmem_ld32(slot_col + lane_addr + (uint32_t)c0, v);
@@ -212,44 +262,47 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
                     const int nc = min(32, op.N - c0);           // 16 or 32
                     uint32_t u[16];
                     if (plain) {                                  // hot path: pack, ReLU on the packed pairs
+                        if (gb) {                                 // per-block bias of the head's first layer
+                            const float4* g4 = reinterpret_cast<const float4*>(gb + c0);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                if (q * 4 < nc) {
+                                    const float4 b = __ldg(g4 + q);
+                                    v[4 * q] = __float_as_uint(__uint_as_float(v[4 * q]) + b.x);
+                                    v[4 * q + 1] = __float_as_uint(__uint_as_float(v[4 * q + 1]) + b.y);
+                                    v[4 * q + 2] = __float_as_uint(__uint_as_float(v[4 * q + 2]) + b.z);
+                                    v[4 * q + 3] = __float_as_uint(__uint_as_float(v[4 * q + 3]) + b.w);
+                                }
+                            }
+                        }
+                        if (op.store_logits && c0 == 0 && row_ok) {   // [B, C, rows] logits: consecutive lanes = consecutive rows
+                            float* lp = p.logits + (long long)cloud * p.n_classes * rows + row0 + row;
+#pragma unroll
+                            for (int n = 0; n < 16; ++n)
+                                if (n < p.n_classes) lp[n * rows] = __uint_as_float(v[n]);
+                        }
+                        if (op.store_f32 && row_ok) {             // fp32 copy of the layer output (local features), before bf16 rounding
+                            const float fl = op.relu ? 0.f : -INFINITY;
+                            float4* o = reinterpret_cast<float4*>(p.out_f32 + grow * p.out_ld + p.out_col0 + c0);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q)
+                                if (q * 4 < nc)
+                                    o[q] = make_float4(fmaxf(__uint_as_float(v[4 * q]), fl), fmaxf(__uint_as_float(v[4 * q + 1]), fl),
+                                                       fmaxf(__uint_as_float(v[4 * q + 2]), fl), fmaxf(__uint_as_float(v[4 * q + 3]), fl));
+                        }
 #pragma unroll
                         for (int q = 0; q < 16; ++q) u[q] = pack_bf16x2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
                         if (op.relu) {
 #pragma unroll
                             for (int q = 0; q < 16; ++q) u[q] = relu_bf16x2(u[q]);
                         }
-                    } else {
-                        float f[32];
+                    } else {                                      // copies: only these live on the stack, v / u stay in registers
+                        uint32_t vv[32], uu[16];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                        if (gb) {
-                            const float4* g4 = reinterpret_cast<const float4*>(gb + c0);
+                        for (int j = 0; j < 32; ++j) vv[j] = v[j];
+                        epilogue_slow(p, op, vv, uu, gb, c0, nc, row_ok, grow, cloud, row0 + row);
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                if (q * 4 < nc) {
-                                    const float4 b = __ldg(g4 + q);
-                                    f[4 * q] += b.x; f[4 * q + 1] += b.y; f[4 * q + 2] += b.z; f[4 * q + 3] += b.w;
-                                }
-                            }
-                        }
-                        if (op.relu) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-                        }
-                        if (op.store_f32 && row_ok) {
-                            float4* o = reinterpret_cast<float4*>(p.out_f32 + grow * p.out_ld + p.out_col0 + c0);
-#pragma unroll
-                            for (int q = 0; q < 8; ++q)
-                                if (q * 4 < nc) o[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-                        }
-                        if (op.store_logits && c0 == 0 && row_ok) {
-#pragma unroll
-                            for (int n = 0; n < 32; ++n)
-                                if (n < p.n_classes)
-                                    p.logits[((long long)cloud * p.n_classes + n) * rows + row0 + row] = f[n];
-                        }
-#pragma unroll
-                        for (int q = 0; q < 16; ++q) u[q] = pack_bf16x2(f[2 * q], f[2 * q + 1]);
+                        for (int q = 0; q < 16; ++q) u[q] = uu[q];
                     }
                     if (op.write_act) {
                         uint4* dst = reinterpret_cast<uint4*>(s_act);
@@ -284,11 +337,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
                 }
             }
             // accumulator reads and A-operand writes of this layer are done before the next MMA is issued
+            AMP_PROF();        // epilogue done
             tc_fence_before();
             fence_proxy_async();
+            AMP_PROF();        // fences done
             slot_bar_sync(slot);
+            AMP_PROF();        // barrier done
         }
     }
+    if (prof) p.prof[255] = pi;
     if (tid == 0 && !w_ready) mbar_wait(wbar, 0);        // never leave with a bulk copy in flight
     tc_fence_before();
     __syncthreads();
@@ -375,6 +432,23 @@ int tc_chain_launch(const TcChainParams& p, cudaStream_t st) {
     const long long n_tiles = (long long)p.n_clouds * ((p.rows_per_cloud + kTcTileRows - 1) / kTcTileRows);
     const int grid = (int)((n_tiles + 1) / 2 < kNumSMs ? (n_tiles + 1) / 2 : kNumSMs);
     const int smem_bytes = sp.total < kMinSmem ? kMinSmem : sp.total;
+    static const bool want_prof = getenv("AMP_CHAIN_PROF") != nullptr;
+    if (want_prof) {                                     // debugging aid: synchronous, prints the phase timeline of CTA 0 / slot 0
+        static long long* dprof = nullptr;
+        if (!dprof) cudaMalloc(&dprof, 256 * sizeof(long long));
+        cudaMemsetAsync(dprof, 0, 256 * sizeof(long long), st);
+        TcChainParams q = p;
+        q.prof = dprof;
+        tc_chain_kernel<<<grid, kThreads, smem_bytes, st>>>(q);
+        long long h[256];
+        cudaMemcpyAsync(h, dprof, sizeof h, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "[tc_chain prof] ops=%d tiles=%lld:", p.n_ops, n_tiles);
+        for (int i = 1; i < (int)h[255] && i < 250; ++i) fprintf(stderr, " %lld", h[i] - h[i - 1]);
+        fprintf(stderr, "\n");
+        count_launch();
+        return check_launch("tc_chain_kernel");
+    }
     tc_chain_kernel<<<grid, kThreads, smem_bytes, st>>>(p);
     count_launch();
     return check_launch("tc_chain_kernel");

@@ -51,6 +51,7 @@ struct TcChainParams {
     unsigned int* pool; const float* pool_bias;         // pool_bias[n]: added to the pooled op's maximum before the ReLU
     float* logits; int n_classes;
     int n_clouds, rows_per_cloud;
+    long long* prof;                                    // debugging aid (AMP_CHAIN_PROF=1): phase timestamps of CTA 0 / slot 0
 };
 
 int tc_chain_launch(const TcChainParams& p, cudaStream_t st);
