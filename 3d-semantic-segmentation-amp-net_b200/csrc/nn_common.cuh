@@ -84,6 +84,7 @@ int wgrad_group_slab(const int* group_sizes, int n_groups);
 int wgrad(const WgParams& p, cudaStream_t st);
 int small_wgrad_try(const WgParams& p, cudaStream_t st);   // nn_small.cu
 int narrow_wgrad_try(const WgParams& p, int slabs, int SLAB, cudaStream_t st);   // nn_small.cu
+int narrow_out_wgrad_try(const WgParams& p, int slabs, int SLAB, cudaStream_t st);   // nn_small.cu
 int tc_wgrad_try(const WgParams& p, int slabs, int SLAB, cudaStream_t st);   // nn_tc_wgrad.cu: 1 launched, 0 not eligible, < 0 error
 
 // packed (value, row) keys for the pooling atomics: larger key = larger value, then lower row

@@ -188,6 +188,7 @@ int wgrad(const WgParams& p, cudaStream_t st) {
     int rc = small_wgrad_try(p, st);                     // few rows: direct deterministic kernel, no partials (nn_small.cu)
     if (rc != 0) return rc < 0 ? rc : AMP_OK;
     rc = narrow_wgrad_try(p, slabs, SLAB, st);           // K <= 16 over many rows: memory-bound exact fp32 partial pass
+    if (rc == 0) rc = narrow_out_wgrad_try(p, slabs, SLAB, st);   // Nout <= 8 (class logits)
     if (rc == 0) rc = tc_wgrad_try(p, slabs, SLAB, st);  // tensor-core partial pass when the shape allows (nn_tc_wgrad.cu)
     if (rc < 0) return rc;
     if (rc == 0) {
