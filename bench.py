@@ -243,7 +243,7 @@ def cpu_fps(sample_clouds, repeat=1):
 # reference arm: the reference's CPU implementation of the path (oracle port; the reference is
 # pure Python and /root/reference does not exist on the GPU box)
 # ------------------------------------------------------------------------------------------------
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -272,10 +272,17 @@ def run_reference(args):
     else:
         from oracle import nn_bench
         line = nn_bench.reference_line("fwd" if wl.startswith("fwd") else wl, args)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
+    # stdout carries exactly ONE JSON line: anything a library prints there (e.g. NCCL's version banner) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -287,7 +294,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, emit)
         return
     import torch
     if not torch.cuda.is_available():
@@ -324,7 +331,7 @@ def main():
         if others:
             line["workloads"] = others
     if dist.rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     dist.close()
 
 
