@@ -14,6 +14,8 @@
 // CTA = 256 threads = 2 independent warpgroups ("slots": own B-operand chunk buffers, 256 TMEM columns, mbarrier),
 // weights (hi + lo, K-major no-swizzle core-matrix layout) resident in shared memory for all tiles of the CTA,
 // K walked in chunks of 64 (stage chunk -> 3 MMAs per 16-wide K step -> commit -> wait).
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "nn_common.cuh"
@@ -23,19 +25,20 @@ namespace amp {
 namespace {
 using namespace tcx;
 
-constexpr int TL_THREADS = 256, TL_ROWS = 128, TL_KC = 64;
+constexpr int TL_THREADS = 512, TL_SLOT = 256, TL_ROWS = 128, TL_KC = 64;
 constexpr int TL_MAX_WELEMS = 32768;                 // Mpad * K
 constexpr int TL_BHALF = TL_ROWS * TL_KC * 2;        // bytes of the hi (or lo) half of one B chunk
 constexpr int TL_MAX_SMEM = 232448, TL_MIN_SMEM = 120 * 1024;
 
-struct TlPlan { int w_lo, b0, tab, bar, total; };
+struct TlPlan { int w_lo, b0, tab, exch, bar, total; };
 __host__ __device__ inline TlPlan tl_plan(int Mpad, int K) {
     TlPlan s;
     const int wbytes = Mpad * K * 2;
     s.w_lo = wbytes;
     s.b0 = 2 * wbytes;
     s.tab = s.b0 + 4 * TL_BHALF;
-    s.bar = s.tab + 16 * K;
+    s.exch = s.tab + 16 * K;                    // [slot][which][half][128] floats: cross-warpgroup sums of the epilogue
+    s.bar = s.exch + 2 * 3 * 2 * 128 * 4;
     s.total = s.bar + 64;
     return s;
 }
@@ -52,15 +55,21 @@ __device__ __forceinline__ void split_store8(const float (&v)[8], uint4* hi_dst,
     *hi_dst = h; *lo_dst = l;
 }
 
+// out of line: the hash is ~25 instructions and only the head's dropout layers use it (code size = cold-start time here)
+__device__ __noinline__ float dropout_keep_ool(unsigned long long seed, unsigned long long idx, float p) { return dropout_keep(seed, idx, p); }
+
 // epilogue specialisations (bit mask): compile-time so that the per-element loop carries no dead branches
 enum { TL_STATS = 1, TL_POOL2 = 2, TL_AFFINE = 4, TL_POOL1 = 8, TL_MASK = 16, TL_DROP = 32, TL_ACC = 64 };
 
 template <int MODE>
-__global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_constant__ PwParams p, const int Mpad) {
+__global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_constant__ PwParams p, const int Mpad, long long* prof_buf) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = warp >> 2, wtid = tid & 127;
+    // two slots of 256 threads (two warpgroups each): `wg` = slot, `sub` = which warpgroup of the slot, `wtid` = thread in slot
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = warp >> 3, sub = (warp >> 2) & 1, wtid = tid & (TL_SLOT - 1);
     const int K = p.K, Nout = p.Nout, rows = p.rows_per_cloud;
     const TlPlan sp = tl_plan(Mpad, K);
+    float* s_exch = reinterpret_cast<float*>(smem + sp.exch) + wg * (3 * 2 * 128);
+    auto slot_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(wg + 1) : "memory"); };
     __nv_bfloat16* s_whi = reinterpret_cast<__nv_bfloat16*>(smem);
     __nv_bfloat16* s_wlo = reinterpret_cast<__nv_bfloat16*>(smem + sp.w_lo);
     unsigned char* s_bhi = smem + sp.b0 + wg * 2 * TL_BHALF;
@@ -106,7 +115,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
         const int k8n = K >> 3, total = Mpad * k8n;
         uint4* whi4 = reinterpret_cast<uint4*>(s_whi);
         uint4* wlo4 = reinterpret_cast<uint4*>(s_wlo);
-#pragma unroll 4
+#pragma unroll 1
         for (int e = tid; e < total; e += TL_THREADS) {
             int n, k8;
             if (p.w_kn == 0) { n = e / k8n; k8 = e - n * k8n; } else { n = e & (Mpad - 1); k8 = e / Mpad; }
@@ -132,94 +141,106 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
     // pull this thread's row of a later tile into L2 while the current tile is being worked on (no registers held)
     auto prefetch_tile = [&](int cloud, int t) {
         const long long r = (long long)cloud * rows + t * TL_ROWS + lrow;
-        if (t * TL_ROWS + lrow < rows) {
+        if (sub == 0 && t * TL_ROWS + lrow < rows) {
             const char* x = reinterpret_cast<const char*>(p.X + r * p.ldx);
+#pragma unroll 1
             for (int b = 0; b < K * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + b));
             if (p.X2) {
                 const char* x2 = reinterpret_cast<const char*>(p.X2 + r * p.ldx);
+#pragma unroll 1
                 for (int b = 0; b < K * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(x2 + b));
             }
         }
     };
 
+    int pi = 0;
+    const bool prof = prof_buf != nullptr && blockIdx.x == 0 && tid == 0;
+#define TL_PROF() do { if (prof && pi < 250) prof_buf[pi++] = clock64(); } while (0)
     auto process = [&](int cloud, int t) {
+        TL_PROF();                                             // tile start
         const int row0 = t * TL_ROWS;
         const int valid = min(TL_ROWS, rows - row0);
         const long long row_base = (long long)cloud * rows + row0;        // global row of tile row 0
         const long long tile = (long long)cloud * tpc + t;
         // ---------------- K chunks: stage B operand (hi, lo), MMA ----------------
         const bool row_ok = lrow < valid;
-        if (row_ok && (MODE & (TL_MASK | TL_ACC))) {          // rows the epilogue of THIS tile will read: start them towards L2 now
+        if (sub == 0 && row_ok && (MODE & (TL_MASK | TL_ACC))) {          // rows the epilogue of THIS tile will read: start them towards L2 now
             if (MODE & TL_MASK) {
                 const char* m = reinterpret_cast<const char*>(p.mask_y + (row_base + lrow) * p.ld_mask);
+#pragma unroll 1
                 for (int b = 0; b < Nout * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(m + b));
             }
             if (MODE & TL_ACC) {
                 const char* y = reinterpret_cast<const char*>(p.Y + (row_base + lrow) * p.ldy);
+#pragma unroll 1
                 for (int b = 0; b < Nout * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + b));
             }
         }
-        const float* __restrict__ xrow = p.X + (row_base + lrow) * p.ldx;
-        const float* __restrict__ x2row = p.X2 ? p.X2 + (row_base + lrow) * p.ldx : nullptr;
         for (int kc = 0; kc * TL_KC < K; ++kc) {
             const int kcur = min(TL_KC, K - kc * TL_KC);
-            // 32 input channels per batch: all global loads of the batch are issued before the first use
-            for (int b0 = 0; b0 < kcur; b0 += 32) {
-                const int k0 = kc * TL_KC + b0;
-                const int ng = min(4, (kcur - b0) >> 3);               // 8-channel groups in this batch (2 or 4)
-                float4 xa[8], ya[8];
+            {
+                // Coalesced staging of a (up to) 64-channel chunk: 16 consecutive lanes read the 256 contiguous bytes of one row
+                // (a warp instruction touches 2 rows instead of 32), a thread keeps the same 4 input channels for all of its
+                // 16 rows, so the prologue constants sit in registers; each float4 becomes one 8-byte half of a 16-byte K group.
+                // (chunks narrower than 64 channels leave the upper channel quads idle)
+                const int q = wtid & 15, rsub = wtid >> 4;               // channel quad, row within a group of 16 rows
+                const bool q_ok = q * 4 < kcur;
+                const int k = kc * TL_KC + (q_ok ? q * 4 : 0);
+                const float4 ca = *reinterpret_cast<const float4*>(s_a + k), cb = *reinterpret_cast<const float4*>(s_b + k);
+                const float4 cm = *reinterpret_cast<const float4*>(s_m + k), cc = *reinterpret_cast<const float4*>(s_c + k);
+                const float* __restrict__ xb = p.X + row_base * p.ldx + k;
+                const float* __restrict__ x2b = p.X2 ? p.X2 + row_base * p.ldx + k : nullptr;
+                unsigned char* dhi = s_bhi + ((q >> 1) * TL_ROWS) * 16 + (q & 1) * 8;
+                unsigned char* dlo = s_blo + ((q >> 1) * TL_ROWS) * 16 + (q & 1) * 8;
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {                   // 4 rows per thread per pass (rolled: small code, warm i-cache)
+                    float4 xv[4], yv[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    xa[i] = (row_ok && (i >> 1) < ng) ? __ldg(reinterpret_cast<const float4*>(xrow + k0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (x2row) {
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = rsub + 16 * (half * 4 + i);
+                        xv[i] = (r < valid && q_ok) ? __ldg(reinterpret_cast<const float4*>(xb + (long long)r * p.ldx)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (x2b) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        ya[i] = (row_ok && (i >> 1) < ng) ? __ldg(reinterpret_cast<const float4*>(x2row + k0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                        for (int i = 0; i < 4; ++i) {
+                            const int r = rsub + 16 * (half * 4 + i);
+                            yv[i] = (r < valid && q_ok) ? __ldg(reinterpret_cast<const float4*>(x2b + (long long)r * p.ldx)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (c < ng) {
-                        const int k = k0 + c * 8;
-                        float v[8] = {xa[2 * c].x, xa[2 * c].y, xa[2 * c].z, xa[2 * c].w, xa[2 * c + 1].x, xa[2 * c + 1].y, xa[2 * c + 1].z, xa[2 * c + 1].w};
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = rsub + 16 * (half * 4 + i);
+                        float v0 = xv[i].x, v1 = xv[i].y, v2 = xv[i].z, v3 = xv[i].w;
                         if (has_pro) {
-                            const float4 a0 = *reinterpret_cast<const float4*>(s_a + k), a1 = *reinterpret_cast<const float4*>(s_a + k + 4);
-                            const float4 q0 = *reinterpret_cast<const float4*>(s_b + k), q1 = *reinterpret_cast<const float4*>(s_b + k + 4);
-                            const float4 m0 = *reinterpret_cast<const float4*>(s_m + k), m1 = *reinterpret_cast<const float4*>(s_m + k + 4);
-                            const float pa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                            const float pb[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-                            const float pm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-                            if (x2row) {
-                                const float4 c0 = *reinterpret_cast<const float4*>(s_c + k), c1 = *reinterpret_cast<const float4*>(s_c + k + 4);
-                                const float y2[8] = {ya[2 * c].x, ya[2 * c].y, ya[2 * c].z, ya[2 * c].w, ya[2 * c + 1].x, ya[2 * c + 1].y, ya[2 * c + 1].z, ya[2 * c + 1].w};
-                                const float pc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) v[i] = fmaf(y2[i] - pm[i], pc[i], fmaf(v[i], pa[i], pb[i]));
+                            if (x2b) {
+                                v0 = fmaf(yv[i].x - cm.x, cc.x, fmaf(v0, ca.x, cb.x)); v1 = fmaf(yv[i].y - cm.y, cc.y, fmaf(v1, ca.y, cb.y));
+                                v2 = fmaf(yv[i].z - cm.z, cc.z, fmaf(v2, ca.z, cb.z)); v3 = fmaf(yv[i].w - cm.w, cc.w, fmaf(v3, ca.w, cb.w));
                             } else {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i] - pm[i], pa[i], pb[i]);
+                                v0 = fmaf(v0 - cm.x, ca.x, cb.x); v1 = fmaf(v1 - cm.y, ca.y, cb.y);
+                                v2 = fmaf(v2 - cm.z, ca.z, cb.z); v3 = fmaf(v3 - cm.w, ca.w, cb.w);
                             }
                         }
-                        if (p.in_relu) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-                        }
+                        if (p.in_relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
                         if (p.in_drop_p > 0.f) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                v[i] *= dropout_keep(p.in_drop_seed, (unsigned long long)(row_base + lrow) * K + k + i, p.in_drop_p);
+                            const unsigned long long di = (unsigned long long)(row_base + r) * K + k;
+                            v0 *= dropout_keep_ool(p.in_drop_seed, di, p.in_drop_p); v1 *= dropout_keep_ool(p.in_drop_seed, di + 1, p.in_drop_p);
+                            v2 *= dropout_keep_ool(p.in_drop_seed, di + 2, p.in_drop_p); v3 *= dropout_keep_ool(p.in_drop_seed, di + 3, p.in_drop_p);
                         }
-                        if (!row_ok) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                        if (r >= valid) { v0 = 0.f; v1 = 0.f; v2 = 0.f; v3 = 0.f; }
+                        uint2 h, l;
+                        split_pair(v0, v1, h.x, l.x);
+                        split_pair(v2, v3, h.y, l.y);
+                        if (q_ok) {
+                            *reinterpret_cast<uint2*>(dhi + r * 16) = h;
+                            *reinterpret_cast<uint2*>(dlo + r * 16) = l;
                         }
-                        const int c8 = (b0 >> 3) + c;
-                        split_store8(v, reinterpret_cast<uint4*>(s_bhi) + c8 * TL_ROWS + lrow, reinterpret_cast<uint4*>(s_blo) + c8 * TL_ROWS + lrow);
                     }
                 }
             }
+            TL_PROF();                                         // chunk staged
             fence_proxy_async();
             tc_fence_before();
-            wg_bar_sync(wg);
+            slot_sync();
             if (wtid == 0) {
                 tc_fence_after();
                 for (int mt = 0; mt < n_mt; ++mt) {
@@ -237,10 +258,12 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
                 }
                 umma_commit(mbar);
             }
+            TL_PROF();                                         // MMAs issued
             __syncwarp();
             mbar_wait(mbar, phase);
             phase ^= 1u;
             tc_fence_after();
+            TL_PROF();                                         // MMAs complete
         }
 
         // ---------------- epilogue: lane = output channel, columns = rows of the tile ----------------
@@ -253,20 +276,31 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
             const int nn = n_ok ? n : 0;
             const uint32_t tcol = slot_col + lane_addr + (uint32_t)mt * 128u;
             const float bias_u = p.bias ? __ldg(p.bias + ((long long)cloud * p.n_groups + g_tile) * p.bias_group_stride + nn) : 0.f;
+            // The loops below are ROLLED over 8-column pieces (tcgen05.ld x8): these kernels run two tiles per slot, so the
+            // first pass through the code is an instruction-cache miss stream; 4x less code beats 4x fewer loop branches.
+            // this warpgroup's half of the tile rows: accumulator columns [c_lo, c_hi); sums are combined through shared memory
+            const int c_lo = sub * 64, c_hi = min(valid, c_lo + 64);
             float mean_t = 0.f;
             if (MODE & TL_STATS) {
                 float s = 0.f;
-                for (int c0 = 0; c0 < valid; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(tcol + (uint32_t)c0, v);
+                uint32_t vn[8];
+                if (c_lo < c_hi) tmem_ld8(tcol + (uint32_t)c_lo, vn);
+#pragma unroll 1
+                for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
+                    uint32_t v[8];
                     tmem_wait_ld();
-                    const bool full = c0 + 32 <= valid;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (full || c0 + j < valid) s += __uint_as_float(v[j]) + bias_u;
+                    for (int j = 0; j < 8; ++j) v[j] = vn[j];
+                    if (c0 + 8 < c_hi) tmem_ld8(tcol + (uint32_t)(c0 + 8), vn);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (c0 + j < c_hi) s += __uint_as_float(v[j]) + bias_u;
                 }
+                s_exch[sub * 128 + lrow] = s;
+                slot_sync();
+                s = s_exch[lrow] + s_exch[128 + lrow];               // fixed order: rows 0..63 then 64..127
                 mean_t = s / (float)valid;
-                if (n_ok) p.part_sum[tile * Nout + n] = s;
+                if (n_ok && sub == 0) p.part_sum[tile * Nout + n] = s;
             }
             float osc = 1.f, osh = 0.f, msc = 0.f, msh = 0.f, mmu = 0.f, mis = 0.f;
             if (MODE & TL_AFFINE) { osc = __ldg(p.out_scale + nn); osh = __ldg(p.out_shift + nn); }
@@ -279,27 +313,36 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
             int rmax = 0, rmin = 0;
             const bool store = p.Y != nullptr && n_ok;
             const float floor_v = ((MODE & TL_AFFINE) && p.out_relu) ? 0.f : -INFINITY;
-            auto chunk = [&](int c0, auto full_tag) {
-                constexpr bool full = decltype(full_tag)::value;
-                uint32_t v[32];
-                tmem_ld32(tcol + (uint32_t)c0, v);
-                float ym[32], yo[32];
+            const float* __restrict__ My = (MODE & TL_MASK) ? p.mask_y + row_base * p.ld_mask + nn : nullptr;
+            float* __restrict__ yp = p.Y ? p.Y + row_base * p.ldy + nn : nullptr;
+            // software pipeline: the TMEM load and the global loads (mask rows, accumulate target) of piece c0 + 8 are in
+            // flight while piece c0 is processed
+            uint32_t vn[8];
+            float ymn[8], yon[8];
+            auto issue = [&](int c0) {
+                tmem_ld8(tcol + (uint32_t)c0, vn);
                 if (MODE & TL_MASK) {
-                    const float* __restrict__ My = p.mask_y + (row_base + c0) * p.ld_mask + nn;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { ym[j] = (full || c0 + j < valid) ? __ldg(My) : 0.f; My += p.ld_mask; }
+                    for (int j = 0; j < 8; ++j) ymn[j] = (n_ok && c0 + j < valid) ? __ldg(My + (long long)(c0 + j) * p.ld_mask) : 0.f;
                 }
                 if (MODE & TL_ACC) {
-                    const float* __restrict__ Yo = p.Y + (row_base + c0) * p.ldy + nn;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { yo[j] = (full || c0 + j < valid) ? *Yo : 0.f; Yo += p.ldy; }
+                    for (int j = 0; j < 8; ++j) yon[j] = (n_ok && c0 + j < valid) ? yp[(long long)(c0 + j) * p.ldy] : 0.f;
                 }
+            };
+            if (c_lo < c_hi) issue(c_lo);
+#pragma unroll 1
+            for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
+                uint32_t v[8];
+                float ym[8], yo[8];
                 tmem_wait_ld();
-                float* __restrict__ yp = p.Y ? p.Y + (row_base + c0) * p.ldy + nn : nullptr;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
+                for (int j = 0; j < 8; ++j) { v[j] = vn[j]; ym[j] = ymn[j]; yo[j] = yon[j]; }
+                if (c0 + 8 < c_hi) issue(c0 + 8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
                     const int r = c0 + j;
-                    const bool ok = full || r < valid;
+                    const bool ok = r < valid;
                     float x = __uint_as_float(v[j]) + bias_u;
                     if (MODE & TL_ACC) x += yo[j];
                     if (MODE & TL_STATS) { const float d = ok ? x - mean_t : 0.f; q = fmaf(d, d, q); }
@@ -311,24 +354,28 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
                     if (MODE & TL_MASK) {
                         float dz = x;
                         if (MODE & TL_DROP)
-                            dz *= dropout_keep(p.out_drop_seed, (unsigned long long)(row_base + r) * Nout + n, p.out_drop_p);
+                            dz *= dropout_keep_ool(p.out_drop_seed, (unsigned long long)(row_base + r) * Nout + n, p.out_drop_p);
                         dz = (ok && fmaf(ym[j] - mmu, msc, msh) > 0.f) ? dz : 0.f;
                         s2 += dz;
                         q2 = fmaf(dz, (ym[j] - mmu) * mis, q2);
                         x = dz;
                     }
                     if ((MODE & TL_POOL1) && ok && x > vmax) { vmax = x; rmax = r; }
-                    if (store && ok) *yp = x;
-                    yp += p.ldy;
+                    if (store && ok) yp[(long long)r * p.ldy] = x;
                 }
-            };
-            for (int c0 = 0; c0 < valid; c0 += 32) {
-                if (c0 + 32 <= valid) chunk(c0, std::true_type{});
-                else chunk(c0, std::false_type{});
             }
-            if (n_ok) {
-                if (MODE & TL_STATS) p.part_sq[tile * Nout + n] = q;
-                if ((MODE & TL_MASK) && p.part_sum) { p.part_sum[tile * Nout + n] = s2; p.part_sq[tile * Nout + n] = q2; }
+            if (MODE & (TL_STATS | TL_MASK)) {                           // combine the two row halves in a fixed order
+                s_exch[256 + sub * 128 + lrow] = (MODE & TL_STATS) ? q : s2;
+                s_exch[512 + sub * 128 + lrow] = q2;
+                slot_sync();
+                if (n_ok && sub == 0) {
+                    const float a = s_exch[256 + lrow] + s_exch[256 + 128 + lrow], b = s_exch[512 + lrow] + s_exch[512 + 128 + lrow];
+                    if (MODE & TL_STATS) p.part_sq[tile * Nout + n] = a;
+                    if ((MODE & TL_MASK) && p.part_sum) { p.part_sum[tile * Nout + n] = a; p.part_sq[tile * Nout + n] = b; }
+                }
+                slot_sync();                                             // exchange buffer free for the next M tile
+            }
+            if (n_ok && c_lo < c_hi) {
                 if (MODE & (TL_POOL1 | TL_POOL2)) {
                     const unsigned long long kmax = ((unsigned long long)ordered_bits(vmax) << 32) | (0xffffffffu - (unsigned)(row0 + rmax));
                     atomicMax(p.pool_max + (long long)cloud * Nout + n, kmax);
@@ -340,30 +387,43 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
             }
         }
         // accumulator reads done before this slot's next MMA overwrites the columns
+        TL_PROF();                                             // epilogue done
         tc_fence_before();
-        wg_bar_sync(wg);
+        slot_sync();
     };
 
-    if (!per_cloud_w) {
-        stage_weights(0);
-        __syncthreads();
-        const int n_tiles = p.n_clouds * tpc;
-        for (int tile = blockIdx.x * 2 + wg; tile < n_tiles; tile += gridDim.x * 2) {
-            const int nxt = tile + gridDim.x * 2;
-            if (nxt < n_tiles) prefetch_tile(nxt / tpc, nxt % tpc);
-            process(tile / tpc, tile % tpc);
+    // One loop, one call site of stage_weights / process (they are big: a second inlined copy doubles the cold-start
+    // instruction fetch). Shared weights: tiles strided over (CTA, slot). Per-cloud weights: clouds strided over CTAs, the
+    // two slots take alternating tiles of the cloud and both pass the CTA barriers around the weight restaging.
+    const int n_tiles = p.n_clouds * tpc;
+    const int tps = (tpc + 1) >> 1;
+    const int n_it = per_cloud_w ? ((p.n_clouds - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * tps
+                                 : (n_tiles - (int)blockIdx.x * 2 + (int)gridDim.x * 2 - 1) / ((int)gridDim.x * 2);
+    auto work = [&](int it, int& cloud, int& t) -> bool {
+        if (per_cloud_w) {
+            const int ci = it / tps, j = it - ci * tps;
+            cloud = blockIdx.x + ci * gridDim.x;
+            t = j * 2 + wg;
+            return cloud < p.n_clouds && t < tpc;
         }
-    } else {
-        for (int cloud = blockIdx.x; cloud < p.n_clouds; cloud += gridDim.x) {
-            __syncthreads();                  // every MMA that read the previous cloud's weights has been waited for
-            stage_weights(cloud);
+        const int tile = blockIdx.x * 2 + wg + it * gridDim.x * 2;
+        cloud = tile / tpc;
+        t = tile - cloud * tpc;
+        return tile < n_tiles;
+    };
+#pragma unroll 1
+    for (int it = 0; it < n_it; ++it) {
+        int cloud, t, cn, tn;
+        const bool have = work(it, cloud, t);
+        if (per_cloud_w ? (it % tps == 0) : (it == 0)) {
+            __syncthreads();                  // every MMA that read the previous weights has been waited for
+            stage_weights(per_cloud_w ? cloud : 0);
             __syncthreads();
-            for (int t = wg; t < tpc; t += 2) {
-                if (t + 2 < tpc) prefetch_tile(cloud, t + 2);
-                process(cloud, t);
-            }
         }
+        if (it + 1 < n_it && work(it + 1, cn, tn)) prefetch_tile(cn, tn);
+        if (have) process(cloud, t);
     }
+    if (prof) prof_buf[255] = pi;
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
@@ -400,6 +460,10 @@ int tc_layer_try(const PwParams& p, cudaStream_t st) {
     long long grid = p.w_cloud_stride ? p.n_clouds : (n_tiles + 1) / 2;
     if (grid > kNumSMs) grid = kNumSMs;
     const int smem_bytes = sp.total < TL_MIN_SMEM ? TL_MIN_SMEM : sp.total;
+    static const bool want_prof = getenv("AMP_LAYER_PROF") != nullptr;       // debugging aid: phase timeline of CTA 0 / thread 0
+    static long long* dprof = nullptr;
+    if (want_prof && !dprof) cudaMalloc(&dprof, 256 * sizeof(long long));
+    if (want_prof) cudaMemsetAsync(dprof, 0, 256 * sizeof(long long), st);
     switch (mode) {
 #define TL_CASE(M) case M: { \
         static bool attr_set = false; \
@@ -408,12 +472,20 @@ int tc_layer_try(const PwParams& p, cudaStream_t st) {
             if (e != cudaSuccess) return fail(AMP_E_CUDA, "tc_layer: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); \
             attr_set = true; \
         } \
-        tc_layer_kernel<M><<<(int)grid, TL_THREADS, smem_bytes, st>>>(q, Mpad); \
+        tc_layer_kernel<M><<<(int)grid, TL_THREADS, smem_bytes, st>>>(q, Mpad, want_prof ? dprof : nullptr); \
         break; }
         TL_CASE(0) TL_CASE(TL_ACC) TL_CASE(TL_STATS) TL_CASE(TL_STATS | TL_POOL2) TL_CASE(TL_AFFINE) TL_CASE(TL_AFFINE | TL_POOL1)
         TL_CASE(TL_MASK) TL_CASE(TL_MASK | TL_ACC) TL_CASE(TL_MASK | TL_DROP)
 #undef TL_CASE
         default: return 0;        // an epilogue combination without a specialisation: CUDA-core path
+    }
+    if (want_prof) {
+        long long h[256];
+        cudaMemcpyAsync(h, dprof, sizeof h, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "[tc_layer prof] mode=%d K=%d N=%d rows=%lld:", mode, p.K, p.Nout, (long long)p.n_clouds * p.rows_per_cloud);
+        for (int i = 1; i < (int)h[255] && i < 40; ++i) fprintf(stderr, " %lld", h[i] - h[i - 1]);
+        fprintf(stderr, "\n");
     }
     count_launch();
     const int rc = check_launch("tc_layer_kernel");
