@@ -47,6 +47,7 @@ kmeans_assign_kernel(const float* __restrict__ feats, const float* __restrict__ 
         int bj[4];
 #pragma unroll
         for (int p = 0; p < 4; ++p) { best[p] = INFINITY; bj[p] = 0; }
+#pragma unroll 3
         for (int j = 0; j < k; ++j) {
             float c0 = sc[3 * j], c1 = sc[3 * j + 1], c2 = sc[3 * j + 2];
 #pragma unroll

@@ -240,6 +240,63 @@ def cpu_fps(sample_clouds, repeat=1):
 
 
 # ------------------------------------------------------------------------------------------------
+# workload: k-means assignment step (the distance + argmin stream of 3_kmeans.py:82 / utils.py:505)
+# ------------------------------------------------------------------------------------------------
+KM_POINTS, KM_K = 1 << 24, 9
+
+
+def bench_kmeans(dist, amp, steps, warmup, with_cpu):
+    """One step = one Lloyd assignment pass over 16.8 M points (3 clustering features) against k = 9 centroids:
+    12 B read + 4 B label written per point, centroids on chip. The 201 MB of features exceed the 126 MB L2."""
+    torch = dist.torch
+    g = torch.Generator(device="cpu").manual_seed(4000 + dist.rank)
+    host = torch.rand((KM_POINTS, 3), generator=g, dtype=torch.float32).pin_memory()
+    cent = torch.rand((KM_K, 3), generator=g, dtype=torch.float32).to(dist.device)
+    dev = host.to(dist.device)
+    flush = L2Flush(torch, dist.device)
+    out = {}
+
+    def step():
+        out["labels"] = amp.kmeans_assign(dev, cent)
+
+    n0 = amp._lib.launch_count()
+    ms, _ = timed_steps(dist, step, steps, warmup, flush)
+    launches = (amp._lib.launch_count() - n0) // (steps + warmup) * steps
+    lab_host = torch.empty((KM_POINTS,), dtype=torch.int32).pin_memory()
+
+    def step_e2e():
+        lab_host.copy_(amp.kmeans_assign(host.to(dist.device, non_blocking=True), cent), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e_ms, _ = timed_steps(dist, step_e2e, max(2, steps // 2), 1, flush)
+    es = max(2, steps // 2)
+    pk = peaks()
+    ach = KM_POINTS * 16.0 / (ms / steps * 1e-3) / 1e9
+    res = {
+        "value": KM_POINTS * dist.world * steps / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms / steps,
+        "gpu_launches": int(launches),
+        "e2e": {"value": KM_POINTS * dist.world * es / (e_ms * 1e-3), "unit": "points/s",
+                "h2d_bytes_per_step": KM_POINTS * 12, "d2h_bytes_per_step": KM_POINTS * 4},
+        "roofline": {"bound": "hbm", "kernel": "kmeans_assign_kernel", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"] + " (burst copy)",
+                     "model": "16 B per point per assignment pass (12 B features read + 4 B int32 label written), k = %d" % KM_K},
+        "config": {"workload": "k-means assignment pass, %d points x 3 features, k = %d (block split of configs[3])" % (KM_POINTS, KM_K),
+                   "l2": "flushed between steps (256 MiB write); working set 268 MB > L2"},
+        "dtype": "f32",
+    }
+    if with_cpu:
+        from oracle import kmeans_oracle
+        n = 1 << 21
+        x = host[:n].numpy(); c = cent.cpu().numpy()
+        t = time.perf_counter()
+        kmeans_oracle.assign(x, c)
+        dt = time.perf_counter() - t
+        res["cpu_baseline"] = {"value": n / dt, "unit": "points/s", "cores": 1, "kind": "port",
+                               "sample": "%d points, numpy restatement of the assignment step, %.2f s" % (n, dt)}
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU implementation of the path (oracle port; the reference is
 # pure Python and /root/reference does not exist on the GPU box)
 # ------------------------------------------------------------------------------------------------
@@ -269,9 +326,28 @@ def run_reference(args, emit):
                                  "sample": "each step = %d clouds on %d threads (C port of utils/utils.py:889-933)"
                                            % (sample, cores)},
                 "e2e": {"value": v, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    elif wl == "kmeans":
+        from oracle import kmeans_oracle
+        rng = np.random.default_rng(4000)
+        n = 1 << 21
+        x = rng.random((n, 3), dtype=np.float32); c = rng.random((KM_K, 3), dtype=np.float32)
+        ts = []
+        for i in range(args.warmup + max(1, args.steps)):
+            t = time.perf_counter(); kmeans_oracle.assign(x, c); dt = time.perf_counter() - t
+            if i >= args.warmup:
+                ts.append(dt)
+        v = n * len(ts) / sum(ts)
+        line = {"impl": "reference", "metric": "k-means assigned points/sec", "value": v, "unit": "points/s", "n_gpus": args.gpus,
+                "steps": len(ts), "warmup": args.warmup, "ms_per_step": 1e3 * sum(ts) / len(ts) * KM_POINTS / n, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "k-means assignment pass, %d points x 3 features, k = %d" % (KM_POINTS, KM_K)},
+                "cpu_baseline": {"value": v, "unit": "points/s", "cores": 1, "kind": "port",
+                                 "sample": "each step = %d points (numpy restatement of the assignment step; the reference's "
+                                           "third-party solver is not installable here)" % n},
+                "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     else:
         from oracle import nn_bench
-        line = nn_bench.reference_line("fwd" if wl.startswith("fwd") else wl, args)
+        line = nn_bench.reference_line("fwd" if wl.startswith("fwd") else ("train" if wl == "train" else "fwd"), args)
     emit(line)
 
 
@@ -288,7 +364,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="fps", choices=["fps", "fwd", "fwd_bf16", "train", "tile", "tile_bf16"])
+    ap.add_argument("--workload", default="fps", choices=["fps", "kmeans", "fwd", "fwd_bf16", "train", "tile", "tile_bf16"])
     ap.add_argument("--only", action="store_true", help="measure only the headline workload")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
@@ -303,7 +379,7 @@ def main():
     amp._lib.lib()
     dist = Dist(args.gpus)
     with_cpu = (dist.rank == 0 and dist.world == 1 and not args.no_cpu)
-    table = {"fps": bench_fps}
+    table = {"fps": bench_fps, "kmeans": bench_kmeans}
     if hasattr(amp, "bench_hooks"):
         table.update(amp.bench_hooks())
     if args.workload not in table:
@@ -311,7 +387,7 @@ def main():
     with ClockSampler(dist.local_rank) as clk:
         head = table[args.workload](dist, amp, args.steps, args.warmup, with_cpu)
     line = {"metric": {"fps": "FPS clouds/sec", "fwd": "segmented points/sec (fwd)", "fwd_bf16": "segmented points/sec (fwd)",
-                       "train": "train pts/sec", "tile": "segmented points/sec (fwd)", "tile_bf16": "segmented points/sec (fwd)"}[args.workload],
+                       "kmeans": "k-means assigned points/sec", "train": "train pts/sec", "tile": "segmented points/sec (fwd)", "tile_bf16": "segmented points/sec (fwd)"}[args.workload],
             "value": head.pop("value"), "unit": head.pop("unit"), "n_gpus": dist.world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": head.pop("ms_per_step"), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "data": "synthetic"}

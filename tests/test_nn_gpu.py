@@ -358,3 +358,43 @@ def test_tile_pipeline_blocks_and_logits(amp, cuda):
         logits, _ = seg(gl, lo, xy[w:w + 1, :k, :], [2048] * k, None)
         assert tuple(logits.shape) == (1, 5, k * 2048) and torch.isfinite(logits).all()
         b0 += k
+
+
+def test_training_shape_of_the_script_nine_windows_padded(amp, cuda):
+    """The real training shape (train_pointnet-attention.py:396-470 on a collate_seq_padd batch): W = 9 windows of 2048
+    points per sample, the trailing windows of a sample are replicas of its last real window with targets -1
+    (collate_fns.py:42-44), CE with ignore_index -1 + 0.001 reg, backward, two Adam steps. Logits / loss against the
+    CPU oracle, every parameter gets a finite gradient, padded windows contribute nothing to the loss gradient."""
+    B, N, W, seed = 4, 2048, 9, 71
+    enc, seg, sd_e, sd_s = _build(amp, seed, cuda)
+    xs, cent = nn_params.synthetic_blocks(B, N, W, seed)
+    # clouds that differ from each other, so that the T-Net BatchNorms over the B pooled rows are well conditioned
+    # (see test_all_gradients_match_oracle)
+    g = torch.Generator().manual_seed(9)
+    xs = [x * (0.15 + 0.85 * torch.rand(B, 1, 9, generator=g)) + 0.3 * torch.randn(B, 1, 9, generator=g) for x in xs]
+    cent = torch.stack([x[:, :, :2].mean(1) for x in xs], 1)
+    real = [5, 9, 3, 7]                                      # real windows per sample; the rest replicate the last real one
+    for b in range(B):
+        for w in range(real[b], W):
+            xs[w][b] = xs[real[b] - 1][b]
+    tg = torch.randint(0, 5, (B, W * N), generator=torch.Generator().manual_seed(2))
+    for b in range(B):
+        tg[b, real[b] * N:] = -1
+    enc.train(); seg.train()
+    opt_e = torch.optim.Adam(enc.parameters(), lr=1e-3); opt_s = torch.optim.Adam(seg.parameters(), lr=1e-3)
+    logits, ft, _ = _run(enc, seg, xs, cent, None, cuda)
+    ce = torch.nn.CrossEntropyLoss(weight=torch.tensor([1., 2., 2., 1., 1.], device=cuda), ignore_index=-1)
+    loss = ce(logits, tg.to(cuda)) + 0.001 * torch.norm(torch.eye(64, device=cuda) - torch.bmm(ft, ft.transpose(2, 1)))
+    loss.backward()
+    o_logits, o_ft = nn_oracle.forward_windows(sd_e, sd_s, xs, cent, None, training=True, stats_enc={}, stats_seg={})
+    o_loss, _, _ = nn_oracle.train_step_loss(o_logits, tg, o_ft)
+    assert tuple(logits.shape) == (B, 5, W * N)
+    assert _rel(logits, o_logits) < TOL_LOGITS
+    assert abs(float(loss.detach()) - float(o_loss)) < 1e-4 * abs(float(o_loss))
+    for m in (enc, seg):
+        for k, p in m.named_parameters():
+            assert p.grad is not None and torch.isfinite(p.grad).all(), k
+    before = seg.conv_4.weight.detach().clone()
+    opt_e.step(); opt_s.step()
+    assert not torch.equal(before, seg.conv_4.weight.detach())
+    assert int(enc.bn_1.num_batches_tracked) == 7 + W        # one BatchNorm update per encoder call (quirk 7 of SURVEY 3.5)
