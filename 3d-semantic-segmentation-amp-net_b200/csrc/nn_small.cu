@@ -89,18 +89,31 @@ __global__ void __launch_bounds__(256) small_fwd_kernel(const PwParams p) {
             }
         }
         __syncthreads();
+        // all weight loads of this chunk (2 columns x up to 16 lane-strided elements) are issued before the first FMA:
+        // these layers are latency bound, not bandwidth bound
+        float wv[2][SM_MAXK / 32];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int n = blockIdx.x * SM_COLS + warp + 8 * j;
-            if (n < N) {
-                // w_kn == 0: W[n][k] (a contiguous row per output); w_kn == 1: W[k][n] (transposed weights of the backward)
-                const float* __restrict__ w = p.w_kn ? p.W + (long long)k0 * p.ldw + n : p.W + (long long)n * p.ldw + k0;
-                const long long ws = p.w_kn ? p.ldw : 1;
-#pragma unroll 4
-                for (int kk = lane; kk < kc; kk += 32) {
-                    const float wv = __ldg(w + kk * ws);
+            // w_kn == 0: W[n][k] (a contiguous row per output); w_kn == 1: W[k][n] (transposed weights of the backward)
+            const float* __restrict__ w = p.w_kn ? p.W + (long long)k0 * p.ldw + n : p.W + (long long)n * p.ldw + k0;
+            const long long ws = p.w_kn ? p.ldw : 1;
 #pragma unroll
-                    for (int r = 0; r < SM_ROWS; ++r) acc[j][r] = fmaf(xs[r * kc + kk], wv, acc[j][r]);
+            for (int i = 0; i < SM_MAXK / 32; ++i) {
+                const int kk = lane + 32 * i;
+                wv[j][i] = (n < N && kk < kc) ? __ldg(w + kk * ws) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < SM_MAXK / 32; ++i) {
+            const int kk = lane + 32 * i;
+            if (32 * i < kc) {                               // warp-uniform
+                const int ks = kk < kc ? kk : 0;
+#pragma unroll
+                for (int r = 0; r < SM_ROWS; ++r) {
+                    const float xv = xs[r * kc + ks];
+                    acc[0][r] = fmaf(xv, wv[0][i], acc[0][r]);
+                    acc[1][r] = fmaf(xv, wv[1][i], acc[1][r]);
                 }
             }
         }

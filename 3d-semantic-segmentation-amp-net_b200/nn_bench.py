@@ -280,8 +280,8 @@ def bench_tile(dist, amp, steps, warmup, with_cpu, precision="fp32"):
         x9[:, :2] = x9[:, :2] * 2 - 1                                                 # datasets.py:378-379
         blocks = x9.view(-1, NN_POINTS, NN_DIMS)
         feats_out = []
-        for b0 in range(0, blocks.shape[0], 64):                                      # encoder over all blocks, 64 per call
-            o, _ = enc(blocks[b0:b0 + 64])
+        for b0 in range(0, blocks.shape[0], 256):                                     # encoder over all blocks, 256 per call
+            o, _ = enc(blocks[b0:b0 + 256])
             feats_out.append(o)
         enc_out = torch.cat(feats_out, 0)
         blk0 = np.concatenate([[0], np.cumsum(ks)])

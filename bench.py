@@ -204,7 +204,8 @@ def bench_fps(dist, amp, steps, warmup, with_cpu):
         "e2e": {"value": clouds / (e_ms * 1e-3), "unit": "clouds/s",
                 "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": int(rows_host.numel() * 4)},
         "roofline": {"bound": "hbm", "kernel": "fps_cluster_kernel", "achieved": ach, "peak": pk["hbm_gbs"],
-                     "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+                     "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                     "traffic": 127.5e6,   # dram__bytes_read + write of one launch, ncu --set full (profiles/r01_fps_ncu_full.txt)
                      "peak_source": pk["source"] + " (burst copy)",
                      "model": "20 B per candidate per pick (12 B coords + 8 B running-min r/w) x (S-1) x P x clouds; "
                               "the kernel keeps the whole cloud on chip (registers + SMEM), so frac > 1 is expected: "
