@@ -269,37 +269,50 @@ __global__ void __launch_bounds__(256) narrow_wgrad_kernel(const WgParams p, int
 // memory bound on the activation. thread == (input channel k, row phase); the per-row gradients are 5 broadcast loads.
 constexpr int NO_MAXN = 8;
 __global__ void __launch_bounds__(256) narrow_out_wgrad_kernel(const WgParams p, int slabs, int SLAB) {
+    __shared__ float dys[NW_SLAB_MAX * NO_MAXN];                 // the slab's gradients [row][class], staged once (coalesced)
     __shared__ float red[256 * (NO_MAXN + 1)];
     const int tid = threadIdx.x;
     const int K = p.K, N = p.Nout, rows = p.rows_per_cloud;
     const int unit = blockIdx.x, cloud = unit / slabs, slab = unit - cloud * slabs;
-    const int r_begin = slab * SLAB, r_end = min(rows, r_begin + SLAB);
+    const int r_begin = slab * SLAB, r_end = min(rows, r_begin + SLAB), nr = r_end - r_begin;
     const long long cloud_row = (long long)cloud * rows;
+    if (p.dy_transposed) {                                       // [B, C, rows]: consecutive threads = consecutive rows of one class
+        for (int e = tid; e < nr * N; e += 256) {
+            const int n = e / nr, r = e - n * nr;
+            dys[r * NO_MAXN + n] = __ldg(p.dY + ((long long)cloud * N + n) * rows + r_begin + r);
+        }
+    } else {
+        for (int e = tid; e < nr * N; e += 256) {
+            const int r = e / N, n = e - r * N;
+            dys[r * NO_MAXN + n] = __ldg(p.dY + (cloud_row + r_begin + r) * p.lddy + n);
+        }
+    }
+    __syncthreads();
     const int phases = 256 / K, k = tid % K, ph = tid / K;       // K in {64, 128, 256}
     const float aa = p.a_a ? __ldg(p.a_a + k) : 1.f, ab = p.a_b ? __ldg(p.a_b + k) : 0.f, am = p.a_m ? __ldg(p.a_m + k) : 0.f;
     float acc[NO_MAXN], bsum[NO_MAXN];
 #pragma unroll
     for (int n = 0; n < NO_MAXN; ++n) { acc[n] = 0.f; bsum[n] = 0.f; }
-    for (int rb = r_begin + ph; rb < r_end; rb += 4 * phases) {
-        float av[4];
+    for (int rb = r_begin + ph; rb < r_end; rb += 8 * phases) {  // 8 activation loads in flight per thread
+        float av[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
             const int r = rb + u * phases;
             av[u] = r < r_end ? __ldg(p.A + (cloud_row + r) * p.lda + k) : 0.f;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
             const int r = rb + u * phases;
             if (r < r_end) {
                 float a = av[u];
                 if (p.a_a) a = fmaf(a - am, aa, ab);
                 if (p.a_relu) a = fmaxf(a, 0.f);
                 if (p.a_drop_p > 0.f) a *= dropout_keep(p.a_drop_seed, (unsigned long long)(cloud_row + r) * K + k, p.a_drop_p);
+                const float* dyr = dys + (r - r_begin) * NO_MAXN;
 #pragma unroll
                 for (int n = 0; n < NO_MAXN; ++n) {
                     if (n < N) {
-                        const float dy = p.dy_transposed ? __ldg(p.dY + ((long long)cloud * N + n) * rows + r)
-                                                         : __ldg(p.dY + (cloud_row + r) * p.lddy + n);
+                        const float dy = dyr[n];
                         acc[n] = fmaf(dy, a, acc[n]);
                         bsum[n] += dy;
                     }
@@ -318,7 +331,7 @@ __global__ void __launch_bounds__(256) narrow_out_wgrad_kernel(const WgParams p,
         part[e] = sum;
     }
     __syncthreads();
-    // bias partial: every thread of one phase holds the same row set only if phases == 1; sum the phases of channel k == 0
+    // bias partial: the threads of one phase all saw the same rows; add the phases of channel k == 0 in order
     if (k == 0) {
 #pragma unroll
         for (int n = 0; n < NO_MAXN; ++n) red[ph * (NO_MAXN + 1) + n] = bsum[n];
@@ -335,7 +348,7 @@ __global__ void __launch_bounds__(256) narrow_out_wgrad_kernel(const WgParams p,
 
 int narrow_out_wgrad_try(const WgParams& p, int slabs, int SLAB, cudaStream_t st) {
     if (path_disabled("narrow_out_wgrad")) return 0;
-    if (p.Nout > NO_MAXN || p.y_a || p.Y2 || p.dbg) return 0;
+    if (p.Nout > NO_MAXN || p.y_a || p.Y2 || p.dbg || SLAB > NW_SLAB_MAX) return 0;
     if (p.K != 64 && p.K != 128 && p.K != 256) return 0;
     narrow_out_wgrad_kernel<<<p.n_clouds * slabs, 256, 0, st>>>(p, slabs, SLAB);
     count_launch();

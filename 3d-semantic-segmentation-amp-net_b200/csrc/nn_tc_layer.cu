@@ -65,7 +65,7 @@ template <int MODE>
 __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_constant__ PwParams p, const int Mpad, long long* prof_buf) {
     extern __shared__ __align__(1024) unsigned char smem[];
     // two slots of 256 threads (two warpgroups each): `wg` = slot, `sub` = which warpgroup of the slot, `wtid` = thread in slot
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = warp >> 3, sub = (warp >> 2) & 1, wtid = tid & (TL_SLOT - 1);
+    const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31, wg = warp >> 3, sub = (warp >> 2) & 1, wtid = tid & (TL_SLOT - 1);
     const int K = p.K, Nout = p.Nout, rows = p.rows_per_cloud;
     const TlPlan sp = tl_plan(Mpad, K);
     float* s_exch = reinterpret_cast<float*>(smem + sp.exch) + wg * (3 * 2 * 128);
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *s_tmem;
+    const uint32_t tmem_base = uniform_u32(*s_tmem);
 
     const int tpc = (rows + TL_ROWS - 1) / TL_ROWS;
     const int n_mt = Mpad >> 7;
@@ -241,8 +241,9 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
             fence_proxy_async();
             tc_fence_before();
             slot_sync();
-            if (wtid == 0) {
+            if ((warp & 7) == 0) {                         // first warp of the slot; one elected lane issues (uniform descriptors)
                 tc_fence_after();
+                if (elect_one_sync()) {
                 for (int mt = 0; mt < n_mt; ++mt) {
                     const uint32_t d = slot_col + (uint32_t)mt * 128u;
                     for (int ks = 0; ks < (kcur >> 4); ++ks) {
@@ -257,6 +258,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
                     }
                 }
                 umma_commit(mbar);
+                }
+                __syncwarp();
             }
             TL_PROF();                                         // MMAs issued
             __syncwarp();

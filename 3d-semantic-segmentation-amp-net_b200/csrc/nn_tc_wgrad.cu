@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ WgParams p, const int Mpad, const int Kp, const int Kext, const int slabs, const int SLAB,
                 const int a_vec, const int out_vec) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = warp >> 2, wtid = tid & 127;
+    const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31, wg = warp >> 2, wtid = tid & 127;
     const int K = p.K, Nout = p.Nout, rows = p.rows_per_cloud;
     const TwPlan sp = tw_plan(Mpad, Kext, Nout, K);
     unsigned char* s_slot = smem + wg * sp.slot;
@@ -91,7 +91,7 @@ tc_wgrad_kernel(const __grid_constant__ WgParams p, const int Mpad, const int Kp
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *s_tmem;
+    const uint32_t tmem_base = uniform_u32(*s_tmem);
 
     const int n_mt = Mpad >> 7;
     const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32) << 16);
@@ -229,8 +229,9 @@ tc_wgrad_kernel(const __grid_constant__ WgParams p, const int Mpad, const int Kp
             fence_proxy_async();
             tc_fence_before();
             wg_bar_sync(wg);
-            if (wtid == 0) {
+            if ((warp & 3) == 0) {                         // first warp of the slot; one elected lane issues (uniform descriptors)
                 tc_fence_after();
+                if (elect_one_sync()) {
                 for (int mt = 0; mt < n_mt; ++mt) {
                     const uint32_t d = slot_col + (uint32_t)(mt * Kext);
 #pragma unroll
@@ -244,6 +245,8 @@ tc_wgrad_kernel(const __grid_constant__ WgParams p, const int Mpad, const int Kp
                     }
                 }
                 umma_commit(mbar);
+                }
+                __syncwarp();
             }
             __syncwarp();
             mbar_wait(mbar, phase);

@@ -97,7 +97,7 @@ __device__ __noinline__ void epilogue_slow(const TcChainParams& p, const TcOp& o
 
 __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_constant__ TcChainParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
     const int slot = warp >> 3, sub = (warp >> 2) & 1, stid = tid & (kSlotThreads - 1);
     const SmemPlan sp = smem_plan(p.wblob_bytes, p.wcloud_bytes);
     unsigned char* s_w = smem;
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *s_tmem;
+    const uint32_t tmem_base = uniform_u32(*s_tmem);
     if (tid == 0 && p.wblob_bytes > 0) {
         mbar_expect_tx(wbar, (uint32_t)p.wblob_bytes);
         for (int off = 0; off < p.wblob_bytes; off += 32768) {
@@ -219,10 +219,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
 
         for (int l = 0; l < p.n_ops; ++l) {
             const TcOp& op = p.op[l];
-            // ---- MMA issue: one thread per slot ----
-            if (stid == 0) {
+            // ---- MMA issue: the first warp of the slot enters, one elected lane issues (uniform descriptors) ----
+            if ((warp & 7) == 0) {
                 if (!w_ready) { mbar_wait(wbar, 0); w_ready = true; }
                 tc_fence_after();
+                if (elect_one_sync()) {
                 // descriptors advance linearly with the K step: build them once, then one 64-bit add per MMA
                 const uint32_t wreg = op.w_cloud ? smem_u32(s_wc) : smem_u32(s_w);
                 const uint32_t w_lbo = (uint32_t)op.N * 16u;
@@ -243,6 +244,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
                     }
                 }
                 umma_commit(mbar);
+                }
+                __syncwarp();
             }
             AMP_PROF();        // issued
             __syncwarp();

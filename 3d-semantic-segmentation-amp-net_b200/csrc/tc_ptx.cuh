@@ -12,6 +12,22 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+// One lane of a converged warp. tcgen05.mma takes its descriptors from UNIFORM registers: when the issuing code is entered
+// by a whole warp whose operands are provably warp-uniform (derive the warp index with warp_index_uniform()) and only
+// the instruction itself is predicated by the elected lane, the compiler keeps the descriptors in uniform registers;
+// an `if (threadIdx.x == 0)` around the issue loop instead costs an elect / R2UR broadcast loop (~150 cycles) per MMA.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ int warp_index_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // non-suspending poll (mbarrier.test_wait): returns at once; used where the wake-up latency of try_wait matters
 __device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
     uint32_t done;
