@@ -19,7 +19,7 @@ namespace {
 constexpr float kBnEps = 1e-5f, kBnMomentum = 0.1f;
 constexpr int kSegBn2 = 0, kSegBn3 = 128, kSegBnTotal = 192;   // offsets into the scale/shift tables
 // bf16 tensor-core head: conv_2 local half (128 x 64), conv_3 (64 x 128), conv_4 (<= 32 x 64) packed; biases of conv_3 / conv_4
-constexpr int kSegTcBlob = 16384 + (16384 + 1024) + (4096 + 512), kSegTcTab = 64;
+constexpr int kSegTcBlob = 16384 + (16384 + 1024) + (4096 + 512);
 
 #define AMP_TRY(expr) do { int rc_ = (expr); if (rc_ != AMP_OK) return rc_; } while (0)
 #define AMP_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fail(AMP_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); } while (0)
@@ -43,7 +43,7 @@ SegSaved seg_carve(Arena& a, long long B, long long W, long long R, int E, int h
 }
 
 struct SegWs {
-    unsigned char* tc_blob; float* tc_tab;                      // bf16 tensor-core path: packed head weights, bias tables
+    unsigned char* tc_blob;                                     // bf16 tensor-core path: packed head weights + bias K groups
     float *part_sum, *part_sq, *k1, *k2, *k3, *wg; size_t wg_floats;
     float *dz3, *dz2, *dcb, *dg_w, *dattn_o, *dqkv, *dtokens, *dpre;
 };
@@ -64,7 +64,7 @@ SegWs seg_ws_carve(Arena& a, long long B, long long W, long long R, int E, int h
     const size_t tiles = (size_t)pw_tiles((int)B, (int)R);
     w.part_sum = a.take<float>(tiles * 128); w.part_sq = a.take<float>(tiles * 128);
     if (!backward) {
-        w.tc_blob = a.take<unsigned char>(kSegTcBlob); w.tc_tab = a.take<float>(kSegTcTab);
+        w.tc_blob = a.take<unsigned char>(kSegTcBlob);
         return w;
     }
     w.k1 = a.take<float>(kSegBnTotal); w.k2 = a.take<float>(kSegBnTotal); w.k3 = a.take<float>(kSegBnTotal);

@@ -15,7 +15,7 @@
 namespace amp {
 namespace {
 
-constexpr int SM_ROWS = 32, SM_COLS = 16, SM_MAXK = 512;
+constexpr int SM_ROWS = 32, SM_CPW = 1, SM_COLS = 8 * SM_CPW, SM_MAXK = 512;   // one output column per warp: more CTAs, shorter chains
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -60,9 +60,9 @@ __global__ void __launch_bounds__(256) small_fwd_kernel(const PwParams p) {
     const int M = p.rows_per_cloud, K = p.K, N = p.Nout;
     const int r0 = blockIdx.y * SM_ROWS;
     const int KC = K < SM_MAXK ? K : SM_MAXK;
-    float acc[2][SM_ROWS];                        // this warp's two output columns: c = warp, warp + 8
+    float acc[SM_CPW][SM_ROWS];                   // this warp's output columns: c = warp + 8 j
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
+    for (int j = 0; j < SM_CPW; ++j)
 #pragma unroll
         for (int r = 0; r < SM_ROWS; ++r) acc[j][r] = 0.f;
     for (int k0 = 0; k0 < K; k0 += KC) {
@@ -91,9 +91,9 @@ __global__ void __launch_bounds__(256) small_fwd_kernel(const PwParams p) {
         __syncthreads();
         // all weight loads of this chunk (2 columns x up to 16 lane-strided elements) are issued before the first FMA:
         // these layers are latency bound, not bandwidth bound
-        float wv[2][SM_MAXK / 32];
+        float wv[SM_CPW][SM_MAXK / 32];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < SM_CPW; ++j) {
             const int n = blockIdx.x * SM_COLS + warp + 8 * j;
             // w_kn == 0: W[n][k] (a contiguous row per output); w_kn == 1: W[k][n] (transposed weights of the backward)
             const float* __restrict__ w = p.w_kn ? p.W + (long long)k0 * p.ldw + n : p.W + (long long)n * p.ldw + k0;
@@ -112,15 +112,15 @@ __global__ void __launch_bounds__(256) small_fwd_kernel(const PwParams p) {
 #pragma unroll
                 for (int r = 0; r < SM_ROWS; ++r) {
                     const float xv = xs[r * kc + ks];
-                    acc[0][r] = fmaf(xv, wv[0][i], acc[0][r]);
-                    acc[1][r] = fmaf(xv, wv[1][i], acc[1][r]);
+#pragma unroll
+                    for (int j = 0; j < SM_CPW; ++j) acc[j][r] = fmaf(xv, wv[j][i], acc[j][r]);
                 }
             }
         }
     }
     const SmallEpi epi{p, M, r0};
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < SM_CPW; ++j) {
         const int n = blockIdx.x * SM_COLS + warp + 8 * j;
         if (n >= N) break;
         // butterfly: after the five steps lane L holds the full sum of row L

@@ -25,7 +25,8 @@ _default_precision = "fp32"
 
 def set_default_precision(name):
     """Arithmetic of the eval forward for modules that do not set `.precision` themselves:
-    "fp32" (CUDA cores, the parity path) or "bf16" (fused tcgen05 chains). Training always runs in fp32."""
+    "fp32" (the parity path: split-bf16 tensor-core GEMMs at fp32-class accuracy + fp32 CUDA-core layers) or "bf16"
+    (fused tcgen05 chains, bf16 operands). Training always runs the parity path."""
     global _default_precision
     if name not in PRECISIONS:
         raise ValueError("precision must be one of %s" % sorted(PRECISIONS))
