@@ -101,7 +101,6 @@ tc_wgrad_kernel(const __grid_constant__ WgParams p, const int Mpad, const int Kp
     const uint32_t idesc = umma_idesc_mn(128, Kext);
     const bool y_pro = p.y_a != nullptr, a_pro = p.a_a != nullptr;
     uint32_t phase = 0;
-    const int sr = wtid & 63, shalf = wtid >> 6;                // staging: row within the block, which half of the channels
     const int n_units = p.n_clouds * slabs;
 
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
@@ -111,116 +110,106 @@ tc_wgrad_kernel(const __grid_constant__ WgParams p, const int Mpad, const int Kp
         const int nb = (r_end - r_begin + TW_RB - 1) / TW_RB;
         const int nb0 = (nb + 1) >> 1;
         const int blk_lo = wg == 0 ? 0 : nb0, blk_hi = wg == 0 ? nb0 : nb;
+#pragma unroll 1
         for (int blk = blk_lo; blk < blk_hi; ++blk) {
-            const int r = r_begin + blk * TW_RB + sr;
-            const bool row_ok = r < r_end;
-            const long long grow = cloud_row + r;
-            if (blk + 1 < blk_hi && r + TW_RB < r_end) {        // this thread's share of the next block's rows -> L2
-                const long long gn = grow + TW_RB;
-                const int nb_y = (Nout * 4) >> 1, nb_a = (K * 4) >> 1;
-                const char* y = reinterpret_cast<const char*>(p.dY + gn * p.lddy) + shalf * nb_y;
-                for (int b = 0; b < nb_y; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + b));
-                if (p.Y2) {
-                    const char* y2 = reinterpret_cast<const char*>(p.Y2 + gn * p.lddy) + shalf * nb_y;
-                    for (int b = 0; b < nb_y; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(y2 + b));
-                }
-                const char* a = reinterpret_cast<const char*>(p.A + gn * p.lda) + shalf * nb_a;
-                for (int b = 0; b < nb_a; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + b));
-            }
-            // ---- A operand: dy'[r, n] for this thread's half of the channels ----
-            {
+            // Coalesced staging: within a warp, 8 lanes = the 8 rows of one row group, 4 lane groups = 4 consecutive
+            // 8-channel pieces: a warp load touches 8 rows x 128 contiguous bytes (not 32 separate lines) and a warp store
+            // writes 4 whole core matrices (conflict-free). Each thread keeps 4 pieces (8 + 8 float4 loads) in flight.
+            const int rr = lane & 7, gq = lane >> 3, wq = warp & 3;
+            const int blk_row0 = r_begin + blk * TW_RB;
+            const int kgd = Kp >> 3;                                  // B groups that carry data
+#pragma unroll 1
+            for (int rg = wq; rg < TW_RB / 8; rg += 4) {
+                const int rl = rg * 8 + rr, r = blk_row0 + rl;
+                const bool row_ok = r < r_end;
+                const long long grow = cloud_row + r;
                 const float* __restrict__ yrow = p.dY + grow * p.lddy;
                 const float* __restrict__ y2row = p.Y2 ? p.Y2 + grow * p.lddy : nullptr;
-                const int g0 = shalf * (a_groups >> 1), g1 = g0 + (a_groups >> 1);
-                for (int gb = g0; gb < g1; gb += 4) {           // batches of 32 channels
-                    float4 xa[8], ya[8];
+                const float* __restrict__ arow = p.A + grow * p.lda;
+                // ---- A operand: dy'[r, n], pieces g = gq + 4 i ----
+#pragma unroll 1
+                for (int g0 = gq; g0 < a_groups; g0 += 16) {
+                    float4 xa[4][2], ya[4][2];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int n = gb * 8 + i * 4;
-                        xa[i] = (row_ok && n < Nout) ? __ldg(reinterpret_cast<const float4*>(yrow + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int i = 0; i < 4; ++i) {
+                        const int n = (g0 + 4 * i) * 8;
+                        const bool ok = row_ok && n < Nout;
+                        xa[i][0] = ok ? __ldg(reinterpret_cast<const float4*>(yrow + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        xa[i][1] = ok ? __ldg(reinterpret_cast<const float4*>(yrow + n + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                     if (y2row) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int n = gb * 8 + i * 4;
-                            ya[i] = (row_ok && n < Nout) ? __ldg(reinterpret_cast<const float4*>(y2row + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int i = 0; i < 4; ++i) {
+                            const int n = (g0 + 4 * i) * 8;
+                            const bool ok = row_ok && n < Nout;
+                            ya[i][0] = ok ? __ldg(reinterpret_cast<const float4*>(y2row + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            ya[i][1] = ok ? __ldg(reinterpret_cast<const float4*>(y2row + n + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
                     }
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int g = gb + c, n = g * 8;
-                        float v[8] = {xa[2 * c].x, xa[2 * c].y, xa[2 * c].z, xa[2 * c].w, xa[2 * c + 1].x, xa[2 * c + 1].y, xa[2 * c + 1].z, xa[2 * c + 1].w};
-                        if (row_ok && n < Nout) {
-                            if (y_pro) {
+                    for (int i = 0; i < 4; ++i) {
+                        const int g = g0 + 4 * i, n = g * 8;
+                        if (g < a_groups) {
+                            float v[8] = {xa[i][0].x, xa[i][0].y, xa[i][0].z, xa[i][0].w, xa[i][1].x, xa[i][1].y, xa[i][1].z, xa[i][1].w};
+                            if (row_ok && n < Nout) {
+                                if (y_pro) {
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], s_ya[n + i], s_yb[n + i]);
+                                    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], s_ya[n + j], s_yb[n + j]);
+                                }
+                                if (y2row) {
+                                    const float y2[8] = {ya[i][0].x, ya[i][0].y, ya[i][0].z, ya[i][0].w, ya[i][1].x, ya[i][1].y, ya[i][1].z, ya[i][1].w};
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) v[j] = fmaf(y2[j] - s_ym[n + j], s_yc[n + j], v[j]);
+                                }
                             }
-                            if (y2row) {
-                                const float y2[8] = {ya[2 * c].x, ya[2 * c].y, ya[2 * c].z, ya[2 * c].w, ya[2 * c + 1].x, ya[2 * c + 1].y, ya[2 * c + 1].z, ya[2 * c + 1].w};
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) v[i] = fmaf(y2[i] - s_ym[n + i], s_yc[n + i], v[i]);
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                            const int off = g * 8 + (rl >> 3) * (a_groups * 8) + (rl & 7);
+                            split_store8_w(v, s_ahi + off, s_alo + off);
                         }
-                        const int off = g * 8 + (sr >> 3) * (a_groups * 8) + (sr & 7);
-                        split_store8_w(v, s_ahi + off, s_alo + off);
                     }
                 }
-            }
-            // ---- B operand: a'[r, k] for this thread's half of the input channels ----
-            {
-                const float* __restrict__ arow = p.A + grow * p.lda;
-                const int kg = Kp >> 3;                         // groups with data (Kp % 16 == 0 -> even)
-                const int g0 = shalf * (kg >> 1), g1 = g0 + (kg >> 1);
-                for (int gb = g0; gb < g1; gb += 4) {
-                    float4 xa[8];
-                    if (a_vec) {
+                // ---- B operand: a'[r, k] ----
+#pragma unroll 1
+                for (int g0 = gq; g0 < kgd; g0 += 16) {
+                    float4 xa[4][2];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int g = gb + (i >> 1);
-                            xa[i] = (row_ok && g < g1) ? __ldg(reinterpret_cast<const float4*>(arow + gb * 8) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                    } else {                                    // narrow / unaligned rows (K = 3, 9): scalar gather, zero padding
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int k = gb * 8 + i * 4;
-                            const bool gok = row_ok && (gb + (i >> 1)) < g1;
-                            xa[i].x = (gok && k < K) ? __ldg(arow + k) : 0.f;
-                            xa[i].y = (gok && k + 1 < K) ? __ldg(arow + k + 1) : 0.f;
-                            xa[i].z = (gok && k + 2 < K) ? __ldg(arow + k + 2) : 0.f;
-                            xa[i].w = (gok && k + 3 < K) ? __ldg(arow + k + 3) : 0.f;
+                    for (int i = 0; i < 4; ++i) {
+                        const int k = (g0 + 4 * i) * 8;
+                        const bool ok = row_ok && g0 + 4 * i < kgd;
+                        if (a_vec) {
+                            xa[i][0] = ok ? __ldg(reinterpret_cast<const float4*>(arow + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            xa[i][1] = ok ? __ldg(reinterpret_cast<const float4*>(arow + k + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        } else {
+                            xa[i][0].x = (ok && k < K) ? __ldg(arow + k) : 0.f; xa[i][0].y = (ok && k + 1 < K) ? __ldg(arow + k + 1) : 0.f;
+                            xa[i][0].z = (ok && k + 2 < K) ? __ldg(arow + k + 2) : 0.f; xa[i][0].w = (ok && k + 3 < K) ? __ldg(arow + k + 3) : 0.f;
+                            xa[i][1].x = (ok && k + 4 < K) ? __ldg(arow + k + 4) : 0.f; xa[i][1].y = (ok && k + 5 < K) ? __ldg(arow + k + 5) : 0.f;
+                            xa[i][1].z = (ok && k + 6 < K) ? __ldg(arow + k + 6) : 0.f; xa[i][1].w = (ok && k + 7 < K) ? __ldg(arow + k + 7) : 0.f;
                         }
                     }
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int g = gb + c, k = g * 8;
-                        if (g < g1) {
-                            float v[8] = {xa[2 * c].x, xa[2 * c].y, xa[2 * c].z, xa[2 * c].w, xa[2 * c + 1].x, xa[2 * c + 1].y, xa[2 * c + 1].z, xa[2 * c + 1].w};
+                    for (int i = 0; i < 4; ++i) {
+                        const int g = g0 + 4 * i, k = g * 8;
+                        if (g < kgd) {
+                            float v[8] = {xa[i][0].x, xa[i][0].y, xa[i][0].z, xa[i][0].w, xa[i][1].x, xa[i][1].y, xa[i][1].z, xa[i][1].w};
                             if (row_ok) {
                                 if (a_pro) {
 #pragma unroll
-                                    for (int i = 0; i < 8; ++i)
-                                        if (k + i < K) v[i] = fmaf(v[i] - s_am[k + i], s_aa[k + i], s_ab[k + i]);
+                                    for (int j = 0; j < 8; ++j)
+                                        if (k + j < K) v[j] = fmaf(v[j] - s_am[k + j], s_aa[k + j], s_ab[k + j]);
                                 }
                                 if (p.a_relu) {
 #pragma unroll
-                                    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                                    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
                                 }
                                 if (p.a_drop_p > 0.f) {
 #pragma unroll
-                                    for (int i = 0; i < 8; ++i)
-                                        v[i] *= dropout_keep(p.a_drop_seed, (unsigned long long)grow * K + k + i, p.a_drop_p);
+                                    for (int j = 0; j < 8; ++j)
+                                        v[j] *= dropout_keep(p.a_drop_seed, (unsigned long long)grow * K + k + j, p.a_drop_p);
                                 }
 #pragma unroll
-                                for (int i = 0; i < 8; ++i)
-                                    if (k + i >= K) v[i] = 0.f;
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                                for (int j = 0; j < 8; ++j)
+                                    if (k + j >= K) v[j] = 0.f;
                             }
-                            const int off = g * 8 + (sr >> 3) * (b_groups * 8) + (sr & 7);
+                            const int off = g * 8 + (rl >> 3) * (b_groups * 8) + (rl & 7);
                             split_store8_w(v, s_bhi + off, s_blo + off);
                         }
                     }
