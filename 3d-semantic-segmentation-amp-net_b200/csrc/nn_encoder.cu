@@ -86,6 +86,17 @@ int fwd_layer(EncCtx& c, const float* X, long long ldx, int K, int in_bn, const 
     return AMP_OK;
 }
 
+// eval-mode FC stack of a T-Net (:38-46) in one cluster launch; the wide fc_3 of the 64 x 64 transform stays a separate launch
+int tnet_fc_stack_eval(EncCtx& c, int pbase, int L1, int d, const float* pool, float* f1, float* f2, float* out) {
+    const int o4 = enc_bn_offset(L1 + 3), o5 = enc_bn_offset(L1 + 4);
+    const int inside = d * d <= 64 ? 1 : 0;
+    AMP_TRY(tnet_fc_eval(pool, c.B, c.pf(pbase + T_FC1), c.S.scale + o4, c.S.shift + o4, c.pf(pbase + T_FC2), c.S.scale + o5, c.S.shift + o5,
+                         c.pf(pbase + T_FC3W), c.pf(pbase + T_FC3B), d, inside, f1, f2, out, c.st));
+    if (inside) return AMP_OK;
+    AMP_TRY(fwd_layer(c, f2, 128, 128, -1, c.pf(pbase + T_FC3W), 128, 0, 0, c.pf(pbase + T_FC3B), out, d * d, d * d, -1, nullptr, nullptr, 1, c.B));
+    return add_identity(out, c.B, d, c.st);
+}
+
 // TransformationNet.forward (pointnetAtt.py:28-47): A = input rows (with the BatchNorm+ReLU of layer a_bn pending
 // in training mode), out = [B, d*d] transform (+ identity)
 int tnet_fwd(EncCtx& c, int pbase, int L1, int d, const float* A, long long lda, int K, int a_bn, float* y1, float* y2,
@@ -94,6 +105,7 @@ int tnet_fwd(EncCtx& c, int pbase, int L1, int d, const float* A, long long lda,
     AMP_TRY(fwd_layer(c, A, lda, K, a_bn, c.pf(pbase + T_CONV1), K, 0, 0, nullptr, y1, 64, 64, L1, nullptr, nullptr, B, N));
     AMP_TRY(fwd_layer(c, y1, 64, 64, L1, c.pf(pbase + T_CONV2), 64, 0, 0, nullptr, y2, 128, 128, L1 + 1, nullptr, nullptr, B, N));
     AMP_TRY(fwd_layer(c, y2, 128, 128, L1 + 1, c.pf(pbase + T_CONV3), 128, 0, 0, nullptr, y3, 256, 256, L1 + 2, pool, arg, B, N));
+    if (!c.train) return tnet_fc_stack_eval(c, pbase, L1, d, pool, f1, f2, out);
     AMP_TRY(fwd_layer(c, pool, 256, 256, -1, c.pf(pbase + T_FC1), 256, 0, 0, nullptr, f1, 256, 256, L1 + 3, nullptr, nullptr, 1, B));
     AMP_TRY(fwd_layer(c, f1, 256, 256, L1 + 3, c.pf(pbase + T_FC2), 256, 0, 0, nullptr, f2, 128, 128, L1 + 4, nullptr, nullptr, 1, B));
     AMP_TRY(fwd_layer(c, f2, 128, 128, L1 + 4, c.pf(pbase + T_FC3W), 128, 0, 0, c.pf(pbase + T_FC3B), out, d * d, d * d, -1,
@@ -258,12 +270,7 @@ inline TcPackJob tc_job(const float* w, int ld, const float* scale, const float*
 }
 
 int tnet_fc_fwd(EncCtx& c, int pbase, int L1, int d, const float* pool, float* f1, float* f2, float* out) {
-    const int B = c.B;
-    AMP_TRY(fwd_layer(c, pool, 256, 256, -1, c.pf(pbase + T_FC1), 256, 0, 0, nullptr, f1, 256, 256, L1 + 3, nullptr, nullptr, 1, B));
-    AMP_TRY(fwd_layer(c, f1, 256, 256, L1 + 3, c.pf(pbase + T_FC2), 256, 0, 0, nullptr, f2, 128, 128, L1 + 4, nullptr, nullptr, 1, B));
-    AMP_TRY(fwd_layer(c, f2, 128, 128, L1 + 4, c.pf(pbase + T_FC3W), 128, 0, 0, c.pf(pbase + T_FC3B), out, d * d, d * d, -1,
-                      nullptr, nullptr, 1, B));
-    return add_identity(out, B, d, c.st);
+    return tnet_fc_stack_eval(c, pbase, L1, d, pool, f1, f2, out);
 }
 
 int encoder_fwd_bf16(EncCtx& c, const float* x, float* out, float* feat_t, Arena& wa) {

@@ -10,6 +10,8 @@
 //                                                     order (deterministic, no partial buffers)
 // Prologues / epilogues are those of PwParams / WgParams (BatchNorm apply or backward, ReLU mask, batch statistics).
 // Because a warp holds a whole column of <= 32 rows, the BatchNorm sums are warp shuffles in a fixed order.
+#include <cooperative_groups.h>
+
 #include "nn_common.cuh"
 
 namespace amp {
@@ -344,7 +346,117 @@ __global__ void __launch_bounds__(256) narrow_out_wgrad_kernel(const WgParams p,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Eval-mode T-Net FC stack (pointNet/model/pointnetAtt.py:38-46) in ONE launch: relu(bn_4(fc_1)) -> relu(bn_5(fc_2)) ->
+// fc_3 + bias + identity. One cluster of 8 CTAs per tile of 32 clouds; every CTA computes a slice of each layer's output
+// columns for all rows of the tile (the small_fwd scheme), the intermediate [32 x 256] / [32 x 128] activations go through
+// global scratch, and a cluster barrier (release / acquire) separates the layers. Replaces 4 dependent launches.
+// ---------------------------------------------------------------------------------------------------------------
+struct TnetFcArgs {
+    const float* pooled;                                   // [B, 256]
+    const float* fc1; const float* s4; const float* t4;    // [256, 256]; folded BatchNorm scale / shift [256]
+    const float* fc2; const float* s5; const float* t5;    // [128, 256]; [128]
+    const float* fc3w; const float* fc3b;                  // [d * d, 128]; [d * d]
+    float* h1; float* h2; float* out;                      // scratch [B, 256], [B, 128]; result [B, d * d]
+    int B, d, do_fc3;
+};
+
+// weights of the NC consecutive output columns of this warp (lane <-> k mod 32), issued before the tile of the layer is
+// available so that their DRAM latency overlaps the previous layer / the cluster barrier
+template <int NC, int KI>
+__device__ __forceinline__ void tnet_fc_load_w(float (&wv)[NC][KI], const float* __restrict__ W, int n0, int n_end) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int i = 0; i < KI; ++i) wv[c][i] = (n0 + c < n_end) ? __ldg(W + (long long)(n0 + c) * (32 * KI) + lane + 32 * i) : 0.f;
+}
+
+template <int NC, int KI>
+__device__ __forceinline__ void tnet_fc_layer(float* xs, const float* __restrict__ X, int r0, int M, const float (&wv)[NC][KI], int n0,
+                                              int n_end, const float* __restrict__ bias, const float* __restrict__ scale,
+                                              const float* __restrict__ shift, bool relu, int eye_d, float* __restrict__ Y, int ldy) {
+    constexpr int K = 32 * KI;
+    const int tid = threadIdx.x, lane = tid & 31;
+    __syncthreads();                                       // previous layer's reads of xs are done
+    for (int k = tid; k < K; k += 256) {
+#pragma unroll
+        for (int r = 0; r < SM_ROWS; ++r) xs[r * K + k] = (r0 + r < M) ? __ldcg(X + (long long)(r0 + r) * K + k) : 0.f;
+    }
+    __syncthreads();
+    if (n0 >= n_end) return;
+    float acc[NC][SM_ROWS];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int r = 0; r < SM_ROWS; ++r) acc[c][r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < KI; ++i) {
+#pragma unroll
+        for (int r = 0; r < SM_ROWS; ++r) {
+            const float x = xs[r * K + lane + 32 * i];     // one shared-memory read feeds the NC columns of the warp
+#pragma unroll
+            for (int c = 0; c < NC; ++c) acc[c][r] = fmaf(x, wv[c][i], acc[c][r]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+#pragma unroll
+        for (int o = 16, n2 = 16; o >= 1; o >>= 1, n2 >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int i = 0; i < n2; ++i) {
+                const float send = up ? acc[c][i] : acc[c][i + n2];
+                const float keep = up ? acc[c][i + n2] : acc[c][i];
+                acc[c][i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+        }
+        const int n = n0 + c;
+        if (n < n_end) {
+            float v = acc[c][0] + (bias ? __ldg(bias + n) : 0.f);
+            if (scale) v = fmaf(v, __ldg(scale + n), __ldg(shift + n));
+            if (relu) v = fmaxf(v, 0.f);
+            if (eye_d && n % (eye_d + 1) == 0) v += 1.f;  // + identity on the diagonal of the d x d transform
+            if (r0 + lane < M) Y[(long long)(r0 + lane) * ldy + n] = v;
+        }
+    }
+}
+
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(256) tnet_fc_eval_kernel(const TnetFcArgs a) {
+    extern __shared__ float xs[];                          // [32][256]
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank(), warp = threadIdx.x >> 5;
+    const int r0 = (blockIdx.x / 8) * SM_ROWS;
+    float w1[4][8], w2[2][8], w3[1][4];
+    tnet_fc_load_w<4, 8>(w1, a.fc1, rank * 32 + warp * 4, 256);
+    tnet_fc_layer<4, 8>(xs, a.pooled, r0, a.B, w1, rank * 32 + warp * 4, 256, nullptr, a.s4, a.t4, true, 0, a.h1, 256);
+    tnet_fc_load_w<2, 8>(w2, a.fc2, rank * 16 + warp * 2, 128);
+    __threadfence();
+    cluster.sync();
+    tnet_fc_layer<2, 8>(xs, a.h1, r0, a.B, w2, rank * 16 + warp * 2, 128, nullptr, a.s5, a.t5, true, 0, a.h2, 128);
+    if (!a.do_fc3) return;
+    const int nout = a.d * a.d;                            // <= 64: one column per warp
+    tnet_fc_load_w<1, 4>(w3, a.fc3w, rank * 8 + warp, nout);
+    __threadfence();
+    cluster.sync();
+    tnet_fc_layer<1, 4>(xs, a.h2, r0, a.B, w3, rank * 8 + warp, nout, a.fc3b, nullptr, nullptr, false, a.d, a.out, nout);
+}
+
 }  // namespace
+
+// Eval-mode T-Net FC stack in one cluster launch; with fc3_inside == 0 the caller runs fc_3 (wide) itself on h2.
+int tnet_fc_eval(const float* pooled, int B, const float* fc1, const float* s4, const float* t4, const float* fc2, const float* s5,
+                 const float* t5, const float* fc3w, const float* fc3b, int d, int fc3_inside, float* h1, float* h2, float* out,
+                 cudaStream_t st) {
+    if (!pooled || !fc1 || !fc2 || !h1 || !h2 || B < 1 || (fc3_inside && (!fc3w || !fc3b || !out)))
+        return fail(AMP_E_BADARG, "tnet_fc_eval: null pointer");
+    TnetFcArgs a{pooled, fc1, s4, t4, fc2, s5, t5, fc3w, fc3b, h1, h2, out, B, d, fc3_inside};
+    const size_t smem = sizeof(float) * SM_ROWS * 256;
+    tnet_fc_eval_kernel<<<8 * ((B + SM_ROWS - 1) / SM_ROWS), 256, smem, st>>>(a);
+    count_launch();
+    return check_launch("tnet_fc_eval");
+}
 
 int narrow_out_wgrad_try(const WgParams& p, int slabs, int SLAB, cudaStream_t st) {
     if (path_disabled("narrow_out_wgrad")) return 0;
