@@ -37,9 +37,9 @@ SIGNATURES = {
     "amp_seg_param_name": (_c.c_char_p, [_c.c_int]),
     "amp_seg_saved_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32]),
     "amp_seg_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32]),
-    "amp_seg_fwd": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _u64,
+    "amp_seg_fwd": (_c.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _u64,
                                _vp, _vp, _sz, _vp, _sz, _vp]),
-    "amp_seg_bwd": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _f32, _u64,
+    "amp_seg_bwd": (_c.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _f32, _u64,
                                _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     "amp_tc_linear_workspace_bytes": (_sz, [_i32, _i32]),
     "amp_tc_linear_bf16": (_c.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),

@@ -163,7 +163,7 @@ int colsum_rows(const float* dout, long long ldo, int n_clouds, int rows_per_clo
                 cudaStream_t st);
 size_t colsum_scratch_floats(int n_clouds, int rows_per_cloud, int C);
 // tokens[b, w, :] = gl[w, b, :] + fc2(leaky_relu(fc1(centroids[b, w])))      (:183-185); h_pre [B*W, 16] optional
-int posenc_add(const float* gl, const float* centroids, const float* fc1_w, const float* fc1_b, const float* fc2_w,
+int posenc_add(const float* gl, long long gl_ld, const float* centroids, const float* fc1_w, const float* fc1_b, const float* fc2_w,
                const float* fc2_b, int n_clouds, int n_tokens, int E, float* tokens, float* h_pre, cudaStream_t st);
 // backward of posenc_add: dgl[w, b, :] = dtokens[b, w, :]; gradients of fc1 / fc2
 int posenc_bwd(const float* dtokens, const float* centroids, const float* h_pre, const float* fc2_w, int n_clouds,

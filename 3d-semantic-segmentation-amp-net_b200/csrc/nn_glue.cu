@@ -134,7 +134,7 @@ __global__ void broadcast_rows_kernel(const float* __restrict__ g, int rows_per_
     }
 }
 
-__global__ void posenc_add_kernel(const float* __restrict__ gl, const float* __restrict__ cent, const float* __restrict__ w1,
+__global__ void posenc_add_kernel(const float* __restrict__ gl, long long gl_ld, const float* __restrict__ cent, const float* __restrict__ w1,
                                   const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
                                   int n_clouds, int n_tokens, int E, float* __restrict__ tokens,
                                   float* __restrict__ h_pre) {
@@ -152,7 +152,7 @@ __global__ void posenc_add_kernel(const float* __restrict__ gl, const float* __r
         float v = b2[e];
 #pragma unroll
         for (int k = 0; k < 16; ++k) v = fmaf(w2[e * 16 + k], h[k], v);
-        tokens[((long long)b * n_tokens + w) * E + e] = gl[((long long)w * n_clouds + b) * E + e] + v;
+        tokens[((long long)b * n_tokens + w) * E + e] = gl[((long long)w * n_clouds + b) * gl_ld + e] + v;
     }
 }
 
@@ -507,9 +507,9 @@ int colsum_rows(const float* dout, long long ldo, int n_clouds, int rows_per_clo
     return check_launch("colsum_stage2");
 }
 
-int posenc_add(const float* gl, const float* centroids, const float* fc1_w, const float* fc1_b, const float* fc2_w,
+int posenc_add(const float* gl, long long gl_ld, const float* centroids, const float* fc1_w, const float* fc1_b, const float* fc2_w,
                const float* fc2_b, int n_clouds, int n_tokens, int E, float* tokens, float* h_pre, cudaStream_t st) {
-    posenc_add_kernel<<<n_clouds * n_tokens, 128, 0, st>>>(gl, centroids, fc1_w, fc1_b, fc2_w, fc2_b, n_clouds, n_tokens, E,
+    posenc_add_kernel<<<n_clouds * n_tokens, 128, 0, st>>>(gl, gl_ld, centroids, fc1_w, fc1_b, fc2_w, fc2_b, n_clouds, n_tokens, E,
                                                            tokens, h_pre);
     count_launch();
     return check_launch("posenc_add");

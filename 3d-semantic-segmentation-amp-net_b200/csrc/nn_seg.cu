@@ -122,7 +122,8 @@ size_t amp_seg_workspace_bytes(int64_t B, int64_t W, int64_t rows, int32_t embed
     return a.off + 256;
 }
 
-int amp_seg_fwd(const void* const* params, const float* gl_feats, const float* lo_feats, const float* centroids,
+int amp_seg_fwd(const void* const* params, const float* gl_feats, int64_t gl_ld, const float* lo_feats, int64_t lo_ld,
+                const float* centroids,
                 const int32_t* np_cluster, const int32_t* group_rows, const uint8_t* key_padding_mask, int64_t B,
                 int64_t W, int64_t rows, int32_t embed_dim, int32_t heads, int32_t num_classes, int32_t training,
                 int32_t precision, float dropout_p, uint64_t seed, float* logits, void* saved, size_t saved_bytes,
@@ -134,6 +135,8 @@ int amp_seg_fwd(const void* const* params, const float* gl_feats, const float* l
     if (precision == AMP_PREC_BF16 && num_classes > 32) return fail(AMP_E_BADARG, "seg_fwd: the bf16 head supports up to 32 classes");
     if (!params || !gl_feats || !lo_feats || !centroids || !np_cluster || !group_rows || !logits || !saved || !workspace)
         return fail(AMP_E_BADARG, "seg_fwd: null pointer");
+    if (gl_ld < embed_dim || lo_ld < 64 || (lo_ld & 3) || (reinterpret_cast<uintptr_t>(lo_feats) & 15))
+        return fail(AMP_E_BADARG, "seg_fwd: gl_ld >= embed_dim, lo_ld >= 64 and a multiple of 4, lo_feats 16-byte aligned");
     const SegShape sh{B, W, rows, embed_dim, heads, num_classes, embed_dim / 2};
     AMP_TRY(seg_check(sh, np_cluster, "seg_fwd"));
     if (dropout_p < 0.f || dropout_p >= 1.f) return fail(AMP_E_BADARG, "seg_fwd: dropout p must be in [0, 1)");
@@ -151,7 +154,7 @@ int amp_seg_fwd(const void* const* params, const float* gl_feats, const float* l
     SegWs ws = seg_ws_carve(wa, B, W, rows, E, hid, false);
 
     // positional encoding + token-major layout (:183-185)
-    AMP_TRY(posenc_add(gl_feats, centroids, pf(params, S_FC1W), pf(params, S_FC1B), pf(params, S_FC2W), pf(params, S_FC2B), Bi, Wi, E,
+    AMP_TRY(posenc_add(gl_feats, gl_ld, centroids, pf(params, S_FC1W), pf(params, S_FC1B), pf(params, S_FC2W), pf(params, S_FC2B), Bi, Wi, E,
                        S.tokens, S.h_pre, st));
     // nn.MultiheadAttention (:187-190): in_proj, per-head softmax(QK^T)V, out_proj
     {
@@ -202,7 +205,7 @@ int amp_seg_fwd(const void* const* params, const float* gl_feats, const float* l
         p.op[0] = TcOp{64, hid, o_w2, 0, -1, 1, 1, 1, 0, 0, 0};
         p.op[1] = TcOp{hid, 64, o_w3, 0, o_b3, 1, 0, 1, 0, 0, 0};
         p.op[2] = TcOp{64, Cp, o_w4, 0, o_b4, 0, 0, 0, 0, 0, 1};
-        p.in_mode = 1; p.in_x = lo_feats; p.in_ld = 64; p.in_k = 64;
+        p.in_mode = 1; p.in_x = lo_feats; p.in_ld = lo_ld; p.in_k = 64;
         p.wblob = ws.tc_blob; p.wblob_bytes = o_b4 + Cp * 16;
         p.gbias = S.cb; p.group_rows = group_rows; p.n_groups = Wi;
         p.logits = logits; p.n_classes = num_classes;
@@ -224,7 +227,7 @@ int amp_seg_fwd(const void* const* params, const float* gl_feats, const float* l
     // conv_2 on the local half + per-block bias, bn_2, relu (:203)
     {
         PwParams p{};
-        p.X = lo_feats; p.ldx = 64; p.K = 64; p.W = pf(params, S_C2W); p.ldw = 64 + E;
+        p.X = lo_feats; p.ldx = lo_ld; p.K = 64; p.W = pf(params, S_C2W); p.ldw = 64 + E;
         p.bias = S.cb; p.bias_group_stride = hid; p.group_rows = group_rows; p.n_groups = Wi;
         p.groups_tile_aligned = 1;
         for (int i = 0; i < Wi; ++i) if (np_cluster[i] % 128) p.groups_tile_aligned = 0;
@@ -258,7 +261,7 @@ int amp_seg_fwd(const void* const* params, const float* gl_feats, const float* l
     return AMP_OK;
 }
 
-int amp_seg_bwd(const void* const* params, void* const* grads, const float* lo_feats, const float* centroids,
+int amp_seg_bwd(const void* const* params, void* const* grads, const float* lo_feats, int64_t lo_ld, const float* centroids,
                 const int32_t* np_cluster, const int32_t* group_rows, const float* d_logits, int64_t B, int64_t W,
                 int64_t rows, int32_t embed_dim, int32_t heads, int32_t num_classes, float dropout_p, uint64_t seed,
                 float* d_gl_feats, float* d_lo_feats, void* saved, size_t saved_bytes, void* workspace,
@@ -267,6 +270,8 @@ int amp_seg_bwd(const void* const* params, void* const* grads, const float* lo_f
     if (!params || !grads || !lo_feats || !centroids || !np_cluster || !group_rows || !d_logits || !d_gl_feats || !d_lo_feats ||
         !saved || !workspace)
         return fail(AMP_E_BADARG, "seg_bwd: null pointer");
+    if (lo_ld < 64 || (lo_ld & 3) || (reinterpret_cast<uintptr_t>(lo_feats) & 15))
+        return fail(AMP_E_BADARG, "seg_bwd: lo_ld >= 64 and a multiple of 4, lo_feats 16-byte aligned");
     const SegShape sh{B, W, rows, embed_dim, heads, num_classes, embed_dim / 2};
     AMP_TRY(seg_check(sh, np_cluster, "seg_bwd"));
     if (W > 64) return fail(AMP_E_BADARG, "seg_bwd: more than 64 blocks per window");
@@ -334,7 +339,7 @@ int amp_seg_bwd(const void* const* params, void* const* grads, const float* lo_f
     {
         WgParams g{};
         g.dY = ws.dz2; g.lddy = hid; g.Nout = hid; g.y_a = ws.k1 + kSegBn2; g.y_b = ws.k3 + kSegBn2; g.y_c = ws.k2 + kSegBn2; g.y_m = S.mean + kSegBn2; g.Y2 = S.y2;
-        g.A = lo_feats; g.lda = 64; g.K = 64;
+        g.A = lo_feats; g.lda = lo_ld; g.K = 64;
         g.n_clouds = Bi; g.rows_per_cloud = Ri; g.dW = gf(grads, S_C2W); g.ldw = 64 + E;
         g.group_rows = group_rows; g.n_groups = Wi; g.dbg = ws.dcb; g.slab_rows = gslab;
         g.partials = ws.wg; g.partial_floats = ws.wg_floats;

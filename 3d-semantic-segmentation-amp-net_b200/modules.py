@@ -100,6 +100,18 @@ def _input(t, name, device):
     return t.contiguous()
 
 
+def _row_strided(t, name, device, align=1):
+    """[A, B, C] float32 input read in place when its rows are dense and evenly spaced (a slice of a wider tensor, as the
+    scripts pass: train_pointnet-attention.py:427-433); anything else is copied. Returns (tensor, floats between rows)."""
+    if (isinstance(t, torch.Tensor) and t.is_cuda and t.device == device and t.dtype == torch.float32 and t.dim() == 3
+            and t.stride(2) == 1 and t.stride(1) >= t.shape[2] and t.stride(1) % align == 0
+            and (t.shape[0] == 1 or t.stride(0) == t.shape[1] * t.stride(1))
+            and t.data_ptr() % (4 * align) == 0):
+        return t, t.stride(1)
+    t = _input(t, name, device)
+    return t, (t.shape[-1] if t.dim() == 3 else 0)
+
+
 class TransformationNet(nn.Module):
     """Parameter container with the reference's layout (pointnetAtt.py:10-26). It runs inside BasePointNet's
     fused forward; the reference scripts never call it on its own."""
@@ -221,7 +233,7 @@ class _SegFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, gl, lo, cent, training, meta, *tensors):
         lib = _lib.lib()
-        npc, group_rows, mask, E, heads, C, p, seed, precision = meta
+        npc, group_rows, mask, E, heads, C, p, seed, precision, gl_ld, lo_ld = meta
         W, B, _ = gl.shape
         R = lo.shape[1]
         dev = lo.device
@@ -231,7 +243,7 @@ class _SegFn(torch.autograd.Function):
         ws_bytes = lib.amp_seg_workspace_bytes(B, W, R, E, 0)
         ws = _bytes(ws_bytes, dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.amp_seg_fwd(_ptr_array(tensors), gl.data_ptr(), lo.data_ptr(), cent.data_ptr(), npc,
+            _lib.check(lib.amp_seg_fwd(_ptr_array(tensors), gl.data_ptr(), gl_ld, lo.data_ptr(), lo_ld, cent.data_ptr(), npc,
                                        group_rows.data_ptr(), mask.data_ptr() if mask is not None else None, B, W, R, E,
                                        heads, C, 1 if training else 0, precision, p, seed, logits.data_ptr(), saved.data_ptr(),
                                        saved_bytes, ws.data_ptr(), ws_bytes, _lib.stream_ptr()))
@@ -248,7 +260,7 @@ class _SegFn(torch.autograd.Function):
     def backward(ctx, d_logits):
         lib = _lib.lib()
         gl, lo, cent = ctx.saved_tensors
-        npc, group_rows, mask, E, heads, C, p, seed, _ = ctx.meta
+        npc, group_rows, mask, E, heads, C, p, seed, _, _, lo_ld = ctx.meta
         tensors = ctx.tensors
         W, B, _ = gl.shape
         R = lo.shape[1]
@@ -257,13 +269,13 @@ class _SegFn(torch.autograd.Function):
         grads = [torch.empty_like(t) if (t.is_floating_point() and t.requires_grad) else None for t in tensors]
         targets = [g if g is not None else (torch.empty_like(t) if isinstance(t, nn.Parameter) else None)
                    for g, t in zip(grads, tensors)]
-        d_gl = torch.empty_like(gl)
-        d_lo = torch.empty_like(lo)
+        d_gl = torch.empty(gl.shape, dtype=torch.float32, device=dev)       # dense, whatever the strides of the inputs
+        d_lo = torch.empty(lo.shape, dtype=torch.float32, device=dev)
         ws_bytes = lib.amp_seg_workspace_bytes(B, W, R, E, 1)
         ws = _bytes(ws_bytes, dev)
         saved = ctx.saved
         with torch.cuda.device(dev):
-            _lib.check(lib.amp_seg_bwd(_ptr_array(tensors), _ptr_array(targets), lo.data_ptr(), cent.data_ptr(), npc,
+            _lib.check(lib.amp_seg_bwd(_ptr_array(tensors), _ptr_array(targets), lo.data_ptr(), lo_ld, cent.data_ptr(), npc,
                                        group_rows.data_ptr(), d_logits.data_ptr(), B, W, R, E, heads, C, p, seed,
                                        d_gl.data_ptr(), d_lo.data_ptr(), saved.data_ptr(), saved.numel(), ws.data_ptr(),
                                        ws_bytes, _lib.stream_ptr()))
@@ -319,8 +331,8 @@ class SegmentationWithAttention(_NativeModule):
                                "(the configuration of train_pointnet-attention.py:118)")
         tensors = self._native_tensors()
         dev = tensors[0].device
-        gl = _input(gl_feats, "gl_feats", dev)
-        lo = _input(lo_feats, "lo_feats", dev)
+        gl, gl_ld = _row_strided(gl_feats, "gl_feats", dev)
+        lo, lo_ld = _row_strided(lo_feats, "lo_feats", dev, align=4)
         cent = centroids.to(device=dev, dtype=torch.float32).contiguous()
         W, B, E = gl.shape
         npc, group_rows, total = self._groups(np_cluster, dev)
@@ -337,6 +349,6 @@ class SegmentationWithAttention(_NativeModule):
                 raise ValueError("attn_mask must be [B, W]")
         p = self.dropout_p if self.training else 0.0
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0.0 else 0
-        meta = (npc, group_rows, mask, E, self.num_heads, self.num_classes, p, seed, self._precision())
+        meta = (npc, group_rows, mask, E, self.num_heads, self.num_classes, p, seed, self._precision(), gl_ld, lo_ld)
         logits = _SegFn.apply(gl, lo, cent, self.training, meta, *tensors)
         return logits, 0

@@ -135,6 +135,9 @@ int amp_encoder_bwd(const void* const* params, void* const* grads, const float* 
  *   params      host array of amp_seg_param_count() DEVICE pointers in state_dict order of
  *               SegmentationWithAttention(256, heads, num_classes, local_dim=64)
  *   gl_feats    [W, B, E] f32 (sequence first, as the script passes it)      lo_feats [B, rows, 64] f32
+ *   gl_ld, lo_ld  floats between consecutive rows of gl_feats (row w * B + b, >= E) and lo_feats (row b * rows + r, >= 64,
+ *               a multiple of 4, 16-byte aligned rows): the scripts pass slices of the encoder output
+ *               (train_pointnet-attention.py:427-433 `out[:, :, -64:]`, `out[:, 0, :-64]`), which are read in place
  *   centroids   [B, W, 2] f32      np_cluster HOST int32 [W] points per block, sum = rows
  *   group_rows  DEVICE int32 [W]: first row of each block (exclusive prefix sum of np_cluster)
  *   key_padding_mask  DEVICE uint8 [B, W] (1 = ignore key) or NULL
@@ -150,12 +153,13 @@ int amp_seg_param_count(void);
 const char* amp_seg_param_name(int i);
 size_t amp_seg_saved_bytes(int64_t B, int64_t W, int64_t rows, int32_t embed_dim, int32_t heads);
 size_t amp_seg_workspace_bytes(int64_t B, int64_t W, int64_t rows, int32_t embed_dim, int32_t training);
-int amp_seg_fwd(const void* const* params, const float* gl_feats, const float* lo_feats, const float* centroids,
+int amp_seg_fwd(const void* const* params, const float* gl_feats, int64_t gl_ld, const float* lo_feats, int64_t lo_ld,
+                const float* centroids,
                 const int32_t* np_cluster, const int32_t* group_rows, const uint8_t* key_padding_mask, int64_t B,
                 int64_t W, int64_t rows, int32_t embed_dim, int32_t heads, int32_t num_classes, int32_t training,
                 int32_t precision, float dropout_p, uint64_t seed, float* logits, void* saved, size_t saved_bytes,
                 void* workspace, size_t workspace_bytes, void* stream);
-int amp_seg_bwd(const void* const* params, void* const* grads, const float* lo_feats, const float* centroids,
+int amp_seg_bwd(const void* const* params, void* const* grads, const float* lo_feats, int64_t lo_ld, const float* centroids,
                 const int32_t* np_cluster, const int32_t* group_rows, const float* d_logits, int64_t B, int64_t W,
                 int64_t rows, int32_t embed_dim, int32_t heads, int32_t num_classes, float dropout_p, uint64_t seed,
                 float* d_gl_feats, float* d_lo_feats, void* saved, size_t saved_bytes, void* workspace,

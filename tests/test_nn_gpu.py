@@ -398,3 +398,32 @@ def test_training_shape_of_the_script_nine_windows_padded(amp, cuda):
     opt_e.step(); opt_s.step()
     assert not torch.equal(before, seg.conv_4.weight.detach())
     assert int(enc.bn_1.num_batches_tracked) == 7 + W        # one BatchNorm update per encoder call (quirk 7 of SURVEY 3.5)
+
+
+def test_seg_reads_encoder_output_slices_in_place(amp, cuda):
+    """One block per window: out[:, :, -64:] / out[:, 0, :-64] (train_pointnet-attention.py:427-433) go to the head as strided
+    views (gl_ld / lo_ld of amp_seg_fwd) and must give exactly what dense copies give, forward and backward."""
+    B, N, seed = 4, 512, 71
+    enc, seg, _, _ = _build(amp, seed, cuda)
+    xs, cent = nn_params.synthetic_blocks(B, N, 1, seed)
+    cent = cent.to(cuda)
+    results = []
+    for dense in (False, True):
+        enc.train(); seg.train()
+        enc.zero_grad(); seg.zero_grad()
+        out, _ = enc(xs[0].to(cuda))
+        lo = out[:, :, -64:]
+        gl = torch.transpose(out[:, 0, :-64].view(-1, 1, 256), 0, 1)
+        if dense:
+            lo, gl = lo.contiguous(), gl.contiguous()
+        else:
+            assert not lo.is_contiguous()
+        logits, _ = seg(gl, lo, cent, [N], None)
+        logits.square().mean().backward()
+        results.append((logits.detach().clone(), [p.grad.clone() for p in list(enc.parameters()) + list(seg.parameters())]))
+        # running statistics advance once per pass: restore them so that both passes see the same state
+        enc.load_state_dict(nn_params.synthetic_state_dict(nn_params.encoder_shapes(), seed))
+        seg.load_state_dict(nn_params.synthetic_state_dict(nn_params.seg_shapes(), seed + 1))
+    assert torch.equal(results[0][0], results[1][0])
+    for a, b in zip(results[0][1], results[1][1]):
+        assert _rel(a, b) < 1e-6
