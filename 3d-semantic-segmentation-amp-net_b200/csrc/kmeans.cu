@@ -75,6 +75,88 @@ kmeans_assign_kernel(const float* __restrict__ feats, const float* __restrict__ 
     }
 }
 
+// Small k (the block split uses k = ceil(points / 2048), 9 on configs[3]): centroids live in registers, the loop over the
+// centroids is fully unrolled, and half of the arithmetic goes through the packed fp32 pair instructions of sm_100
+// (FFMA2: two points per instruction, each half rounded exactly like the scalar operation). Packed instructions only
+// issue to one of the two fp32 pipes, scalar ones to either, so the work is split: the subtractions and the third
+// product stay scalar, the first two products and the two additions are packed. ptxas contracts mul.f32x2 + add.f32x2
+// into one FFMA2 even with .rn, which would change the result, so products and sums are written as fused multiply-adds
+// that restate the unfused operations exactly, rn(a * b) = fma(a, b, -0) and rn(a + b) = fma(a, 1, b), with the
+// constants -0 and 1 arriving as kernel arguments (opaque to the compiler).
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+template <int K>
+__global__ void __launch_bounds__(kAssignThreads)
+kmeans_assign_small_k_kernel(const float* __restrict__ feats, const float* __restrict__ cent, long long n, int* __restrict__ labels,
+                             float* __restrict__ min_d2, float neg_zero, float plus_one) {
+    float cx[K], cy[K], cz[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) { cx[j] = __ldg(cent + 3 * j); cy[j] = __ldg(cent + 3 * j + 1); cz[j] = __ldg(cent + 3 * j + 2); }
+    const f32x2_t neg0 = pack2(neg_zero, neg_zero), one = pack2(plus_one, plus_one);
+    const long long nquad = n >> 2;
+    const float4* f4 = reinterpret_cast<const float4*>(feats);
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nquad; q += (long long)gridDim.x * blockDim.x) {
+        const float4 a = __ldg(f4 + 3 * q), b = __ldg(f4 + 3 * q + 1), c = __ldg(f4 + 3 * q + 2);
+        const float px[4] = {a.x, a.w, b.z, c.y};
+        const float py[4] = {a.y, b.x, b.w, c.z};
+        const float pz[4] = {a.z, b.y, c.x, c.w};
+        float best[4];
+        int bj[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) { best[p] = INFINITY; bj[p] = 0; }
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {             // points (0, 1) and (2, 3)
+                const int p0 = 2 * h, p1 = 2 * h + 1;
+                const float d0a = __fsub_rn(px[p0], cx[j]), d0b = __fsub_rn(px[p1], cx[j]);
+                const float d1a = __fsub_rn(py[p0], cy[j]), d1b = __fsub_rn(py[p1], cy[j]);
+                const float d2a = __fsub_rn(pz[p0], cz[j]), d2b = __fsub_rn(pz[p1], cz[j]);
+                const f32x2_t d0 = pack2(d0a, d0b), d1 = pack2(d1a, d1b);
+                const f32x2_t m2 = pack2(__fmul_rn(d2a, d2a), __fmul_rn(d2b, d2b));
+                const f32x2_t s = fma2(fma2(fma2(d0, d0, neg0), one, fma2(d1, d1, neg0)), one, m2);
+                float da, db;
+                unpack2(s, da, db);
+                if (da < best[p0]) { best[p0] = da; bj[p0] = j; }
+                if (db < best[p1]) { best[p1] = db; bj[p1] = j; }
+            }
+        }
+        reinterpret_cast<int4*>(labels)[q] = make_int4(bj[0], bj[1], bj[2], bj[3]);
+        if (min_d2) reinterpret_cast<float4*>(min_d2)[q] = make_float4(best[0], best[1], best[2], best[3]);
+    }
+    if (blockIdx.x == 0) {                            // tail (n % 4 points)
+        for (long long i = (nquad << 2) + threadIdx.x; i < n; i += blockDim.x) {
+            const float x0 = feats[3 * i], x1 = feats[3 * i + 1], x2 = feats[3 * i + 2];
+            float best = INFINITY;
+            int bj = 0;
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const float d = sqd3(x0, x1, x2, cx[j], cy[j], cz[j]);
+                if (d < best) { best = d; bj = j; }
+            }
+            labels[i] = bj;
+            if (min_d2) min_d2[i] = best;
+        }
+    }
+}
+
+template <int K>
+void launch_assign_small_k(const float* feats, const float* cent, long long n, int* labels, float* min_d2, unsigned blocks,
+                           cudaStream_t st) {
+    kmeans_assign_small_k_kernel<K><<<blocks, kAssignThreads, 0, st>>>(feats, cent, n, labels, min_d2, -0.0f, 1.0f);
+}
+
 __global__ void gather_feats_kernel(const float* __restrict__ pc, long long n, long long row_stride,
                                     int c0, int c1, int c2, float* __restrict__ feats) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
@@ -484,8 +566,15 @@ int amp_kmeans_assign_f32(const float* feats, const float* centroids, int64_t n,
     long long cap = (long long)amp::kNumSMs * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    amp::kmeans_assign_kernel<<<(unsigned)blocks, amp::kAssignThreads, 0, (cudaStream_t)stream>>>(
-        feats, centroids, n, k, labels, min_d2);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (k) {
+#define AMP_ASSIGN_K(K) case K: amp::launch_assign_small_k<K>(feats, centroids, n, labels, min_d2, (unsigned)blocks, st); break;
+        AMP_ASSIGN_K(1) AMP_ASSIGN_K(2) AMP_ASSIGN_K(3) AMP_ASSIGN_K(4) AMP_ASSIGN_K(5) AMP_ASSIGN_K(6) AMP_ASSIGN_K(7) AMP_ASSIGN_K(8)
+        AMP_ASSIGN_K(9) AMP_ASSIGN_K(10) AMP_ASSIGN_K(11) AMP_ASSIGN_K(12) AMP_ASSIGN_K(13) AMP_ASSIGN_K(14) AMP_ASSIGN_K(15) AMP_ASSIGN_K(16)
+#undef AMP_ASSIGN_K
+        default:
+            amp::kmeans_assign_kernel<<<(unsigned)blocks, amp::kAssignThreads, 0, st>>>(feats, centroids, n, k, labels, min_d2);
+    }
     amp::count_launch();
     return amp::check_launch("kmeans_assign");
 }
