@@ -12,6 +12,14 @@ char* last_error_buf() {
     return buf;
 }
 
+static thread_local bool t_pdl_scope = false;
+bool pdl_enabled() {
+    static const bool allowed = !path_disabled("pdl");
+    return allowed && t_pdl_scope;
+}
+PdlScope::PdlScope(bool on) : prev(t_pdl_scope) { t_pdl_scope = on; }
+PdlScope::~PdlScope() { t_pdl_scope = prev; }
+
 bool path_disabled(const char* name) {
     static const char* env = getenv("AMP_DISABLE");
     return env && strstr(env, name) != nullptr;

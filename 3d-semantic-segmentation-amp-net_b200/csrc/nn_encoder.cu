@@ -448,6 +448,7 @@ int amp_encoder_fwd(const void* const* params, const float* x, int64_t B, int64_
     if (workspace_bytes < fwd_ws_bytes(B, N, training != 0)) return fail(AMP_E_WORKSPACE, "encoder_fwd: workspace too small");
     if (training && (!saved || saved_bytes < amp_encoder_saved_bytes(B, N, 1)))
         return fail(AMP_E_WORKSPACE, "encoder_fwd: saved-for-backward buffer too small");
+    PdlScope pdl(training == 0);
     EncCtx c{};
     c.P = params; c.st = (cudaStream_t)stream; c.B = (int)B; c.N = (int)N; c.train = training != 0;
     Arena wa(workspace, workspace_bytes);

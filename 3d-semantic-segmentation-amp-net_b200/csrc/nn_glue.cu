@@ -8,6 +8,7 @@ namespace amp {
 namespace {
 
 __global__ void bn_fold_eval_kernel(const BnTable table, float eps) {
+    pdl_sync();
     const BnDesc d = table.d[blockIdx.x];
     for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
         const float s = d.gamma[c] / sqrtf(d.var[c] + eps);
@@ -21,6 +22,7 @@ __global__ void bn_finalize_train_kernel(const float* __restrict__ part_sum, con
                                          const float* __restrict__ gamma, float* running_mean, float* running_var,
                                          long long* nbt, float momentum, float eps, float* __restrict__ scale,
                                          float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+    pdl_sync();
     // one warp per channel, fixed lane-strided order, double accumulation; the per-tile (sum, M2) pairs are
     // combined exactly (Chan et al.): M2 = sum_t [ M2_t + n_t (mean_t - mean)^2 ]
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -82,6 +84,7 @@ __global__ void pool_decode_kernel(const unsigned long long* __restrict__ pmax, 
                                    int mode, const float* __restrict__ scale, const float* __restrict__ shift,
                                    const float* __restrict__ mean, int total, int C, float* __restrict__ pooled,
                                    int* __restrict__ arg) {
+    pdl_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int c = i % C;
@@ -104,6 +107,7 @@ __global__ void pool_decode_kernel(const unsigned long long* __restrict__ pmax, 
 }
 
 __global__ void add_identity_kernel(float* t, int total, int d) {
+    pdl_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int e = i % (d * d);
@@ -112,6 +116,7 @@ __global__ void add_identity_kernel(float* t, int total, int d) {
 
 __global__ void fold_input_transform_kernel(const float* __restrict__ W1, const float* __restrict__ T, int n_clouds,
                                             float* __restrict__ W1eff) {
+    pdl_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;        // over clouds * 64 * 9
     if (i >= n_clouds * 64 * 9) return;
     const int b = i / (64 * 9), c = (i / 9) % 64, k = i % 9;
@@ -125,6 +130,7 @@ __global__ void fold_input_transform_kernel(const float* __restrict__ W1, const 
 
 __global__ void broadcast_rows_kernel(const float* __restrict__ g, int rows_per_cloud, int C4, float4* __restrict__ out,
                                       long long ldo4, long long total) {
+    pdl_sync();
     // total = clouds * rows * C4 float4 elements
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C4);
@@ -138,6 +144,7 @@ __global__ void posenc_add_kernel(const float* __restrict__ gl, long long gl_ld,
                                   const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
                                   int n_clouds, int n_tokens, int E, float* __restrict__ tokens,
                                   float* __restrict__ h_pre) {
+    pdl_sync();
     // one block per token (b, w)
     const int b = blockIdx.x / n_tokens, w = blockIdx.x % n_tokens;
     __shared__ float h[16];
@@ -160,6 +167,7 @@ __global__ void posenc_add_kernel(const float* __restrict__ gl, long long gl_ld,
 __global__ void attention_core_kernel(const float* __restrict__ qkv, const unsigned char* __restrict__ key_mask,
                                       float drop_p, unsigned long long drop_seed, int n_clouds, int L, int E,
                                       int heads, float* __restrict__ out, float* __restrict__ probs) {
+    pdl_sync();
     const int hd = E / heads;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int total = n_clouds * heads * L;
@@ -213,6 +221,7 @@ __global__ void bn_backward_finalize_kernel(const float* __restrict__ part_sum, 
                                             const float* __restrict__ mean, const float* __restrict__ invstd,
                                             float* dgamma, float* dbeta, int accumulate, float* __restrict__ c1,
                                             float* __restrict__ c2, float* __restrict__ c3) {
+    pdl_sync();
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (c >= C) return;
@@ -257,6 +266,7 @@ __global__ void pool_scatter_bwd_kernel(const float* __restrict__ dpool, const i
                                         const float* __restrict__ mean, const float* __restrict__ invstd, int n_clouds,
                                         int rows, int C, float* __restrict__ dz, float* __restrict__ part_sum,
                                         float* __restrict__ part_sq) {
+    pdl_sync();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float sc = scale[c], sh = shift[c], mu = mean[c], is = invstd[c];
@@ -276,6 +286,7 @@ __global__ void pool_scatter_bwd_kernel(const float* __restrict__ dpool, const i
 __global__ void fold_input_transform_bwd_kernel(const float* __restrict__ dW1eff, const float* __restrict__ W1,
                                                 const float* __restrict__ T, int n_clouds, float* __restrict__ dW1,
                                                 float* __restrict__ dT) {
+    pdl_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 64 * 12) {
         const int c = i / 12, j = i % 12;
@@ -298,6 +309,7 @@ __global__ void fold_input_transform_bwd_kernel(const float* __restrict__ dW1eff
 // stage 1: slab (128 rows) column sums; stage 2: sum of the slabs
 __global__ void colsum_stage1_kernel(const float* __restrict__ dout, long long ldo, int rows, int C, int slabs,
                                      float* __restrict__ scratch) {
+    pdl_sync();
     const int b = blockIdx.y, sl = blockIdx.x;
     const int r_lo = sl * 128, r_hi = min(rows, r_lo + 128);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -307,6 +319,7 @@ __global__ void colsum_stage1_kernel(const float* __restrict__ dout, long long l
     }
 }
 __global__ void colsum_stage2_kernel(const float* __restrict__ scratch, int slabs, int C, int total, float* __restrict__ dg) {
+    pdl_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int b = i / C, c = i % C;
@@ -319,6 +332,7 @@ __global__ void colsum_stage2_kernel(const float* __restrict__ scratch, int slab
 __global__ void posenc_bwd_token_kernel(const float* __restrict__ dtok, const float* __restrict__ h_pre,
                                         const float* __restrict__ w2, int n_clouds, int n_tokens, int E,
                                         float* __restrict__ dgl, float* __restrict__ dpre) {
+    pdl_sync();
     const int b = blockIdx.x / n_tokens, w = blockIdx.x % n_tokens;
     const long long t = (long long)b * n_tokens + w;
     for (int e = threadIdx.x; e < E; e += blockDim.x) dgl[((long long)w * n_clouds + b) * E + e] = dtok[t * E + e];
@@ -336,6 +350,7 @@ __global__ void posenc_bwd_param_kernel(const float* __restrict__ dtok, const fl
                                         const float* __restrict__ h_pre, const float* __restrict__ dpre, int T, int E,
                                         float* __restrict__ dfc1_w, float* __restrict__ dfc1_b,
                                         float* __restrict__ dfc2_w, float* __restrict__ dfc2_b) {
+    pdl_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n2w = E * 16;
     if (i < n2w) {
@@ -368,6 +383,7 @@ __global__ void posenc_bwd_param_kernel(const float* __restrict__ dtok, const fl
 __global__ void attention_core_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ qkv,
                                           const float* __restrict__ probs, float drop_p, unsigned long long drop_seed,
                                           int L, int E, int heads, float* __restrict__ dqkv) {
+    pdl_sync();
     extern __shared__ float sm[];
     float* dS = sm;            // [L][L]
     float* Pd = sm + L * L;    // [L][L]
@@ -414,7 +430,7 @@ int bn_fold_eval(const BnDesc* table, int n_layers, float eps, cudaStream_t st) 
     if (n_layers > BnTable::kMax) return fail(AMP_E_BADARG, "bn_fold_eval: more than %d layers", BnTable::kMax);
     BnTable t;
     for (int i = 0; i < n_layers; ++i) t.d[i] = table[i];
-    bn_fold_eval_kernel<<<n_layers, 256, 0, st>>>(t, eps);
+    launch_pdl(bn_fold_eval_kernel, dim3((unsigned)(n_layers)), dim3(256), 0, st, t, eps);
     count_launch();
     return check_launch("bn_fold_eval");
 }
@@ -423,7 +439,7 @@ int bn_finalize_train(const float* part_sum, const float* part_m2, int n_clouds,
                       const float* gamma, float* running_mean, float* running_var, long long* nbt, float momentum,
                       float eps, float* scale, float* save_mean, float* save_invstd, cudaStream_t st) {
     const int tpc = (rows_per_cloud + 127) / 128;
-    bn_finalize_train_kernel<<<(C + 7) / 8, 256, 0, st>>>(part_sum, part_m2, n_clouds * tpc, tpc, rows_per_cloud,
+    launch_pdl(bn_finalize_train_kernel, dim3((unsigned)((C + 7) / 8)), dim3(256), 0, st, part_sum, part_m2, n_clouds * tpc, tpc, rows_per_cloud,
                                                          (long long)n_clouds * rows_per_cloud, C, gamma, running_mean,
                                                          running_var, nbt, momentum, eps, scale, save_mean, save_invstd);
     count_launch();
@@ -433,7 +449,7 @@ int bn_finalize_train(const float* part_sum, const float* part_m2, int n_clouds,
 int bn_backward_finalize(const float* part_sum, const float* part_sq, int tiles, long long count, int C,
                          const float* gamma, const float* mean, const float* invstd, float* dgamma, float* dbeta,
                          int accumulate, float* c1, float* c2, float* c3, cudaStream_t st) {
-    bn_backward_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part_sum, part_sq, tiles, count, C, gamma, mean, invstd,
+    launch_pdl(bn_backward_finalize_kernel, dim3((unsigned)((C + 7) / 8)), dim3(256), 0, st, part_sum, part_sq, tiles, count, C, gamma, mean, invstd,
                                                             dgamma, dbeta, accumulate, c1, c2, c3);
     count_launch();
     return check_launch("bn_backward_finalize");
@@ -442,7 +458,7 @@ int bn_backward_finalize(const float* part_sum, const float* part_sq, int tiles,
 int pool_decode(const unsigned long long* pmax, const unsigned long long* pmin, int mode, const float* scale,
                 const float* shift, const float* mean, int n_clouds, int C, float* pooled, int* arg, cudaStream_t st) {
     const int total = n_clouds * C;
-    pool_decode_kernel<<<(total + 255) / 256, 256, 0, st>>>(pmax, pmin, mode, scale, shift, mean, total, C, pooled, arg);
+    launch_pdl(pool_decode_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, pmax, pmin, mode, scale, shift, mean, total, C, pooled, arg);
     count_launch();
     return check_launch("pool_decode");
 }
@@ -450,7 +466,7 @@ int pool_decode(const unsigned long long* pmax, const unsigned long long* pmin, 
 int pool_scatter_bwd(const float* dpool, const int* arg, const float* y, const float* scale, const float* shift,
                      const float* mean, const float* invstd, int n_clouds, int rows_per_cloud, int C, float* dz,
                      float* part_sum, float* part_sq, cudaStream_t st) {
-    pool_scatter_bwd_kernel<<<(C + 63) / 64, 64, 0, st>>>(dpool, arg, y, scale, shift, mean, invstd, n_clouds,
+    launch_pdl(pool_scatter_bwd_kernel, dim3((unsigned)((C + 63) / 64)), dim3(64), 0, st, dpool, arg, y, scale, shift, mean, invstd, n_clouds,
                                                          rows_per_cloud, C, dz, part_sum, part_sq);
     count_launch();
     return check_launch("pool_scatter_bwd");
@@ -458,14 +474,14 @@ int pool_scatter_bwd(const float* dpool, const int* arg, const float* y, const f
 
 int add_identity(float* t, int n_mats, int d, cudaStream_t st) {
     const int total = n_mats * d * d;
-    add_identity_kernel<<<(total + 255) / 256, 256, 0, st>>>(t, total, d);
+    launch_pdl(add_identity_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, t, total, d);
     count_launch();
     return check_launch("add_identity");
 }
 
 int fold_input_transform(const float* W1, const float* T, int n_clouds, float* W1eff, cudaStream_t st) {
     const int total = n_clouds * 64 * 9;
-    fold_input_transform_kernel<<<(total + 255) / 256, 256, 0, st>>>(W1, T, n_clouds, W1eff);
+    launch_pdl(fold_input_transform_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, W1, T, n_clouds, W1eff);
     count_launch();
     return check_launch("fold_input_transform");
 }
@@ -473,7 +489,7 @@ int fold_input_transform(const float* W1, const float* T, int n_clouds, float* W
 int fold_input_transform_bwd(const float* dW1eff, const float* W1, const float* T, int n_clouds, float* dW1,
                              float* dT, cudaStream_t st) {
     const int total = 64 * 12 + n_clouds * 9;
-    fold_input_transform_bwd_kernel<<<(total + 127) / 128, 128, 0, st>>>(dW1eff, W1, T, n_clouds, dW1, dT);
+    launch_pdl(fold_input_transform_bwd_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, st, dW1eff, W1, T, n_clouds, dW1, dT);
     count_launch();
     return check_launch("fold_input_transform_bwd");
 }
@@ -484,7 +500,7 @@ int broadcast_rows(const float* g, int n_clouds, int rows_per_cloud, int C, floa
     const long long total = (long long)n_clouds * rows_per_cloud * (C / 4);
     long long blocks = (total + 255) / 256;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    broadcast_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(g, rows_per_cloud, C / 4, reinterpret_cast<float4*>(out), ldo / 4, total);
+    launch_pdl(broadcast_rows_kernel, dim3((unsigned)((unsigned)blocks)), dim3(256), 0, st, g, rows_per_cloud, C / 4, reinterpret_cast<float4*>(out), ldo / 4, total);
     count_launch();
     return check_launch("broadcast_rows");
 }
@@ -497,19 +513,19 @@ int colsum_rows(const float* dout, long long ldo, int n_clouds, int rows_per_clo
                 cudaStream_t st) {
     const int slabs = (rows_per_cloud + 127) / 128;
     if (n_clouds > 65535) return fail(AMP_E_BADARG, "colsum_rows: more than 65535 clouds");
-    colsum_stage1_kernel<<<dim3(slabs, n_clouds), 256, 0, st>>>(dout, ldo, rows_per_cloud, C, slabs, scratch);
+    launch_pdl(colsum_stage1_kernel, dim3(slabs, n_clouds), dim3(256), 0, st, dout, ldo, rows_per_cloud, C, slabs, scratch);
     count_launch();
     int rc = check_launch("colsum_stage1");
     if (rc) return rc;
     const int total = n_clouds * C;
-    colsum_stage2_kernel<<<(total + 255) / 256, 256, 0, st>>>(scratch, slabs, C, total, dg);
+    launch_pdl(colsum_stage2_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, scratch, slabs, C, total, dg);
     count_launch();
     return check_launch("colsum_stage2");
 }
 
 int posenc_add(const float* gl, long long gl_ld, const float* centroids, const float* fc1_w, const float* fc1_b, const float* fc2_w,
                const float* fc2_b, int n_clouds, int n_tokens, int E, float* tokens, float* h_pre, cudaStream_t st) {
-    posenc_add_kernel<<<n_clouds * n_tokens, 128, 0, st>>>(gl, gl_ld, centroids, fc1_w, fc1_b, fc2_w, fc2_b, n_clouds, n_tokens, E,
+    launch_pdl(posenc_add_kernel, dim3((unsigned)(n_clouds * n_tokens)), dim3(128), 0, st, gl, gl_ld, centroids, fc1_w, fc1_b, fc2_w, fc2_b, n_clouds, n_tokens, E,
                                                            tokens, h_pre);
     count_launch();
     return check_launch("posenc_add");
@@ -518,12 +534,12 @@ int posenc_add(const float* gl, long long gl_ld, const float* centroids, const f
 int posenc_bwd(const float* dtokens, const float* centroids, const float* h_pre, const float* fc2_w, int n_clouds,
                int n_tokens, int E, float* dgl, float* dpre_scratch, float* dfc1_w, float* dfc1_b, float* dfc2_w,
                float* dfc2_b, cudaStream_t st) {
-    posenc_bwd_token_kernel<<<n_clouds * n_tokens, 128, 0, st>>>(dtokens, h_pre, fc2_w, n_clouds, n_tokens, E, dgl, dpre_scratch);
+    launch_pdl(posenc_bwd_token_kernel, dim3((unsigned)(n_clouds * n_tokens)), dim3(128), 0, st, dtokens, h_pre, fc2_w, n_clouds, n_tokens, E, dgl, dpre_scratch);
     count_launch();
     int rc = check_launch("posenc_bwd_token");
     if (rc) return rc;
     const int total = E * 16 + E + 48;
-    posenc_bwd_param_kernel<<<(total + 127) / 128, 128, 0, st>>>(dtokens, centroids, h_pre, dpre_scratch, n_clouds * n_tokens, E,
+    launch_pdl(posenc_bwd_param_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, st, dtokens, centroids, h_pre, dpre_scratch, n_clouds * n_tokens, E,
                                                                dfc1_w, dfc1_b, dfc2_w, dfc2_b);
     count_launch();
     return check_launch("posenc_bwd_param");
@@ -535,7 +551,7 @@ int attention_core(const float* qkv, const unsigned char* key_mask, float drop_p
     if (n_tokens > 1024) return fail(AMP_E_BADARG, "attention_core: more than 1024 tokens per cloud");
     const int warps = n_clouds * heads * n_tokens;
     const int wpb = 4;
-    attention_core_kernel<<<(warps + wpb - 1) / wpb, wpb * 32, wpb * n_tokens * sizeof(float), st>>>(
+    launch_pdl(attention_core_kernel, dim3((unsigned)((warps + wpb - 1) / wpb)), dim3(wpb * 32), wpb * n_tokens * sizeof(float), st, 
         qkv, key_mask, drop_p, drop_seed, n_clouds, n_tokens, E, heads, out, probs);
     count_launch();
     return check_launch("attention_core");
@@ -545,7 +561,7 @@ int attention_core_bwd(const float* dout, const float* qkv, const float* probs, 
                        unsigned long long drop_seed, int n_clouds, int n_tokens, int E, int heads, float* dqkv,
                        cudaStream_t st) {
     if (n_tokens > 64) return fail(AMP_E_BADARG, "attention_core_bwd: more than 64 tokens per cloud");
-    attention_core_bwd_kernel<<<n_clouds * heads, 128, 2 * n_tokens * n_tokens * sizeof(float), st>>>(
+    launch_pdl(attention_core_bwd_kernel, dim3((unsigned)(n_clouds * heads)), dim3(128), 2 * n_tokens * n_tokens * sizeof(float), st, 
         dout, qkv, probs, drop_p, drop_seed, n_tokens, E, heads, dqkv);
     count_launch();
     return check_launch("attention_core_bwd");

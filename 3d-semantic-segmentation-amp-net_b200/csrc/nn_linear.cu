@@ -21,6 +21,7 @@ constexpr int BM = 128, BK = 16, NT = 256, PAD = 4;
 template <int BN>
 __global__ void __launch_bounds__(NT, 2)
 pw_linear_kernel(const PwParams p) {
+    pdl_sync();
     constexpr int TN = BN / 16;                 // output channels per thread: 8 or 4
     constexpr int WREG = BN * BK / NT;          // W elements staged per thread per chunk
     constexpr int XREG = BM * BK / NT;          // = 8
@@ -371,8 +372,8 @@ int pw_linear(const PwParams& p, cudaStream_t st) {
     const bool wide = p.Nout > 64;
     const int bn = wide ? 128 : 64;
     dim3 grid((p.rows_per_cloud + BM - 1) / BM, (p.Nout + bn - 1) / bn, p.n_clouds);
-    if (wide) pw_linear_kernel<128><<<grid, NT, 0, st>>>(q);
-    else pw_linear_kernel<64><<<grid, NT, 0, st>>>(q);
+    if (wide) launch_pdl(pw_linear_kernel<128>, grid, dim3(NT), 0, st, q);
+    else launch_pdl(pw_linear_kernel<64>, grid, dim3(NT), 0, st, q);
     count_launch();
     return check_launch("pw_linear");
 }

@@ -146,6 +146,7 @@ int amp_seg_fwd(const void* const* params, const float* gl_feats, int64_t gl_ld,
     if (workspace_bytes < amp_seg_workspace_bytes(B, W, rows, embed_dim, 0)) return fail(AMP_E_WORKSPACE, "seg_fwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     const bool train = training != 0;
+    PdlScope pdl(!train);
     const float dp = train ? dropout_p : 0.f;
     const int E = embed_dim, hid = sh.hid, Bi = (int)B, Wi = (int)W, Ri = (int)rows, T = Bi * Wi;
     Arena sa(saved, saved_bytes);

@@ -57,6 +57,7 @@ struct SmallEpi {
 };
 
 __global__ void __launch_bounds__(256) small_fwd_kernel(const PwParams p) {
+    pdl_sync();
     extern __shared__ float xs[];                 // [SM_ROWS][kc] chunk of the (prologue-applied) input rows
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int M = p.rows_per_cloud, K = p.K, N = p.Nout;
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(256) small_fwd_kernel(const PwParams p) {
 // dW[n, k] = sum_r dy'[r, n] * a'[r, k], db[n] = sum_r dy'[r, n]: thread == k, 8 output channels n per CTA
 constexpr int SW_N = 8;
 __global__ void __launch_bounds__(256) small_wgrad_kernel(const WgParams p) {
+    pdl_sync();
     __shared__ float ys[SM_ROWS][SW_N];
     const int tid = threadIdx.x;
     const int M = p.rows_per_cloud, K = p.K, N = p.Nout;
@@ -207,6 +209,7 @@ __global__ void __launch_bounds__(256) small_wgrad_kernel(const WgParams p) {
 // the slab's input rows sit in shared memory, the row phases are added in a fixed order.
 constexpr int NW_MAXK = 16, NW_SLAB_MAX = 512;
 __global__ void __launch_bounds__(256) narrow_wgrad_kernel(const WgParams p, int slabs, int SLAB) {
+    pdl_sync();
     __shared__ float as[NW_SLAB_MAX * NW_MAXK];                  // input rows of the slab; reused for the phase partials
     float* red = as;
     const int tid = threadIdx.x;
@@ -271,6 +274,7 @@ __global__ void __launch_bounds__(256) narrow_wgrad_kernel(const WgParams p, int
 // memory bound on the activation. thread == (input channel k, row phase); the per-row gradients are 5 broadcast loads.
 constexpr int NO_MAXN = 8;
 __global__ void __launch_bounds__(256) narrow_out_wgrad_kernel(const WgParams p, int slabs, int SLAB) {
+    pdl_sync();
     __shared__ float dys[NW_SLAB_MAX * NO_MAXN];                 // the slab's gradients [row][class], staged once (coalesced)
     __shared__ float red[256 * (NO_MAXN + 1)];
     const int tid = threadIdx.x;
@@ -423,6 +427,7 @@ __device__ __forceinline__ void tnet_fc_layer(float* xs, const float* __restrict
 }
 
 __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(256) tnet_fc_eval_kernel(const TnetFcArgs a) {
+    pdl_sync();
     extern __shared__ float xs[];                          // [32][256]
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -453,7 +458,7 @@ int tnet_fc_eval(const float* pooled, int B, const float* fc1, const float* s4, 
         return fail(AMP_E_BADARG, "tnet_fc_eval: null pointer");
     TnetFcArgs a{pooled, fc1, s4, t4, fc2, s5, t5, fc3w, fc3b, h1, h2, out, B, d, fc3_inside};
     const size_t smem = sizeof(float) * SM_ROWS * 256;
-    tnet_fc_eval_kernel<<<8 * ((B + SM_ROWS - 1) / SM_ROWS), 256, smem, st>>>(a);
+    launch_pdl(tnet_fc_eval_kernel, dim3((unsigned)(8 * ((B + SM_ROWS - 1) / SM_ROWS))), dim3(256), smem, st, a);
     count_launch();
     return check_launch("tnet_fc_eval");
 }
@@ -462,7 +467,7 @@ int narrow_out_wgrad_try(const WgParams& p, int slabs, int SLAB, cudaStream_t st
     if (path_disabled("narrow_out_wgrad")) return 0;
     if (p.Nout > NO_MAXN || p.y_a || p.Y2 || p.dbg || SLAB > NW_SLAB_MAX) return 0;
     if (p.K != 64 && p.K != 128 && p.K != 256) return 0;
-    narrow_out_wgrad_kernel<<<p.n_clouds * slabs, 256, 0, st>>>(p, slabs, SLAB);
+    launch_pdl(narrow_out_wgrad_kernel, dim3((unsigned)(p.n_clouds * slabs)), dim3(256), 0, st, p, slabs, SLAB);
     count_launch();
     const int rc = check_launch("narrow_out_wgrad");
     return rc == AMP_OK ? 1 : rc;
@@ -473,7 +478,7 @@ int narrow_wgrad_try(const WgParams& p, int slabs, int SLAB, cudaStream_t st) {
     if (path_disabled("narrow_wgrad")) return 0;
     if (p.K > NW_MAXK || SLAB > NW_SLAB_MAX || p.dy_transposed || p.a_drop_p != 0.f) return 0;
     if (p.Nout != 64 && p.Nout != 128 && p.Nout != 256) return 0;
-    narrow_wgrad_kernel<<<p.n_clouds * slabs, 256, 0, st>>>(p, slabs, SLAB);
+    launch_pdl(narrow_wgrad_kernel, dim3((unsigned)(p.n_clouds * slabs)), dim3(256), 0, st, p, slabs, SLAB);
     count_launch();
     const int rc = check_launch("narrow_wgrad");
     return rc == AMP_OK ? 1 : rc;
@@ -496,7 +501,7 @@ int small_linear_try(const PwParams& p, cudaStream_t st) {
             cudaFuncSetAttribute(small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * SM_ROWS * SM_MAXK));
             attr_set = true;
         }
-        small_fwd_kernel<<<grid, 256, smem, st>>>(p);
+        launch_pdl(small_fwd_kernel, grid, dim3(256), smem, st, p);
     }
     count_launch();
     const int rc = check_launch("small_linear");
@@ -506,7 +511,7 @@ int small_linear_try(const PwParams& p, cudaStream_t st) {
 int small_wgrad_try(const WgParams& p, cudaStream_t st) {
     if (path_disabled("small_wgrad")) return 0;
     if (p.n_clouds != 1 || p.rows_per_cloud > 1024 || p.dy_transposed || p.per_cloud || p.dbg || p.K > 256 || p.a_drop_p != 0.f) return 0;
-    small_wgrad_kernel<<<(p.Nout + SW_N - 1) / SW_N, 256, 0, st>>>(p);
+    launch_pdl(small_wgrad_kernel, dim3((unsigned)((p.Nout + SW_N - 1) / SW_N)), dim3(256), 0, st, p);
     count_launch();
     const int rc = check_launch("small_wgrad");
     return rc == AMP_OK ? 1 : rc;

@@ -63,6 +63,7 @@ enum { TL_STATS = 1, TL_POOL2 = 2, TL_AFFINE = 4, TL_POOL1 = 8, TL_MASK = 16, TL
 
 template <int MODE>
 __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_constant__ PwParams p, const int Mpad, long long* prof_buf) {
+    pdl_trigger();
     extern __shared__ __align__(1024) unsigned char smem[];
     // two slots of 256 threads (two warpgroups each): `wg` = slot, `sub` = which warpgroup of the slot, `wtid` = thread in slot
     const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31, wg = warp >> 3, sub = (warp >> 2) & 1, wtid = tid & (TL_SLOT - 1);
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(s_tmem), 512);
+    pdl_wait();                                                 // first global-memory access below
     for (int k = tid; k < K; k += TL_THREADS) {
         s_a[k] = p.in_a ? __ldg(p.in_a + k) : 1.f;
         s_b[k] = p.in_b ? __ldg(p.in_b + k) : 0.f;
@@ -475,7 +477,7 @@ int tc_layer_try(const PwParams& p, cudaStream_t st) {
             if (e != cudaSuccess) return fail(AMP_E_CUDA, "tc_layer: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); \
             attr_set = true; \
         } \
-        tc_layer_kernel<M><<<(int)grid, TL_THREADS, smem_bytes, st>>>(q, Mpad, want_prof ? dprof : nullptr); \
+        launch_pdl(tc_layer_kernel<M>, dim3((unsigned)((int)grid)), dim3(TL_THREADS), smem_bytes, st, q, Mpad, want_prof ? dprof : nullptr); \
         break; }
         TL_CASE(0) TL_CASE(TL_ACC) TL_CASE(TL_STATS) TL_CASE(TL_STATS | TL_POOL2) TL_CASE(TL_AFFINE) TL_CASE(TL_AFFINE | TL_POOL1)
         TL_CASE(TL_MASK) TL_CASE(TL_MASK | TL_ACC) TL_CASE(TL_MASK | TL_DROP)

@@ -51,6 +51,7 @@ __device__ __forceinline__ uint32_t umma_idesc_mn(int M, int N) { return umma_id
 __global__ void __launch_bounds__(TW_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ WgParams p, const int Mpad, const int Kp, const int Kext, const int slabs, const int SLAB,
                 const int a_vec, const int out_vec) {
+    pdl_trigger();
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31, wg = warp >> 2, wtid = tid & 127;
     const int K = p.K, Nout = p.Nout, rows = p.rows_per_cloud;
@@ -73,6 +74,7 @@ tc_wgrad_kernel(const __grid_constant__ WgParams p, const int Mpad, const int Kp
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(s_tmem), 512);
+    pdl_wait();                                                 // first global-memory access below
     for (int n = tid; n < Nout; n += TW_THREADS) {
         s_ya[n] = p.y_a ? __ldg(p.y_a + n) : 1.f; s_yb[n] = p.y_b ? __ldg(p.y_b + n) : 0.f;
         s_yc[n] = p.y_c ? __ldg(p.y_c + n) : 0.f; s_ym[n] = p.y_m ? __ldg(p.y_m + n) : 0.f;
@@ -323,7 +325,7 @@ int tc_wgrad_try(const WgParams& p, int slabs, int SLAB, cudaStream_t st) {
     long long grid = (long long)p.n_clouds * slabs;
     if (grid > kNumSMs) grid = kNumSMs;
     const int smem_bytes = sp.total < TW_MIN_SMEM ? TW_MIN_SMEM : sp.total;
-    tc_wgrad_kernel<<<(int)grid, TW_THREADS, smem_bytes, st>>>(p, Mpad, Kp, Kext, slabs, SLAB, a_vec, out_vec);
+    launch_pdl(tc_wgrad_kernel, dim3((unsigned)((int)grid)), dim3(TW_THREADS), smem_bytes, st, p, Mpad, Kp, Kext, slabs, SLAB, a_vec, out_vec);
     count_launch();
     const int rc = check_launch("tc_wgrad_kernel");
     return rc == AMP_OK ? 1 : rc;

@@ -16,6 +16,7 @@ constexpr int kDefaultSlab = 512, TNo = 128, TKo = 64, RB = 16, NT = 256, PAD = 
 
 __global__ void __launch_bounds__(NT)
 wgrad_partial_kernel(const WgParams p, int n_tiles, int k_tiles, int slabs, int SLAB) {
+    pdl_sync();
     __shared__ __align__(16) float Ys[2][RB][TNo + PAD];
     __shared__ __align__(16) float As[2][RB][TKo + PAD];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -133,6 +134,7 @@ __device__ __forceinline__ float chunk_sum(const float* __restrict__ src, long l
 }
 
 __global__ void wgrad_reduce_kernel(const WgParams p, int slabs, int SLAB) {
+    pdl_sync();
     const long long per = (long long)p.Nout * p.K + p.Nout;
     const int out_clouds = p.per_cloud ? p.n_clouds : 1;
     const long long n_w = (long long)out_clouds * p.Nout * p.K;
@@ -193,7 +195,7 @@ int wgrad(const WgParams& p, cudaStream_t st) {
     if (rc < 0) return rc;
     if (rc == 0) {
         dim3 grid(slabs, n_tiles * k_tiles, p.n_clouds);
-        wgrad_partial_kernel<<<grid, NT, 0, st>>>(p, n_tiles, k_tiles, slabs, SLAB);
+        launch_pdl(wgrad_partial_kernel, grid, dim3(NT), 0, st, p, n_tiles, k_tiles, slabs, SLAB);
         count_launch();
         rc = check_launch("wgrad_partial");
         if (rc) return rc;
@@ -202,7 +204,7 @@ int wgrad(const WgParams& p, cudaStream_t st) {
                             (p.dbg ? (long long)p.n_clouds * p.n_groups * p.Nout : 0);
     long long blocks = (total + 255) / 256;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, slabs, SLAB);
+    launch_pdl(wgrad_reduce_kernel, dim3((unsigned)((unsigned)blocks)), dim3(256), 0, st, p, slabs, SLAB);
     count_launch();
     return check_launch("wgrad_reduce");
 }

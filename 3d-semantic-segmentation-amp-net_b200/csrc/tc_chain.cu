@@ -96,6 +96,7 @@ __device__ __noinline__ void epilogue_slow(const TcChainParams& p, const TcOp& o
 }
 
 __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_constant__ TcChainParams p) {
+    pdl_trigger();
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
     const int slot = warp >> 3, sub = (warp >> 2) & 1, stid = tid & (kSlotThreads - 1);
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = uniform_u32(*s_tmem);
+    pdl_wait();                                                  // first global-memory access below (the packed weights)
     if (tid == 0 && p.wblob_bytes > 0) {
         mbar_expect_tx(wbar, (uint32_t)p.wblob_bytes);
         for (int off = 0; off < p.wblob_bytes; off += 32768) {
@@ -356,6 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
 }
 
 __global__ void tc_pack_kernel(const TcPackTable t, unsigned char* __restrict__ dst) {
+    pdl_sync();
     const TcPackJob& j = t.job[blockIdx.y];
     const int cloud = blockIdx.z;
     if (cloud > 0 && j.src_cloud_stride == 0) return;
@@ -442,7 +445,7 @@ int tc_chain_launch(const TcChainParams& p, cudaStream_t st) {
         cudaMemsetAsync(dprof, 0, 256 * sizeof(long long), st);
         TcChainParams q = p;
         q.prof = dprof;
-        tc_chain_kernel<<<grid, kThreads, smem_bytes, st>>>(q);
+        launch_pdl(tc_chain_kernel, dim3((unsigned)(grid)), dim3(kThreads), smem_bytes, st, q);
         long long h[256];
         cudaMemcpyAsync(h, dprof, sizeof h, cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
@@ -452,7 +455,7 @@ int tc_chain_launch(const TcChainParams& p, cudaStream_t st) {
         count_launch();
         return check_launch("tc_chain_kernel");
     }
-    tc_chain_kernel<<<grid, kThreads, smem_bytes, st>>>(p);
+    launch_pdl(tc_chain_kernel, dim3((unsigned)(grid)), dim3(kThreads), smem_bytes, st, p);
     count_launch();
     return check_launch("tc_chain_kernel");
 }
@@ -468,7 +471,7 @@ int tc_pack_weights(const TcPackTable& t, unsigned char* dst, cudaStream_t st) {
     }
     int bx = (mx + 255) / 256;
     if (bx > 32) bx = 32;
-    tc_pack_kernel<<<dim3(bx, t.n, t.n_clouds < 1 ? 1 : t.n_clouds), 256, 0, st>>>(t, dst);
+    launch_pdl(tc_pack_kernel, dim3(bx, t.n, t.n_clouds < 1 ? 1 : t.n_clouds), dim3(256), 0, st, t, dst);
     count_launch();
     return check_launch("tc_pack_kernel");
 }

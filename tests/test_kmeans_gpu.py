@@ -8,7 +8,8 @@ from oracle import kmeans_oracle as ko
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("n,k", [(1, 1), (3, 2), (1023, 5), (4096, 9), (100003, 18), (1 << 20, 33)])
+@pytest.mark.parametrize("n,k", [(1, 1), (3, 2), (1023, 5), (4096, 9), (262147, 12), ((1 << 20) + 3, 16), (100003, 17),
+                                  (100003, 18), (1 << 20, 33)])
 def test_assign_bit_exact(amp, cuda, n, k):
     rng = np.random.default_rng(n)
     x = rng.random((n, 3), dtype=np.float32); x[:, :2] = x[:, :2] * 2 - 1
@@ -18,6 +19,20 @@ def test_assign_bit_exact(amp, cuda, n, k):
     lab, md = amp.kmeans_assign(torch.from_numpy(x).to(cuda), torch.from_numpy(c).to(cuda), return_min_d2=True)
     elab, emd = ko.assign(x, c)
     assert (lab.cpu().numpy() == elab).all() and (md.cpu().numpy() == emd).all()
+
+
+@pytest.mark.parametrize("k", [4, 9, 16, 27])
+def test_assign_ties_and_rounding_cases(amp, cuda, k):
+    """Lattice points and lattice centroids: many exact ties (the first minimum must win) and sums whose unfused and fused
+    roundings differ (coordinates scaled by an odd constant), on both the register-resident (k <= 16) and the generic kernel."""
+    rng = np.random.default_rng(k)
+    x = (rng.integers(-8, 9, size=(50001, 3)).astype(np.float32) * np.float32(0.3))
+    c = (rng.integers(-8, 9, size=(k, 3)).astype(np.float32) * np.float32(0.3))
+    c[k - 1] = c[0]
+    lab, md = amp.kmeans_assign(torch.from_numpy(x).to(cuda), torch.from_numpy(c).to(cuda), return_min_d2=True)
+    elab, emd = ko.assign(x, c)
+    assert (lab.cpu().numpy() == elab).all() and (md.cpu().numpy() == emd).all()
+    assert (elab != k - 1).all()            # the duplicate of centroid 0 never wins a tie
 
 
 def test_gather_feats(amp, cuda):
