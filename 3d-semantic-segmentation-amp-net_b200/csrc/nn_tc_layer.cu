@@ -25,18 +25,23 @@ namespace amp {
 namespace {
 using namespace tcx;
 
-constexpr int TL_THREADS = 512, TL_SLOT = 256, TL_ROWS = 128, TL_KC = 64;
+constexpr int TL_THREADS = 512, TL_SLOT = 256, TL_ROWS = 128;
 constexpr int TL_MAX_WELEMS = 32768;                 // Mpad * K
-constexpr int TL_BHALF = TL_ROWS * TL_KC * 2;        // bytes of the hi (or lo) half of one B chunk
 constexpr int TL_MAX_SMEM = 232448, TL_MIN_SMEM = 120 * 1024;
 
-struct TlPlan { int w_lo, b0, tab, exch, bar, total; };
-__host__ __device__ inline TlPlan tl_plan(int Mpad, int K) {
+// Shared memory: weights (hi, lo) | per slot: B operand chunk (hi, lo) | per slot: raw fp32 chunk(s) filled by cp.async |
+// prologue tables | exchange | barriers. `kcw` = input channels per chunk (64, 32 or 16: the widest that fits), `x2` = the
+// prologue reads a second tensor (BatchNorm backward), which gets its own raw buffer.
+struct TlPlan { int w_lo, b0, bhalf, raw0, rawsz, tab, exch, bar, total; };
+__host__ __device__ inline TlPlan tl_plan(int Mpad, int K, int kcw, int x2) {
     TlPlan s;
     const int wbytes = Mpad * K * 2;
     s.w_lo = wbytes;
     s.b0 = 2 * wbytes;
-    s.tab = s.b0 + 4 * TL_BHALF;
+    s.bhalf = TL_ROWS * kcw * 2;                // bytes of the hi (or lo) half of one B chunk
+    s.raw0 = s.b0 + 4 * s.bhalf;
+    s.rawsz = TL_ROWS * (kcw * 4 + 16);         // one raw fp32 chunk; rows padded by 16 B (conflict-free column reads)
+    s.tab = s.raw0 + 2 * (1 + x2) * s.rawsz;
     s.exch = s.tab + 16 * K;                    // [slot][which][half][128] floats: cross-warpgroup sums of the epilogue
     s.bar = s.exch + 2 * 3 * 2 * 128 * 4;
     s.total = s.bar + 64;
@@ -62,19 +67,21 @@ __device__ __noinline__ float dropout_keep_ool(unsigned long long seed, unsigned
 enum { TL_STATS = 1, TL_POOL2 = 2, TL_AFFINE = 4, TL_POOL1 = 8, TL_MASK = 16, TL_DROP = 32, TL_ACC = 64 };
 
 template <int MODE>
-__global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_constant__ PwParams p, const int Mpad, long long* prof_buf) {
+__global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_constant__ PwParams p, const int Mpad, const int kcw, long long* prof_buf) {
     pdl_trigger();
     extern __shared__ __align__(1024) unsigned char smem[];
     // two slots of 256 threads (two warpgroups each): `wg` = slot, `sub` = which warpgroup of the slot, `wtid` = thread in slot
     const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31, wg = warp >> 3, sub = (warp >> 2) & 1, wtid = tid & (TL_SLOT - 1);
     const int K = p.K, Nout = p.Nout, rows = p.rows_per_cloud;
-    const TlPlan sp = tl_plan(Mpad, K);
+    const bool has_x2 = p.X2 != nullptr;
+    const TlPlan sp = tl_plan(Mpad, K, kcw, has_x2 ? 1 : 0);
     float* s_exch = reinterpret_cast<float*>(smem + sp.exch) + wg * (3 * 2 * 128);
     auto slot_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(wg + 1) : "memory"); };
     __nv_bfloat16* s_whi = reinterpret_cast<__nv_bfloat16*>(smem);
     __nv_bfloat16* s_wlo = reinterpret_cast<__nv_bfloat16*>(smem + sp.w_lo);
-    unsigned char* s_bhi = smem + sp.b0 + wg * 2 * TL_BHALF;
-    unsigned char* s_blo = s_bhi + TL_BHALF;
+    unsigned char* s_bhi = smem + sp.b0 + wg * 2 * sp.bhalf;
+    unsigned char* s_blo = s_bhi + sp.bhalf;
+    unsigned char* s_raw = smem + sp.raw0 + wg * (has_x2 ? 2 : 1) * sp.rawsz;      // this slot's raw chunk (then the X2 chunk)
     float* s_a = reinterpret_cast<float*>(smem + sp.tab);       // prologue constants per input channel
     float* s_b = s_a + K; float* s_c = s_b + K; float* s_m = s_c + K;
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + sp.bar);
@@ -140,25 +147,41 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
         fence_proxy_async();
     };
 
-    // pull this thread's row of a later tile into L2 while the current tile is being worked on (no registers held)
-    auto prefetch_tile = [&](int cloud, int t) {
-        const long long r = (long long)cloud * rows + t * TL_ROWS + lrow;
-        if (sub == 0 && t * TL_ROWS + lrow < rows) {
-            const char* x = reinterpret_cast<const char*>(p.X + r * p.ldx);
+    // Input staging is asynchronous: the slot copies a raw fp32 chunk into shared memory with cp.async (coalesced: the lanes of
+    // a half warp read the contiguous bytes of one row), converts it into the bf16 hi / lo operand, and issues the copy of the
+    // NEXT chunk (same tile, or the first chunk of this slot's next tile) right away, so that it is in flight during the MMAs
+    // and the epilogue of the current one. (One TMA bulk copy per row instead of cp.async measured slower: the per-lane
+    // addresses serialise the issue.)
+    //   copy:    thread = (channel quad q, rows rsub + rstep * i)
+    //   convert: warp = one 8-channel K group (and a block of rows), lanes = consecutive rows: 16-byte operand stores of a
+    //            warp are contiguous, raw reads are conflict free thanks to the 16-byte row padding
+    const int qn = kcw >> 2, q = wtid & (qn - 1), rsub = wtid / qn, rstep = TL_SLOT / qn, n_rit = TL_ROWS / rstep;
+    const int raw_ld = kcw * 4 + 16;                                  // bytes per raw row
+    const int ng = kcw >> 3, cg = (wtid >> 5) & (ng - 1), crow0 = ((wtid >> 5) / ng) * (16 * ng) + lane, n_cit = ng >> 1;
+    const uint32_t raw_addr = smem_u32(s_raw);
+    auto issue_chunk = [&](int cloud, int t, int kc) {
+        const int row0 = t * TL_ROWS, valid = min(TL_ROWS, rows - row0);
+        const int k = kc * kcw + q * 4;
+        if (k < K) {
+            const long long row_base = (long long)cloud * rows + row0;
+            const float* __restrict__ xb = p.X + row_base * p.ldx + k;
+            const float* __restrict__ x2b = has_x2 ? p.X2 + row_base * p.ldx + k : nullptr;
 #pragma unroll 1
-            for (int b = 0; b < K * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + b));
-            if (p.X2) {
-                const char* x2 = reinterpret_cast<const char*>(p.X2 + r * p.ldx);
-#pragma unroll 1
-                for (int b = 0; b < K * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(x2 + b));
+            for (int i = 0; i < n_rit; ++i) {
+                const int r = rsub + rstep * i;
+                const bool ok = r < valid;
+                const uint32_t dst = raw_addr + (uint32_t)(r * raw_ld + q * 16);
+                cp_async16(dst, ok ? xb + (long long)r * p.ldx : p.X, ok ? 16u : 0u);
+                if (has_x2) cp_async16(dst + (uint32_t)sp.rawsz, ok ? x2b + (long long)r * p.ldx : p.X2, ok ? 16u : 0u);
             }
         }
+        cp_async_commit();
     };
 
     int pi = 0;
     const bool prof = prof_buf != nullptr && blockIdx.x == 0 && tid == 0;
 #define TL_PROF() do { if (prof && pi < 250) prof_buf[pi++] = clock64(); } while (0)
-    auto process = [&](int cloud, int t) {
+    auto process = [&](int cloud, int t, bool have_next, int cn, int tn) {
         TL_PROF();                                             // tile start
         const int row0 = t * TL_ROWS;
         const int valid = min(TL_ROWS, rows - row0);
@@ -178,64 +201,53 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
                 for (int b = 0; b < Nout * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + b));
             }
         }
-        for (int kc = 0; kc * TL_KC < K; ++kc) {
-            const int kcur = min(TL_KC, K - kc * TL_KC);
+        for (int kc = 0; kc * kcw < K; ++kc) {
+            const int kcur = min(kcw, K - kc * kcw);
             {
-                // Coalesced staging of a (up to) 64-channel chunk: 16 consecutive lanes read the 256 contiguous bytes of one row
-                // (a warp instruction touches 2 rows instead of 32), a thread keeps the same 4 input channels for all of its
-                // 16 rows, so the prologue constants sit in registers; each float4 becomes one 8-byte half of a 16-byte K group.
-                // (chunks narrower than 64 channels leave the upper channel quads idle)
-                const int q = wtid & 15, rsub = wtid >> 4;               // channel quad, row within a group of 16 rows
-                const bool q_ok = q * 4 < kcur;
-                const int k = kc * TL_KC + (q_ok ? q * 4 : 0);
-                const float4 ca = *reinterpret_cast<const float4*>(s_a + k), cb = *reinterpret_cast<const float4*>(s_b + k);
-                const float4 cm = *reinterpret_cast<const float4*>(s_m + k), cc = *reinterpret_cast<const float4*>(s_c + k);
-                const float* __restrict__ xb = p.X + row_base * p.ldx + k;
-                const float* __restrict__ x2b = p.X2 ? p.X2 + row_base * p.ldx + k : nullptr;
-                unsigned char* dhi = s_bhi + ((q >> 1) * TL_ROWS) * 16 + (q & 1) * 8;
-                unsigned char* dlo = s_blo + ((q >> 1) * TL_ROWS) * 16 + (q & 1) * 8;
+                // convert the raw chunk: prologue (BatchNorm / BatchNorm backward, ReLU, dropout), split into bf16 hi + lo;
+                // a thread turns 8 consecutive channels of a row into one 16-byte K-group row of each operand half
+                cp_async_wait_all();
+                slot_sync();                                             // every thread's part of the raw chunk has landed
+                const bool g_ok = cg * 8 < kcur;
+                const int k = kc * kcw + (g_ok ? cg * 8 : 0);
+                if (g_ok) {
+                    float ca[8], cb[8], cm[8], cc[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { ca[j] = s_a[k + j]; cb[j] = s_b[k + j]; cm[j] = s_m[k + j]; cc[j] = s_c[k + j]; }
+                    uint4* dhi = reinterpret_cast<uint4*>(s_bhi) + cg * TL_ROWS;
+                    uint4* dlo = reinterpret_cast<uint4*>(s_blo) + cg * TL_ROWS;
 #pragma unroll 1
-                for (int half = 0; half < 2; ++half) {                   // 4 rows per thread per pass (rolled: small code, warm i-cache)
-                    float4 xv[4], yv[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = rsub + 16 * (half * 4 + i);
-                        xv[i] = (r < valid && q_ok) ? __ldg(reinterpret_cast<const float4*>(xb + (long long)r * p.ldx)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    if (x2b) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int r = rsub + 16 * (half * 4 + i);
-                            yv[i] = (r < valid && q_ok) ? __ldg(reinterpret_cast<const float4*>(x2b + (long long)r * p.ldx)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = rsub + 16 * (half * 4 + i);
-                        float v0 = xv[i].x, v1 = xv[i].y, v2 = xv[i].z, v3 = xv[i].w;
+                    for (int i = 0; i < n_cit; ++i) {
+                        const int r = crow0 + 32 * i;
+                        const float4* rx = reinterpret_cast<const float4*>(s_raw + r * raw_ld + cg * 32);
+                        const float4 x0 = rx[0], x1 = rx[1];
+                        float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
                         if (has_pro) {
-                            if (x2b) {
-                                v0 = fmaf(yv[i].x - cm.x, cc.x, fmaf(v0, ca.x, cb.x)); v1 = fmaf(yv[i].y - cm.y, cc.y, fmaf(v1, ca.y, cb.y));
-                                v2 = fmaf(yv[i].z - cm.z, cc.z, fmaf(v2, ca.z, cb.z)); v3 = fmaf(yv[i].w - cm.w, cc.w, fmaf(v3, ca.w, cb.w));
+                            if (has_x2) {
+                                const float4* ry = reinterpret_cast<const float4*>(s_raw + sp.rawsz + r * raw_ld + cg * 32);
+                                const float4 y0 = ry[0], y1 = ry[1];
+                                const float y[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] = fmaf(y[j] - cm[j], cc[j], fmaf(v[j], ca[j], cb[j]));
                             } else {
-                                v0 = fmaf(v0 - cm.x, ca.x, cb.x); v1 = fmaf(v1 - cm.y, ca.y, cb.y);
-                                v2 = fmaf(v2 - cm.z, ca.z, cb.z); v3 = fmaf(v3 - cm.w, ca.w, cb.w);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j] - cm[j], ca[j], cb[j]);
                             }
                         }
-                        if (p.in_relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+                        if (p.in_relu) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+                        }
                         if (p.in_drop_p > 0.f) {
                             const unsigned long long di = (unsigned long long)(row_base + r) * K + k;
-                            v0 *= dropout_keep_ool(p.in_drop_seed, di, p.in_drop_p); v1 *= dropout_keep_ool(p.in_drop_seed, di + 1, p.in_drop_p);
-                            v2 *= dropout_keep_ool(p.in_drop_seed, di + 2, p.in_drop_p); v3 *= dropout_keep_ool(p.in_drop_seed, di + 3, p.in_drop_p);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] *= dropout_keep_ool(p.in_drop_seed, di + j, p.in_drop_p);
                         }
-                        if (r >= valid) { v0 = 0.f; v1 = 0.f; v2 = 0.f; v3 = 0.f; }
-                        uint2 h, l;
-                        split_pair(v0, v1, h.x, l.x);
-                        split_pair(v2, v3, h.y, l.y);
-                        if (q_ok) {
-                            *reinterpret_cast<uint2*>(dhi + r * 16) = h;
-                            *reinterpret_cast<uint2*>(dlo + r * 16) = l;
+                        if (r >= valid) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = 0.f;
                         }
+                        split_store8(v, dhi + r, dlo + r);
                     }
                 }
             }
@@ -249,7 +261,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
                 for (int mt = 0; mt < n_mt; ++mt) {
                     const uint32_t d = slot_col + (uint32_t)mt * 128u;
                     for (int ks = 0; ks < (kcur >> 4); ++ks) {
-                        const uint32_t kg = (uint32_t)(kc * (TL_KC >> 4) + ks);
+                        const uint32_t kg = (uint32_t)(kc * (kcw >> 4) + ks);
                         const uint32_t woff = (uint32_t)mt * 2048u + kg * 2u * w_lbo;
                         const uint64_t a_hi = umma_desc(whi_addr + woff, w_lbo, 128u), a_lo = umma_desc(wlo_addr + woff, w_lbo, 128u);
                         const uint64_t b_hi = umma_desc(bhi_addr + (uint32_t)ks * 4096u, 2048u, 128u);
@@ -263,6 +275,9 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
                 }
                 __syncwarp();
             }
+            // the raw chunk is consumed by the whole slot (barrier above): start the copy of the next one
+            if ((kc + 1) * kcw < K) issue_chunk(cloud, t, kc + 1);
+            else if (have_next) issue_chunk(cn, tn, 0);
             TL_PROF();                                         // MMAs issued
             __syncwarp();
             mbar_wait(mbar, phase);
@@ -285,28 +300,10 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
             // first pass through the code is an instruction-cache miss stream; 4x less code beats 4x fewer loop branches.
             // this warpgroup's half of the tile rows: accumulator columns [c_lo, c_hi); sums are combined through shared memory
             const int c_lo = sub * 64, c_hi = min(valid, c_lo + 64);
-            float mean_t = 0.f;
-            if (MODE & TL_STATS) {
-                float s = 0.f;
-                uint32_t vn[8];
-                if (c_lo < c_hi) tmem_ld8(tcol + (uint32_t)c_lo, vn);
-#pragma unroll 1
-                for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
-                    uint32_t v[8];
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = vn[j];
-                    if (c0 + 8 < c_hi) tmem_ld8(tcol + (uint32_t)(c0 + 8), vn);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (c0 + j < c_hi) s += __uint_as_float(v[j]) + bias_u;
-                }
-                s_exch[sub * 128 + lrow] = s;
-                slot_sync();
-                s = s_exch[lrow] + s_exch[128 + lrow];               // fixed order: rows 0..63 then 64..127
-                mean_t = s / (float)valid;
-                if (n_ok && sub == 0) p.part_sum[tile * Nout + n] = s;
-            }
+            // BatchNorm statistics in ONE pass over the accumulator: sums of (x - shift) and (x - shift)^2 with shift = the first
+            // value of this thread's rows (a sample of the same distribution, so nothing cancels), turned into the tile's sum
+            // and centred sum of squares when the two row halves are merged (pairwise update of Chan et al.)
+            float shift = 0.f, s1 = 0.f;
             float osc = 1.f, osh = 0.f, msc = 0.f, msh = 0.f, mmu = 0.f, mis = 0.f;
             if (MODE & TL_AFFINE) { osc = __ldg(p.out_scale + nn); osh = __ldg(p.out_shift + nn); }
             if (MODE & TL_MASK) {
@@ -350,7 +347,12 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
                     const bool ok = r < valid;
                     float x = __uint_as_float(v[j]) + bias_u;
                     if (MODE & TL_ACC) x += yo[j];
-                    if (MODE & TL_STATS) { const float d = ok ? x - mean_t : 0.f; q = fmaf(d, d, q); }
+                    if (MODE & TL_STATS) {
+                        if (j == 0 && c0 == c_lo) shift = x;
+                        const float d = ok ? x - shift : 0.f;
+                        s1 += d;
+                        q = fmaf(d, d, q);
+                    }
                     if (MODE & TL_POOL2) {
                         if (ok && x > vmax) { vmax = x; rmax = r; }
                         if (ok && x < vmin) { vmin = x; rmin = r; }
@@ -370,13 +372,26 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
                 }
             }
             if (MODE & (TL_STATS | TL_MASK)) {                           // combine the two row halves in a fixed order
-                s_exch[256 + sub * 128 + lrow] = (MODE & TL_STATS) ? q : s2;
-                s_exch[512 + sub * 128 + lrow] = q2;
+                s_exch[sub * 128 + lrow] = (MODE & TL_STATS) ? shift : 0.f;
+                s_exch[256 + sub * 128 + lrow] = (MODE & TL_STATS) ? s1 : s2;
+                s_exch[512 + sub * 128 + lrow] = (MODE & TL_STATS) ? q : q2;
                 slot_sync();
                 if (n_ok && sub == 0) {
-                    const float a = s_exch[256 + lrow] + s_exch[256 + 128 + lrow], b = s_exch[512 + lrow] + s_exch[512 + 128 + lrow];
-                    if (MODE & TL_STATS) p.part_sq[tile * Nout + n] = a;
-                    if ((MODE & TL_MASK) && p.part_sum) { p.part_sum[tile * Nout + n] = a; p.part_sq[tile * Nout + n] = b; }
+                    if (MODE & TL_STATS) {
+                        const float na = (float)min(valid, 64), nb = (float)(valid - min(valid, 64));
+                        const float sa = s_exch[256 + lrow], sb = s_exch[256 + 128 + lrow];
+                        const float sum_a = fmaf(s_exch[lrow], na, sa), sum_b = fmaf(s_exch[128 + lrow], nb, sb);
+                        float m2 = s_exch[512 + lrow] - sa * sa / na;
+                        if (nb > 0.f) {
+                            const float delta = sum_b / nb - sum_a / na;
+                            m2 += s_exch[512 + 128 + lrow] - sb * sb / nb + delta * delta * (na * nb / (na + nb));
+                        }
+                        p.part_sum[tile * Nout + n] = sum_a + sum_b;
+                        p.part_sq[tile * Nout + n] = m2;
+                    } else if (p.part_sum) {
+                        p.part_sum[tile * Nout + n] = s_exch[256 + lrow] + s_exch[256 + 128 + lrow];
+                        p.part_sq[tile * Nout + n] = s_exch[512 + lrow] + s_exch[512 + 128 + lrow];
+                    }
                 }
                 slot_sync();                                             // exchange buffer free for the next M tile
             }
@@ -416,17 +431,19 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
         t = tile - cloud * tpc;
         return tile < n_tiles;
     };
+    bool pending = false;                     // the raw chunk 0 of this slot's tile of iteration `it` is already in flight
 #pragma unroll 1
     for (int it = 0; it < n_it; ++it) {
-        int cloud, t, cn, tn;
+        int cloud, t, cn = 0, tn = 0;
         const bool have = work(it, cloud, t);
+        if (have && !pending) issue_chunk(cloud, t, 0);
         if (per_cloud_w ? (it % tps == 0) : (it == 0)) {
             __syncthreads();                  // every MMA that read the previous weights has been waited for
             stage_weights(per_cloud_w ? cloud : 0);
             __syncthreads();
         }
-        if (it + 1 < n_it && work(it + 1, cn, tn)) prefetch_tile(cn, tn);
-        if (have) process(cloud, t);
+        const bool have_next = it + 1 < n_it && work(it + 1, cn, tn);
+        if (have) { process(cloud, t, have_next, cn, tn); pending = have_next; }
     }
     if (prof) prof_buf[255] = pi;
     tc_fence_before();
@@ -446,7 +463,9 @@ int tc_layer_try(const PwParams& p, cudaStream_t st) {
     if (p.X2 && (reinterpret_cast<uintptr_t>(p.X2) & 15)) return 0;
     if (p.group_rows && p.n_groups > 64) return 0;
     if (p.pool_mode && !p.pool_max) return 0;
-    const TlPlan sp = tl_plan(Mpad, p.K);
+    int kcw = 64;                              // widest input chunk whose buffers fit next to the weights
+    while (kcw > 16 && tl_plan(Mpad, p.K, kcw, p.X2 ? 1 : 0).total > TL_MAX_SMEM) kcw >>= 1;
+    const TlPlan sp = tl_plan(Mpad, p.K, kcw, p.X2 ? 1 : 0);
     if (sp.total > TL_MAX_SMEM) return 0;
     if (p.bias && p.group_rows && !p.groups_tile_aligned) return 0;
     int mode = 0;
@@ -477,7 +496,7 @@ int tc_layer_try(const PwParams& p, cudaStream_t st) {
             if (e != cudaSuccess) return fail(AMP_E_CUDA, "tc_layer: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); \
             attr_set = true; \
         } \
-        launch_pdl(tc_layer_kernel<M>, dim3((unsigned)((int)grid)), dim3(TL_THREADS), smem_bytes, st, q, Mpad, want_prof ? dprof : nullptr); \
+        launch_pdl(tc_layer_kernel<M>, dim3((unsigned)((int)grid)), dim3(TL_THREADS), smem_bytes, st, q, Mpad, kcw, want_prof ? dprof : nullptr); \
         break; }
         TL_CASE(0) TL_CASE(TL_ACC) TL_CASE(TL_STATS) TL_CASE(TL_STATS | TL_POOL2) TL_CASE(TL_AFFINE) TL_CASE(TL_AFFINE | TL_POOL1)
         TL_CASE(TL_MASK) TL_CASE(TL_MASK | TL_ACC) TL_CASE(TL_MASK | TL_DROP)
