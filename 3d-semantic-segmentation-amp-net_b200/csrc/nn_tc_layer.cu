@@ -317,6 +317,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
             const float floor_v = ((MODE & TL_AFFINE) && p.out_relu) ? 0.f : -INFINITY;
             const float* __restrict__ My = (MODE & TL_MASK) ? p.mask_y + row_base * p.ld_mask + nn : nullptr;
             float* __restrict__ yp = p.Y ? p.Y + row_base * p.ldy + nn : nullptr;
+            const int ldy32 = (int)p.ldy, ldm32 = (int)p.ld_mask;     // tile-local offsets fit 32 bits: one IMAD per element, not a 64-bit multiply
             // software pipeline: the TMEM load and the global loads (mask rows, accumulate target) of piece c0 + 8 are in
             // flight while piece c0 is processed
             uint32_t vn[8];
@@ -324,12 +325,14 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
             auto issue = [&](int c0) {
                 tmem_ld8(tcol + (uint32_t)c0, vn);
                 if (MODE & TL_MASK) {
+                    const float* mq = My + c0 * ldm32;                  // running pointers: one 64-bit add per element
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) ymn[j] = (n_ok && c0 + j < valid) ? __ldg(My + (long long)(c0 + j) * p.ld_mask) : 0.f;
+                    for (int j = 0; j < 8; ++j, mq += ldm32) ymn[j] = (n_ok && c0 + j < valid) ? __ldg(mq) : 0.f;
                 }
                 if (MODE & TL_ACC) {
+                    const float* yq = yp + c0 * ldy32;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) yon[j] = (n_ok && c0 + j < valid) ? yp[(long long)(c0 + j) * p.ldy] : 0.f;
+                    for (int j = 0; j < 8; ++j, yq += ldy32) yon[j] = (n_ok && c0 + j < valid) ? *yq : 0.f;
                 }
             };
             if (c_lo < c_hi) issue(c_lo);
@@ -341,8 +344,9 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { v[j] = vn[j]; ym[j] = ymn[j]; yo[j] = yon[j]; }
                 if (c0 + 8 < c_hi) issue(c0 + 8);
+                float* ys = yp + c0 * ldy32;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < 8; ++j, ys += ldy32) {
                     const int r = c0 + j;
                     const bool ok = r < valid;
                     float x = __uint_as_float(v[j]) + bias_u;
@@ -368,7 +372,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
                         x = dz;
                     }
                     if ((MODE & TL_POOL1) && ok && x > vmax) { vmax = x; rmax = r; }
-                    if (store && ok) yp[(long long)r * p.ldy] = x;
+                    if (store && ok) *ys = x;
                 }
             }
             if (MODE & (TL_STATS | TL_MASK)) {                           // combine the two row halves in a fixed order
@@ -458,7 +462,8 @@ int tc_layer_try(const PwParams& p, cudaStream_t st) {
     if (path_disabled("tc_layer")) return 0;
     const long long total_rows = (long long)p.n_clouds * p.rows_per_cloud;
     const int Mpad = (p.Nout + 127) / 128 * 128;
-    if (total_rows < 2048 || p.K % 16 || p.K < 16 || p.K > 256 || p.Nout > 256 || (long long)Mpad * p.K > TL_MAX_WELEMS) return 0;
+    // K: whole 64-channel chunks (every wide layer of the network has K = 64, 128 or 256; other widths take the CUDA-core kernel)
+    if (total_rows < 2048 || p.K % 64 || p.K > 256 || p.Nout > 256 || (long long)Mpad * p.K > TL_MAX_WELEMS) return 0;
     if (p.x_transposed || p.y_transposed || p.ldx % 4 || (reinterpret_cast<uintptr_t>(p.X) & 15)) return 0;
     if (p.X2 && (reinterpret_cast<uintptr_t>(p.X2) & 15)) return 0;
     if (p.group_rows && p.n_groups > 64) return 0;
