@@ -260,8 +260,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
             if (!op.pool) {
                 const float* gb = op.bias_grouped ? p.gbias + ((long long)cloud * p.n_groups + group) * op.N : nullptr;
                 const bool plain = !op.store_logits || p.n_classes <= 16;
-                for (int c0 = sub * 32; c0 < op.N; c0 += 64) {
+                // fp32 copy of a layer output (the local features): a thread holds 32 consecutive channels of ONE row, so direct
+                // stores touch 32 rows (lines) per instruction. When the upper half of the activation buffer is free
+                // (K <= 64 and at most 64 output channels kept) the chunk is staged there (16 KB, XOR-swizzled 16-byte pieces)
+                // and leaves as whole 128-byte row segments, 4 rows per warp instruction.
+                const bool stage_f32 = op.store_f32 && op.K <= 64 && (!op.write_act || op.N <= 64);
+                for (int it = 0; it * 64 < op.N; ++it) {
+                    const int c0 = it * 64 + sub * 32;
                     uint32_t v[32];
+                    if (c0 < op.N) {
                     tmem_ld32(slot_col + lane_addr + (uint32_t)c0, v);
                     tmem_wait_ld();
                     const int nc = min(32, op.N - c0);           // 16 or 32
@@ -286,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
                             for (int n = 0; n < 16; ++n)
                                 if (n < p.n_classes) lp[n * rows] = __uint_as_float(v[n]);
                         }
-                        if (op.store_f32 && row_ok) {             // fp32 copy of the layer output (local features), before bf16 rounding
+                        if (op.store_f32 && row_ok && !stage_f32) {   // fp32 copy of the layer output, before bf16 rounding
                             const float fl = op.relu ? 0.f : -INFINITY;
                             float4* o = reinterpret_cast<float4*>(p.out_f32 + grow * p.out_ld + p.out_col0 + c0);
 #pragma unroll
@@ -314,6 +321,34 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
                             if (q * 8 < nc) dst[((c0 >> 3) + q) * 128 + row] = make_uint4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
+                    }
+                    }
+                    if (stage_f32) {
+                        float4* stg = reinterpret_cast<float4*>(s_act + kActBytes / 2);
+                        const float fl = op.relu ? 0.f : -INFINITY;
+#pragma unroll 1
+                        for (int round = 0; round < 2; ++round) {         // the two warpgroups' chunks take turns in the buffer
+                            const int cr = it * 64 + round * 32;
+                            if (sub == round && cr < op.N) {
+#pragma unroll
+                                for (int q = 0; q < 8; ++q)
+                                    stg[row * 8 + (q ^ (row & 7))] =
+                                        make_float4(fmaxf(__uint_as_float(v[4 * q]), fl), fmaxf(__uint_as_float(v[4 * q + 1]), fl),
+                                                    fmaxf(__uint_as_float(v[4 * q + 2]), fl), fmaxf(__uint_as_float(v[4 * q + 3]), fl));
+                            }
+                            slot_bar_sync(slot);
+                            if (cr < op.N) {
+                                const int piece = stid & 7, ncr = min(32, op.N - cr);
+                                float* ob = p.out_f32 + ((long long)cloud * rows + row0) * p.out_ld + p.out_col0 + cr + piece * 4;
+#pragma unroll
+                                for (int ps = 0; ps < 4; ++ps) {
+                                    const int r = ps * 32 + (stid >> 3);
+                                    if (r < valid && piece * 4 < ncr)
+                                        *reinterpret_cast<float4*>(ob + (long long)r * p.out_ld) = stg[r * 8 + (piece ^ (r & 7))];
+                                }
+                            }
+                            slot_bar_sync(slot);
+                        }
                     }
                 }
             } else {
