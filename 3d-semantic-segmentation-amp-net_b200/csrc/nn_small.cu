@@ -271,21 +271,23 @@ __global__ void __launch_bounds__(256) narrow_wgrad_kernel(const WgParams p, int
 }
 
 // Narrow OUTPUT (Nout <= 8: the 5 class logits of the head's last layer, [B, C, N]-transposed gradients) over many rows:
-// memory bound on the activation. thread == (input channel k, row phase); the per-row gradients are 5 broadcast loads.
+// memory bound on the activation. thread == (4 consecutive input channels, row phase): 16-byte activation loads, 8 in flight
+// per thread (32 KB per CTA); the per-row gradients are broadcast reads of the slab's staged [row][class] table.
 constexpr int NO_MAXN = 8;
 __global__ void __launch_bounds__(256) narrow_out_wgrad_kernel(const WgParams p, int slabs, int SLAB) {
     pdl_sync();
     __shared__ float dys[NW_SLAB_MAX * NO_MAXN];                 // the slab's gradients [row][class], staged once (coalesced)
-    __shared__ float red[256 * (NO_MAXN + 1)];
+    __shared__ float4 red[256];
+    __shared__ float bred[64 * NO_MAXN];
     const int tid = threadIdx.x;
     const int K = p.K, N = p.Nout, rows = p.rows_per_cloud;
     const int unit = blockIdx.x, cloud = unit / slabs, slab = unit - cloud * slabs;
     const int r_begin = slab * SLAB, r_end = min(rows, r_begin + SLAB), nr = r_end - r_begin;
     const long long cloud_row = (long long)cloud * rows;
     if (p.dy_transposed) {                                       // [B, C, rows]: consecutive threads = consecutive rows of one class
-        for (int e = tid; e < nr * N; e += 256) {
-            const int n = e / nr, r = e - n * nr;
-            dys[r * NO_MAXN + n] = __ldg(p.dY + ((long long)cloud * N + n) * rows + r_begin + r);
+        for (int n = 0; n < N; ++n) {
+            const float* src = p.dY + ((long long)cloud * N + n) * rows + r_begin;
+            for (int r = tid; r < nr; r += 256) dys[r * NO_MAXN + n] = __ldg(src + r);
         }
     } else {
         for (int e = tid; e < nr * N; e += 256) {
@@ -294,58 +296,79 @@ __global__ void __launch_bounds__(256) narrow_out_wgrad_kernel(const WgParams p,
         }
     }
     __syncthreads();
-    const int phases = 256 / K, k = tid % K, ph = tid / K;       // K in {64, 128, 256}
-    const float aa = p.a_a ? __ldg(p.a_a + k) : 1.f, ab = p.a_b ? __ldg(p.a_b + k) : 0.f, am = p.a_m ? __ldg(p.a_m + k) : 0.f;
-    float acc[NO_MAXN], bsum[NO_MAXN];
+    const int kq = K >> 2, phases = 256 / kq, q = tid % kq, ph = tid / kq, k = q * 4;     // K in {64, 128, 256}: 16 / 8 / 4 row phases
+    float4 aa = make_float4(1.f, 1.f, 1.f, 1.f), ab = make_float4(0.f, 0.f, 0.f, 0.f), am = ab;
+    if (p.a_a) {
+        aa = __ldg(reinterpret_cast<const float4*>(p.a_a + k)); ab = __ldg(reinterpret_cast<const float4*>(p.a_b + k));
+        am = __ldg(reinterpret_cast<const float4*>(p.a_m + k));
+    }
+    float acc[NO_MAXN][4], bsum[NO_MAXN];
 #pragma unroll
-    for (int n = 0; n < NO_MAXN; ++n) { acc[n] = 0.f; bsum[n] = 0.f; }
-    for (int rb = r_begin + ph; rb < r_end; rb += 8 * phases) {  // 8 activation loads in flight per thread
-        float av[8];
+    for (int n = 0; n < NO_MAXN; ++n) { acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f; bsum[n] = 0.f; }
+#pragma unroll 1
+    for (int rb = r_begin + ph; rb < r_end; rb += 8 * phases) {
+        float4 av[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int r = rb + u * phases;
-            av[u] = r < r_end ? __ldg(p.A + (cloud_row + r) * p.lda + k) : 0.f;
+            av[u] = r < r_end ? __ldg(reinterpret_cast<const float4*>(p.A + (cloud_row + r) * p.lda + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int r = rb + u * phases;
             if (r < r_end) {
-                float a = av[u];
-                if (p.a_a) a = fmaf(a - am, aa, ab);
-                if (p.a_relu) a = fmaxf(a, 0.f);
-                if (p.a_drop_p > 0.f) a *= dropout_keep(p.a_drop_seed, (unsigned long long)(cloud_row + r) * K + k, p.a_drop_p);
+                float a[4] = {av[u].x, av[u].y, av[u].z, av[u].w};
+                if (p.a_a) {
+                    a[0] = fmaf(a[0] - am.x, aa.x, ab.x); a[1] = fmaf(a[1] - am.y, aa.y, ab.y);
+                    a[2] = fmaf(a[2] - am.z, aa.z, ab.z); a[3] = fmaf(a[3] - am.w, aa.w, ab.w);
+                }
+                if (p.a_relu) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) a[j] = fmaxf(a[j], 0.f);
+                }
+                if (p.a_drop_p > 0.f) {
+                    const unsigned long long di = (unsigned long long)(cloud_row + r) * K + k;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) a[j] *= dropout_keep(p.a_drop_seed, di + j, p.a_drop_p);
+                }
                 const float* dyr = dys + (r - r_begin) * NO_MAXN;
 #pragma unroll
                 for (int n = 0; n < NO_MAXN; ++n) {
                     if (n < N) {
                         const float dy = dyr[n];
-                        acc[n] = fmaf(dy, a, acc[n]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[n][j] = fmaf(dy, a[j], acc[n][j]);
                         bsum[n] += dy;
                     }
                 }
             }
         }
     }
+    // fixed-order sums over the row phases, one class at a time
     float* part = p.partials + (long long)unit * ((long long)N * K + N);
 #pragma unroll
-    for (int n = 0; n < NO_MAXN; ++n) red[tid * (NO_MAXN + 1) + n] = acc[n];
-    __syncthreads();
-    for (int e = tid; e < N * K; e += 256) {
-        const int n = e / K, kk = e - n * K;
-        float sum = 0.f;
-        for (int q = 0; q < phases; ++q) sum += red[(q * K + kk) * (NO_MAXN + 1) + n];
-        part[e] = sum;
+    for (int n = 0; n < NO_MAXN; ++n) {
+        if (n < N) {
+            __syncthreads();
+            red[tid] = make_float4(acc[n][0], acc[n][1], acc[n][2], acc[n][3]);
+            __syncthreads();
+            if (tid < K) {
+                const float* rf = reinterpret_cast<const float*>(red);
+                float sum = 0.f;
+                for (int qq = 0; qq < phases; ++qq) sum += rf[(qq * kq + (tid >> 2)) * 4 + (tid & 3)];
+                part[(long long)n * K + tid] = sum;
+            }
+        }
     }
-    __syncthreads();
-    // bias partial: the threads of one phase all saw the same rows; add the phases of channel k == 0 in order
-    if (k == 0) {
+    // bias partial: the threads of one phase all saw the same rows; add the phases (channel quad 0) in order
+    if (q == 0) {
 #pragma unroll
-        for (int n = 0; n < NO_MAXN; ++n) red[ph * (NO_MAXN + 1) + n] = bsum[n];
+        for (int n = 0; n < NO_MAXN; ++n) bred[ph * NO_MAXN + n] = bsum[n];
     }
     __syncthreads();
     if (tid < N) {
         float sum = 0.f;
-        for (int q = 0; q < phases; ++q) sum += red[q * (NO_MAXN + 1) + tid];
+        for (int qq = 0; qq < phases; ++qq) sum += bred[qq * NO_MAXN + tid];
         part[(long long)N * K + tid] = sum;
     }
 }
@@ -467,6 +490,8 @@ int narrow_out_wgrad_try(const WgParams& p, int slabs, int SLAB, cudaStream_t st
     if (path_disabled("narrow_out_wgrad")) return 0;
     if (p.Nout > NO_MAXN || p.y_a || p.Y2 || p.dbg || SLAB > NW_SLAB_MAX) return 0;
     if (p.K != 64 && p.K != 128 && p.K != 256) return 0;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (p.lda % 4 || !al16(p.A) || (p.a_a && (!al16(p.a_a) || !al16(p.a_b) || !al16(p.a_m)))) return 0;   // 16-byte loads
     launch_pdl(narrow_out_wgrad_kernel, dim3((unsigned)(p.n_clouds * slabs)), dim3(256), 0, st, p, slabs, SLAB);
     count_launch();
     const int rc = check_launch("narrow_out_wgrad");

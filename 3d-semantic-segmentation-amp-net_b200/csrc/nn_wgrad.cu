@@ -133,36 +133,52 @@ __device__ __forceinline__ float chunk_sum(const float* __restrict__ src, long l
     return s;
 }
 
-__global__ void wgrad_reduce_kernel(const WgParams p, int slabs, int SLAB) {
+// A block reduces 32 consecutive outputs: lanes = outputs (coalesced reads of every partial), the 8 warps take 8 consecutive
+// slices of the chunk list, so a thread's loads are all in flight at once and even a 64 x 64 layer fills the machine; the
+// slices are then added in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgParams p, int slabs, int SLAB) {
     pdl_sync();
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long per = (long long)p.Nout * p.K + p.Nout;
     const int out_clouds = p.per_cloud ? p.n_clouds : 1;
     const long long n_w = (long long)out_clouds * p.Nout * p.K;
     const long long n_b = p.db ? (long long)out_clouds * p.Nout : 0;
     const long long n_g = p.dbg ? (long long)p.n_clouds * p.n_groups * p.Nout : 0;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_w + n_b + n_g;
-         i += (long long)gridDim.x * blockDim.x) {
+    const long long count = (long long)(p.per_cloud ? 1 : p.n_clouds) * slabs;       // chunks per output
+    const long long cs = (count + 7) / 8, ch_lo = min(count, w * cs), ch_hi = min(count, ch_lo + cs);
+    for (long long base = (long long)blockIdx.x * 32; base < n_w + n_b; base += (long long)gridDim.x * 32) {
+        const long long i = base + lane;
+        const float* src = nullptr;
+        float* dst = nullptr;
         if (i < n_w) {
             const int k = (int)(i % p.K), n = (int)((i / p.K) % p.Nout), c = (int)(i / ((long long)p.K * p.Nout));
-            const int c_lo = p.per_cloud ? c : 0, c_hi = p.per_cloud ? c + 1 : p.n_clouds;
-            const float s = chunk_sum(p.partials + (long long)c_lo * slabs * per + (long long)n * p.K + k, per, (long long)(c_hi - c_lo) * slabs);
-            float* dst = p.dW + (long long)c * p.w_cloud_stride + (p.w_kn ? (long long)k * p.ldw + n : (long long)n * p.ldw + k);
-            *dst = p.accumulate ? *dst + s : s;
+            src = p.partials + (long long)(p.per_cloud ? c : 0) * slabs * per + (long long)n * p.K + k;
+            dst = p.dW + (long long)c * p.w_cloud_stride + (p.w_kn ? (long long)k * p.ldw + n : (long long)n * p.ldw + k);
         } else if (i < n_w + n_b) {
             const long long e = i - n_w;
             const int n = (int)(e % p.Nout), c = (int)(e / p.Nout);
-            const int c_lo = p.per_cloud ? c : 0, c_hi = p.per_cloud ? c + 1 : p.n_clouds;
-            const float s = chunk_sum(p.partials + (long long)c_lo * slabs * per + (long long)p.Nout * p.K + n, per, (long long)(c_hi - c_lo) * slabs);
-            p.db[e] = p.accumulate ? p.db[e] + s : s;
-        } else {
-            const long long e = i - n_w - n_b;
-            const int n = (int)(e % p.Nout), g = (int)((e / p.Nout) % p.n_groups), c = (int)(e / ((long long)p.Nout * p.n_groups));
-            const int r_lo = p.group_rows[g], r_hi = (g + 1 < p.n_groups) ? p.group_rows[g + 1] : p.rows_per_cloud;
-            float s = 0.f;
-            for (int sl = r_lo / SLAB; sl < (r_hi + SLAB - 1) / SLAB; ++sl)
-                s += p.partials[((long long)c * slabs + sl) * per + (long long)p.Nout * p.K + n];
-            p.dbg[e] = s;
+            src = p.partials + (long long)(p.per_cloud ? c : 0) * slabs * per + (long long)p.Nout * p.K + n;
+            dst = p.db + e;
         }
+        red[w][lane] = src ? chunk_sum(src + ch_lo * per, per, ch_hi - ch_lo) : 0.f;
+        __syncthreads();
+        if (w == 0 && dst) {
+            float s = red[0][lane];
+#pragma unroll
+            for (int q = 1; q < 8; ++q) s += red[q][lane];
+            *dst = p.accumulate ? *dst + s : s;
+        }
+        __syncthreads();
+    }
+    // per-(cloud, block) bias gradients of the head: a handful of slabs each
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n_g; e += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(e % p.Nout), g = (int)((e / p.Nout) % p.n_groups), c = (int)(e / ((long long)p.Nout * p.n_groups));
+        const int r_lo = p.group_rows[g], r_hi = (g + 1 < p.n_groups) ? p.group_rows[g + 1] : p.rows_per_cloud;
+        float s = 0.f;
+        for (int sl = r_lo / SLAB; sl < (r_hi + SLAB - 1) / SLAB; ++sl)
+            s += p.partials[((long long)c * slabs + sl) * per + (long long)p.Nout * p.K + n];
+        p.dbg[e] = s;
     }
 }
 
@@ -202,7 +218,7 @@ int wgrad(const WgParams& p, cudaStream_t st) {
     }
     const long long total = (long long)(p.per_cloud ? p.n_clouds : 1) * p.Nout * (p.K + 1) +
                             (p.dbg ? (long long)p.n_clouds * p.n_groups * p.Nout : 0);
-    long long blocks = (total + 255) / 256;
+    long long blocks = (total + 31) / 32;                  // 32 outputs per block
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     launch_pdl(wgrad_reduce_kernel, dim3((unsigned)((unsigned)blocks)), dim3(256), 0, st, p, slabs, SLAB);
     count_launch();
