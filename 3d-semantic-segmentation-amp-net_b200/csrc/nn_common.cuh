@@ -57,6 +57,8 @@ int pw_linear(const PwParams& p, cudaStream_t st);
 int tnet_fc_eval(const float* pooled, int B, const float* fc1, const float* s4, const float* t4, const float* fc2, const float* s5,
                  const float* t5, const float* fc3w, const float* fc3b, int d, int fc3_inside, float* h1, float* h2, float* out,
                  cudaStream_t st);
+// forward of the narrow-input (K <= 12) 64-channel layers over many rows, exact fp32 (nn_small.cu)
+int narrow_fwd_try(const PwParams& p, cudaStream_t st);
 int small_linear_try(const PwParams& p, cudaStream_t st);   // nn_small.cu: few-row layers; 1 launched, 0 not eligible, < 0 error
 int tc_layer_try(const PwParams& p, cudaStream_t st);   // nn_tc_layer.cu: 1 = launched, 0 = not eligible, < 0 = error
 int pw_tiles(int n_clouds, int rows_per_cloud);      // number of row tiles (= rows of part_sum)

@@ -362,6 +362,11 @@ int pw_linear(const PwParams& p, cudaStream_t st) {
         const int rc = small_linear_try(p, st);
         if (rc != 0) return rc < 0 ? rc : AMP_OK;
     }
+    // many rows, 3 / 9 input columns, 64 channels: exact fp32, output-bandwidth bound (nn_small.cu)
+    {
+        const int rc = narrow_fwd_try(p, st);
+        if (rc != 0) return rc < 0 ? rc : AMP_OK;
+    }
     // many rows, tensor-core friendly K: split-bf16 tcgen05 path (nn_tc_layer.cu)
     {
         const int rc = tc_layer_try(p, st);

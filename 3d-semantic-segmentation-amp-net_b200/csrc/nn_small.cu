@@ -270,6 +270,96 @@ __global__ void __launch_bounds__(256) narrow_wgrad_kernel(const WgParams p, int
     }
 }
 
+// Narrow INPUT forward (K <= 12: the xyz / 9-feature columns into the first Conv1d of the encoder and of the two T-Nets,
+// pointnetAtt.py:31, :90), 64 output channels, exact fp32: memory bound on the 256-byte output rows. One warp owns a
+// 128-row tile (the unit of the BatchNorm partials): the input rows go through shared memory, lane = (channel quad, row
+// parity) keeps its 4 x K weights in registers and writes one 16-byte piece per row, so a warp store covers two whole rows.
+// Epilogue: raw value + per-tile BatchNorm sums (training; one pass with a shift, merged like tc_layer) or folded
+// BatchNorm + ReLU (eval).
+template <int KP>
+__global__ void __launch_bounds__(128) narrow_fwd_kernel(const PwParams p) {
+    pdl_sync();
+    __shared__ __align__(16) float xs[4][128 * KP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = lane & 15, par = lane >> 4;
+    const int K = p.K, rows = p.rows_per_cloud;
+    const int tpc = (rows + 127) >> 7, n_tiles = p.n_clouds * tpc;
+    float* xw = xs[warp];
+    const bool stats = p.part_sum != nullptr;
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f), bs = sh;
+    if (p.out_scale) { sc = __ldg(reinterpret_cast<const float4*>(p.out_scale) + q); sh = __ldg(reinterpret_cast<const float4*>(p.out_shift) + q); }
+    if (p.bias) bs = __ldg(reinterpret_cast<const float4*>(p.bias) + q);
+    int w_cloud = -1;
+    float w[4][KP];
+    for (int tile = blockIdx.x * 4 + warp; tile < n_tiles; tile += gridDim.x * 4) {
+        const int cloud = tile / tpc, r0 = (tile - cloud * tpc) << 7, valid = min(128, rows - r0);
+        const long long row_base = (long long)cloud * rows + r0;
+        if (w_cloud != (p.w_cloud_stride ? cloud : 0)) {           // this lane's 4 x K weights (per cloud for the folded input transform)
+            w_cloud = p.w_cloud_stride ? cloud : 0;
+            const float* __restrict__ W = p.W + (long long)w_cloud * p.w_cloud_stride;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int k = 0; k < KP; ++k)
+                    w[j][k] = k < K ? __ldg(p.w_kn ? W + (long long)k * p.ldw + q * 4 + j : W + (long long)(q * 4 + j) * p.ldw + k) : 0.f;
+        }
+        __syncwarp();                                              // the previous tile's reads of xw are done
+        for (int e = lane; e < 128 * KP; e += 32) {
+            const int r = e / KP, k = e - r * KP;
+            xw[e] = (r < valid && k < K) ? __ldg(p.X + (row_base + r) * p.ldx + k) : 0.f;
+        }
+        __syncwarp();
+        float shift[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+        float* __restrict__ yrow = p.Y + row_base * p.ldy + q * 4;
+#pragma unroll 4
+        for (int it = 0; it < 64; ++it) {
+            const int r = 2 * it + par;
+            float x[KP];
+#pragma unroll
+            for (int k4 = 0; k4 < KP / 4; ++k4) {
+                const float4 t = *reinterpret_cast<const float4*>(xw + r * KP + k4 * 4);
+                x[k4 * 4] = t.x; x[k4 * 4 + 1] = t.y; x[k4 * 4 + 2] = t.z; x[k4 * 4 + 3] = t.w;
+            }
+            float v[4] = {bs.x, bs.y, bs.z, bs.w};
+#pragma unroll
+            for (int k = 0; k < KP; ++k)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = fmaf(x[k], w[j][k], v[j]);
+            if (r < valid) {
+                if (stats) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (it == 0) shift[j] = v[j];
+                        const float d = v[j] - shift[j];
+                        s1[j] += d;
+                        s2[j] = fmaf(d, d, s2[j]);
+                    }
+                }
+                if (p.out_scale) { v[0] = fmaf(v[0], sc.x, sh.x); v[1] = fmaf(v[1], sc.y, sh.y); v[2] = fmaf(v[2], sc.z, sh.z); v[3] = fmaf(v[3], sc.w, sh.w); }
+                if (p.out_relu) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
+                *reinterpret_cast<float4*>(yrow + (long long)r * p.ldy) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+        if (stats) {                                               // merge the even-row and the odd-row half (lanes q and q + 16)
+            const float na = (float)((valid + 1) >> 1), nb = (float)(valid >> 1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float o_shift = __shfl_xor_sync(0xffffffffu, shift[j], 16), o_s1 = __shfl_xor_sync(0xffffffffu, s1[j], 16);
+                const float o_s2 = __shfl_xor_sync(0xffffffffu, s2[j], 16);
+                if (par == 0) {
+                    const float sum_a = fmaf(shift[j], na, s1[j]), sum_b = fmaf(o_shift, nb, o_s1);
+                    float m2 = s2[j] - s1[j] * s1[j] / na;
+                    if (nb > 0.f) {
+                        const float delta = sum_b / nb - sum_a / na;
+                        m2 += o_s2 - o_s1 * o_s1 / nb + delta * delta * (na * nb / (na + nb));
+                    }
+                    p.part_sum[(long long)tile * 64 + q * 4 + j] = sum_a + sum_b;
+                    p.part_sq[(long long)tile * 64 + q * 4 + j] = m2;
+                }
+            }
+        }
+    }
+}
+
 // Narrow OUTPUT (Nout <= 8: the 5 class logits of the head's last layer, [B, C, N]-transposed gradients) over many rows:
 // memory bound on the activation. thread == (4 consecutive input channels, row phase): 16-byte activation loads, 8 in flight
 // per thread (32 KB per CTA); the per-row gradients are broadcast reads of the slab's staged [row][class] table.
@@ -484,6 +574,25 @@ int tnet_fc_eval(const float* pooled, int B, const float* fc1, const float* s4, 
     launch_pdl(tnet_fc_eval_kernel, dim3((unsigned)(8 * ((B + SM_ROWS - 1) / SM_ROWS))), dim3(256), smem, st, a);
     count_launch();
     return check_launch("tnet_fc_eval");
+}
+
+// Forward of the narrow-input layers: 1 = launched, 0 = not eligible (the caller continues down the dispatch list).
+int narrow_fwd_try(const PwParams& p, cudaStream_t st) {
+    if (path_disabled("narrow_fwd")) return 0;
+    if (p.K > 12 || p.Nout != 64 || !p.Y || p.x_transposed || p.y_transposed || p.X2 || p.in_a || p.in_relu || p.in_drop_p != 0.f ||
+        p.out_drop_p != 0.f || p.mask_y || p.pool_mode || p.accumulate || p.group_rows || p.n_groups > 1 || p.bias_group_stride != 0 || (p.out_relu && !p.out_scale))
+        return 0;
+    if ((long long)p.n_clouds * p.rows_per_cloud < 2048 || p.ldy % 4 || (reinterpret_cast<uintptr_t>(p.Y) & 15)) return 0;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if ((p.bias && !al16(p.bias)) || (p.out_scale && (!al16(p.out_scale) || !al16(p.out_shift)))) return 0;
+    const long long tiles = (long long)p.n_clouds * ((p.rows_per_cloud + 127) / 128);
+    long long grid = (tiles + 3) / 4;
+    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+    if (p.K <= 4) launch_pdl(narrow_fwd_kernel<4>, dim3((unsigned)grid), dim3(128), 0, st, p);
+    else launch_pdl(narrow_fwd_kernel<12>, dim3((unsigned)grid), dim3(128), 0, st, p);
+    count_launch();
+    const int rc = check_launch("narrow_fwd");
+    return rc == AMP_OK ? 1 : rc;
 }
 
 int narrow_out_wgrad_try(const WgParams& p, int slabs, int SLAB, cudaStream_t st) {
