@@ -100,6 +100,30 @@ def _input(t, name, device):
     return t.contiguous()
 
 
+def _grad_targets(tensors):
+    """Where the library writes each parameter gradient, and what the autograd Function returns for it.
+
+    Default: a fresh tensor per trainable parameter, handed to autograd (which stores or accumulates it in `.grad`).
+    A parameter with a gradient sink (`parallel.GradAllReduce(..., zero_copy=True)` makes `p.grad` a view of its flat
+    all-reduce buffer and sets `p._amp_grad_sink`) is written in place by the FIRST backward of a step and returned as
+    None: no pack / unpack copies around the collective. Further backward calls of the same step (the scripts run the encoder
+    once per window, train_pointnet-attention.py:396-435) return ordinary gradients, which autograd adds to `.grad` --
+    the same view -- in place. `GradAllReduce.all_reduce()` ends the step. Frozen parameters get a scratch target
+    because the library writes every gradient."""
+    grads, targets = [], []
+    for t in tensors:
+        sink = getattr(t, "_amp_grad_sink", None)
+        if sink is not None and t.requires_grad and not getattr(t, "_amp_sink_written", False):
+            t._amp_sink_written = True
+            grads.append(None); targets.append(sink)
+        elif t.is_floating_point() and t.requires_grad:
+            g = torch.empty_like(t)
+            grads.append(g); targets.append(g)
+        else:
+            grads.append(None); targets.append(torch.empty_like(t) if isinstance(t, nn.Parameter) else None)
+    return grads, targets
+
+
 def _row_strided(t, name, device, align=1):
     """[A, B, C] float32 input read in place when its rows are dense and evenly spaced (a slice of a wider tensor, as the
     scripts pass: train_pointnet-attention.py:427-433); anything else is copied. Returns (tensor, floats between rows)."""
@@ -170,10 +194,7 @@ class _EncoderFn(torch.autograd.Function):
         tensors = ctx.tensors
         d_out = torch.zeros_like(out) if d_out is None else d_out.contiguous()
         d_ft = None if d_ft is None else d_ft.contiguous()
-        grads = [torch.empty_like(t) if (t.is_floating_point() and t.requires_grad) else None for t in tensors]
-        # the library writes every parameter gradient; give frozen parameters a scratch target
-        targets = [g if g is not None else (torch.empty_like(t) if isinstance(t, nn.Parameter) else None)
-                   for g, t in zip(grads, tensors)]
+        grads, targets = _grad_targets(tensors)
         ws_bytes = lib.amp_encoder_workspace_bytes(B, N, 1)
         ws = _bytes(ws_bytes, dev)
         saved = ctx.saved
@@ -266,9 +287,7 @@ class _SegFn(torch.autograd.Function):
         R = lo.shape[1]
         dev = lo.device
         d_logits = d_logits.contiguous()
-        grads = [torch.empty_like(t) if (t.is_floating_point() and t.requires_grad) else None for t in tensors]
-        targets = [g if g is not None else (torch.empty_like(t) if isinstance(t, nn.Parameter) else None)
-                   for g, t in zip(grads, tensors)]
+        grads, targets = _grad_targets(tensors)
         d_gl = torch.empty(gl.shape, dtype=torch.float32, device=dev)       # dense, whatever the strides of the inputs
         d_lo = torch.empty(lo.shape, dtype=torch.float32, device=dev)
         ws_bytes = lib.amp_seg_workspace_bytes(B, W, R, E, 1)

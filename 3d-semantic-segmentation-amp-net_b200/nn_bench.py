@@ -161,10 +161,11 @@ def bench_train(dist, amp, steps, warmup, with_cpu):
     flat = None
     if dist.pg:
         from .parallel import GradAllReduce
-        flat = GradAllReduce(params, dist.world)
+        flat = GradAllReduce(params, dist.world, zero_copy=True)      # .grad = slices of one flat buffer, written in place
 
     def train_step(xd, cd, td):
-        opt_e.zero_grad(set_to_none=True); opt_s.zero_grad(set_to_none=True)
+        if flat is None:                                              # (zero-copy gradients are overwritten by every backward)
+            opt_e.zero_grad(set_to_none=True); opt_s.zero_grad(set_to_none=True)
         logits, ft = forward_pass(enc, seg, xd, cd)
         loss = ce(logits, td) + 0.001 * torch.norm(eye - torch.bmm(ft, ft.transpose(2, 1)))
         loss.backward()

@@ -30,31 +30,72 @@ def shard_windows(blocks_per_window, world):
 
 
 class GradAllReduce:
-    """Averages the gradients of `params` over the process group with ONE collective on a flat buffer."""
+    """Averages the gradients of `params` over the process group with ONE collective on a flat buffer.
 
-    def __init__(self, params, world=None, group=None):
+    zero_copy=False: `all_reduce()` packs the `.grad` tensors into the flat buffer (one multi-tensor copy), reduces, and
+    unpacks. zero_copy=True (parameters of the ampnet_b200 modules): every `p.grad` IS its slice of the flat buffer; the first
+    backward of a step writes it in place, later backward calls of the same step (one encoder call per window) are added to
+    it by autograd (`modules._grad_targets`), and `all_reduce()` is the collective alone and ends the step. Do not clear the
+    optimizers with `zero_grad(set_to_none=True)` in this mode (`.grad` must keep pointing into the buffer); no zero_grad
+    is needed at all, the first backward of the next step overwrites."""
+
+    def __init__(self, params, world=None, group=None, zero_copy=False):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         self.world = world if world is not None else dist.get_world_size(group)
-        n = sum(p.numel() for p in self.params)
+        self.zero_copy = zero_copy
+        # every slice starts on a 256-byte boundary, like a tensor of its own (the library's kernels use 16-byte accesses on
+        # gradient targets); the padding is reduced along with the rest and costs < 1 % of the buffer
+        pad = lambda k: (k + 63) // 64 * 64
+        n = sum(pad(p.numel()) for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         self.views, off = [], 0
         for p in self.params:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
+            off += pad(p.numel())
+        if zero_copy:
+            for p, v in zip(self.params, self.views):
+                p.grad = v
+                p._amp_grad_sink = v
+                p._amp_sink_written = False
+
+    def detach(self):
+        """Undo zero_copy: parameters get ordinary gradients again."""
+        for p in self.params:
+            if getattr(p, "_amp_grad_sink", None) is not None:
+                del p._amp_grad_sink
+                del p._amp_sink_written
+                p.grad = None
+        self.zero_copy = False
+
+    def begin_step(self):
+        """zero_copy: the next backward overwrites the gradients (all_reduce() calls this; call it yourself when a step
+        ends without a collective, e.g. world size 1)."""
+        for p in self.params:
+            p._amp_sink_written = False
+
+    def _reduce_flat(self):
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)       # averaged inside the collective
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.mul_(1.0 / self.world)
 
     def all_reduce(self):
-        """Pack (one multi-tensor copy), all-reduce, average, unpack (one multi-tensor copy): 4 launches + the collective
-        instead of two small copies per parameter."""
+        """zero_copy: the collective alone. Otherwise pack (one multi-tensor copy), all-reduce, unpack (one multi-tensor
+        copy): 4 launches + the collective instead of two small copies per parameter."""
+        if self.zero_copy:
+            self._reduce_flat()
+            self.begin_step()
+            return
         have = [(p, v) for p, v in zip(self.params, self.views) if p.grad is not None]
         missing = [v for p, v in zip(self.params, self.views) if p.grad is None]
         if missing:
             torch._foreach_zero_(missing)
         if have:
             torch._foreach_copy_([v for _, v in have], [p.grad for p, _ in have])
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-        self.flat.mul_(1.0 / self.world)
+        self._reduce_flat()
         if have:
             torch._foreach_copy_([p.grad for p, _ in have], [v for _, v in have])
         for p, v in zip(self.params, self.views):

@@ -427,3 +427,34 @@ def test_seg_reads_encoder_output_slices_in_place(amp, cuda):
     assert torch.equal(results[0][0], results[1][0])
     for a, b in zip(results[0][1], results[1][1]):
         assert _rel(a, b) < 1e-6
+
+
+def test_zero_copy_gradient_sinks_match_autograd_gradients(amp, cuda):
+    """GradAllReduce(zero_copy=True): p.grad is a slice of the flat all-reduce buffer; the first backward of a step writes
+    it in place, the second encoder call of the same step (two windows) is accumulated by autograd, and the next step
+    overwrites -- same numbers as the ordinary autograd path."""
+    B, N, seed = 4, 512, 81
+    xs, cent = nn_params.synthetic_blocks(B, N, 2, seed)
+
+    def run(zero_copy):
+        enc, seg, _, _ = _build(amp, seed, cuda)
+        enc.train(); seg.train()
+        params = list(enc.parameters()) + list(seg.parameters())
+        red = amp.GradAllReduce(params, world=1, zero_copy=True) if zero_copy else None
+        for _ in range(2 if zero_copy else 1):            # the second step must overwrite, not add
+            enc.load_state_dict(nn_params.synthetic_state_dict(nn_params.encoder_shapes(), seed))
+            seg.load_state_dict(nn_params.synthetic_state_dict(nn_params.seg_shapes(), seed + 1))
+            logits, ft, _ = _run(enc, seg, xs, cent, None, cuda)
+            (logits.square().mean() + 0.01 * ft.square().mean()).backward()
+            if zero_copy:
+                red.begin_step()                           # what all_reduce() does at the end of a step
+        if zero_copy:
+            assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(red.params, red.views))
+            out = [v.clone() for v in red.views]
+            red.detach()
+            assert all(p.grad is None for p in params)
+            return out
+        return [p.grad.clone() for p in params]
+
+    for a, b in zip(run(False), run(True)):
+        assert _rel(a, b) < 1e-6

@@ -45,6 +45,16 @@ def _worker(rank, world, port, q):
     red.all_reduce()
     ok = torch.allclose(params[0].grad, torch.full((5, 3), (1 + world) / 2.0)) and torch.count_nonzero(params[1].grad) == 0 \
         and params[2].grad is None
+    # zero-copy mode: .grad is a slice of the flat buffer, "backward" writes the sink in place, all_reduce is the collective alone
+    zc = amp.GradAllReduce(params[:2], world, zero_copy=True)
+    ok = ok and params[0].grad.data_ptr() == zc.views[0].data_ptr()
+    params[0]._amp_grad_sink.fill_(float(10 * (rank + 1)))
+    params[1]._amp_grad_sink.fill_(float(rank))
+    zc.all_reduce()
+    ok = ok and torch.allclose(params[0].grad, torch.full((5, 3), 10 * (1 + world) / 2.0)) \
+        and torch.allclose(params[1].grad, torch.full((7,), (world - 1) / 2.0))
+    zc.detach()
+    ok = ok and params[0].grad is None and not hasattr(params[0], "_amp_grad_sink") and not hasattr(params[0], "_amp_sink_written")
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
