@@ -279,7 +279,9 @@ def bench_kmeans(dist, amp, steps, warmup, with_cpu):
         "e2e": {"value": KM_POINTS * dist.world * es / (e_ms * 1e-3), "unit": "points/s",
                 "h2d_bytes_per_step": KM_POINTS * 12, "d2h_bytes_per_step": KM_POINTS * 4},
         "roofline": {"bound": "hbm", "kernel": "kmeans_assign_small_k_kernel<9>", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"] + " (burst copy)",
+                     "frac": ach / pk["hbm_gbs"],
+                     "traffic": 250.1e6,   # dram__bytes_read + write of one launch, ncu --set full (profiles/r01_final_kmeans_ncu.txt)
+                     "peak_source": pk["source"] + " (burst copy)",
                      "model": "16 B per point per assignment pass (12 B features read + 4 B int32 label written), k = %d" % KM_K},
         "config": {"workload": "k-means assignment pass, %d points x 3 features, k = %d (block split of configs[3])" % (KM_POINTS, KM_K),
                    "l2": "flushed between steps (256 MiB write); working set 268 MB > L2"},
