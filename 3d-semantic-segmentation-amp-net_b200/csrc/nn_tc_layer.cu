@@ -124,25 +124,40 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
         const int k8n = K >> 3, total = Mpad * k8n;
         uint4* whi4 = reinterpret_cast<uint4*>(s_whi);
         uint4* wlo4 = reinterpret_cast<uint4*>(s_wlo);
+        const bool wvec = p.w_kn == 0 && (p.ldw & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0;
+        // two items per thread and pass, their loads issued together (a 256 x 128 layer is 8 items per thread: every pass
+        // is a memory round trip in the kernel's prologue)
 #pragma unroll 1
-        for (int e = tid; e < total; e += TL_THREADS) {
-            int n, k8;
-            if (p.w_kn == 0) { n = e / k8n; k8 = e - n * k8n; } else { n = e & (Mpad - 1); k8 = e / Mpad; }
-            float v[8];
+        for (int e0 = tid; e0 < total; e0 += 2 * TL_THREADS) {
+            float v[2][8];
+            int dst[2];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = 0.f;
-            if (n < Nout) {
-                if (p.w_kn == 0) {
-                    const float* src = W + (long long)n * p.ldw + k8 * 8;
+            for (int u = 0; u < 2; ++u) {
+                const int e = e0 + u * TL_THREADS;
+                int n, k8;
+                if (p.w_kn == 0) { n = e / k8n; k8 = e - n * k8n; } else { n = e & (Mpad - 1); k8 = e / Mpad; }
+                dst[u] = e < total ? k8 * Mpad + n : -1;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = __ldg(src + i);
-                } else {
-                    const float* src = W + (long long)(k8 * 8) * p.ldw + n;
+                for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
+                if (e < total && n < Nout) {
+                    if (wvec) {
+                        const float4* src = reinterpret_cast<const float4*>(W + (long long)n * p.ldw + k8 * 8);
+                        const float4 a = __ldg(src), c = __ldg(src + 1);
+                        v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w; v[u][4] = c.x; v[u][5] = c.y; v[u][6] = c.z; v[u][7] = c.w;
+                    } else if (p.w_kn == 0) {
+                        const float* src = W + (long long)n * p.ldw + k8 * 8;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = __ldg(src + (long long)i * p.ldw);
+                        for (int i = 0; i < 8; ++i) v[u][i] = __ldg(src + i);
+                    } else {
+                        const float* src = W + (long long)(k8 * 8) * p.ldw + n;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[u][i] = __ldg(src + (long long)i * p.ldw);
+                    }
                 }
             }
-            split_store8(v, whi4 + k8 * Mpad + n, wlo4 + k8 * Mpad + n);
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (dst[u] >= 0) split_store8(v[u], whi4 + dst[u], wlo4 + dst[u]);
         }
         fence_proxy_async();
     };
