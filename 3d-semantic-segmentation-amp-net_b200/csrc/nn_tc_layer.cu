@@ -125,14 +125,15 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
         uint4* whi4 = reinterpret_cast<uint4*>(s_whi);
         uint4* wlo4 = reinterpret_cast<uint4*>(s_wlo);
         const bool wvec = p.w_kn == 0 && (p.ldw & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0;
-        // two items per thread and pass, their loads issued together (a 256 x 128 layer is 8 items per thread: every pass
+        // WI items per thread and pass, their loads issued together (a 256 x 128 layer is 8 items per thread: every pass
         // is a memory round trip in the kernel's prologue)
+        constexpr int WI = 4;
 #pragma unroll 1
-        for (int e0 = tid; e0 < total; e0 += 2 * TL_THREADS) {
-            float v[2][8];
-            int dst[2];
+        for (int e0 = tid; e0 < total; e0 += WI * TL_THREADS) {
+            float v[WI][8];
+            int dst[WI];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < WI; ++u) {
                 const int e = e0 + u * TL_THREADS;
                 int n, k8;
                 if (p.w_kn == 0) { n = e / k8n; k8 = e - n * k8n; } else { n = e & (Mpad - 1); k8 = e / Mpad; }
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
+            for (int u = 0; u < WI; ++u)
                 if (dst[u] >= 0) split_store8(v[u], whi4 + dst[u], wlo4 + dst[u]);
         }
         fence_proxy_async();
