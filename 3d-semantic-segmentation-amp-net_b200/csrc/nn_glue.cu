@@ -260,18 +260,20 @@ __global__ void bn_backward_finalize_kernel(const float* __restrict__ part_sum, 
     }
 }
 
-// one thread per channel: scatter dpool through the saved argmax rows, apply the ReLU mask, sum for BatchNorm backward
+// one warp per channel, lanes = clouds: scatter dpool through the saved argmax rows, apply the ReLU mask, sum for BatchNorm
+// backward. The argmax -> activation -> store chain of every (cloud, channel) is independent, so the whole kernel is two
+// memory round trips; the per-channel sums are reduced over the lanes in a fixed (tree) order.
 __global__ void pool_scatter_bwd_kernel(const float* __restrict__ dpool, const int* __restrict__ arg, const float* __restrict__ y,
                                         const float* __restrict__ scale, const float* __restrict__ shift,
                                         const float* __restrict__ mean, const float* __restrict__ invstd, int n_clouds,
                                         int rows, int C, float* __restrict__ dz, float* __restrict__ part_sum,
                                         float* __restrict__ part_sq) {
     pdl_sync();
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= C) return;
     const float sc = scale[c], sh = shift[c], mu = mean[c], is = invstd[c];
     float s = 0.f, q = 0.f;
-    for (int b = 0; b < n_clouds; ++b) {
+    for (int b = lane; b < n_clouds; b += 32) {
         const long long off = ((long long)b * rows + arg[b * C + c]) * C + c;
         const float yv = y[off];
         const float g = fmaf(yv - mu, sc, sh) > 0.f ? dpool[b * C + c] : 0.f;
@@ -279,8 +281,15 @@ __global__ void pool_scatter_bwd_kernel(const float* __restrict__ dpool, const i
         s += g;
         q = fmaf(g, (yv - mu) * is, q);
     }
-    part_sum[c] = s;
-    part_sq[c] = q;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane == 0) {
+        part_sum[c] = s;
+        part_sq[c] = q;
+    }
 }
 
 __global__ void fold_input_transform_bwd_kernel(const float* __restrict__ dW1eff, const float* __restrict__ W1,
@@ -466,7 +475,7 @@ int pool_decode(const unsigned long long* pmax, const unsigned long long* pmin, 
 int pool_scatter_bwd(const float* dpool, const int* arg, const float* y, const float* scale, const float* shift,
                      const float* mean, const float* invstd, int n_clouds, int rows_per_cloud, int C, float* dz,
                      float* part_sum, float* part_sq, cudaStream_t st) {
-    launch_pdl(pool_scatter_bwd_kernel, dim3((unsigned)((C + 63) / 64)), dim3(64), 0, st, dpool, arg, y, scale, shift, mean, invstd, n_clouds,
+    launch_pdl(pool_scatter_bwd_kernel, dim3((unsigned)((C + 7) / 8)), dim3(256), 0, st, dpool, arg, y, scale, shift, mean, invstd, n_clouds,
                                                          rows_per_cloud, C, dz, part_sum, part_sq);
     count_launch();
     return check_launch("pool_scatter_bwd");

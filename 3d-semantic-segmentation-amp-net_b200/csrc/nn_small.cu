@@ -231,17 +231,18 @@ __global__ void __launch_bounds__(256) narrow_wgrad_kernel(const WgParams p, int
     for (int k = 0; k < NW_MAXK; ++k) acc[k] = 0.f;
     const float ya = p.y_a ? __ldg(p.y_a + n) : 1.f, yb = p.y_b ? __ldg(p.y_b + n) : 0.f;
     const float yc = p.Y2 ? __ldg(p.y_c + n) : 0.f, ym = (p.Y2 && p.y_m) ? __ldg(p.y_m + n) : 0.f;
-    for (int rb = r_begin + ph; rb < r_end; rb += 8 * phases) {      // 8 rows per step: their loads are issued together
-        float dv[8], y2[8];
+    constexpr int NW_INFLIGHT = 16;                                  // rows per step: their loads are issued together
+    for (int rb = r_begin + ph; rb < r_end; rb += NW_INFLIGHT * phases) {
+        float dv[NW_INFLIGHT], y2[NW_INFLIGHT];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < NW_INFLIGHT; ++u) {
             const int r = rb + u * phases;
             const long long off = (cloud_row + r) * p.lddy + n;
             dv[u] = r < r_end ? __ldg(p.dY + off) : 0.f;
             y2[u] = (p.Y2 && r < r_end) ? __ldg(p.Y2 + off) : ym;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < NW_INFLIGHT; ++u) {
             const int r = rb + u * phases;
             if (r < r_end) {
                 float v = dv[u];
