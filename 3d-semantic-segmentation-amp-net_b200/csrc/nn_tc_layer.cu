@@ -334,32 +334,33 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
             const float* __restrict__ My = (MODE & TL_MASK) ? p.mask_y + row_base * p.ld_mask + nn : nullptr;
             float* __restrict__ yp = p.Y ? p.Y + row_base * p.ldy + nn : nullptr;
             const int ldy32 = (int)p.ldy, ldm32 = (int)p.ld_mask;     // tile-local offsets fit 32 bits: one IMAD per element, not a 64-bit multiply
-            // software pipeline: the TMEM load and the global loads (mask rows, accumulate target) of piece c0 + 8 are in
-            // flight while piece c0 is processed
+            // software pipeline: the TMEM load (and the accumulate target) of piece c0 + 8 is in flight while piece c0 is
+            // processed; the saved activations that feed the ReLU mask / BatchNorm-backward sums are TWO pieces ahead (two
+            // buffers, the loop body is instantiated twice so that no pending register is ever moved): their ~1.8 k cycles of
+            // latency were half of the backward epilogue with a one-piece lead
             uint32_t vn[8];
-            float ymn[8], yon[8];
+            float yon[8], ymA[8], ymB[8];
+            auto load_mask = [&](float (&buf)[8], int c0) {
+                const float* mq = My + c0 * ldm32;                      // running pointers: one 64-bit add per element
+#pragma unroll
+                for (int j = 0; j < 8; ++j, mq += ldm32) buf[j] = (n_ok && c0 + j < c_hi) ? __ldg(mq) : 0.f;
+            };
             auto issue = [&](int c0) {
                 tmem_ld8(tcol + (uint32_t)c0, vn);
-                if (MODE & TL_MASK) {
-                    const float* mq = My + c0 * ldm32;                  // running pointers: one 64-bit add per element
-#pragma unroll
-                    for (int j = 0; j < 8; ++j, mq += ldm32) ymn[j] = (n_ok && c0 + j < valid) ? __ldg(mq) : 0.f;
-                }
                 if (MODE & TL_ACC) {
                     const float* yq = yp + c0 * ldy32;
 #pragma unroll
                     for (int j = 0; j < 8; ++j, yq += ldy32) yon[j] = (n_ok && c0 + j < valid) ? *yq : 0.f;
                 }
             };
-            if (c_lo < c_hi) issue(c_lo);
-#pragma unroll 1
-            for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
+            auto piece = [&](int c0, float (&ymq)[8]) {
                 uint32_t v[8];
                 float ym[8], yo[8];
                 tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { v[j] = vn[j]; ym[j] = ymn[j]; yo[j] = yon[j]; }
+                for (int j = 0; j < 8; ++j) { v[j] = vn[j]; yo[j] = yon[j]; ym[j] = (MODE & TL_MASK) ? ymq[j] : 0.f; }
                 if (c0 + 8 < c_hi) issue(c0 + 8);
+                if ((MODE & TL_MASK) && c0 + 16 < c_hi) load_mask(ymq, c0 + 16);
                 float* ys = yp + c0 * ldy32;
 #pragma unroll
                 for (int j = 0; j < 8; ++j, ys += ldy32) {
@@ -390,6 +391,20 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
                     if ((MODE & TL_POOL1) && ok && x > vmax) { vmax = x; rmax = r; }
                     if (store && ok) *ys = x;
                 }
+            };
+            if (c_lo < c_hi) {
+                issue(c_lo);
+                if (MODE & TL_MASK) { load_mask(ymA, c_lo); load_mask(ymB, c_lo + 8); }
+            }
+            if (MODE & TL_MASK) {
+#pragma unroll 1
+                for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+                    piece(c0, ymA);
+                    if (c0 + 8 < c_hi) piece(c0 + 8, ymB);
+                }
+            } else {
+#pragma unroll 1
+                for (int c0 = c_lo; c0 < c_hi; c0 += 8) piece(c0, ymA);
             }
             if (MODE & (TL_STATS | TL_MASK)) {                           // combine the two row halves in a fixed order
                 s_exch[sub * 128 + lrow] = (MODE & TL_STATS) ? shift : 0.f;
