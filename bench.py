@@ -217,7 +217,7 @@ def bench_fps(dist, amp, steps, warmup, with_cpu):
         "dtype": "f32",
     }
     if with_cpu:
-        res["cpu_baseline"] = cpu_fps(sample_clouds=max(2 * (os.cpu_count() or 1), 8))
+        res["cpu_baseline"] = cpu_fps(sample_clouds=min(max(4 * (os.cpu_count() or 1), 16), 128))   # ~10-20 s of CPU work
     return res
 
 
