@@ -70,3 +70,30 @@ def test_grad_all_reduce_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_grad_targets_first_write_then_accumulate(amp):
+    """Host logic of the zero-copy gradient sinks (modules._grad_targets), no GPU: the first backward of a step gets the
+    sink as its write target and returns None to autograd; a second call in the same step gets a fresh tensor (autograd
+    adds it to .grad = the sink); begin_step() re-arms; frozen parameters and buffers are handled as before."""
+    import importlib
+    modules = importlib.import_module("3d-semantic-segmentation-amp-net_b200.modules")
+    w = torch.nn.Parameter(torch.zeros(4, 3)); b = torch.nn.Parameter(torch.zeros(4)); frozen = torch.nn.Parameter(torch.zeros(2), requires_grad=False)
+    running = torch.zeros(4); counter = torch.zeros((), dtype=torch.long)
+    tensors = [w, b, frozen, running, counter]
+    grads, targets = modules._grad_targets(tensors)                 # no sinks: ordinary gradients
+    assert grads[0] is targets[0] and grads[1] is targets[1] and grads[2] is None and targets[2] is not None
+    assert grads[3] is None and targets[3] is None and grads[4] is None and targets[4] is None
+    red = amp.GradAllReduce([w, b, frozen], world=1, zero_copy=True)
+    assert w.grad.data_ptr() == red.views[0].data_ptr() and frozen.grad is None
+    assert (red.views[1].data_ptr() - red.flat.data_ptr()) % 256 == 0   # every slice starts on a 256-byte boundary of the buffer
+    grads, targets = modules._grad_targets(tensors)                 # first backward of the step: written in place
+    assert grads[0] is None and targets[0] is red.views[0] and grads[1] is None and targets[1] is red.views[1]
+    grads, targets = modules._grad_targets(tensors)                 # second backward of the step: accumulated by autograd
+    assert grads[0] is targets[0] and grads[0].data_ptr() != red.views[0].data_ptr()
+    red.begin_step()
+    grads, targets = modules._grad_targets(tensors)
+    assert grads[0] is None and targets[0] is red.views[0]
+    red.detach()
+    grads, targets = modules._grad_targets(tensors)
+    assert grads[0] is targets[0] and w.grad is None
