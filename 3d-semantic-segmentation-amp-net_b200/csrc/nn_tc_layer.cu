@@ -11,9 +11,12 @@
 // is a per-thread loop over accumulator columns with per-channel constants in registers; stores and mask reads are
 // coalesced across the warp (consecutive lanes = consecutive channels of one row).
 //
-// CTA = 256 threads = 2 independent warpgroups ("slots": own B-operand chunk buffers, 256 TMEM columns, mbarrier),
-// weights (hi + lo, K-major no-swizzle core-matrix layout) resident in shared memory for all tiles of the CTA,
-// K walked in chunks of 64 (stage chunk -> 3 MMAs per 16-wide K step -> commit -> wait).
+// CTA = 512 threads = 2 independent slots of 256 threads (own raw / B-operand chunk buffers, 256 TMEM columns, mbarrier,
+// tile stream); weights (hi + lo, K-major no-swizzle core-matrix layout) resident in shared memory for all tiles of the
+// CTA; K walked in chunks of 64 (32 / 16 when the buffers would not fit next to the weights):
+//   cp.async raw fp32 chunk (issued one chunk ahead: in flight during the MMAs and the epilogue of the previous one)
+//   -> prologue + bf16 hi / lo split into the B operand (warp = 8-channel K group, lanes = rows: conflict free)
+//   -> 3 MMAs per 16-wide K step, issued by one elected lane -> commit -> mbarrier wait -> epilogue (MODE).
 #include <stdlib.h>
 
 #include <type_traits>
