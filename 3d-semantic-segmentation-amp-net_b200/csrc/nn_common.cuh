@@ -59,6 +59,8 @@ int tnet_fc_eval(const float* pooled, int B, const float* fc1, const float* s4, 
                  cudaStream_t st);
 // forward of the narrow-input (K <= 12) 64-channel layers over many rows, exact fp32 (nn_small.cu)
 int narrow_fwd_try(const PwParams& p, cudaStream_t st);
+// forward of the narrow-output (class logits, K = 64) layer over many rows, exact fp32 (nn_small.cu)
+int narrow_out_fwd_try(const PwParams& p, cudaStream_t st);
 int small_linear_try(const PwParams& p, cudaStream_t st);   // nn_small.cu: few-row layers; 1 launched, 0 not eligible, < 0 error
 int tc_layer_try(const PwParams& p, cudaStream_t st);   // nn_tc_layer.cu: 1 = launched, 0 = not eligible, < 0 = error
 int pw_tiles(int n_clouds, int rows_per_cloud);      // number of row tiles (= rows of part_sum)

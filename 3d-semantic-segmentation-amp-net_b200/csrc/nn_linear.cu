@@ -367,6 +367,11 @@ int pw_linear(const PwParams& p, cudaStream_t st) {
         const int rc = narrow_fwd_try(p, st);
         if (rc != 0) return rc < 0 ? rc : AMP_OK;
     }
+    // many rows, a handful of output channels (class logits): exact fp32, input-bandwidth bound (nn_small.cu)
+    {
+        const int rc = narrow_out_fwd_try(p, st);
+        if (rc != 0) return rc < 0 ? rc : AMP_OK;
+    }
     // many rows, tensor-core friendly K: split-bf16 tcgen05 path (nn_tc_layer.cu)
     {
         const int rc = tc_layer_try(p, st);

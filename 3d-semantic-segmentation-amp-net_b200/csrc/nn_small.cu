@@ -361,6 +361,72 @@ __global__ void __launch_bounds__(128) narrow_fwd_kernel(const PwParams p) {
     }
 }
 
+// Narrow OUTPUT forward (Nout <= 8, K = 64: conv_4 of the head, pointnetAtt.py:206-207, logits stored [B, C, rows]), exact
+// fp32: memory bound on the 256-byte input rows. CTA = 128-row tile; 16 lanes read one row (float4 each, 8 rows in flight per
+// thread), apply the prologue (BatchNorm + ReLU + Dropout of the raw input in training), form the partial dot products of
+// their 4 channels with every class and reduce them over the 16 lanes; the tile's logits leave through shared memory so
+// that the transposed store is contiguous along the rows.
+constexpr int NOF_MAXN = 8;
+__global__ void __launch_bounds__(256) narrow_out_fwd_kernel(const PwParams p) {
+    pdl_sync();
+    __shared__ float outs[NOF_MAXN][128];
+    const int tid = threadIdx.x, q = tid & 15, rsub = tid >> 4, k = q * 4;
+    const int rows = p.rows_per_cloud, N = p.Nout;
+    const int tpc = (rows + 127) >> 7, tile = blockIdx.x, cloud = tile / tpc, r0 = (tile - cloud * tpc) << 7, valid = min(128, rows - r0);
+    const long long row_base = (long long)cloud * rows + r0;
+    float w[NOF_MAXN][4];
+#pragma unroll
+    for (int n = 0; n < NOF_MAXN; ++n)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[n][j] = n < N ? __ldg(p.W + (long long)n * p.ldw + k + j) : 0.f;
+    float4 aa = make_float4(1.f, 1.f, 1.f, 1.f), ab = make_float4(0.f, 0.f, 0.f, 0.f), am = ab;
+    if (p.in_a) {
+        aa = __ldg(reinterpret_cast<const float4*>(p.in_a + k)); ab = __ldg(reinterpret_cast<const float4*>(p.in_b + k));
+        if (p.in_m) am = __ldg(reinterpret_cast<const float4*>(p.in_m + k));
+    }
+    float4 xv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = rsub + 16 * i;
+        xv[i] = r < valid ? __ldg(reinterpret_cast<const float4*>(p.X + (row_base + r) * p.ldx + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = rsub + 16 * i;
+        float a[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+        if (p.in_a) {
+            a[0] = fmaf(a[0] - am.x, aa.x, ab.x); a[1] = fmaf(a[1] - am.y, aa.y, ab.y);
+            a[2] = fmaf(a[2] - am.z, aa.z, ab.z); a[3] = fmaf(a[3] - am.w, aa.w, ab.w);
+        }
+        if (p.in_relu) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[j] = fmaxf(a[j], 0.f);
+        }
+        if (p.in_drop_p > 0.f) {
+            const unsigned long long di = (unsigned long long)(row_base + r) * 64 + k;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[j] *= dropout_keep(p.in_drop_seed, di + j, p.in_drop_p);
+        }
+#pragma unroll
+        for (int n = 0; n < NOF_MAXN; ++n) {
+            if (n < N) {
+                float s = fmaf(a[3], w[n][3], fmaf(a[2], w[n][2], fmaf(a[1], w[n][1], a[0] * w[n][0])));
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (q == 0) outs[n][r] = s + (p.bias ? __ldg(p.bias + n) : 0.f);
+            }
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < N * 128; e += 256) {
+        const int n = e >> 7, r = e & 127;
+        if (r < valid) {
+            if (p.y_transposed) p.Y[((long long)cloud * N + n) * rows + r0 + r] = outs[n][r];
+            else p.Y[(row_base + r) * p.ldy + n] = outs[n][r];
+        }
+    }
+}
+
 // Narrow OUTPUT (Nout <= 8: the 5 class logits of the head's last layer, [B, C, N]-transposed gradients) over many rows:
 // memory bound on the activation. thread == (4 consecutive input channels, row phase): 16-byte activation loads, 8 in flight
 // per thread (32 KB per CTA); the per-row gradients are broadcast reads of the slab's staged [row][class] table.
@@ -575,6 +641,24 @@ int tnet_fc_eval(const float* pooled, int B, const float* fc1, const float* s4, 
     launch_pdl(tnet_fc_eval_kernel, dim3((unsigned)(8 * ((B + SM_ROWS - 1) / SM_ROWS))), dim3(256), smem, st, a);
     count_launch();
     return check_launch("tnet_fc_eval");
+}
+
+// Forward of the narrow-output layer (class logits): 1 = launched, 0 = not eligible.
+int narrow_out_fwd_try(const PwParams& p, cudaStream_t st) {
+    if (path_disabled("narrow_out_fwd")) return 0;
+    if (p.Nout > NOF_MAXN || p.K != 64 || !p.Y || p.x_transposed || p.X2 || p.in_c || p.out_scale || p.out_relu || p.out_drop_p != 0.f ||
+        p.mask_y || p.pool_mode || p.part_sum || p.accumulate || p.group_rows || p.n_groups > 1 || p.bias_group_stride != 0 ||
+        p.w_cloud_stride != 0 || p.w_kn)
+        return 0;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if ((long long)p.n_clouds * p.rows_per_cloud < 2048 || p.ldx % 4 || !al16(p.X)) return 0;
+    if (p.in_a && (!p.in_b || !al16(p.in_a) || !al16(p.in_b) || (p.in_m && !al16(p.in_m)))) return 0;
+    const long long tiles = (long long)p.n_clouds * ((p.rows_per_cloud + 127) / 128);
+    if (tiles > 0x7fffffffLL) return 0;
+    launch_pdl(narrow_out_fwd_kernel, dim3((unsigned)tiles), dim3(256), 0, st, p);
+    count_launch();
+    const int rc = check_launch("narrow_out_fwd");
+    return rc == AMP_OK ? 1 : rc;
 }
 
 // Forward of the narrow-input layers: 1 = launched, 0 = not eligible (the caller continues down the dispatch list).
