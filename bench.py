@@ -311,7 +311,7 @@ def run_reference(args, emit):
     wl = args.workload
     if wl == "fps":
         cores = os.cpu_count() or 1
-        sample = max(cores, 4)
+        sample = min(max(4 * cores, 16), 128)         # ~1 s of wall clock per step on the box's host cores
         t_all = []
         for _ in range(args.warmup and 1):
             cpu_fps(min(sample, cores))
