@@ -17,6 +17,8 @@ SIGNATURES = {
     "amp_last_error": (_c.c_char_p, []),
     "amp_abi_version": (_c.c_int, []),
     "amp_launch_count": (_i64, []),
+    "amp_path_count": (_i64, [_c.c_char_p]),
+    "amp_debug_set_disabled": (_c.c_int, [_c.c_char_p]),
     "amp_fps_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "amp_fps_f32": (_c.c_int, [_vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "amp_fps_f64": (_c.c_int, [_vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
@@ -73,6 +75,16 @@ def check(rc):
 
 def launch_count():
     return int(lib().amp_launch_count())
+
+
+def path_count(name):
+    """Launches served so far by the kernel family `name` (amp_path_count of include/ampnet_b200.h)."""
+    return int(lib().amp_path_count(name.encode()))
+
+
+def set_disabled(names):
+    """Debug switch: turn optional fast paths off by name (None restores the AMP_DISABLE environment list)."""
+    check(lib().amp_debug_set_disabled(None if names is None else ",".join(names).encode()))
 
 
 def stream_ptr():

@@ -2,6 +2,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "amp_common.cuh"
 
 namespace amp {
@@ -20,9 +22,31 @@ bool pdl_enabled() {
 PdlScope::PdlScope(bool on) : prev(t_pdl_scope) { t_pdl_scope = on; }
 PdlScope::~PdlScope() { t_pdl_scope = prev; }
 
+// AMP_DISABLE from the environment, or the list set at run time by amp_debug_set_disabled() (tests switch the tensor-core
+// paths off and on inside one process to compare them with the CUDA-core kernels on the same inputs)
+static std::mutex g_dbg_mu;
+static char g_disabled[256];
+static bool g_disabled_set = false;
 bool path_disabled(const char* name) {
     static const char* env = getenv("AMP_DISABLE");
-    return env && strstr(env, name) != nullptr;
+    std::lock_guard<std::mutex> lk(g_dbg_mu);
+    const char* list = g_disabled_set ? g_disabled : env;
+    return list && strstr(list, name) != nullptr;
+}
+
+// per-path launch counters (amp_path_count): which kernel family actually served a call
+struct PathCounter { char name[32]; long long n; };
+static PathCounter g_paths[48];
+static int g_n_paths = 0;
+void count_path(const char* name, int n) {
+    std::lock_guard<std::mutex> lk(g_dbg_mu);
+    for (int i = 0; i < g_n_paths; ++i)
+        if (strcmp(g_paths[i].name, name) == 0) { g_paths[i].n += n; return; }
+    if (g_n_paths < 48) {
+        strncpy(g_paths[g_n_paths].name, name, 31);
+        g_paths[g_n_paths].name[31] = 0;
+        g_paths[g_n_paths++].n = n;
+    }
 }
 
 int fail(int code, const char* fmt, ...) {
@@ -38,4 +62,19 @@ extern "C" {
 const char* amp_last_error(void) { return amp::last_error_buf(); }
 int amp_abi_version(void) { return 1000; }
 int64_t amp_launch_count(void) { return (int64_t)amp::g_launches.load(); }
+int64_t amp_path_count(const char* name) {
+    if (!name) return -1;
+    std::lock_guard<std::mutex> lk(amp::g_dbg_mu);
+    for (int i = 0; i < amp::g_n_paths; ++i)
+        if (strcmp(amp::g_paths[i].name, name) == 0) return (int64_t)amp::g_paths[i].n;
+    return 0;
+}
+int amp_debug_set_disabled(const char* csv) {
+    std::lock_guard<std::mutex> lk(amp::g_dbg_mu);
+    if (!csv) { amp::g_disabled_set = false; return AMP_OK; }
+    if (strlen(csv) >= sizeof amp::g_disabled) return AMP_E_BADARG;
+    strcpy(amp::g_disabled, csv);
+    amp::g_disabled_set = true;
+    return AMP_OK;
+}
 }

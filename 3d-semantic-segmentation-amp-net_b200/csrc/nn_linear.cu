@@ -382,6 +382,7 @@ int pw_linear(const PwParams& p, cudaStream_t st) {
     const bool wide = p.Nout > 64;
     const int bn = wide ? 128 : 64;
     dim3 grid((p.rows_per_cloud + BM - 1) / BM, (p.Nout + bn - 1) / bn, p.n_clouds);
+    count_path("pw_linear");
     if (wide) launch_pdl(pw_linear_kernel<128>, grid, dim3(NT), 0, st, q);
     else launch_pdl(pw_linear_kernel<64>, grid, dim3(NT), 0, st, q);
     count_launch();

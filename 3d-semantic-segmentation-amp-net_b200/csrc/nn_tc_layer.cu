@@ -551,6 +551,8 @@ int tc_layer_try(const PwParams& p, cudaStream_t st) {
         fprintf(stderr, "\n");
     }
     count_launch();
+    count_path("tc_layer");
+    if (mode & TL_MASK) count_path("tc_layer_dgrad");
     const int rc = check_launch("tc_layer_kernel");
     return rc == AMP_OK ? 1 : rc;
 }

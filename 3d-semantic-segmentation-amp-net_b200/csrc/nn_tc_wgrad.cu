@@ -327,6 +327,7 @@ int tc_wgrad_try(const WgParams& p, int slabs, int SLAB, cudaStream_t st) {
     const int smem_bytes = sp.total < TW_MIN_SMEM ? TW_MIN_SMEM : sp.total;
     launch_pdl(tc_wgrad_kernel, dim3((unsigned)((int)grid)), dim3(TW_THREADS), smem_bytes, st, p, Mpad, Kp, Kext, slabs, SLAB, a_vec, out_vec);
     count_launch();
+    count_path("tc_wgrad");
     const int rc = check_launch("tc_wgrad_kernel");
     return rc == AMP_OK ? 1 : rc;
 }

@@ -213,6 +213,7 @@ int wgrad(const WgParams& p, cudaStream_t st) {
         dim3 grid(slabs, n_tiles * k_tiles, p.n_clouds);
         launch_pdl(wgrad_partial_kernel, grid, dim3(NT), 0, st, p, n_tiles, k_tiles, slabs, SLAB);
         count_launch();
+        count_path("wgrad_partial");
         rc = check_launch("wgrad_partial");
         if (rc) return rc;
     }

@@ -492,6 +492,7 @@ int tc_chain_launch(const TcChainParams& p, cudaStream_t st) {
     }
     launch_pdl(tc_chain_kernel, dim3((unsigned)(grid)), dim3(kThreads), smem_bytes, st, p);
     count_launch();
+    count_path("tc_chain");
     return check_launch("tc_chain_kernel");
 }
 

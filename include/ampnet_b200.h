@@ -46,6 +46,15 @@ int amp_abi_version(void);
 /* Number of kernel launches the library has enqueued since process start (all threads);
  * bench.py uses the difference over its timed region for `gpu_launches`. */
 int64_t amp_launch_count(void);
+/* Debugging / test hooks (no reference counterpart).
+ *   amp_path_count(name)        launches served so far by the kernel family `name`: "tc_layer" (split-bf16 tcgen05 layer),
+ *                               "tc_layer_dgrad" (its input-gradient modes), "tc_wgrad", "tc_chain" (bf16 fused chains),
+ *                               "tc_chain32" (fp32-class fused chains), "pw_linear" / "wgrad_partial" (CUDA-core tiles)
+ *   amp_debug_set_disabled(csv) switches optional fast paths off by name ("tc_layer,tc_wgrad,..."; same names as the
+ *                               AMP_DISABLE environment variable, which it overrides); NULL restores the environment's list.
+ *                               The generic kernels then serve the call: tests compare both on the same inputs. */
+int64_t amp_path_count(const char* name);
+int amp_debug_set_disabled(const char* csv);
 
 /* ------------------------------------------------------------------------------------------
  * Farthest-point sampling.  Replaces utils/utils.py:889-933 `fps(pc, n_samples)` and its

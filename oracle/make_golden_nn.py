@@ -15,6 +15,23 @@ CASES = {  # name: (B, N, W, seed, masked)
 }
 
 
+# >= 2048 rows per encoder call: the shapes at which the tensor-core layers (tc_layer_kernel / tc_wgrad_kernel) serve the
+# forward AND the backward (the cases above stay below that threshold and exercise the CUDA-core kernels). Inputs are
+# nn_params.conditioned_blocks; fixture: tests/golden/nn_reference_tc.npz
+CASES_TC = {  # name: (B, N, W, seed)
+    "tc_w1_b8_n512": (8, 512, 1, 21),
+    "tc_w2_b4_n1024": (4, 1024, 2, 22),
+}
+
+
+def subsample_tc(g):
+    """At most ~12 rows of a large gradient (every k-th row): the tensor-core fixture holds every parameter."""
+    if g.size <= 2048:
+        return g.copy()
+    k = max(1, g.shape[0] // 12)
+    return g[::k].copy()
+
+
 def subsample(g):
     """Keep at most ~48 rows of a large gradient (every k-th row) so the fixture stays small."""
     if g.size <= 20000:
@@ -90,3 +107,40 @@ def make(model, gold_dir):
     path = os.path.join(gold_dir, "nn_reference.npz")
     np.savez_compressed(path, **out)
     print("nn_reference.npz: %d arrays, %.1f KiB" % (len(out), os.path.getsize(path) / 1024))
+    make_tc(model, gold_dir)
+
+
+def make_tc(model, gold_dir):
+    """Training step of the UNMODIFIED reference modules at tensor-core shapes: logits (every 16th point), loss, EVERY
+    parameter gradient (subsampled rows), and the gradients of the two tensors that cross from the encoder to the head."""
+    out = {}
+    for name, (B, N, W, seed) in CASES_TC.items():
+        enc, seg, _, _ = build_reference(model, seed)
+        xs, cent = nn_params.conditioned_blocks(B, N, W, seed)
+        tg = torch.from_numpy(np.random.default_rng(seed).integers(-1, 5, (B, N * W)).astype(np.int64))
+        enc.train(True); seg.train(True)
+        lo = torch.FloatTensor(); gl = torch.FloatTensor(); npc = []
+        for xw in xs:                                                  # train_pointnet-attention.py:396-417
+            o, ft = enc(xw)
+            local_feat = o[:, :, -64:]
+            global_feat = o[:, 0, :-64].view(-1, 1, 256)
+            npc.append(local_feat.shape[1])
+            lo = torch.cat((lo, local_feat), dim=1)
+            gl = torch.cat((gl, global_feat), dim=1)
+        gl = torch.transpose(gl, 0, 1)
+        lo.retain_grad(); gl.retain_grad()
+        logits, _ = seg(gl, lo, cent, npc, None)
+        ce = torch.nn.CrossEntropyLoss(weight=torch.FloatTensor([1, 2, 2, 1, 1]), reduction="mean", ignore_index=-1)
+        loss = ce(logits, tg) + 0.001 * torch.norm(torch.eye(64) - torch.bmm(ft, ft.transpose(2, 1)))
+        loss.backward()
+        out[name + "__train_logits"] = logits.detach().numpy()[:, :, ::16].copy()
+        out[name + "__train_loss"] = loss.detach().numpy()
+        out[name + "__targets"] = tg.numpy().astype(np.int8)
+        out[name + "__dlo"] = lo.grad.numpy()[:, ::101, :].copy()
+        out[name + "__dgl"] = gl.grad.numpy().copy()
+        for mod, tag in ((enc, "enc"), (seg, "seg")):
+            for k, p in mod.named_parameters():
+                out["%s__grad_%s_%s" % (name, tag, k)] = subsample_tc(p.grad.numpy()).astype(np.float32)
+    path = os.path.join(gold_dir, "nn_reference_tc.npz")
+    np.savez_compressed(path, **out)
+    print("nn_reference_tc.npz: %d arrays, %.1f KiB" % (len(out), os.path.getsize(path) / 1024))

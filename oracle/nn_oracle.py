@@ -128,11 +128,12 @@ def seg_attention(sd, gl_feats, lo_feats, centroids, np_cluster, attn_mask=None,
 
 
 def forward_windows(sd_enc, sd_seg, x_windows, centroids, attn_mask=None, training=False, stats_enc=None,
-                    stats_seg=None):
+                    stats_seg=None, taps=None):
     """The per-window encoder loop + attention head of train_pointnet-attention.py:396-435 /
     test_pointnet_att_segmen.py:160-177. x_windows: list of [B, N_w, 9]. Returns (logits, last F64).
     stats_enc / stats_seg (dicts): when given, BN running statistics in sd_* are updated in place, once per
-    encoder call (9 sequential updates per step for W=9: quirk 7 of SURVEY 3.5)."""
+    encoder call (9 sequential updates per step for W=9: quirk 7 of SURVEY 3.5).
+    taps (dict): receives gl_feats [W, B, 256] / lo_feats [B, sumN, 64] (gradients retained) for the backward parity tests."""
     lo, gl, npc, F64 = [], [], [], None
     for xw in x_windows:
         out, F64 = base_pointnet(sd_enc, xw, training, stats_enc)
@@ -140,7 +141,12 @@ def forward_windows(sd_enc, sd_seg, x_windows, centroids, attn_mask=None, traini
         gl.append(out[:, 0, :-64])                                # :412
         npc.append(xw.shape[1])
     gl_feats = torch.stack(gl, 0)                                 # [W, B, 256]  (:417,432)
-    logits = seg_attention(sd_seg, gl_feats, torch.cat(lo, 1), centroids, npc, attn_mask, training, stats_seg)
+    lo_feats = torch.cat(lo, 1)
+    if taps is not None:                                          # the two tensors that cross from the encoder to the head
+        taps["gl_feats"], taps["lo_feats"] = gl_feats, lo_feats
+        if gl_feats.requires_grad:
+            gl_feats.retain_grad(); lo_feats.retain_grad()
+    logits = seg_attention(sd_seg, gl_feats, lo_feats, centroids, npc, attn_mask, training, stats_seg)
     return logits, F64
 
 
