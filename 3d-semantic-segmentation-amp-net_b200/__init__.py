@@ -13,7 +13,3 @@ from .modules import BasePointNet, TransformationNet, SegmentationWithAttention,
 from .parallel import shard_windows, GradAllReduce  # noqa: F401
 from .tensorcore import tc_linear, linear_wgrad  # noqa: F401
 
-
-def bench_hooks():
-    from . import nn_bench
-    return nn_bench.hooks()

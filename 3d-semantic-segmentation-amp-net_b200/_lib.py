@@ -33,14 +33,16 @@ SIGNATURES = {
     "amp_encoder_param_name": (_c.c_char_p, [_c.c_int]),
     "amp_encoder_saved_bytes": (_sz, [_i64, _i64, _i32]),
     "amp_encoder_workspace_bytes": (_sz, [_i64, _i64, _i32]),
-    "amp_encoder_fwd": (_c.c_int, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
+    "amp_encoder_pack_bytes": (_sz, []),
+    "amp_encoder_fwd": (_c.c_int, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz, _i32, _vp]),
     "amp_encoder_bwd": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _sz, _vp, _sz, _vp]),
     "amp_seg_param_count": (_c.c_int, []),
     "amp_seg_param_name": (_c.c_char_p, [_c.c_int]),
     "amp_seg_saved_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32]),
     "amp_seg_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32, _i32]),
+    "amp_seg_pack_bytes": (_sz, [_i32]),
     "amp_seg_fwd": (_c.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _u64,
-                               _vp, _vp, _sz, _vp, _sz, _vp]),
+                               _vp, _vp, _sz, _vp, _sz, _vp, _sz, _i32, _vp]),
     "amp_seg_bwd": (_c.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _f32, _u64,
                                _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     "amp_tc_linear_workspace_bytes": (_sz, [_i32, _i32]),

@@ -27,8 +27,13 @@ PdlScope::~PdlScope() { t_pdl_scope = prev; }
 static std::mutex g_dbg_mu;
 static char g_disabled[256];
 static bool g_disabled_set = false;
+static thread_local bool t_strict = false;
+StrictScope::StrictScope(bool on) : prev(t_strict) { t_strict = t_strict || on; }
+StrictScope::~StrictScope() { t_strict = prev; }
 bool path_disabled(const char* name) {
     static const char* env = getenv("AMP_DISABLE");
+    // AMP_PREC_FP32_STRICT: no split-bf16 tensor-core arithmetic anywhere in the call (plain fp32 FMA kernels serve it)
+    if (t_strict && (!strcmp(name, "tc_layer") || !strcmp(name, "tc_wgrad") || !strcmp(name, "tc_chain32"))) return true;
     std::lock_guard<std::mutex> lk(g_dbg_mu);
     const char* list = g_disabled_set ? g_disabled : env;
     return list && strstr(list, name) != nullptr;

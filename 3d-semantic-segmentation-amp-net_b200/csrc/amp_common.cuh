@@ -59,6 +59,11 @@ __device__ __forceinline__ void pdl_sync() { pdl_trigger(); pdl_wait(); }
 
 // debugging aid: AMP_DISABLE=name1,name2 switches optional fast paths off (they fall back to the generic kernels)
 bool path_disabled(const char* name);
+struct StrictScope {                    // RAII: calls of this thread avoid the split-bf16 tensor-core kernels while alive
+    explicit StrictScope(bool on);
+    ~StrictScope();
+    bool prev;
+};
 // per-path launch counter behind amp_path_count() (tests assert which kernel family served a call)
 void count_path(const char* name, int n = 1);
 

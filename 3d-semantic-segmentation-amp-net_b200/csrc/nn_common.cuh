@@ -31,6 +31,9 @@ struct PwParams {
     // (group_rows[g] = first row of group g; the per-cluster bias of the segmentation head)
     const float* bias; long long bias_group_stride; const int* group_rows; int n_groups;
     int groups_tile_aligned;            // host hint: every group starts on a multiple of 128 rows (tensor-core path)
+    // tensor-core path: split the operands into fp16 (not bf16) hi + lo terms: fp32-class products (2^-23) for operands of
+    // moderate magnitude -- set by the training FORWARD (normalised activations, weights), never for gradients
+    int fp16_split;
     // accumulate: acc += Y (previous content) before the rest of the epilogue (gradient fan-in)
     int accumulate;
     // forward epilogue per output channel: y = y * out_scale[n] + out_shift[n]; then ReLU if out_relu

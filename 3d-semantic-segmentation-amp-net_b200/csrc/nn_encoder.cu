@@ -13,6 +13,7 @@
 
 #include "nn_layout.cuh"
 #include "tc_chain.cuh"
+#include "tc_chain32.cuh"
 
 namespace amp {
 namespace {
@@ -50,6 +51,7 @@ int fwd_layer(EncCtx& c, const float* X, long long ldx, int K, int in_bn, const 
     }
     p.W = W; p.ldw = ldw; p.w_cloud_stride = wstride; p.w_kn = w_kn;
     p.bias = bias; p.n_groups = 1;
+    p.fp16_split = c.train ? 1 : 0;
     p.Y = Y; p.ldy = ldy; p.n_clouds = clouds; p.rows_per_cloud = rows; p.Nout = Nout;
     const int o = out_bn >= 0 ? enc_bn_offset(out_bn) : 0;
     if (out_bn >= 0) {
@@ -137,13 +139,15 @@ EncTc enc_tc_carve(Arena& a, long long B) {
     return t;
 }
 
+size_t enc_fused32_bytes(long long B);       // per-call buffers + in-workspace pack of the fp32-class fused eval path (below)
+
 size_t fwd_ws_bytes(long long B, long long N, bool training) {
     Arena a(nullptr, std::numeric_limits<size_t>::max());
     const size_t tiles = (size_t)pw_tiles((int)B, (int)N);
     a.take<float>(tiles * 256); a.take<float>(tiles * 256);
     a.take<unsigned long long>(B * 256); a.take<unsigned long long>(B * 256);
     if (!training) { enc_carve(a, B, N, false); enc_tc_carve(a, B); }
-    return a.off + 256;
+    return a.off + 256 + (training ? 0 : enc_fused32_bytes(B));
 }
 
 struct BwdWs {
@@ -381,6 +385,191 @@ int encoder_fwd_bf16(EncCtx& c, const float* x, float* out, float* feat_t, Arena
     return broadcast_rows(G, B, N, 256, out, 320, c.st);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// fp32-class fused eval path (AMP_PREC_FP32, eval): the same chains as above on tc_chain32_kernel (split-bf16 operands,
+// activations resident in tensor memory), chain 3 cut at the local features (a module output that is stored anyway):
+//   chain 1: xyz -> input T-Net convs -> max            chain 2: x -> conv_1, conv_2 -> feature T-Net convs -> max
+//   chain 3a: x -> conv_1, conv_2 -> bmm(F) = local features (stored)
+//   chain 3b: local -> conv_3 .. conv_5 -> conv_6 (weights streamed) -> max
+// The BatchNorm-folded, hi / lo split weights live in a caller-owned pack cache that is rebuilt only when the caller says
+// the parameters changed (pack_valid == 0).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kP32W_it1 = 0, kP32W_it2 = kP32W_it1 + 64 * 16 * 4, kP32W_it3 = kP32W_it2 + 128 * 64 * 4, kP32Blob1 = kP32W_it3 + 256 * 128 * 4;
+constexpr int kP32W_c2 = 0, kP32W_ft1 = kP32W_c2 + 64 * 64 * 4, kP32W_ft2 = kP32W_ft1 + 64 * 64 * 4, kP32W_ft3 = kP32W_ft2 + 128 * 64 * 4,
+              kP32Blob2 = kP32W_ft3 + 256 * 128 * 4;
+constexpr int kP32Blob3a = 64 * 64 * 4;                                                   // conv_2
+constexpr int kP32W_c3 = 0, kP32W_c4 = kP32W_c3 + 64 * 64 * 4, kP32W_c5 = kP32W_c4 + 128 * 64 * 4, kP32Blob3b = kP32W_c5 + 128 * 128 * 4;
+constexpr int kP32Stream = 256 * 128 * 4;                                                 // conv_6, 4 chunks of 64 channels
+constexpr int kP32CloudW1 = 64 * 16 * 4, kP32CloudF = 64 * 64 * 4, kP32CloudStride = kP32CloudW1 + kP32CloudF;
+
+struct EncPack { float *scale, *shift; unsigned char *blob1, *blob2, *blob3a, *blob3b, *stream; };
+struct EncT32 { unsigned char* wcloud; float *pools, *f1, *f2, *T, *W1eff; };      // per-call buffers
+EncT32 enc_t32_carve(Arena& a, long long B) {
+    EncT32 t{};
+    t.wcloud = a.take<unsigned char>((size_t)B * kP32CloudStride);
+    t.pools = a.take<float>((size_t)B * 256 * 3);
+    t.f1 = a.take<float>(B * 256); t.f2 = a.take<float>(B * 128); t.T = a.take<float>(B * 9 + 7); t.W1eff = a.take<float>(B * 576);
+    return t;
+}
+EncPack enc_pack_carve(Arena& a) {
+    EncPack k{};
+    k.scale = a.take<float>(kEncBnTotal); k.shift = a.take<float>(kEncBnTotal);
+    k.blob1 = a.take<unsigned char>(kP32Blob1); k.blob2 = a.take<unsigned char>(kP32Blob2); k.blob3a = a.take<unsigned char>(kP32Blob3a);
+    k.blob3b = a.take<unsigned char>(kP32Blob3b); k.stream = a.take<unsigned char>(kP32Stream);
+    return k;
+}
+size_t enc_pack_bytes() {
+    Arena a(nullptr, std::numeric_limits<size_t>::max());
+    enc_pack_carve(a);
+    return a.off + 256;
+}
+
+size_t enc_fused32_bytes(long long B) {
+    Arena a(nullptr, std::numeric_limits<size_t>::max());
+    enc_t32_carve(a, B); enc_pack_carve(a);
+    return a.off + 512;
+}
+
+inline T32Op t32_op(int K, int N, int w_off, int w_cloud, int bias_off, int relu) {
+    T32Op o{}; o.K = K; o.N = N; o.w_off = w_off; o.w_cloud = w_cloud; o.bias_off = bias_off; o.relu = relu; o.write_act = 1;
+    return o;
+}
+inline T32PackJob t32_job(const float* w, int ld, const float* scale, int N, int K, int Kpad, long long dst_off, int chunk_n = 0) {
+    return T32PackJob{w, ld, 0, scale, N, K, N, Kpad, 0, chunk_n, dst_off, 0};
+}
+
+int encoder_pack_fp32(EncCtx& c, const EncPack& k) {
+    BnDesc d[L_ENC_BN];
+    for (int L = 0; L < L_ENC_BN; ++L) {
+        const int pb = kEncBnParam[L], o = enc_bn_offset(L);
+        d[L] = BnDesc{c.pf(pb + BN_W), c.pf(pb + BN_B), c.pf(pb + BN_RM), c.pf(pb + BN_RV), k.scale + o, k.shift + o, kEncBnChannels[L]};
+    }
+    AMP_TRY(bn_fold_eval(d, L_ENC_BN, kBnEps, c.st));
+    auto sc = [&](int L) { return k.scale + enc_bn_offset(L); };
+    // one pack launch per destination buffer (dst offsets are relative to it)
+    {
+        T32PackTable pt{}; pt.n = 3; pt.n_clouds = 1;
+        pt.job[0] = t32_job(c.pf(E_IT + T_CONV1), 3, sc(L_IT1), 64, 3, 16, kP32W_it1);
+        pt.job[1] = t32_job(c.pf(E_IT + T_CONV2), 64, sc(L_IT2), 128, 64, 64, kP32W_it2);
+        pt.job[2] = t32_job(c.pf(E_IT + T_CONV3), 128, sc(L_IT3), 256, 128, 128, kP32W_it3);
+        AMP_TRY(t32_pack_weights(pt, k.blob1, c.st));
+    }
+    {
+        T32PackTable pt{}; pt.n = 4; pt.n_clouds = 1;
+        pt.job[0] = t32_job(c.pf(E_CONV2), 64, sc(L_C2), 64, 64, 64, kP32W_c2);
+        pt.job[1] = t32_job(c.pf(E_FT + T_CONV1), 64, sc(L_FT1), 64, 64, 64, kP32W_ft1);
+        pt.job[2] = t32_job(c.pf(E_FT + T_CONV2), 64, sc(L_FT2), 128, 64, 64, kP32W_ft2);
+        pt.job[3] = t32_job(c.pf(E_FT + T_CONV3), 128, sc(L_FT3), 256, 128, 128, kP32W_ft3);
+        AMP_TRY(t32_pack_weights(pt, k.blob2, c.st));
+    }
+    {
+        T32PackTable pt{}; pt.n = 1; pt.n_clouds = 1;
+        pt.job[0] = t32_job(c.pf(E_CONV2), 64, sc(L_C2), 64, 64, 64, 0);
+        AMP_TRY(t32_pack_weights(pt, k.blob3a, c.st));
+    }
+    {
+        T32PackTable pt{}; pt.n = 3; pt.n_clouds = 1;
+        pt.job[0] = t32_job(c.pf(E_CONV3), 64, sc(L_C3), 64, 64, 64, kP32W_c3);
+        pt.job[1] = t32_job(c.pf(E_CONV4), 64, sc(L_C4), 128, 64, 64, kP32W_c4);
+        pt.job[2] = t32_job(c.pf(E_CONV5), 128, sc(L_C5), 128, 128, 128, kP32W_c5);
+        AMP_TRY(t32_pack_weights(pt, k.blob3b, c.st));
+    }
+    {
+        T32PackTable pt{}; pt.n = 1; pt.n_clouds = 1;
+        pt.job[0] = t32_job(c.pf(E_CONV6), 128, sc(L_C6), 256, 128, 128, 0, kT32ChunkChannels);
+        AMP_TRY(t32_pack_weights(pt, k.stream, c.st));
+    }
+    return AMP_OK;
+}
+
+int encoder_fwd_fp32_fused(EncCtx& c, const float* x, float* out, float* feat_t, Arena& wa, void* pack, size_t pack_bytes, int pack_valid) {
+    const int B = c.B, N = c.N;
+    EncT32 t = enc_t32_carve(wa, B);                     // per-call buffers (pools, FC activations, per-cloud packed weights)
+    EncPack k;
+    if (pack) {
+        if (pack_bytes < enc_pack_bytes()) return fail(AMP_E_WORKSPACE, "encoder_fwd: pack cache too small");
+        Arena pa(pack, pack_bytes);
+        k = enc_pack_carve(pa);
+    } else {
+        k = enc_pack_carve(wa);
+        pack_valid = 0;
+    }
+    if (!wa.ok()) return fail(AMP_E_WORKSPACE, "encoder_fwd: workspace too small");
+    if (!pack_valid) AMP_TRY(encoder_pack_fp32(c, k));
+    c.S.scale = k.scale; c.S.shift = k.shift;            // tnet_fc_stack_eval reads the folded bn_4 / bn_5 from here
+    auto sc = [&](int L) { return k.scale + enc_bn_offset(L); };
+    AMP_CUDA(cudaMemsetAsync(t.pools, 0, sizeof(float) * B * 256 * 3, c.st));
+    float* it_pool = t.pools; float* ft_pool = t.pools + (size_t)B * 256; float* G = t.pools + (size_t)B * 512;
+    T32Params base{};
+    base.in_mode = 0; base.in_x = x; base.in_ld = 9; base.n_groups = 1; base.n_clouds = B; base.rows_per_cloud = N;
+    base.bias = k.shift; base.n_bias = kEncBnTotal;      // every op's bias is a slice of the folded-BatchNorm shift table
+    // chain 1: input T-Net convs on xyz + max-pool (:31-35)
+    {
+        T32Params p = base;
+        p.in_k = 3; p.n_ops = 3;
+        p.wblob = k.blob1; p.wblob_bytes = kP32Blob1;
+        p.op[0] = t32_op(16, 64, kP32W_it1, 0, enc_bn_offset(L_IT1), 1);
+        p.op[1] = t32_op(64, 128, kP32W_it2, 0, enc_bn_offset(L_IT2), 1);
+        p.op[2] = t32_op(128, 256, kP32W_it3, 0, enc_bn_offset(L_IT3), 1); p.op[2].write_act = 0; p.op[2].pool = 1;
+        p.pool = reinterpret_cast<unsigned int*>(it_pool);
+        AMP_TRY(tc_chain32_launch(p, c.st));
+    }
+    AMP_TRY(tnet_fc_stack_eval(c, E_IT, L_IT1, 3, it_pool, t.f1, t.f2, t.T));
+    // bmm + cat + conv_1 (:85-90) as per-cloud conv_1 weights (bn_1 scale folded in), packed per cloud
+    AMP_TRY(fold_input_transform(c.pf(E_CONV1), t.T, B, t.W1eff, c.st));
+    {
+        T32PackTable pt{}; pt.n = 1; pt.n_clouds = B;
+        pt.job[0] = T32PackJob{t.W1eff, 9, 576, sc(L_C1), 64, 9, 64, 16, 0, 0, 0, kP32CloudStride};
+        AMP_TRY(t32_pack_weights(pt, t.wcloud, c.st));
+    }
+    // chain 2: conv_1, conv_2, feature T-Net convs + max-pool (:90-94)
+    {
+        T32Params p = base;
+        p.in_k = 9; p.n_ops = 5;
+        p.wblob = k.blob2; p.wblob_bytes = kP32Blob2;
+        p.wcloud = t.wcloud; p.wcloud_stride = kP32CloudStride; p.wcloud_bytes = kP32CloudW1;
+        p.op[0] = t32_op(16, 64, 0, 1, enc_bn_offset(L_C1), 1);
+        p.op[1] = t32_op(64, 64, kP32W_c2, 0, enc_bn_offset(L_C2), 1);
+        p.op[2] = t32_op(64, 64, kP32W_ft1, 0, enc_bn_offset(L_FT1), 1);
+        p.op[3] = t32_op(64, 128, kP32W_ft2, 0, enc_bn_offset(L_FT2), 1);
+        p.op[4] = t32_op(128, 256, kP32W_ft3, 0, enc_bn_offset(L_FT3), 1); p.op[4].write_act = 0; p.op[4].pool = 1;
+        p.pool = reinterpret_cast<unsigned int*>(ft_pool);
+        AMP_TRY(tc_chain32_launch(p, c.st));
+    }
+    AMP_TRY(tnet_fc_stack_eval(c, E_FT, L_FT1, 64, ft_pool, t.f1, t.f2, feat_t));
+    {
+        T32PackTable pt{}; pt.n = 1; pt.n_clouds = B;    // local = h @ F: weight [n][k] = F[k][n]
+        pt.job[0] = T32PackJob{feat_t, 64, 4096, nullptr, 64, 64, 64, 64, 1, 0, kP32CloudW1, kP32CloudStride};
+        AMP_TRY(t32_pack_weights(pt, t.wcloud, c.st));
+    }
+    // chain 3a: conv_1, conv_2, bmm with the feature transform = local features (:96-97), stored into out[:, :, 256:320]
+    {
+        T32Params p = base;
+        p.in_k = 9; p.n_ops = 3;
+        p.wblob = k.blob3a; p.wblob_bytes = kP32Blob3a;
+        p.wcloud = t.wcloud; p.wcloud_stride = kP32CloudStride; p.wcloud_bytes = kP32CloudStride;
+        p.op[0] = t32_op(16, 64, 0, 1, enc_bn_offset(L_C1), 1);
+        p.op[1] = t32_op(64, 64, 0, 0, enc_bn_offset(L_C2), 1);
+        p.op[2] = t32_op(64, 64, kP32CloudW1, 1, -1, 0); p.op[2].write_act = 0; p.op[2].store_f32 = 1;
+        p.out_f32 = out; p.out_ld = 320; p.out_col0 = 256;
+        AMP_TRY(tc_chain32_launch(p, c.st));
+    }
+    // chain 3b: conv_3 .. conv_6 on the local features + global max-pool (:100-106)
+    {
+        T32Params p = base;
+        p.in_mode = 1; p.in_x = out + 256; p.in_ld = 320; p.in_k = 64; p.n_ops = 4;
+        p.wblob = k.blob3b; p.wblob_bytes = kP32Blob3b; p.wstream = k.stream;
+        p.op[0] = t32_op(64, 64, kP32W_c3, 0, enc_bn_offset(L_C3), 1);
+        p.op[1] = t32_op(64, 128, kP32W_c4, 0, enc_bn_offset(L_C4), 1);
+        p.op[2] = t32_op(128, 128, kP32W_c5, 0, enc_bn_offset(L_C5), 1);
+        p.op[3] = t32_op(128, 256, 0, 0, enc_bn_offset(L_C6), 1); p.op[3].write_act = 0; p.op[3].pool = 1; p.op[3].w_stream = 1;
+        p.pool = reinterpret_cast<unsigned int*>(G);
+        AMP_TRY(tc_chain32_launch(p, c.st));
+    }
+    // repeat + cat (:109-110)
+    return broadcast_rows(G, B, N, 256, out, 320, c.st);
+}
+
 int check_sizes(int64_t B, int64_t N, const char* who) {
     if (B < 1 || N < 1 || B > 65535 || B * N > (1LL << 31) / 320)
         return fail(AMP_E_BADARG, "%s: unsupported shape B=%lld N=%lld", who, (long long)B, (long long)N);
@@ -432,13 +621,18 @@ size_t amp_encoder_workspace_bytes(int64_t B, int64_t N, int32_t training) {
     return f;
 }
 
+size_t amp_encoder_pack_bytes(void) { return amp::enc_pack_bytes(); }
+
 int amp_encoder_fwd(const void* const* params, const float* x, int64_t B, int64_t N, int32_t training, int32_t precision,
                     float* out, float* feat_t, void* saved, size_t saved_bytes, void* workspace,
-                    size_t workspace_bytes, void* stream) {
+                    size_t workspace_bytes, void* pack_cache, size_t pack_bytes, int32_t pack_valid, void* stream) {
     using namespace amp;
     if (!params || !x || !out || !feat_t || !workspace) return fail(AMP_E_BADARG, "encoder_fwd: null pointer");
     AMP_TRY(check_sizes(B, N, "encoder_fwd"));
-    if (precision != AMP_PREC_FP32 && precision != AMP_PREC_BF16) return fail(AMP_E_BADARG, "encoder_fwd: unknown precision %d", precision);
+    if (precision != AMP_PREC_FP32 && precision != AMP_PREC_BF16 && precision != AMP_PREC_FP32_STRICT)
+        return fail(AMP_E_BADARG, "encoder_fwd: unknown precision %d", precision);
+    StrictScope strict(precision == AMP_PREC_FP32_STRICT);
+    if (precision == AMP_PREC_FP32_STRICT) precision = AMP_PREC_FP32;
     if (training && precision != AMP_PREC_FP32)
         return fail(AMP_E_BADARG, "encoder_fwd: the bf16 tensor-core path is eval-only; training runs in AMP_PREC_FP32");
     if (training && B * N < 2) return fail(AMP_E_BADARG, "encoder_fwd: BatchNorm in training mode needs more than 1 row");
@@ -453,6 +647,8 @@ int amp_encoder_fwd(const void* const* params, const float* x, int64_t B, int64_
     c.P = params; c.st = (cudaStream_t)stream; c.B = (int)B; c.N = (int)N; c.train = training != 0;
     Arena wa(workspace, workspace_bytes);
     if (precision == AMP_PREC_BF16) return encoder_fwd_bf16(c, x, out, feat_t, wa);
+    if (!c.train && precision == AMP_PREC_FP32 && !path_disabled("tc_chain32"))
+        return encoder_fwd_fp32_fused(c, x, out, feat_t, wa, pack_cache, pack_bytes, pack_valid);
     const size_t tiles = (size_t)pw_tiles(c.B, c.N);
     c.part_sum = wa.take<float>(tiles * 256); c.part_sq = wa.take<float>(tiles * 256);
     c.pmax = wa.take<unsigned long long>(B * 256); c.pmin = wa.take<unsigned long long>(B * 256);

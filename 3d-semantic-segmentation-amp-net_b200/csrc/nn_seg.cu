@@ -12,6 +12,7 @@
 
 #include "nn_layout.cuh"
 #include "tc_chain.cuh"
+#include "tc_chain32.cuh"
 
 namespace amp {
 namespace {
@@ -20,6 +21,22 @@ constexpr float kBnEps = 1e-5f, kBnMomentum = 0.1f;
 constexpr int kSegBn2 = 0, kSegBn3 = 128, kSegBnTotal = 192;   // offsets into the scale/shift tables
 // bf16 tensor-core head: conv_2 local half (128 x 64), conv_3 (64 x 128), conv_4 (<= 32 x 64) packed; biases of conv_3 / conv_4
 constexpr int kSegTcBlob = 16384 + (16384 + 1024) + (4096 + 512);
+
+// fp32-class fused head (tc_chain32): conv_2 local half (128 x 64), conv_3 (64 x 128), conv_4 (<= 32 x 64), hi + lo split;
+// bias table = [scale3 * b3 + shift3 (64) | b4 (Cp)]; kept in a caller-owned pack cache between calls
+constexpr int kSeg32W2 = 0, kSeg32W3 = 128 * 64 * 4, kSeg32W4 = kSeg32W3 + 64 * 128 * 4;
+struct SegPack { float *scale, *shift, *bias; unsigned char* blob; };
+SegPack seg_pack_carve(Arena& a, int Cp) {
+    SegPack k{};
+    k.scale = a.take<float>(kSegBnTotal); k.shift = a.take<float>(kSegBnTotal); k.bias = a.take<float>(64 + Cp);
+    k.blob = a.take<unsigned char>(kSeg32W4 + Cp * 64 * 4);
+    return k;
+}
+size_t seg_pack_bytes(int num_classes) {
+    Arena a(nullptr, std::numeric_limits<size_t>::max());
+    seg_pack_carve(a, (num_classes + 15) / 16 * 16);
+    return a.off + 256;
+}
 
 #define AMP_TRY(expr) do { int rc_ = (expr); if (rc_ != AMP_OK) return rc_; } while (0)
 #define AMP_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fail(AMP_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); } while (0)
@@ -44,6 +61,7 @@ SegSaved seg_carve(Arena& a, long long B, long long W, long long R, int E, int h
 
 struct SegWs {
     unsigned char* tc_blob;                                     // bf16 tensor-core path: packed head weights + bias K groups
+    unsigned char* pack32;                                      // fp32-class fused path without a caller-owned pack cache
     float *part_sum, *part_sq, *k1, *k2, *k3, *wg; size_t wg_floats;
     float *dz3, *dz2, *dcb, *dg_w, *dattn_o, *dqkv, *dtokens, *dpre;
 };
@@ -65,6 +83,7 @@ SegWs seg_ws_carve(Arena& a, long long B, long long W, long long R, int E, int h
     w.part_sum = a.take<float>(tiles * 128); w.part_sq = a.take<float>(tiles * 128);
     if (!backward) {
         w.tc_blob = a.take<unsigned char>(kSegTcBlob);
+        w.pack32 = a.take<unsigned char>(seg_pack_bytes(32));          // used when the caller passes no pack cache
         return w;
     }
     w.k1 = a.take<float>(kSegBnTotal); w.k2 = a.take<float>(kSegBnTotal); w.k3 = a.take<float>(kSegBnTotal);
@@ -107,6 +126,7 @@ inline float* gf(void* const* G, int i) { return reinterpret_cast<float*>(G[i]);
 
 extern "C" {
 
+size_t amp_seg_pack_bytes(int32_t num_classes) { return amp::seg_pack_bytes(num_classes); }
 int amp_seg_param_count(void) { return amp::S_COUNT; }
 const char* amp_seg_param_name(int i) { return (i < 0 || i >= amp::S_COUNT) ? nullptr : amp::kSegNames[i]; }
 
@@ -127,9 +147,12 @@ int amp_seg_fwd(const void* const* params, const float* gl_feats, int64_t gl_ld,
                 const int32_t* np_cluster, const int32_t* group_rows, const uint8_t* key_padding_mask, int64_t B,
                 int64_t W, int64_t rows, int32_t embed_dim, int32_t heads, int32_t num_classes, int32_t training,
                 int32_t precision, float dropout_p, uint64_t seed, float* logits, void* saved, size_t saved_bytes,
-                void* workspace, size_t workspace_bytes, void* stream) {
+                void* workspace, size_t workspace_bytes, void* pack_cache, size_t pack_bytes, int32_t pack_valid, void* stream) {
     using namespace amp;
-    if (precision != AMP_PREC_FP32 && precision != AMP_PREC_BF16) return fail(AMP_E_BADARG, "seg_fwd: unknown precision %d", precision);
+    if (precision != AMP_PREC_FP32 && precision != AMP_PREC_BF16 && precision != AMP_PREC_FP32_STRICT)
+        return fail(AMP_E_BADARG, "seg_fwd: unknown precision %d", precision);
+    StrictScope strict(precision == AMP_PREC_FP32_STRICT);
+    if (precision == AMP_PREC_FP32_STRICT) precision = AMP_PREC_FP32;
     if (precision == AMP_PREC_BF16 && training)
         return fail(AMP_E_BADARG, "seg_fwd: the bf16 tensor-core path is eval-only; training runs in AMP_PREC_FP32");
     if (precision == AMP_PREC_BF16 && num_classes > 32) return fail(AMP_E_BADARG, "seg_fwd: the bf16 head supports up to 32 classes");
@@ -154,6 +177,7 @@ int amp_seg_fwd(const void* const* params, const float* gl_feats, int64_t gl_ld,
     Arena wa(workspace, workspace_bytes);
     SegWs ws = seg_ws_carve(wa, B, W, rows, E, hid, false);
 
+    const bool fused32 = !train && precision == AMP_PREC_FP32 && num_classes <= 32 && hid == 128 && !path_disabled("tc_chain32");
     // positional encoding + token-major layout (:183-185)
     AMP_TRY(posenc_add(gl_feats, gl_ld, centroids, pf(params, S_FC1W), pf(params, S_FC1B), pf(params, S_FC2W), pf(params, S_FC2B), Bi, Wi, E,
                        S.tokens, S.h_pre, st));
@@ -176,7 +200,54 @@ int amp_seg_fwd(const void* const* params, const float* gl_feats, int64_t gl_ld,
         PwParams p{};
         p.X = S.g_w; p.ldx = E; p.K = E; p.W = pf(params, S_C2W) + 64; p.ldw = 64 + E; p.bias = pf(params, S_C2B); p.n_groups = 1;
         p.Y = S.cb; p.ldy = hid; p.n_clouds = 1; p.rows_per_cloud = T; p.Nout = hid;
-        if (precision != AMP_PREC_BF16) AMP_TRY(pw_linear(p, st));
+        if (precision != AMP_PREC_BF16 && !fused32) AMP_TRY(pw_linear(p, st));
+    }
+    if (fused32) {
+        // fused head on the tensor cores at fp32-class accuracy: bn_2 / bn_3 folded into the packed weights and the biases;
+        // the per-block bias becomes cb' = scale2 * (W2[:, 64:] g_w + b2) + shift2
+        const int Cp = (num_classes + 15) / 16 * 16;
+        SegPack k;
+        if (pack_cache) {
+            if (pack_bytes < seg_pack_bytes(num_classes)) return fail(AMP_E_WORKSPACE, "seg_fwd: pack cache too small");
+            Arena pa(pack_cache, pack_bytes);
+            k = seg_pack_carve(pa, Cp);
+        } else {
+            Arena pa(ws.pack32, seg_pack_bytes(32));
+            k = seg_pack_carve(pa, Cp);
+            pack_valid = 0;
+        }
+        if (!pack_valid) {
+            BnDesc t[2] = {
+                {pf(params, S_BN2 + BN_W), pf(params, S_BN2 + BN_B), pf(params, S_BN2 + BN_RM), pf(params, S_BN2 + BN_RV), k.scale + kSegBn2, k.shift + kSegBn2, hid},
+                {pf(params, S_BN3 + BN_W), pf(params, S_BN3 + BN_B), pf(params, S_BN3 + BN_RM), pf(params, S_BN3 + BN_RV), k.scale + kSegBn3, k.shift + kSegBn3, 64}};
+            AMP_TRY(bn_fold_eval(t, 2, kBnEps, st));
+            T32PackTable pt{}; pt.n = 3; pt.n_clouds = 1;
+            pt.job[0] = T32PackJob{pf(params, S_C2W), 64 + E, 0, k.scale + kSegBn2, hid, 64, hid, 64, 0, 0, kSeg32W2, 0};
+            pt.job[1] = T32PackJob{pf(params, S_C3W), hid, 0, k.scale + kSegBn3, 64, hid, 64, hid, 0, 0, kSeg32W3, 0};
+            pt.job[2] = T32PackJob{pf(params, S_C4W), 64, 0, nullptr, num_classes, 64, Cp, 64, 0, 0, kSeg32W4, 0};
+            AMP_TRY(t32_pack_weights(pt, k.blob, st));
+            AMP_TRY(t32_affine_bias(pf(params, S_C3B), k.scale + kSegBn3, k.shift + kSegBn3, 64, 64, k.bias, st));
+            AMP_TRY(t32_affine_bias(pf(params, S_C4B), nullptr, nullptr, num_classes, Cp, k.bias + 64, st));
+        }
+        {
+            PwParams p{};
+            p.X = S.g_w; p.ldx = E; p.K = E; p.W = pf(params, S_C2W) + 64; p.ldw = 64 + E; p.bias = pf(params, S_C2B); p.n_groups = 1;
+            p.out_scale = k.scale + kSegBn2; p.out_shift = k.shift + kSegBn2;
+            p.Y = S.cb; p.ldy = hid; p.n_clouds = 1; p.rows_per_cloud = T; p.Nout = hid;
+            AMP_TRY(pw_linear(p, st));
+        }
+        T32Params p{};
+        p.n_ops = 3;
+        p.op[0] = T32Op{64, hid, kSeg32W2, 0, 0, -1, 1, 1, 1, 0, 0, 0};
+        p.op[1] = T32Op{hid, 64, kSeg32W3, 0, 0, 0, 1, 0, 1, 0, 0, 0};
+        p.op[2] = T32Op{64, Cp, kSeg32W4, 0, 0, 64, 0, 0, 0, 0, 0, 1};
+        p.in_mode = 1; p.in_x = lo_feats; p.in_ld = lo_ld; p.in_k = 64;
+        p.wblob = k.blob; p.wblob_bytes = kSeg32W4 + Cp * 64 * 4;
+        p.bias = k.bias; p.n_bias = 64 + Cp;
+        p.gbias = S.cb; p.group_rows = group_rows; p.n_groups = Wi;
+        p.logits = logits; p.n_classes = num_classes;
+        p.n_clouds = Bi; p.rows_per_cloud = Ri;
+        return tc_chain32_launch(p, st);
     }
     if (precision == AMP_PREC_BF16) {
         // fused head on the tensor cores: bn_2 / bn_3 folded into the packed weights and the biases; the per-block bias
@@ -232,6 +303,7 @@ int amp_seg_fwd(const void* const* params, const float* gl_feats, int64_t gl_ld,
         p.bias = S.cb; p.bias_group_stride = hid; p.group_rows = group_rows; p.n_groups = Wi;
         p.groups_tile_aligned = 1;
         for (int i = 0; i < Wi; ++i) if (np_cluster[i] % 128) p.groups_tile_aligned = 0;
+        p.fp16_split = train ? 1 : 0;
         p.Y = S.y2; p.ldy = hid; p.n_clouds = Bi; p.rows_per_cloud = Ri; p.Nout = hid;
         if (train) { p.part_sum = ws.part_sum; p.part_sq = ws.part_sq; }
         else { p.out_scale = S.scale + kSegBn2; p.out_shift = S.shift + kSegBn2; p.out_relu = 1; }
@@ -244,6 +316,7 @@ int amp_seg_fwd(const void* const* params, const float* gl_feats, int64_t gl_ld,
         p.X = S.y2; p.ldx = hid; p.K = hid;
         if (train) { p.in_a = S.scale + kSegBn2; p.in_b = pf(params, S_BN2 + BN_B); p.in_m = S.mean + kSegBn2; p.in_relu = 1; p.in_drop_p = dp; p.in_drop_seed = seed + 2; }
         p.W = pf(params, S_C3W); p.ldw = hid; p.bias = pf(params, S_C3B); p.n_groups = 1;
+        p.fp16_split = train ? 1 : 0;
         p.Y = S.y3; p.ldy = 64; p.n_clouds = Bi; p.rows_per_cloud = Ri; p.Nout = 64;
         if (train) { p.part_sum = ws.part_sum; p.part_sq = ws.part_sq; }
         else { p.out_scale = S.scale + kSegBn3; p.out_shift = S.shift + kSegBn3; p.out_relu = 1; }

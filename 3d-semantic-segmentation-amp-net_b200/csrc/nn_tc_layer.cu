@@ -21,6 +21,8 @@
 
 #include <type_traits>
 
+#include <cuda_fp16.h>
+
 #include "nn_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -51,23 +53,45 @@ __host__ __device__ inline TlPlan tl_plan(int Mpad, int K, int kcw, int x2) {
     return s;
 }
 
-// v = hi + lo (+ 2^-18 residual): one packed convert per pair, the bf16 -> fp32 widening is a shift / mask
-__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
-    hi = pack_bf16x2(a, b);
-    lo = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+// v = hi + lo (+ residual): one packed convert per pair.
+//   H16 == false: bf16 terms (8 + 8 mantissa bits, 2^-17 residual, fp32 exponent range): gradients of any magnitude
+//   H16 == true:  fp16 terms (11 + 11 bits, 2^-23 residual = fp32 class; saturating converts): the TRAINING FORWARD, whose
+//                 operands are BatchNorm-normalised activations and weights (|x| << 65504; a lo term that underflows to an
+//                 fp16 subnormal costs <= 3e-8 absolute). The forward needs this: max-pool winners closer than the forward
+//                 error flip, and one flipped winner moves a gradient by percents (tests/test_nn_backward_tc_gpu.py).
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
+template <bool H16>
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+    if (H16) {
+        hi = pack_f16x2_sat(a, b);
+        const __half2 h = *reinterpret_cast<const __half2*>(&hi);
+        lo = pack_f16x2_sat(a - __low2float(h), b - __high2float(h));
+    } else {
+        hi = pack_bf16x2(a, b);
+        lo = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+    }
+}
+template <bool H16>
 __device__ __forceinline__ void split_store8(const float (&v)[8], uint4* hi_dst, uint4* lo_dst) {
     uint4 h, l;
-    split_pair(v[0], v[1], h.x, l.x); split_pair(v[2], v[3], h.y, l.y);
-    split_pair(v[4], v[5], h.z, l.z); split_pair(v[6], v[7], h.w, l.w);
+    split_pair<H16>(v[0], v[1], h.x, l.x); split_pair<H16>(v[2], v[3], h.y, l.y);
+    split_pair<H16>(v[4], v[5], h.z, l.z); split_pair<H16>(v[6], v[7], h.w, l.w);
     *hi_dst = h; *lo_dst = l;
+}
+// instruction descriptor, kind::f16 with fp16 operands (a_format = b_format = 0), D = fp32, both K-major
+__device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // out of line: the hash is ~25 instructions and only the head's dropout layers use it (code size = cold-start time here)
 __device__ __noinline__ float dropout_keep_ool(unsigned long long seed, unsigned long long idx, float p) { return dropout_keep(seed, idx, p); }
 
 // epilogue specialisations (bit mask): compile-time so that the per-element loop carries no dead branches
-enum { TL_STATS = 1, TL_POOL2 = 2, TL_AFFINE = 4, TL_POOL1 = 8, TL_MASK = 16, TL_DROP = 32, TL_ACC = 64 };
+enum { TL_STATS = 1, TL_POOL2 = 2, TL_AFFINE = 4, TL_POOL1 = 8, TL_MASK = 16, TL_DROP = 32, TL_ACC = 64, TL_FP16 = 128 };
 
 template <int MODE>
 __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_constant__ PwParams p, const int Mpad, const int kcw, long long* prof_buf) {
@@ -116,7 +140,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
     const uint32_t slot_col = tmem_base + (uint32_t)(wg * 256);
     const uint32_t whi_addr = smem_u32(s_whi), wlo_addr = smem_u32(s_wlo), bhi_addr = smem_u32(s_bhi), blo_addr = smem_u32(s_blo);
     const uint32_t w_lbo = (uint32_t)Mpad * 16u;
-    const uint32_t idesc = umma_idesc(128, 128);
+    constexpr bool H16 = (MODE & TL_FP16) != 0;
+    const uint32_t idesc = H16 ? umma_idesc_f16(128, 128) : umma_idesc(128, 128);
     const bool per_cloud_w = p.w_cloud_stride != 0;
     const bool has_pro = p.in_a != nullptr;
     uint32_t phase = 0;
@@ -161,7 +186,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
             }
 #pragma unroll
             for (int u = 0; u < WI; ++u)
-                if (dst[u] >= 0) split_store8(v[u], whi4 + dst[u], wlo4 + dst[u]);
+                if (dst[u] >= 0) split_store8<H16>(v[u], whi4 + dst[u], wlo4 + dst[u]);
         }
         fence_proxy_async();
     };
@@ -266,7 +291,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[j] = 0.f;
                         }
-                        split_store8(v, dhi + r, dlo + r);
+                        split_store8<H16>(v, dhi + r, dlo + r);
                     }
                 }
             }
@@ -515,6 +540,7 @@ int tc_layer_try(const PwParams& p, cudaStream_t st) {
     if (p.mask_y) mode |= TL_MASK;
     if (p.mask_y && p.out_drop_p > 0.f) mode |= TL_DROP;
     if (p.accumulate && p.Y) mode |= TL_ACC;
+    if (p.fp16_split && !(mode & (TL_MASK | TL_ACC | TL_AFFINE))) mode |= TL_FP16;
     if (!p.out_scale && p.out_relu) return 0;
     if (!p.mask_y && p.out_drop_p > 0.f) return 0;
     PwParams q = p;
@@ -539,6 +565,7 @@ int tc_layer_try(const PwParams& p, cudaStream_t st) {
         break; }
         TL_CASE(0) TL_CASE(TL_ACC) TL_CASE(TL_STATS) TL_CASE(TL_STATS | TL_POOL2) TL_CASE(TL_AFFINE) TL_CASE(TL_AFFINE | TL_POOL1)
         TL_CASE(TL_MASK) TL_CASE(TL_MASK | TL_ACC) TL_CASE(TL_MASK | TL_DROP)
+        TL_CASE(TL_FP16) TL_CASE(TL_FP16 | TL_STATS) TL_CASE(TL_FP16 | TL_STATS | TL_POOL2)
 #undef TL_CASE
         default: return 0;        // an epilogue combination without a specialisation: CUDA-core path
     }

@@ -19,14 +19,15 @@ import torch.nn as nn
 from . import _lib
 
 
-PRECISIONS = {"fp32": 0, "bf16": 1}          # AMP_PREC_* of include/ampnet_b200.h
+PRECISIONS = {"fp32": 0, "bf16": 1, "fp32_strict": 2}          # AMP_PREC_* of include/ampnet_b200.h
 _default_precision = "fp32"
 
 
 def set_default_precision(name):
-    """Arithmetic of the eval forward for modules that do not set `.precision` themselves:
-    "fp32" (the parity path: split-bf16 tensor-core GEMMs at fp32-class accuracy + fp32 CUDA-core layers) or "bf16"
-    (fused tcgen05 chains, bf16 operands). Training always runs the parity path."""
+    """Arithmetic of the forward for modules that do not set `.precision` themselves:
+    "fp32" (the parity path: split-bf16 tensor-core GEMMs at fp32-class accuracy + fp32 CUDA-core layers), "bf16"
+    (eval only: fused tcgen05 chains, bf16 operands; training then runs "fp32") or "fp32_strict" (train + eval: plain fp32
+    FMA kernels only -- slower, for gradient comparisons below the 1e-3 level)."""
     global _default_precision
     if name not in PRECISIONS:
         raise ValueError("precision must be one of %s" % sorted(PRECISIONS))
@@ -54,10 +55,35 @@ class _NativeModule(nn.Module):
         name = self.precision or _default_precision
         if name not in PRECISIONS:
             raise ValueError("precision must be one of %s" % sorted(PRECISIONS))
-        return 0 if self.training else PRECISIONS[name]
+        if self.training and name == "bf16":
+            return 0
+        return PRECISIONS[name]
+
+    def _live_ids(self):
+        """ids of every parameter / buffer object currently registered below this module (cheap: ~25 dict walks)."""
+        subs = self.__dict__.get("_amp_submodules")
+        if subs is None:
+            subs = list(self.modules())
+            self.__dict__["_amp_submodules"] = subs
+        return tuple(id(t) for m in subs for d in (m._parameters, m._buffers) for t in d.values())
+
+    def _pack_cache(self, nbytes, device):
+        """(buffer, valid) of the packed-weight cache of the fused eval path (amp_*_fwd `pack_cache`): rebuilt by the library
+        when a parameter or BatchNorm buffer was replaced or written in place since the last eval call (`_version` counters)."""
+        ts = self._native_tensors()
+        key = (tuple((t.data_ptr(), t._version) for t in ts), str(device))
+        st = self.__dict__.get("_amp_pack")
+        if st is None or st[0].numel() < nbytes or st[0].device != device:
+            st = [_bytes(nbytes, device), None]
+            self.__dict__["_amp_pack"] = st
+        valid = st[1] == key
+        st[1] = key
+        return st[0], 1 if valid else 0
 
     def _native_tensors(self):
         ts = self.__dict__.get("_amp_tensors")
+        if ts is not None and self.__dict__.get("_amp_tensor_ids") != self._live_ids():
+            ts = None           # a parameter / buffer object was replaced (load_state_dict(assign=True) on a parent, p = nn.Parameter(..))
         if ts is None:
             sd = self.state_dict(keep_vars=True)
             lib = _lib.lib()
@@ -68,6 +94,7 @@ class _NativeModule(nn.Module):
                                    % type(self).__name__)
             ts = list(sd.values())
             self.__dict__["_amp_tensors"] = ts
+            self.__dict__["_amp_tensor_ids"] = self._live_ids()
         dev = ts[0].device
         if dev.type != "cuda":
             raise RuntimeError("ampnet_b200: %s must live on a CUDA device (no CPU fallback); call .to('cuda')"
@@ -162,9 +189,10 @@ class TransformationNet(nn.Module):
 
 class _EncoderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, training, precision, *tensors):
+    def forward(ctx, x, training, precision, pack, *tensors):
         lib = _lib.lib()
         B, N, _ = x.shape
+        pack_buf, pack_valid = pack if pack is not None else (None, 0)
         dev = x.device
         out = torch.empty((B, N, 320), dtype=torch.float32, device=dev)
         ft = torch.empty((B, 64, 64), dtype=torch.float32, device=dev)
@@ -176,7 +204,8 @@ class _EncoderFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(lib.amp_encoder_fwd(_ptr_array(tensors), x.data_ptr(), B, N, tr, precision, out.data_ptr(), ft.data_ptr(),
                                            saved.data_ptr() if training else None, saved_bytes, ws.data_ptr(), ws_bytes,
-                                           _lib.stream_ptr()))
+                                           pack_buf.data_ptr() if pack_buf is not None else None,
+                                           pack_buf.numel() if pack_buf is not None else 0, pack_valid, _lib.stream_ptr()))
         if training:
             ctx.tensors = tensors
             ctx.saved = saved
@@ -204,7 +233,7 @@ class _EncoderFn(torch.autograd.Function):
                                            B, N, saved.data_ptr(), saved.numel(), ws.data_ptr(), ws_bytes,
                                            _lib.stream_ptr()))
         ctx.saved = None
-        return (None, None, None) + tuple(grads)
+        return (None, None, None, None) + tuple(grads)
 
 
 class BasePointNet(_NativeModule):
@@ -244,7 +273,14 @@ class BasePointNet(_NativeModule):
         x = _input(x, "x", tensors[0].device)
         if x.dim() != 3 or x.shape[2] != 9:
             raise ValueError("x must be [B, N, 9], got %s" % (tuple(x.shape),))
-        out, ft = _EncoderFn.apply(x, self.training, self._precision(), *tensors)
+        if x.requires_grad and torch.is_grad_enabled():
+            raise RuntimeError("ampnet_b200: BasePointNet has no gradient with respect to its input points (the scripts never "
+                               "ask for one: train_pointnet-attention.py:407-410 builds them from data); detach `x`")
+        prec = self._precision()
+        pack = None
+        if not self.training and prec == 0:
+            pack = self._pack_cache(_lib.lib().amp_encoder_pack_bytes(), x.device)
+        out, ft = _EncoderFn.apply(x, self.training, prec, pack, *tensors)
         if self.return_local_features:
             return out, ft
         return out[:, 0, :256], ft
@@ -254,7 +290,8 @@ class _SegFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, gl, lo, cent, training, meta, *tensors):
         lib = _lib.lib()
-        npc, group_rows, mask, E, heads, C, p, seed, precision, gl_ld, lo_ld = meta
+        npc, group_rows, mask, E, heads, C, p, seed, precision, gl_ld, lo_ld, pack = meta
+        pack_buf, pack_valid = pack if pack is not None else (None, 0)
         W, B, _ = gl.shape
         R = lo.shape[1]
         dev = lo.device
@@ -267,7 +304,9 @@ class _SegFn(torch.autograd.Function):
             _lib.check(lib.amp_seg_fwd(_ptr_array(tensors), gl.data_ptr(), gl_ld, lo.data_ptr(), lo_ld, cent.data_ptr(), npc,
                                        group_rows.data_ptr(), mask.data_ptr() if mask is not None else None, B, W, R, E,
                                        heads, C, 1 if training else 0, precision, p, seed, logits.data_ptr(), saved.data_ptr(),
-                                       saved_bytes, ws.data_ptr(), ws_bytes, _lib.stream_ptr()))
+                                       saved_bytes, ws.data_ptr(), ws_bytes,
+                                       pack_buf.data_ptr() if pack_buf is not None else None,
+                                       pack_buf.numel() if pack_buf is not None else 0, pack_valid, _lib.stream_ptr()))
         if training:
             ctx.tensors = tensors
             ctx.saved = saved
@@ -281,7 +320,7 @@ class _SegFn(torch.autograd.Function):
     def backward(ctx, d_logits):
         lib = _lib.lib()
         gl, lo, cent = ctx.saved_tensors
-        npc, group_rows, mask, E, heads, C, p, seed, _, _, lo_ld = ctx.meta
+        npc, group_rows, mask, E, heads, C, p, seed, _, _, lo_ld, _ = ctx.meta
         tensors = ctx.tensors
         W, B, _ = gl.shape
         R = lo.shape[1]
@@ -368,6 +407,10 @@ class SegmentationWithAttention(_NativeModule):
                 raise ValueError("attn_mask must be [B, W]")
         p = self.dropout_p if self.training else 0.0
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0.0 else 0
-        meta = (npc, group_rows, mask, E, self.num_heads, self.num_classes, p, seed, self._precision(), gl_ld, lo_ld)
+        prec = self._precision()
+        pack = None
+        if not self.training and prec == 0:
+            pack = self._pack_cache(_lib.lib().amp_seg_pack_bytes(self.num_classes), dev)
+        meta = (npc, group_rows, mask, E, self.num_heads, self.num_classes, p, seed, prec, gl_ld, lo_ld, pack)
         logits = _SegFn.apply(gl, lo, cent, self.training, meta, *tensors)
         return logits, 0

@@ -16,17 +16,23 @@ def shard_windows(blocks_per_window, world):
     n = len(blocks_per_window)
     total = float(sum(blocks_per_window))
     bounds, acc, start = [], 0.0, 0
-    r = 1
-    for i, b in enumerate(blocks_per_window):
-        acc += b
-        while r < world and acc >= total * r / world - 1e-9 and n - (i + 1) >= 0:
-            bounds.append((start, i + 1))
-            start = i + 1
-            r += 1
-    bounds.append((start, n))
-    while len(bounds) < world:
-        bounds.append((n, n))
-    return bounds[:world]
+    for r in range(world):
+        left = world - r - 1                                  # ranks still to be served after this one
+        if r == world - 1:
+            end = n
+        else:
+            # at least one window (when any is left), at most what leaves one window for every later rank (when n >= world)
+            lo = min(start + 1, n)
+            hi = max(lo, n - left)
+            end = lo
+            acc_r = acc + sum(blocks_per_window[start:lo])
+            while end < hi and acc_r < total * (r + 1) / world - 1e-9:
+                acc_r += blocks_per_window[end]
+                end += 1
+        acc += sum(blocks_per_window[start:end])
+        bounds.append((start, end))
+        start = end
+    return bounds
 
 
 class GradAllReduce:
@@ -35,9 +41,12 @@ class GradAllReduce:
     zero_copy=False: `all_reduce()` packs the `.grad` tensors into the flat buffer (one multi-tensor copy), reduces, and
     unpacks. zero_copy=True (parameters of the ampnet_b200 modules): every `p.grad` IS its slice of the flat buffer; the first
     backward of a step writes it in place, later backward calls of the same step (one encoder call per window) are added to
-    it by autograd (`modules._grad_targets`), and `all_reduce()` is the collective alone and ends the step. Do not clear the
-    optimizers with `zero_grad(set_to_none=True)` in this mode (`.grad` must keep pointing into the buffer); no zero_grad
-    is needed at all, the first backward of the next step overwrites."""
+    it by autograd (`modules._grad_targets`), and `all_reduce()` is the collective alone and ends the step. No zero_grad is
+    needed (the first backward of the next step overwrites), but the reference's loop calls `optimizer.zero_grad()` every
+    step (train_pointnet-attention.py:372-373), whose default `set_to_none=True` detaches `.grad` from the buffer:
+    `all_reduce()` therefore re-attaches every parameter before the collective -- it folds a detached `.grad` (the windows
+    autograd accumulated outside the buffer) into the slice, zeroes the slices of parameters that received no gradient in
+    the step, and points `.grad` back at the buffer, so both styles train on the same averaged gradients."""
 
     def __init__(self, params, world=None, group=None, zero_copy=False):
         self.params = [p for p in params if p.requires_grad]
@@ -82,10 +91,37 @@ class GradAllReduce:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             self.flat.mul_(1.0 / self.world)
 
+    def _reattach(self):
+        """zero_copy, before the collective: make every slice hold exactly this step's gradient and every `.grad` alias it."""
+        stale, add_dst, add_src, copy_dst, copy_src = [], [], [], [], []
+        for p, v in zip(self.params, self.views):
+            g, written = p.grad, getattr(p, "_amp_sink_written", False)
+            aliased = g is not None and g.data_ptr() == v.data_ptr()
+            if aliased:
+                if not written:                 # no backward touched it this step: last step's average is still in the slice
+                    stale.append(v)
+            elif g is None:
+                if not written:
+                    stale.append(v)
+                p.grad = v
+            else:                               # zero_grad(set_to_none=True) detached it and autograd made a new tensor
+                if written:
+                    add_dst.append(v); add_src.append(g)
+                else:
+                    copy_dst.append(v); copy_src.append(g)
+                p.grad = v
+        if stale:
+            torch._foreach_zero_(stale)
+        if add_dst:
+            torch._foreach_add_(add_dst, add_src)
+        if copy_dst:
+            torch._foreach_copy_(copy_dst, copy_src)
+
     def all_reduce(self):
-        """zero_copy: the collective alone. Otherwise pack (one multi-tensor copy), all-reduce, unpack (one multi-tensor
-        copy): 4 launches + the collective instead of two small copies per parameter."""
+        """zero_copy: re-attach check + the collective. Otherwise pack (one multi-tensor copy), all-reduce, unpack (one
+        multi-tensor copy): 4 launches + the collective instead of two small copies per parameter."""
         if self.zero_copy:
+            self._reattach()
             self._reduce_flat()
             self.begin_step()
             return

@@ -1,16 +1,21 @@
 """bench.py -- throughput of the AMP-Net hot path on B200 (contract: see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload fps|fwd|train] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload fwd|train|fps|kmeans|tile|fwd_bf16] [--impl ours|reference]
 
 One JSON line on stdout (rank 0). Under torchrun every rank processes its own shard (weak scaling,
-no data-path collective for fps/fwd; NCCL gradient all-reduce for train).
+no data-path collective for fps/fwd; NCCL gradient all-reduce for train; the tile is sharded: strong).
 
 Workloads (BASELINE.json `configs`):
-  fps    configs[1]  FPS of 64 windows x 40 000 points -> 2048 per GPU          unit: clouds/s
-  fwd    configs[0]  PointNet-attention segmentation forward, 32 x 2048 points   unit: points/s
-  train  configs[2]  fwd + loss + bwd + 2 x Adam, 32 x 2048 points               unit: points/s
-The default headline is `fps` (configs[1]); the other workloads that are available are measured in
-the same run and reported under "workloads" of the same JSON line.
+  fwd    configs[0]  PointNet-attention segmentation forward, 32 x 2048 points, fp32 parity path   unit: points/s
+  train  configs[2]  fwd + loss + bwd + 2 x Adam, 32 x 2048 points                                 unit: points/s
+  fps    configs[1]  FPS of 64 windows x 40 000 points -> 2048 per GPU                             unit: clouds/s
+  kmeans             one k-means assignment pass over 16.8 M points, k = 9                         unit: points/s
+  tile   configs[3]  1M-point tile: k-means block split + forward, windows sharded over the GPUs   unit: points/s
+  fwd_bf16           configs[0] in bf16 (narrower than the reference: labelled, never the headline)
+The default headline is `fwd` (the first metric BASELINE.json names, in the reference's fp32); every other workload is
+measured in the same run and reported, compactly, under "workloads" of the same JSON line -- each with its own
+`cpu_baseline` (oracle port on the box's host cores), `roofline` and `e2e`. The full records go to
+gpurun_out/bench_detail.json when that directory exists.
 
 Timing: CUDA events on the launching stream around every step, L2 flushed (256 MiB write) between
 steps outside the events, barrier + synchronize on both sides of the region, max over ranks.
@@ -32,6 +37,8 @@ if ROOT not in sys.path:
 PKG = "3d-semantic-segmentation-amp-net_b200"
 
 FPS_CLOUDS, FPS_POINTS, FPS_DIMS, FPS_SAMPLES = 64, 40000, 11, 2048
+# fps_cluster_kernel as built: thread instructions per (candidate, pick) and DRAM bytes per 64-cloud launch, from ncu
+FPS_WARP_INST_PER_UPDATE, FPS_DRAM_BYTES_PER_LAUNCH, FPS_NCU_SOURCE = 24.4, 127.5e6, "profiles/r01_fps_ncu_full.txt"
 NN_BATCH, NN_POINTS, NN_DIMS = 32, 2048, 9
 
 
@@ -43,6 +50,16 @@ def peaks():
         return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
                 "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def clock_mhz():
+    """Current SM clock (MHz) from nvidia-smi; the nominal maximum if it cannot be read."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.max.sm", "--format=csv,noheader,nounits", "-i", "0"],
+                             capture_output=True, text=True, timeout=10).stdout.split()
+        return float(out[0])
+    except Exception:
+        return 1965.0
 
 
 class ClockSampler:
@@ -195,25 +212,27 @@ def bench_fps(dist, amp, steps, warmup, with_cpu):
 
     e_ms, _ = timed_steps(dist, step_e2e, steps, warmup, flush)
     clouds = FPS_CLOUDS * dist.world * steps
-    pk = peaks()
-    alg_bytes = (FPS_SAMPLES - 1) * FPS_POINTS * 20.0 * FPS_CLOUDS        # 20 B / candidate / pick
-    ach = alg_bytes / (k_ms / steps * 1e-3) / 1e9
+    # Roofline of fps_cluster_kernel: the whole cloud lives on chip (registers + shared memory; ncu: dram bytes = 0.3 % of the
+    # HBM model's), so the bound is the instruction issue rate: executed warp instructions (smsp__inst_executed.sum of one
+    # launch, a property of the build, from the ncu capture named below) / kernel time, against 4 issue slots per SM per clock.
+    sm_mhz = clock_mhz()
+    warp_inst = FPS_WARP_INST_PER_UPDATE * (FPS_SAMPLES - 1) * FPS_POINTS * FPS_CLOUDS / 32.0
+    ach = warp_inst / (k_ms / steps * 1e-3) / 1e9
+    peak = 4.0 * 148 * sm_mhz * 1e-3
     res = {
         "value": clouds / (total_ms * 1e-3), "unit": "clouds/s", "ms_per_step": total_ms / steps,
         "gpu_launches": int(launches),
         "e2e": {"value": clouds / (e_ms * 1e-3), "unit": "clouds/s",
                 "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": int(rows_host.numel() * 4)},
-        "roofline": {"bound": "hbm", "kernel": "fps_cluster_kernel", "achieved": ach, "peak": pk["hbm_gbs"],
-                     "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                     "traffic": 127.5e6,   # dram__bytes_read + write of one launch, ncu --set full (profiles/r01_fps_ncu_full.txt)
-                     "peak_source": pk["source"] + " (burst copy)",
-                     "model": "20 B per candidate per pick (12 B coords + 8 B running-min r/w) x (S-1) x P x clouds; "
-                              "the kernel keeps the whole cloud on chip (registers + SMEM), so frac > 1 is expected: "
-                              "see DESIGN.md",
+        "roofline": {"bound": "issue", "kernel": "fps_cluster_kernel", "achieved": ach, "peak": peak, "unit": "Gwarp-inst/s",
+                     "frac": ach / peak, "traffic": FPS_DRAM_BYTES_PER_LAUNCH,
+                     "model": "%.1f thread instructions per candidate update (ncu, %s) x (S-1) x P x clouds / 32 per launch; "
+                              "peak = 4 issue slots x 148 SMs x %.0f MHz; HBM is idle (cloud on chip)"
+                              % (FPS_WARP_INST_PER_UPDATE, FPS_NCU_SOURCE, sm_mhz),
                      "kernel_ms": k_ms / steps},
         "config": {"workload": "configs[1]: FPS %d windows x %d pts -> %d per GPU, float32 rows of %d columns"
-                               % (FPS_CLOUDS, FPS_POINTS, FPS_SAMPLES, FPS_DIMS),
-                   "l2": "flushed between steps (256 MiB write)", "clouds_per_gpu": FPS_CLOUDS},
+                               % (FPS_CLOUDS, FPS_POINTS, FPS_SAMPLES, FPS_DIMS)},
+        "notes": {"l2": "flushed between steps (256 MiB write)", "clouds_per_gpu": FPS_CLOUDS},
         "dtype": "f32",
     }
     if with_cpu:
@@ -283,8 +302,8 @@ def bench_kmeans(dist, amp, steps, warmup, with_cpu):
                      "traffic": 250.1e6,   # dram__bytes_read + write of one launch, ncu --set full (profiles/r01_final_kmeans_ncu.txt)
                      "peak_source": pk["source"] + " (burst copy)",
                      "model": "16 B per point per assignment pass (12 B features read + 4 B int32 label written), k = %d" % KM_K},
-        "config": {"workload": "k-means assignment pass, %d points x 3 features, k = %d (block split of configs[3])" % (KM_POINTS, KM_K),
-                   "l2": "flushed between steps (256 MiB write); working set 268 MB > L2"},
+        "config": {"workload": "k-means assignment pass, %d points x 3 features, k = %d" % (KM_POINTS, KM_K)},
+        "notes": {"l2": "flushed between steps (256 MiB write); working set 268 MB > L2"},
         "dtype": "f32",
     }
     if with_cpu:
@@ -309,6 +328,8 @@ def run_reference(args, emit):
         return
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
     wl = args.workload
+    if wl == "tile":
+        wl = "fwd"                  # the tile's CPU arm is the forward of its blocks (the constrained solver has no CPU reference)
     if wl == "fps":
         cores = os.cpu_count() or 1
         sample = min(max(4 * cores, 16), 128)         # ~1 s of wall clock per step on the box's host cores
@@ -354,6 +375,39 @@ def run_reference(args, emit):
     emit(line)
 
 
+METRICS = {"fps": "FPS clouds/sec", "fwd": "segmented points/sec (fwd)", "fwd_bf16": "segmented points/sec (fwd), bf16",
+           "kmeans": "k-means assigned points/sec", "train": "train pts/sec", "tile": "segmented points/sec (1M-point tile)"}
+ORDER = ["fwd", "train", "fps", "kmeans", "tile", "fwd_bf16"]
+
+
+def _r(x, nd=4):
+    """Round to nd significant digits (compact JSON)."""
+    if not isinstance(x, float) or x == 0.0 or x != x:
+        return x
+    from math import floor, log10
+    return round(x, nd - 1 - int(floor(log10(abs(x)))))
+
+
+def compact(r):
+    """The secondary-workload record: numbers only, short keys (the whole line must fit the driver's stdout tail)."""
+    if "error" in r:
+        return r
+    o = {"value": _r(r["value"]), "unit": r["unit"], "ms": _r(r["ms_per_step"]), "dtype": r.get("dtype")}
+    if "scaling" in r:
+        o["scaling"] = r["scaling"]
+    if "e2e" in r:
+        o["e2e"] = _r(r["e2e"]["value"])
+    rf = r.get("roofline")
+    if rf:
+        o["roofline"] = {"bound": rf["bound"], "achieved": _r(rf["achieved"]), "peak": _r(rf["peak"]), "unit": rf["unit"], "frac": _r(rf["frac"], 3)}
+    cb = r.get("cpu_baseline")
+    if cb:
+        o["cpu"] = {"value": _r(cb["value"]), "cores": cb["cores"], "kind": cb["kind"]}
+    if "stages" in r:
+        o["stages"] = {k: _r(v) if isinstance(v, float) else v for k, v in r["stages"].items()}
+    return o
+
+
 def main():
     # stdout carries exactly ONE JSON line: anything a library prints there (e.g. NCCL's version banner) goes to stderr
     real_stdout = os.dup(1)
@@ -367,9 +421,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="fps", choices=["fps", "kmeans", "fwd", "fwd_bf16", "train", "tile", "tile_bf16"])
+    ap.add_argument("--workload", default="fwd", choices=ORDER)
     ap.add_argument("--only", action="store_true", help="measure only the headline workload")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -380,17 +434,15 @@ def main():
         raise SystemExit("bench.py: no CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
     amp = importlib.import_module(PKG)
     amp._lib.lib()
+    import bench_nn
     dist = Dist(args.gpus)
     with_cpu = (dist.rank == 0 and dist.world == 1 and not args.no_cpu)
     table = {"fps": bench_fps, "kmeans": bench_kmeans}
-    if hasattr(amp, "bench_hooks"):
-        table.update(amp.bench_hooks())
-    if args.workload not in table:
-        raise SystemExit("workload %s is not available in this build" % args.workload)
+    table.update(bench_nn.hooks())
     with ClockSampler(dist.local_rank) as clk:
         head = table[args.workload](dist, amp, args.steps, args.warmup, with_cpu)
-    line = {"metric": {"fps": "FPS clouds/sec", "fwd": "segmented points/sec (fwd)", "fwd_bf16": "segmented points/sec (fwd)",
-                       "kmeans": "k-means assigned points/sec", "train": "train pts/sec", "tile": "segmented points/sec (fwd)", "tile_bf16": "segmented points/sec (fwd)"}[args.workload],
+    detail = {args.workload: dict(head)}
+    line = {"metric": METRICS[args.workload],
             "value": head.pop("value"), "unit": head.pop("unit"), "n_gpus": dist.world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": head.pop("ms_per_step"), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "data": "synthetic"}
@@ -398,19 +450,24 @@ def main():
     line["clocks"] = clk.summary()
     if not args.only:
         others = {}
-        for name, fn in table.items():
+        for name in ORDER:
             if name == args.workload:
                 continue
             try:
-                r = fn(dist, amp, max(3, args.steps // 2), 3, False)
-                others[name] = {k: r[k] for k in ("value", "unit", "ms_per_step", "scaling", "e2e", "roofline", "stages", "config", "dtype")
-                                if k in r}
+                r = table[name](dist, amp, max(3, args.steps // 2), 3, with_cpu)
             except Exception as e:  # a secondary workload must not take the headline down
-                others[name] = {"error": repr(e)[:200]}
-        if others:
-            line["workloads"] = others
+                r = {"error": repr(e)[:160]}
+            detail[name] = r
+            others[name] = compact(r)
+        line["workloads"] = others
     if dist.rank == 0:
         emit(line)
+        try:
+            if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+                with open(os.path.join(ROOT, "gpurun_out", "bench_detail_n%d.json" % dist.world), "w") as f:
+                    json.dump({"line": line, "detail": detail}, f, indent=1, default=str)
+        except OSError:
+            pass
     dist.close()
 
 

@@ -1,4 +1,5 @@
-"""bench.py hooks for the PointNet-attention workloads (BASELINE.json configs[0] and configs[2]).
+"""bench.py workloads of the PointNet-attention stages (BASELINE.json configs[0], configs[2], configs[3]); lives next to bench.py
+(not in the product package: its cpu_baseline legs import oracle/).
 
   fwd    segmentation forward of 32 x 2048-point blocks (eval mode), the loop of
          test_pointnet_att_segmen.py:160-181 / train_pointnet-attention.py:396-450 at W = 1
@@ -20,7 +21,7 @@ TRAIN_FLOP_PER_POINT = 3 * FWD_FLOP_PER_POINT
 
 
 def _peaks():
-    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
@@ -124,14 +125,14 @@ def bench_fwd(dist, amp, steps, warmup, with_cpu, precision="fp32"):
         "value": pts / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms / steps, "gpu_launches": int(launches),
         "e2e": {"value": pts / (e_ms * 1e-3), "unit": "points/s",
                 "h2d_bytes_per_step": int(x_host.numel() * 4 + c_host.numel() * 4), "d2h_bytes_per_step": int(logits_host.numel() * 4)},
-        "roofline": {"bound": "tensor", "kernel": "whole forward (tc_layer_kernel: split-bf16 3-MMA tcgen05 layers at fp32-class accuracy, + few-row fp32 kernels)" if precision == "fp32"
-                     else "whole forward (tc_chain_kernel x 4: tcgen05 bf16 chains + fp32 per-cloud FC / attention kernels)",
+        "roofline": {"bound": "tensor", "kernel": "whole forward: tc_chain32_kernel x 5 (split-bf16 3-MMA tcgen05 chains, activations in TMEM) + fp32 per-cloud FC / attention kernels" if precision == "fp32"
+                     else "whole forward: tc_chain_kernel x 4 (tcgen05 bf16 chains) + fp32 per-cloud FC / attention kernels",
                      "achieved": ach, "peak": peak,
                      "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": src,
-                     "model": "413 143 algorithmic FLOP per point (SURVEY 8d) x 65 536 points / step time"},
-        "config": {"workload": "configs[0]: segmentation forward, batch %d x %d points, 9 channels, eval, random-init weights"
-                               % (NN_BATCH, NN_POINTS), "l2": "flushed between steps (256 MiB write)", "precision": precision,
-                   "launch": "CUDA graph replay of the two module calls (eager: %.3f ms per step)" % (eager_ms / steps)},
+                     "model": "413 143 algorithmic FLOP per point (SURVEY 8d) x 65 536 points / step time; the fp32 path executes 3 MMAs per product"},
+        "config": {"workload": "configs[0]: segmentation forward, batch %d x %d points, 9 channels, eval, random-init weights" % (NN_BATCH, NN_POINTS)},
+        "notes": {"l2": "flushed between steps (256 MiB write)", "precision": precision,
+                  "launch": "CUDA graph replay of the two module calls (eager: %.3f ms per step)" % (eager_ms / steps)},
         "dtype": "f32" if precision == "fp32" else "bf16",
     }
     if with_cpu:
@@ -160,7 +161,7 @@ def bench_train(dist, amp, steps, warmup, with_cpu):
     keep = {}
     flat = None
     if dist.pg:
-        from .parallel import GradAllReduce
+        GradAllReduce = amp.GradAllReduce
         flat = GradAllReduce(params, dist.world, zero_copy=True)      # .grad = slices of one flat buffer, written in place
 
     def train_step(xd, cd, td):
@@ -195,9 +196,9 @@ def bench_train(dist, amp, steps, warmup, with_cpu):
         "roofline": {"bound": "tensor", "kernel": "whole step (tc_layer_kernel / tc_wgrad_kernel: split-bf16 3-MMA tcgen05 GEMMs at fp32-class accuracy, few-row fp32 kernels, torch Adam)", "achieved": ach, "peak": peak,
                      "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": src,
                      "model": "3 x 413 143 algorithmic FLOP per point (SURVEY 8d) x 65 536 points / step time"},
-        "config": {"workload": "configs[2]: training step fwd+loss+bwd+2xAdam(fused), batch %d x %d points per GPU, dropout 0.3%s"
-                               % (NN_BATCH, NN_POINTS, ", NCCL gradient all-reduce" if dist.pg else ""),
-                   "l2": "flushed between steps (256 MiB write)", "precision": "fp32"},
+        "config": {"workload": "configs[2]: training step fwd+loss+bwd+2xAdam, batch %d x %d points per GPU" % (NN_BATCH, NN_POINTS)},
+        "notes": {"l2": "flushed between steps (256 MiB write)", "precision": "fp32", "dropout": 0.3, "adam": "torch fused",
+                  "collective": "NCCL gradient all-reduce (AVG, one flat buffer)" if dist.pg else "none (1 GPU)"},
         "dtype": "f32", "final_loss": float(keep["loss"]),
     }
     if with_cpu:
@@ -319,16 +320,20 @@ def bench_tile(dist, amp, steps, warmup, with_cpu, precision="fp32"):
         "stages": {"kmeans_split_ms_rank0_last_step": km_ms, "blocks_this_rank": int(sum(ks)), "windows_this_rank": len(ks),
                    "rows_with_duplicate_fill_this_rank": n_rows},
         "config": {"workload": "configs[3]: 1M-point synthetic tile, 10 x 10 windows, constrained k-means into 2048-point blocks, "
-                               "blocks sharded by window over %d GPU(s), eval forward" % dist.world,
-                   "l2": "flushed between steps (256 MiB write)", "precision": precision},
+                               "windows sharded over the GPUs, eval forward"},
+        "notes": {"l2": "flushed between steps (256 MiB write)", "precision": precision, "n_gpus": dist.world},
         "dtype": "f32" if precision == "fp32" else "bf16",
     }
+    pk, src = _peaks()
+    fl = n_pts * FWD_FLOP_PER_POINT / (ms / steps * 1e-3) / 1e12
+    res["roofline"] = {"bound": "tensor", "kernel": "whole step (k-means block split + encoder + head)", "achieved": fl, "peak": pk * dist.world,
+                       "unit": "TFLOP/s", "frac": fl / (pk * dist.world), "traffic": None, "peak_source": src,
+                       "model": "413 143 FLOP per real point x 1M points / step time (the k-means stage adds no FLOPs to the model)"}
+    if with_cpu:
+        from oracle import nn_bench as onb
+        res["cpu_baseline"] = onb.cpu_tile(wins[:2], ks[:2])
     return res
 
 
-def bench_tile_bf16(dist, amp, steps, warmup, with_cpu):
-    return bench_tile(dist, amp, steps, warmup, with_cpu, precision="bf16")
-
-
 def hooks():
-    return {"fwd": bench_fwd, "fwd_bf16": bench_fwd_bf16, "train": bench_train, "tile": bench_tile, "tile_bf16": bench_tile_bf16}
+    return {"fwd": bench_fwd, "fwd_bf16": bench_fwd_bf16, "train": bench_train, "tile": bench_tile}

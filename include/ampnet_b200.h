@@ -31,14 +31,19 @@ extern "C" {
 
 /* arithmetic of the PointNet-attention forward (amp_encoder_fwd / amp_seg_fwd `precision`):
  *   AMP_PREC_FP32  the parity path (logits within 1e-3 relative of the fp32 reference; measured 6e-6), train + eval.
- *                  Wide layers (>= 2048 rows, K a multiple of 16) run on the tcgen05 tensor cores at fp32-class accuracy:
- *                  every fp32 operand is split into two bf16 terms and lo*hi + hi*lo + hi*hi is accumulated in fp32
- *                  (~2^-17 relative per product); the 3 / 9 raw input columns, the few-row FC / token layers and all
- *                  BatchNorm statistics are plain fp32 / fp64 on the CUDA cores.
+ *                  The shared-MLP layers run on the tcgen05 tensor cores at fp32-class accuracy: every fp32 operand is split
+ *                  into two 16-bit terms and lo*hi + hi*lo + hi*hi is accumulated in fp32. Eval: bf16 terms (~2^-17 per
+ *                  product), fused chains with the activations resident in tensor memory (tc_chain32). Training forward: fp16
+ *                  terms (2^-23: max-pool ties must not flip), one kernel per layer with batch statistics in the epilogue;
+ *                  backward: bf16 terms (gradient magnitudes need the exponent range). The few-row FC / token layers and all
+ *                  BatchNorm statistics are plain fp32 on the CUDA cores.
+ *   AMP_PREC_FP32_STRICT  as AMP_PREC_FP32 but no split-bf16 arithmetic: every layer of the call is plain fp32 FMA on the
+ *                  CUDA cores (3-4x slower): the arithmetic of the reference itself, for gradient comparisons at the 1e-4 level.
  *   AMP_PREC_BF16  eval only: fused tcgen05 chains, bf16 operands (BatchNorm folded into the weights), fp32 accumulate;
  *                  logits within ~3e-3 .. 7e-3 of the reference. */
 #define AMP_PREC_FP32     0
 #define AMP_PREC_BF16     1
+#define AMP_PREC_FP32_STRICT 2
 
 const char* amp_last_error(void);
 /* ABI version of this header: major*1000 + minor. */
@@ -120,7 +125,10 @@ int amp_kmeans_regroup(const int32_t* labels, const int64_t* offsets, const int3
  *   feat_t      [B, 64, 64] f32 feature transform (second module output, :94)
  *   training    0: eval (BatchNorm running statistics);  1: train (batch statistics; running_mean /
  *               running_var / num_batches_tracked updated in place; `saved` filled for backward)
- *   precision   AMP_PREC_FP32 | AMP_PREC_BF16 (eval only)
+ *   precision   AMP_PREC_FP32 | AMP_PREC_BF16 (eval only) | AMP_PREC_FP32_STRICT
+ *   pack_cache  amp_encoder_pack_bytes() bytes owned by the caller, or NULL: the BatchNorm-folded, hi / lo split weights of the
+ *               fused eval chains. pack_valid = 0: (re)build it in this call (first call, or parameters changed since);
+ *               pack_valid = 1: reuse. Only the eval AMP_PREC_FP32 path reads it. NULL: rebuilt every call in the workspace.
  *   saved       amp_encoder_saved_bytes() bytes, kept by the caller between fwd and bwd (training only)
  *   workspace   amp_encoder_workspace_bytes() bytes of scratch (may be reused after the call's work completes)
  * amp_encoder_bwd: grads = host array of DEVICE pointers like params (NULL for the BatchNorm buffers), every
@@ -130,9 +138,10 @@ int amp_encoder_param_count(void);
 const char* amp_encoder_param_name(int i);
 size_t amp_encoder_saved_bytes(int64_t B, int64_t N, int32_t training);
 size_t amp_encoder_workspace_bytes(int64_t B, int64_t N, int32_t training);
+size_t amp_encoder_pack_bytes(void);
 int amp_encoder_fwd(const void* const* params, const float* x, int64_t B, int64_t N, int32_t training, int32_t precision,
                     float* out, float* feat_t, void* saved, size_t saved_bytes, void* workspace,
-                    size_t workspace_bytes, void* stream);
+                    size_t workspace_bytes, void* pack_cache, size_t pack_bytes, int32_t pack_valid, void* stream);
 int amp_encoder_bwd(const void* const* params, void* const* grads, const float* x, const float* out,
                     const float* feat_t, const float* d_out, const float* d_feat_t, int64_t B, int64_t N,
                     void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes, void* stream);
@@ -153,11 +162,13 @@ int amp_encoder_bwd(const void* const* params, void* const* grads, const float* 
  *   logits      [B, num_classes, rows] f32
  *   training    1: batch-statistics BatchNorm + dropout(dropout_p) driven by the counter-based generator
  *               seeded with `seed` (pass the same seed to amp_seg_bwd)
- *   precision   AMP_PREC_FP32 | AMP_PREC_BF16 (eval only, num_classes <= 32)
+ *   precision   AMP_PREC_FP32 | AMP_PREC_BF16 (eval only, num_classes <= 32) | AMP_PREC_FP32_STRICT
+ *   pack_cache  amp_seg_pack_bytes(num_classes) bytes or NULL, pack_valid: as for amp_encoder_fwd
  *   saved       amp_seg_saved_bytes() bytes (needed in both modes; kept for backward in training)
  * amp_seg_bwd: d_logits [B, num_classes, rows]; writes d_gl_feats [W, B, E], d_lo_feats [B, rows, 64] and every
  * parameter gradient (overwritten). Needs block sizes sharing a factor >= 64 points and W <= 64.
  * ------------------------------------------------------------------------------------------ */
+size_t amp_seg_pack_bytes(int32_t num_classes);
 int amp_seg_param_count(void);
 const char* amp_seg_param_name(int i);
 size_t amp_seg_saved_bytes(int64_t B, int64_t W, int64_t rows, int32_t embed_dim, int32_t heads);
@@ -167,7 +178,7 @@ int amp_seg_fwd(const void* const* params, const float* gl_feats, int64_t gl_ld,
                 const int32_t* np_cluster, const int32_t* group_rows, const uint8_t* key_padding_mask, int64_t B,
                 int64_t W, int64_t rows, int32_t embed_dim, int32_t heads, int32_t num_classes, int32_t training,
                 int32_t precision, float dropout_p, uint64_t seed, float* logits, void* saved, size_t saved_bytes,
-                void* workspace, size_t workspace_bytes, void* stream);
+                void* workspace, size_t workspace_bytes, void* pack_cache, size_t pack_bytes, int32_t pack_valid, void* stream);
 int amp_seg_bwd(const void* const* params, void* const* grads, const float* lo_feats, int64_t lo_ld, const float* centroids,
                 const int32_t* np_cluster, const int32_t* group_rows, const float* d_logits, int64_t B, int64_t W,
                 int64_t rows, int32_t embed_dim, int32_t heads, int32_t num_classes, float dropout_p, uint64_t seed,

@@ -68,6 +68,32 @@ def cpu_train(sample_steps=2):
                       "best %.3f s" % (sample_steps, cores, best), "seconds": ts}
 
 
+def cpu_tile(wins, ks):
+    """CPU arm of the tile workload on a bounded sample: the oracle's constrained k-means (numpy restatement; the reference's
+    third-party solver is not installable) + regroup + the oracle forward of the resulting blocks, for the given windows."""
+    from . import kmeans_oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd_e = nn_params.synthetic_state_dict(nn_params.encoder_shapes(), 0, trained_bn=False)
+    sd_s = nn_params.synthetic_state_dict(nn_params.seg_shapes(), 1, trained_bn=False)
+    t0 = time.perf_counter()
+    n_pts = 0
+    with torch.no_grad():
+        for w, k in zip(wins, ks):
+            lab, _, _ = kmeans_oracle.kmeans_constrained(np.ascontiguousarray(w[:, [0, 1, 9]]), int(k), 2048, 2048)
+            order = np.argsort(lab, kind="stable")
+            g = w[order]
+            x9 = np.concatenate([g[:, 0:3], g[:, 4:10]], 1).reshape(int(k), 2048, 9).copy()
+            x9[:, :, :2] = x9[:, :, :2] * 2 - 1
+            xs = [torch.from_numpy(x9[i:i + 1]) for i in range(int(k))]
+            cent = torch.stack([x[:, :, :2].mean(1) for x in xs], 1)
+            nn_oracle.forward_windows(sd_e, sd_s, xs, cent)
+            n_pts += len(w)
+    dt = time.perf_counter() - t0
+    return {"value": n_pts / dt, "unit": "points/s", "cores": cores, "kind": "port",
+            "sample": "%d windows (%d rows): oracle constrained k-means + forward of their blocks, %d threads, %.1f s" % (len(wins), n_pts, cores, dt)}
+
+
 def reference_line(workload, args):
     fn = cpu_forward if workload == "fwd" else cpu_train
     for _ in range(min(args.warmup, 1)):

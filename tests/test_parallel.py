@@ -25,6 +25,10 @@ def test_shard_windows_partitions_and_balances(amp):
     loads = [sum([9, 1, 1, 1, 9, 1, 1, 1][s:e]) for s, e in b]
     assert max(loads) - min(loads) <= 9
     _shards(amp, [3], 4)                   # fewer windows than ranks: trailing ranks get empty ranges
+    for blocks in ([9, 1, 1, 1], [1, 1, 1, 9], [5, 5, 1, 1, 1, 1, 1, 1], [18, 1, 1]):    # every rank non-empty whenever n >= world
+        for world in (2, 3, 4):
+            if len(blocks) >= world:
+                assert all(e > s for s, e in _shards(amp, blocks, world)), (blocks, world)
     _shards(amp, [], 2)
     for world in (1, 2, 3, 8):
         _shards(amp, [((7 * i) % 18) + 1 for i in range(53)], world)
@@ -48,8 +52,8 @@ def _worker(rank, world, port, q):
     # zero-copy mode: .grad is a slice of the flat buffer, "backward" writes the sink in place, all_reduce is the collective alone
     zc = amp.GradAllReduce(params[:2], world, zero_copy=True)
     ok = ok and params[0].grad.data_ptr() == zc.views[0].data_ptr()
-    params[0]._amp_grad_sink.fill_(float(10 * (rank + 1)))
-    params[1]._amp_grad_sink.fill_(float(rank))
+    params[0]._amp_grad_sink.fill_(float(10 * (rank + 1))); params[0]._amp_sink_written = True      # what modules._grad_targets +
+    params[1]._amp_grad_sink.fill_(float(rank)); params[1]._amp_sink_written = True                 # the library's backward do
     zc.all_reduce()
     ok = ok and torch.allclose(params[0].grad, torch.full((5, 3), 10 * (1 + world) / 2.0)) \
         and torch.allclose(params[1].grad, torch.full((7,), (world - 1) / 2.0))
@@ -70,6 +74,40 @@ def test_grad_all_reduce_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_zero_copy_survives_zero_grad_set_to_none(amp):
+    """The reference's loop calls optimizer.zero_grad() every step (train_pointnet-attention.py:372-373; set_to_none=True by
+    default), which detaches p.grad from the flat buffer. all_reduce() must still deliver the sum of all windows' gradients
+    and leave p.grad aliasing the buffer; a parameter without a gradient in the step must read zero, not last step's value."""
+    import importlib
+    modules = importlib.import_module("3d-semantic-segmentation-amp-net_b200.modules")
+    w = torch.nn.Parameter(torch.zeros(4, 3)); b = torch.nn.Parameter(torch.zeros(4)); idle = torch.nn.Parameter(torch.zeros(3))
+    red = amp.GradAllReduce([w, b, idle], world=1, zero_copy=True)
+    red._reduce_flat = lambda: None                                   # single process: the collective is the identity
+    opt = torch.optim.SGD([w, b, idle], lr=1.0)
+    for step in range(2):
+        opt.zero_grad()                                               # .grad = None on every parameter
+        assert w.grad is None
+        # window 1: the library writes the sink in place and returns None to autograd
+        grads, targets = modules._grad_targets([w, b])
+        assert grads == [None, None]
+        targets[0].fill_(1.0 + step); targets[1].fill_(2.0)
+        # window 2: ordinary gradients; with .grad detached autograd stores them in a NEW tensor
+        grads, targets = modules._grad_targets([w, b])
+        targets[0].fill_(10.0); w.grad = grads[0]
+        # (b gets no second contribution)
+        if step == 0:
+            idle.grad = torch.full((3,), 7.0)                         # a torch-side gradient outside the library
+        red.all_reduce()
+        assert w.grad.data_ptr() == red.views[0].data_ptr() and b.grad.data_ptr() == red.views[1].data_ptr()
+        assert torch.equal(w.grad, torch.full((4, 3), 11.0 + step)) and torch.equal(b.grad, torch.full((4,), 2.0))
+        assert torch.equal(idle.grad, torch.full((3,), 7.0 if step == 0 else 0.0))     # stale value cleared on step 2
+    # without zero_grad: aliasing kept, an untouched parameter is zeroed rather than re-used
+    grads, targets = modules._grad_targets([w])
+    targets[0].fill_(3.0)
+    red.all_reduce()
+    assert torch.equal(w.grad, torch.full((4, 3), 3.0)) and torch.count_nonzero(b.grad) == 0
 
 
 def test_grad_targets_first_write_then_accumulate(amp):
