@@ -62,6 +62,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain32_kernel(const __grid_co
     pdl_trigger();
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
+    int pi = 0;
+    const bool prof = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
+#define T32_PROF() do { if (prof && pi < 250) p.prof[pi++] = clock64(); } while (0)
+    T32_PROF();                                                  // 0: kernel entry
     int stage_f32 = 0, stream = 0;
     for (int l = 0; l < p.n_ops; ++l) { stage_f32 |= p.op[l].store_f32; stream |= p.op[l].w_stream; }
     const Plan sp = plan_of(p.wblob_bytes, p.wcloud_bytes, p.n_bias, stage_f32, stream);
@@ -86,6 +90,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain32_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = uniform_u32(*s_tmem);
+    T32_PROF();                                                  // 1: prologue done (barriers, TMEM, bias table)
 
     const int rows = p.rows_per_cloud;
     const int tiles_per_cloud = (rows + kRows - 1) / kRows;
@@ -193,7 +198,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain32_kernel(const __grid_co
             tmem_wait_st();
             if (new_cloud) fence_proxy_async();
             tc_fence_before();
+            T32_PROF();                                          // input staged
             slot_bar_sync(slot);
+            T32_PROF();                                          // slot barrier
 
             for (int l = 0; l < p.n_ops; ++l) {
                 const T32Op& op = p.op[l];
@@ -228,9 +235,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain32_kernel(const __grid_co
                         }
                         __syncwarp();
                     }
+                    T32_PROF();                                  // issued
                     mbar_wait_bounded(mbar, phase);
                     phase ^= 1u;
                     tc_fence_after();
+                    T32_PROF();                                  // MMAs complete
 
                     if (!op.pool) {
                         const float* gb = op.bias_grouped ? p.gbias + ((long long)cloud * p.n_groups + group) * op.N : nullptr;
@@ -330,12 +339,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain32_kernel(const __grid_co
                     }
                     // accumulator reads and A-operand writes of this layer are done before the next MMA is issued
                     tc_fence_before();
+                    T32_PROF();                                  // epilogue done
                     slot_bar_sync(slot);
+                    T32_PROF();                                  // slot barrier
                 }
             }
         }
         if ((warp & 7) == 0 && !w_ready) mbar_wait(wbar, 0);     // never leave with a bulk copy in flight
     }
+    T32_PROF();                                                  // all tiles done
+    if (prof) p.prof[255] = pi;
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
@@ -425,6 +438,23 @@ int tc_chain32_launch(const T32Params& p, cudaStream_t st) {
     const long long n_tiles = (long long)p.n_clouds * ((p.rows_per_cloud + kRows - 1) / kRows);
     const int grid = (int)((n_tiles + 1) / 2 < kNumSMs ? (n_tiles + 1) / 2 : kNumSMs);
     const int smem_bytes = sp.total < kMinSmem ? kMinSmem : sp.total;
+    static const bool want_prof = getenv("AMP_CHAIN32_PROF") != nullptr;
+    if (want_prof) {                                     // debugging aid: synchronous, prints the phase timeline of CTA 0 / thread 0
+        static long long* dprof = nullptr;
+        if (!dprof) cudaMalloc(&dprof, 256 * sizeof(long long));
+        cudaMemsetAsync(dprof, 0, 256 * sizeof(long long), st);
+        T32Params q = p;
+        q.prof = dprof;
+        launch_pdl(tc_chain32_kernel, dim3((unsigned)grid), dim3(kThreads), smem_bytes, st, q);
+        long long h[256];
+        cudaMemcpyAsync(h, dprof, sizeof h, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "[tc_chain32 prof] ops=%d tiles=%lld smem=%d:", p.n_ops, n_tiles, smem_bytes);
+        for (int i = 1; i < (int)h[255] && i < 250; ++i) fprintf(stderr, " %lld", h[i] - h[i - 1]);
+        fprintf(stderr, "\n");
+        count_launch();
+        return check_launch("tc_chain32_kernel");
+    }
     launch_pdl(tc_chain32_kernel, dim3((unsigned)grid), dim3(kThreads), smem_bytes, st, p);
     count_launch();
     count_path("tc_chain32");

@@ -52,6 +52,7 @@ struct T32Params {
     unsigned int* pool;                                 // [clouds, N] bit patterns of non-negative floats, zero-initialised
     float* logits; int n_classes;
     int n_clouds, rows_per_cloud;
+    long long* prof;                                    // debugging aid (AMP_CHAIN32_PROF=1): phase timestamps of CTA 0 / slot 0
 };
 
 int tc_chain32_launch(const T32Params& p, cudaStream_t st);

@@ -223,7 +223,7 @@ def test_tensor_core_backward_equals_cuda_core_backward(amp, cuda, B, N, W, seed
     assert ran_a["tc_layer_dgrad"] > 0 and ran_a["tc_wgrad"] > 0
     assert ran_b["tc_layer_dgrad"] == 0 and ran_b["tc_wgrad"] == 0, ran_b
     assert amp._lib.path_count("pw_linear") > n_pw and amp._lib.path_count("wgrad_partial") > n_wg
-    assert float(loss_a) == float(loss_b)               # identical forward
+    assert abs(float(loss_a) - float(loss_b)) < 1e-6 * abs(float(loss_b))     # same forward (torch's loss reduction is not bitwise repeatable)
     # (biases in front of a BatchNorm have a mathematically zero gradient: both sides hold rounding noise only)
     scale = max(float(g.norm()) for g in g_cc.values())
     worst = max((_relnorm(g_tc[k], g_cc[k]), k) for k in g_tc if float(g_cc[k].norm()) > 1e-6 * scale)
