@@ -60,6 +60,8 @@ int pw_linear(const PwParams& p, cudaStream_t st);
 int tnet_fc_eval(const float* pooled, int B, const float* fc1, const float* s4, const float* t4, const float* fc2, const float* s5,
                  const float* t5, const float* fc3w, const float* fc3b, int d, int fc3_inside, float* h1, float* h2, float* out,
                  cudaStream_t st);
+// fc_3 of the feature transform (+ bias + identity) -> out [B, 64, 64] and the packed split-bf16 per-cloud operand (nn_small.cu)
+int tnet_fc3_pack(const float* h2, const float* w, const float* b, int B, float* out, unsigned char* pk, long long pk_stride, cudaStream_t st);
 // forward of the narrow-input (K <= 12) 64-channel layers over many rows, exact fp32 (nn_small.cu)
 int narrow_fwd_try(const PwParams& p, cudaStream_t st);
 // forward of the narrow-output (class logits, K = 64) layer over many rows, exact fp32 (nn_small.cu)

@@ -516,12 +516,7 @@ int encoder_fwd_fp32_fused(EncCtx& c, const float* x, float* out, float* feat_t,
     }
     AMP_TRY(tnet_fc_stack_eval(c, E_IT, L_IT1, 3, it_pool, t.f1, t.f2, t.T));
     // bmm + cat + conv_1 (:85-90) as per-cloud conv_1 weights (bn_1 scale folded in), packed per cloud
-    AMP_TRY(fold_input_transform(c.pf(E_CONV1), t.T, B, t.W1eff, c.st));
-    {
-        T32PackTable pt{}; pt.n = 1; pt.n_clouds = B;
-        pt.job[0] = T32PackJob{t.W1eff, 9, 576, sc(L_C1), 64, 9, 64, 16, 0, 0, 0, kP32CloudStride};
-        AMP_TRY(t32_pack_weights(pt, t.wcloud, c.st));
-    }
+    AMP_TRY(t32_fold_w1(c.pf(E_CONV1), t.T, sc(L_C1), B, t.wcloud, kP32CloudStride, c.st));
     // chain 2: conv_1, conv_2, feature T-Net convs + max-pool (:90-94)
     {
         T32Params p = base;
@@ -536,11 +531,11 @@ int encoder_fwd_fp32_fused(EncCtx& c, const float* x, float* out, float* feat_t,
         p.pool = reinterpret_cast<unsigned int*>(ft_pool);
         AMP_TRY(tc_chain32_launch(p, c.st));
     }
-    AMP_TRY(tnet_fc_stack_eval(c, E_FT, L_FT1, 64, ft_pool, t.f1, t.f2, feat_t));
-    {
-        T32PackTable pt{}; pt.n = 1; pt.n_clouds = B;    // local = h @ F: weight [n][k] = F[k][n]
-        pt.job[0] = T32PackJob{feat_t, 64, 4096, nullptr, 64, 64, 64, 64, 1, 0, kP32CloudW1, kP32CloudStride};
-        AMP_TRY(t32_pack_weights(pt, t.wcloud, c.st));
+    {   // fc_1, fc_2 in one cluster launch; fc_3 + identity + the packed operand of local = h @ F in a second one
+        const int o4 = enc_bn_offset(L_FT1 + 3), o5 = enc_bn_offset(L_FT1 + 4);
+        AMP_TRY(tnet_fc_eval(ft_pool, B, c.pf(E_FT + T_FC1), k.scale + o4, k.shift + o4, c.pf(E_FT + T_FC2), k.scale + o5, k.shift + o5,
+                             c.pf(E_FT + T_FC3W), c.pf(E_FT + T_FC3B), 64, 0, t.f1, t.f2, feat_t, c.st));
+        AMP_TRY(tnet_fc3_pack(t.f2, c.pf(E_FT + T_FC3W), c.pf(E_FT + T_FC3B), B, feat_t, t.wcloud + kP32CloudW1, kP32CloudStride, c.st));
     }
     // chain 3a: conv_1, conv_2, bmm with the feature transform = local features (:96-97), stored into out[:, :, 256:320]
     {

@@ -11,6 +11,7 @@
 // Prologues / epilogues are those of PwParams / WgParams (BatchNorm apply or backward, ReLU mask, batch statistics).
 // Because a warp holds a whole column of <= 32 rows, the BatchNorm sums are warp shuffles in a fixed order.
 #include <cooperative_groups.h>
+#include <cuda_bf16.h>
 
 #include "nn_common.cuh"
 
@@ -559,7 +560,8 @@ __device__ __forceinline__ void tnet_fc_load_w(float (&wv)[NC][KI], const float*
 template <int NC, int KI>
 __device__ __forceinline__ void tnet_fc_layer(float* xs, const float* __restrict__ X, int r0, int M, const float (&wv)[NC][KI], int n0,
                                               int n_end, const float* __restrict__ bias, const float* __restrict__ scale,
-                                              const float* __restrict__ shift, bool relu, int eye_d, float* __restrict__ Y, int ldy) {
+                                              const float* __restrict__ shift, bool relu, int eye_d, float* __restrict__ Y, int ldy,
+                                              unsigned char* __restrict__ pk = nullptr, long long pk_stride = 0) {
     constexpr int K = 32 * KI;
     const int tid = threadIdx.x, lane = tid & 31;
     __syncthreads();                                       // previous layer's reads of xs are done
@@ -601,7 +603,18 @@ __device__ __forceinline__ void tnet_fc_layer(float* xs, const float* __restrict
             if (scale) v = fmaf(v, __ldg(scale + n), __ldg(shift + n));
             if (relu) v = fmaxf(v, 0.f);
             if (eye_d && n % (eye_d + 1) == 0) v += 1.f;  // + identity on the diagonal of the d x d transform
-            if (r0 + lane < M) Y[(long long)(r0 + lane) * ldy + n] = v;
+            if (r0 + lane < M) {
+                Y[(long long)(r0 + lane) * ldy + n] = v;
+                if (pk) {
+                    // the 64 x 64 transform F = Y[row] as the B operand of local = h @ F (weight [n'][k'] = F[k'][n'], n = k' * 64 + n'),
+                    // split into bf16 hi + lo blocks [K/8][64][8] (tc_chain32.cuh): fused pack, no extra launch
+                    const int kq = n >> 6, nq = n & 63;
+                    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+                    unsigned char* dst = pk + (long long)(r0 + lane) * pk_stride + ((kq >> 3) * 64 + nq) * 16 + (kq & 7) * 2;
+                    *reinterpret_cast<__nv_bfloat16*>(dst) = h;
+                    *reinterpret_cast<__nv_bfloat16*>(dst + 64 * 64 * 2) = __float2bfloat16_rn(v - __bfloat162float(h));
+                }
+            }
         }
     }
 }
@@ -628,7 +641,28 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(256) tnet_fc_eval_ke
     tnet_fc_layer<1, 4>(xs, a.h2, r0, a.B, w3, rank * 8 + warp, nout, a.fc3b, nullptr, nullptr, false, a.d, a.out, nout);
 }
 
+// fc_3 of the 64 x 64 feature transform (4096 outputs, K = 128) + bias + identity, written as the module output [B, 64, 64]
+// AND as the packed per-cloud operand of the fused chains: 128 CTAs x 32 output columns, all rows of a 32-cloud tile per pass
+__global__ void __launch_bounds__(256) tnet_fc3_pack_kernel(const float* __restrict__ h2, const float* __restrict__ w, const float* __restrict__ b,
+                                                            int B, float* __restrict__ out, unsigned char* __restrict__ pk, long long pk_stride) {
+    pdl_sync();
+    extern __shared__ float xs[];                          // [32][128]
+    const int warp = threadIdx.x >> 5;
+    const int n0 = blockIdx.x * 32 + warp * 4;
+    float w3[4][4];
+    tnet_fc_load_w<4, 4>(w3, w, n0, 4096);
+    for (int r0 = 0; r0 < B; r0 += SM_ROWS)
+        tnet_fc_layer<4, 4>(xs, h2, r0, B, w3, n0, 4096, b, nullptr, nullptr, false, 64, out, 4096, pk, pk_stride);
+}
+
 }  // namespace
+
+int tnet_fc3_pack(const float* h2, const float* w, const float* b, int B, float* out, unsigned char* pk, long long pk_stride, cudaStream_t st) {
+    if (!h2 || !w || !b || !out || !pk || B < 1) return fail(AMP_E_BADARG, "tnet_fc3_pack: null pointer");
+    launch_pdl(tnet_fc3_pack_kernel, dim3(128), dim3(256), sizeof(float) * SM_ROWS * 128, st, h2, w, b, B, out, pk, pk_stride);
+    count_launch();
+    return check_launch("tnet_fc3_pack");
+}
 
 // Eval-mode T-Net FC stack in one cluster launch; with fc3_inside == 0 the caller runs fc_3 (wide) itself on h2.
 int tnet_fc_eval(const float* pooled, int B, const float* fc1, const float* s4, const float* t4, const float* fc2, const float* s5,

@@ -1,16 +1,20 @@
 // Fused shared-MLP chain kernel at fp32-class accuracy (see tc_chain32.cuh for the contract).
 //
-// Layout of one CTA (544 threads, 1 CTA per SM):
-//   * warps 0-7 / 8-15 = two "slots" of 256 threads. A slot walks its own stream of 128-point tiles; per tile and layer
+// Layout of one CTA (288 threads, 1 CTA per SM):
+//   * warps 0-3 / 4-7 = two "slots" of 128 threads. A slot walks its own stream of 128-point tiles; per tile and layer
 //     one elected lane of the slot's first warp issues the tcgen05.mma K steps (three per step: A_hi W_hi, A_lo W_hi,
-//     A_hi W_lo) and commits to the slot's mbarrier, the slot's 8 warps wait, read the accumulator (tcgen05.ld, thread = TMEM
-//     lane = point row; the two warpgroups take alternating 32-column chunks), add the bias, ReLU, split the result into
-//     bf16 hi + lo pairs and write them back into TENSOR MEMORY as the next layer's A operand (tcgen05.st). While one
-//     slot is in its epilogue the other slot's MMAs run.
+//     A_hi W_lo) and commits to the slot's mbarrier; the slot's 4 warps wait and run the epilogue: thread = TMEM lane =
+//     point row, 64 accumulator columns per pass (two tcgen05.ld in flight before one wait: with 8 warps per slot and
+//     16-column pieces the epilogue was bound by TMEM round-trip latency, 4.2 k cycles for a 128-channel layer), bias, ReLU,
+//     split into bf16 hi + lo pairs, written back into TENSOR MEMORY as the next layer's A operand (tcgen05.st). While
+//     one slot is in its epilogue the other slot's MMAs run.
 //   * TMEM columns of a slot (256): [0, 128) fp32 accumulator, [128, 192) A_hi, [192, 256) A_lo (K <= 128 as packed pairs).
-//   * warp 16 = producer: stages the resident weights once (TMA bulk copies) and, for the streamed pooled layer, keeps a
-//     two-stage ring of 32 KB weight chunks full. Both slots consume the same chunk sequence (one pass per pair of
-//     tiles); a stage is released by one tcgen05.commit per slot (mbarrier count 2).
+//   * warp 8 = producer: stages the resident weights (TMA bulk copies, one mbarrier per layer so that the first layers
+//     start while the big last one is still arriving) and, for the streamed pooled layer, keeps a two-stage ring of 32 KB
+//     weight chunks full. Both slots consume the same chunk sequence (one pass per pair of tiles); a stage is released
+//     by one tcgen05.commit per slot (mbarrier count 2).
+//   * per-cloud weights (folded conv_1, feature transform) are double buffered per slot and fetched one tile ahead by TMA
+//     bulk copies; the 3 / 9 input columns of the next tile are fetched one tile ahead into registers.
 // Weight layout in shared memory (B operand): K-major, no swizzle, 8 x 16-byte core matrices, hi block then lo block:
 //   element (n, k) at ((k / 8) * N + n) * 16 + (k % 8) * 2     -> SBO = 128 B, LBO = N * 16 B.
 #include <stdlib.h>
@@ -22,7 +26,7 @@ namespace amp {
 namespace {
 using namespace tcx;
 
-constexpr int kThreads = 544, kSlotThreads = 256, kRows = 128;
+constexpr int kThreads = 288, kSlotThreads = 128, kRows = 128;
 constexpr int kAcc = 0, kAhi = 128, kAlo = 192, kSlotCols = 256;
 constexpr int kStageBytes = kRows * 64 * 4;               // fp32 staging of a 64-channel output tile (store_f32)
 constexpr int kMaxSmem = 232448;                          // 227 KB per CTA on sm_100
@@ -35,15 +39,15 @@ __host__ __device__ inline Plan plan_of(int wblob_bytes, int wcloud_bytes, int n
     Plan s;
     s.w = 0;
     s.wc = align_i(wblob_bytes, 128);
-    s.bias = s.wc + 2 * align_i(wcloud_bytes, 128);
+    s.bias = s.wc + 4 * align_i(wcloud_bytes, 128);          // two slots x two buffers
     s.stage = s.bias + align_i(n_bias * 4, 128);
     s.ring = s.stage + (stage_f32 ? 2 * kStageBytes : 0);
     s.bar = s.ring + (stream ? 2 * kT32ChunkBytes : 0);
-    s.total = s.bar + 128;
+    s.total = s.bar + 256;
     return s;
 }
 
-__device__ __forceinline__ void slot_bar_sync(int slot) { asm volatile("bar.sync %0, 256;" ::"r"(slot + 1) : "memory"); }
+__device__ __forceinline__ void slot_bar_sync(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -70,13 +74,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain32_kernel(const __grid_co
     for (int l = 0; l < p.n_ops; ++l) { stage_f32 |= p.op[l].store_f32; stream |= p.op[l].w_stream; }
     const Plan sp = plan_of(p.wblob_bytes, p.wcloud_bytes, p.n_bias, stage_f32, stream);
     float* s_bias = reinterpret_cast<float*>(smem + sp.bias);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + sp.bar);    // [0] weights, [1 + slot] MMA done, [3 + s] ring full, [5 + s] ring free
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + sp.bar + 64);
-    const uint32_t wbar = smem_u32(&s_bar[0]);
+    // [1 + slot] MMA done, [3 + s] ring full, [5 + s] ring free, [8 + op] resident weights of op (so that the first layers
+    // start while the large last layer of the chain is still streaming in)
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + sp.bar);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + sp.bar + 192);
+    const uint32_t wbar0 = smem_u32(&s_bar[8]);
     const uint32_t full0 = smem_u32(&s_bar[3]), free0 = smem_u32(&s_bar[5]);
 
     if (tid == 0) {
-        mbar_init(wbar, 1);
+        for (int l = 0; l < kT32MaxOps; ++l) mbar_init(wbar0 + 8 * l, 1);
+        for (int i = 16; i < 20; ++i) mbar_init(smem_u32(&s_bar[i]), 1);
         mbar_init(smem_u32(&s_bar[1]), 1);
         mbar_init(smem_u32(&s_bar[2]), 1);
         mbar_init(full0, 1); mbar_init(full0 + 8, 1);
@@ -97,14 +104,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain32_kernel(const __grid_co
     const int n_tiles = p.n_clouds * tiles_per_cloud;
     const int tile_stride = (int)gridDim.x * 2;
 
-    if (warp == 16) {
+    if (warp == 8) {
         // ---- producer: resident weights once, then the streamed chunks of every round of this CTA ----
         if (elect_one_sync()) {
-            if (p.wblob_bytes > 0) {
-                mbar_expect_tx(wbar, (uint32_t)p.wblob_bytes);
-                for (int off = 0; off < p.wblob_bytes; off += 32768) {
-                    const int n = min(32768, p.wblob_bytes - off);
-                    bulk_g2s(smem_u32(smem + sp.w + off), p.wblob + off, (uint32_t)n, wbar);
+            for (int l = 0; l < p.n_ops; ++l) {                  // resident weights, one barrier per op, in layer order
+                const T32Op& op = p.op[l];
+                if (op.w_cloud || op.w_stream) continue;
+                const int bytes = op.N * op.K * 4;
+                mbar_expect_tx(wbar0 + 8 * l, (uint32_t)bytes);
+                for (int off = 0; off < bytes; off += 32768) {
+                    const int n = min(32768, bytes - off);
+                    bulk_g2s(smem_u32(smem + sp.w + op.w_off + off), p.wblob + op.w_off + off, (uint32_t)n, wbar0 + 8 * l);
                 }
             }
             if (stream) {
@@ -121,23 +131,56 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain32_kernel(const __grid_co
         }
         __syncwarp();
     } else {
-        const int slot = warp >> 3, sub = (warp >> 2) & 1, stid = tid & (kSlotThreads - 1);
-        const int row = (warp & 3) * 32 + lane;                      // this thread's TMEM lane == tile row
+        const int slot = warp >> 2, stid = tid & (kSlotThreads - 1);
+        const int row = stid;                                        // this thread's TMEM lane == tile row (warp % 4 == lane quadrant)
         const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32) << 16);
         const uint32_t tcol = tmem_base + (uint32_t)(slot * kSlotCols);
         const uint32_t mbar = smem_u32(&s_bar[1 + slot]);
-        unsigned char* s_wc = smem + sp.wc + slot * align_i(p.wcloud_bytes, 128);
+        const int wc_bytes = align_i(p.wcloud_bytes, 128);
+        // per-cloud weights: two buffers per slot, filled by TMA bulk copies one tile ahead; barriers [16 + 2 * slot + buffer]
+        const uint32_t wc_addr0 = smem_u32(smem + sp.wc + slot * 2 * wc_bytes);
+        const uint32_t cbar0 = smem_u32(&s_bar[16 + 2 * slot]);
         float4* s_stage = reinterpret_cast<float4*>(smem + sp.stage + slot * kStageBytes);
-        const uint32_t w_addr = smem_u32(smem + sp.w), wc_addr = smem_u32(s_wc), ring_addr = smem_u32(smem + sp.ring);
+        const uint32_t w_addr = smem_u32(smem + sp.w), ring_addr = smem_u32(smem + sp.ring);
+        const bool issuer_warp = (warp & 3) == 0;
         uint32_t phase = 0;
-        int cur_cloud = -1;
-        bool w_ready = p.wblob_bytes == 0;
+        uint32_t w_ready = 0;                                        // bit l: resident weights of op l have landed
+        for (int l = 0; l < p.n_ops; ++l)
+            if (p.op[l].w_cloud || p.op[l].w_stream) w_ready |= 1u << l;
+        auto tile_of = [&](int r) { return (int)blockIdx.x * 2 + slot + r * tile_stride; };
+        auto request_cloud = [&](int r) {                            // one elected lane of the slot's first warp
+            const int t = tile_of(r);
+            if (p.wcloud_bytes > 0 && t < n_tiles) {
+                const int cl = t / tiles_per_cloud, b = r & 1;
+                mbar_expect_tx(cbar0 + 8 * b, (uint32_t)p.wcloud_bytes);
+                bulk_g2s(wc_addr0 + (uint32_t)(b * wc_bytes), p.wcloud + (long long)cl * p.wcloud_stride, (uint32_t)p.wcloud_bytes, cbar0 + 8 * b);
+            }
+        };
+        // narrow input rows (in_mode 0) are fetched one tile ahead into registers
+        float xn[10];
+        auto fetch_rows = [&](int r) {
+            const int t = tile_of(r);
+#pragma unroll
+            for (int j = 0; j < 10; ++j) xn[j] = 0.f;
+            if (p.in_mode == 0 && t < n_tiles) {
+                const int cl = t / tiles_per_cloud, r0 = (t - cl * tiles_per_cloud) * kRows, vd = min(kRows, rows - r0);
+                const float* src = p.in_x + ((long long)cl * rows + r0 + (row < vd ? row : vd - 1)) * p.in_ld;
+#pragma unroll
+                for (int j = 0; j < 10; ++j)
+                    if (j < p.in_k) xn[j] = __ldg(src + j);
+            }
+        };
+        if (issuer_warp) {
+            if (elect_one_sync()) request_cloud(0);
+            __syncwarp();
+        }
+        fetch_rows(0);
 
         for (int r = 0;; ++r) {
-            const int tile = (int)blockIdx.x * 2 + slot + r * tile_stride;
+            const int tile = tile_of(r);
             if (tile >= n_tiles) {
                 // the other slot still has a tile in this round: release the streamed chunks it shares with this slot
-                if (stream && slot == 1 && tile - 1 < n_tiles && (warp & 7) == 0) {
+                if (stream && slot == 1 && tile - 1 < n_tiles && issuer_warp) {
                     if (elect_one_sync()) {
                         for (int c = 0; c < 4; ++c) {
                             const int g = r * 4 + c, s = g & 1;
@@ -154,41 +197,42 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain32_kernel(const __grid_co
             const int valid = min(kRows, rows - row0);
             const bool row_ok = row < valid;
             // rows past the end of the cloud repeat its last row: they change no maximum and are never stored
-            const long long srow = (long long)cloud * rows + row0 + (row_ok ? row : valid - 1);
+            const uint32_t wc_addr = wc_addr0 + (uint32_t)((r & 1) * wc_bytes);
 
-            // ---- per-cloud weights (all MMAs of the previous tile have completed: safe to overwrite) ----
-            const bool new_cloud = p.wcloud_bytes > 0 && cloud != cur_cloud;
-            if (new_cloud) {
-                const uint4* src = reinterpret_cast<const uint4*>(p.wcloud + (long long)cloud * p.wcloud_stride);
-                uint4* dst = reinterpret_cast<uint4*>(s_wc);
-                for (int i = stid; i < p.wcloud_bytes / 16; i += kSlotThreads) dst[i] = __ldg(src + i);
-                cur_cloud = cloud;
-            }
             // ---- input stage: fp32 row -> bf16 hi / lo pairs straight into tensor memory ----
             if (p.in_mode == 0) {
-                if (sub == 0) {
-                    const float* src = p.in_x + srow * p.in_ld;
-                    float xv[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) xv[j] = j < p.in_k ? __ldg(src + j) : 0.f;
-                    uint32_t hi[8], lo[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) split_pair(xv[2 * q], xv[2 * q + 1], hi[q], lo[q]);
-                    tmem_st8(tcol + lane_addr + kAhi, hi);
-                    tmem_st8(tcol + lane_addr + kAlo, lo);
-                }
-            } else {
-                const float4* src = reinterpret_cast<const float4*>(p.in_x + srow * p.in_ld) + sub * 8;
-                uint32_t hi[16], lo[16];
+                uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const float4 a = __ldg(src + q);
-                    split_pair(a.x, a.y, hi[2 * q], lo[2 * q]);
-                    split_pair(a.z, a.w, hi[2 * q + 1], lo[2 * q + 1]);
+                    if (q < 5) split_pair(xn[2 * q], xn[2 * q + 1], hi[q], lo[q]);
+                    else { hi[q] = 0u; lo[q] = 0u; }
                 }
-                tmem_st16(tcol + lane_addr + kAhi + sub * 16, hi);
-                tmem_st16(tcol + lane_addr + kAlo + sub * 16, lo);
+                tmem_st8(tcol + lane_addr + kAhi, hi);
+                tmem_st8(tcol + lane_addr + kAlo, lo);
+            } else {
+                const long long srow = (long long)cloud * rows + row0 + (row_ok ? row : valid - 1);
+                const float4* src = reinterpret_cast<const float4*>(p.in_x + srow * p.in_ld);
+                float4 a[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) a[q] = __ldg(src + q);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        split_pair(a[8 * h + q].x, a[8 * h + q].y, hi[2 * q], lo[2 * q]);
+                        split_pair(a[8 * h + q].z, a[8 * h + q].w, hi[2 * q + 1], lo[2 * q + 1]);
+                    }
+                    tmem_st16(tcol + lane_addr + kAhi + h * 16, hi);
+                    tmem_st16(tcol + lane_addr + kAlo + h * 16, lo);
+                }
             }
+            // the next tile's per-cloud weights (other buffer: its readers, the MMAs of the previous tile, are done) and rows
+            if (issuer_warp) {
+                if (elect_one_sync()) request_cloud(r + 1);
+                __syncwarp();
+            }
+            fetch_rows(r + 1);
             // group of this row (per-block bias of the segmentation head)
             int group = 0;
             if (p.n_groups > 1) {
@@ -196,19 +240,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain32_kernel(const __grid_co
                 for (int g = 1; g < p.n_groups; ++g) group += (rr >= __ldg(p.group_rows + g)) ? 1 : 0;
             }
             tmem_wait_st();
-            if (new_cloud) fence_proxy_async();
             tc_fence_before();
             T32_PROF();                                          // input staged
             slot_bar_sync(slot);
             T32_PROF();                                          // slot barrier
 
             for (int l = 0; l < p.n_ops; ++l) {
-                const T32Op& op = p.op[l];
+                // a register copy of the op: read through the reference, every `if (op.x)` of the unrolled epilogue is its own
+                // constant-bank load -> compare -> branch chain (~70 cycles each, 20 of them per 64 columns: measured 1.4 k cycles)
+                const T32Op op = p.op[l];
                 const int parts = op.pool ? (op.N >> 7) : 1;
                 for (int part = 0; part < parts; ++part) {
                     // ---- MMA issue: the first warp of the slot enters, one elected lane issues (uniform descriptors) ----
-                    if ((warp & 7) == 0) {
-                        if (!w_ready) { mbar_wait_bounded(wbar, 0); w_ready = true; }
+                    if (issuer_warp) {
+                        if (!(w_ready & (1u << l))) { mbar_wait_bounded(wbar0 + 8 * l, 0); w_ready |= 1u << l; }
+                        if (op.w_cloud && part == 0) mbar_wait_bounded(cbar0 + 8 * (r & 1), (uint32_t)((r >> 1) & 1));
                         tc_fence_after();
                         if (elect_one_sync()) {
                             const int ksteps = op.K >> 4;
@@ -243,68 +289,84 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain32_kernel(const __grid_co
 
                     if (!op.pool) {
                         const float* gb = op.bias_grouped ? p.gbias + ((long long)cloud * p.n_groups + group) * op.N : nullptr;
-                        for (int c0 = sub * 32; c0 < op.N; c0 += 64) {
-                            uint32_t v[32];
-                            tmem_ld32(tcol + lane_addr + kAcc + (uint32_t)c0, v);
+                        // a thread owns a whole row: 64 accumulator columns per pass, both TMEM loads in flight before the wait
+                        for (int c0 = 0; c0 < op.N; c0 += 64) {
+                            const int nc = min(64, op.N - c0);           // 16, 32 or 64
+                            uint32_t v[64];
+                            tmem_ld32(tcol + lane_addr + kAcc + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                            if (nc > 32) tmem_ld32(tcol + lane_addr + kAcc + (uint32_t)(c0 + 32), *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
                             tmem_wait_ld();
-                            const int nc = min(32, op.N - c0);           // 16 or 32
-                            if (op.bias_off >= 0) {
-                                const float4* b4 = reinterpret_cast<const float4*>(s_bias + op.bias_off + c0);
+                            T32_PROF();                          // (epilogue detail) accumulator columns in registers
 #pragma unroll
-                                for (int q = 0; q < 8; ++q) {
-                                    if (q * 4 < nc) {
-                                        const float4 b = b4[q];
-                                        v[4 * q] = __float_as_uint(__uint_as_float(v[4 * q]) + b.x);
-                                        v[4 * q + 1] = __float_as_uint(__uint_as_float(v[4 * q + 1]) + b.y);
-                                        v[4 * q + 2] = __float_as_uint(__uint_as_float(v[4 * q + 2]) + b.z);
-                                        v[4 * q + 3] = __float_as_uint(__uint_as_float(v[4 * q + 3]) + b.w);
+                            for (int h = 0; h < 4; ++h) {                // 16 columns at a time
+                                if (h * 16 < nc) {
+                                    const int cc = c0 + 16 * h;
+                                    uint32_t* vv = &v[16 * h];
+                                    if (op.bias_off >= 0) {
+                                        const float4* b4 = reinterpret_cast<const float4*>(s_bias + op.bias_off + cc);
+#pragma unroll
+                                        for (int q = 0; q < 4; ++q) {
+                                            const float4 b = b4[q];
+                                            vv[4 * q] = __float_as_uint(__uint_as_float(vv[4 * q]) + b.x);
+                                            vv[4 * q + 1] = __float_as_uint(__uint_as_float(vv[4 * q + 1]) + b.y);
+                                            vv[4 * q + 2] = __float_as_uint(__uint_as_float(vv[4 * q + 2]) + b.z);
+                                            vv[4 * q + 3] = __float_as_uint(__uint_as_float(vv[4 * q + 3]) + b.w);
+                                        }
+                                    }
+                                    if (gb) {
+                                        const float4* g4 = reinterpret_cast<const float4*>(gb + cc);
+#pragma unroll
+                                        for (int q = 0; q < 4; ++q) {
+                                            const float4 b = __ldg(g4 + q);
+                                            vv[4 * q] = __float_as_uint(__uint_as_float(vv[4 * q]) + b.x);
+                                            vv[4 * q + 1] = __float_as_uint(__uint_as_float(vv[4 * q + 1]) + b.y);
+                                            vv[4 * q + 2] = __float_as_uint(__uint_as_float(vv[4 * q + 2]) + b.z);
+                                            vv[4 * q + 3] = __float_as_uint(__uint_as_float(vv[4 * q + 3]) + b.w);
+                                        }
+                                    }
+                                    if (op.relu) {
+#pragma unroll
+                                        for (int j = 0; j < 16; ++j) vv[j] = __float_as_uint(fmaxf(__uint_as_float(vv[j]), 0.f));
+                                    }
+                                    if (op.store_logits && c0 == 0 && h < 2 && row_ok) {   // [B, C, rows]: consecutive lanes = consecutive rows
+                                        float* lp = p.logits + (long long)cloud * p.n_classes * rows + row0 + row;
+#pragma unroll
+                                        for (int n = 0; n < 16; ++n)
+                                            if (16 * h + n < p.n_classes) lp[(long long)(16 * h + n) * rows] = __uint_as_float(vv[n]);
+                                    }
+                                    if (op.store_f32) {                  // 64 channels: 16 x 16-byte pieces per row, XOR-swizzled
+#pragma unroll
+                                        for (int q = 0; q < 4; ++q)
+                                            s_stage[row * 16 + ((4 * h + q) ^ (row & 15))] =
+                                                make_float4(__uint_as_float(vv[4 * q]), __uint_as_float(vv[4 * q + 1]), __uint_as_float(vv[4 * q + 2]),
+                                                            __uint_as_float(vv[4 * q + 3]));
                                     }
                                 }
                             }
-                            if (gb) {
-                                const float4* g4 = reinterpret_cast<const float4*>(gb + c0);
+                            T32_PROF();                          // (epilogue detail) bias / ReLU / stores to memory done
+                            if (op.write_act) {
 #pragma unroll
-                                for (int q = 0; q < 8; ++q) {
-                                    if (q * 4 < nc) {
-                                        const float4 b = __ldg(g4 + q);
-                                        v[4 * q] = __float_as_uint(__uint_as_float(v[4 * q]) + b.x);
-                                        v[4 * q + 1] = __float_as_uint(__uint_as_float(v[4 * q + 1]) + b.y);
-                                        v[4 * q + 2] = __float_as_uint(__uint_as_float(v[4 * q + 2]) + b.z);
-                                        v[4 * q + 3] = __float_as_uint(__uint_as_float(v[4 * q + 3]) + b.w);
-                                    }
-                                }
-                            }
-                            if (op.relu) {
+                                for (int h = 0; h < 2; ++h) {            // 32 columns -> 16 packed hi + 16 packed lo columns
+                                    if (h * 32 < nc) {
+                                        uint32_t hi[16], lo[16];
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaxf(__uint_as_float(v[j]), 0.f));
-                            }
-                            if (op.store_logits && c0 == 0 && row_ok) {   // [B, C, rows] logits: consecutive lanes = consecutive rows
-                                float* lp = p.logits + (long long)cloud * p.n_classes * rows + row0 + row;
+                                        for (int q = 0; q < 16; ++q)
+                                            split_pair(__uint_as_float(v[32 * h + 2 * q]), __uint_as_float(v[32 * h + 2 * q + 1]), hi[q], lo[q]);
+                                        if (nc - h * 32 >= 32) {
+                                            tmem_st16(tcol + lane_addr + kAhi + (uint32_t)((c0 >> 1) + 16 * h), hi);
+                                            tmem_st16(tcol + lane_addr + kAlo + (uint32_t)((c0 >> 1) + 16 * h), lo);
+                                        } else {
+                                            uint32_t h8[8], l8[8];
 #pragma unroll
-                                for (int n = 0; n < 32; ++n)
-                                    if (n < p.n_classes) lp[(long long)n * rows] = __uint_as_float(v[n]);
-                            }
-                            if (op.store_f32) {                          // 64 channels: 16 x 16-byte pieces per row, XOR-swizzled
-#pragma unroll
-                                for (int q = 0; q < 8; ++q)
-                                    s_stage[row * 16 + ((sub * 8 + q) ^ (row & 15))] =
-                                        make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                                                    __uint_as_float(v[4 * q + 3]));
-                            }
-                            if (op.write_act) {                          // 16 columns (8 packed pairs) at a time: fewer live registers
-#pragma unroll
-                                for (int h = 0; h < 2; ++h) {
-                                    if (h * 16 < nc) {
-                                        uint32_t hi[8], lo[8];
-#pragma unroll
-                                        for (int q = 0; q < 8; ++q)
-                                            split_pair(__uint_as_float(v[16 * h + 2 * q]), __uint_as_float(v[16 * h + 2 * q + 1]), hi[q], lo[q]);
-                                        tmem_st8(tcol + lane_addr + kAhi + (uint32_t)((c0 >> 1) + 8 * h), hi);
-                                        tmem_st8(tcol + lane_addr + kAlo + (uint32_t)((c0 >> 1) + 8 * h), lo);
+                                            for (int q = 0; q < 8; ++q) { h8[q] = hi[q]; l8[q] = lo[q]; }
+                                            tmem_st8(tcol + lane_addr + kAhi + (uint32_t)((c0 >> 1) + 16 * h), h8);
+                                            tmem_st8(tcol + lane_addr + kAlo + (uint32_t)((c0 >> 1) + 16 * h), l8);
+                                        }
                                     }
                                 }
                             }
                         }
+                        T32_PROF();                              // (epilogue detail) split + tcgen05.st issued
                         if (op.write_act) tmem_wait_st();
                         if (op.store_f32) {                              // whole 256-byte row segments leave coalesced
                             slot_bar_sync(slot);
@@ -315,26 +377,30 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain32_kernel(const __grid_co
                             }
                         }
                     } else {
-                        // max over the 128 rows of the tile, 32 rows per warp by redux; lane j keeps channel c0 + j
+                        // max over the 128 rows of the tile, 32 rows per warp by redux; lane j keeps channels j, 32 + j, 64 + j, 96 + j
                         const float* b = s_bias + op.bias_off + part * 128;
-                        for (int c0 = sub * 32; c0 < 128; c0 += 64) {
-                            uint32_t v[32];
-                            tmem_ld32(tcol + lane_addr + kAcc + (uint32_t)c0, v);
+                        for (int c0 = 0; c0 < 128; c0 += 64) {
+                            uint32_t v[64];
+                            tmem_ld32(tcol + lane_addr + kAcc + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                            tmem_ld32(tcol + lane_addr + kAcc + (uint32_t)(c0 + 32), *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
                             tmem_wait_ld();
-                            float mine = 0.f;
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const float4 bb = *reinterpret_cast<const float4*>(b + c0 + 4 * q);
-                                const float m0 = warp_max_relu_safe(__uint_as_float(v[4 * q]) + bb.x);
-                                const float m1 = warp_max_relu_safe(__uint_as_float(v[4 * q + 1]) + bb.y);
-                                const float m2 = warp_max_relu_safe(__uint_as_float(v[4 * q + 2]) + bb.z);
-                                const float m3 = warp_max_relu_safe(__uint_as_float(v[4 * q + 3]) + bb.w);
-                                if (lane == 4 * q) mine = m0;
-                                if (lane == 4 * q + 1) mine = m1;
-                                if (lane == 4 * q + 2) mine = m2;
-                                if (lane == 4 * q + 3) mine = m3;
+                            for (int h = 0; h < 2; ++h) {
+                                float mine = 0.f;
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    const float4 bb = *reinterpret_cast<const float4*>(b + c0 + 32 * h + 4 * q);
+                                    const float m0 = warp_max_relu_safe(__uint_as_float(v[32 * h + 4 * q]) + bb.x);
+                                    const float m1 = warp_max_relu_safe(__uint_as_float(v[32 * h + 4 * q + 1]) + bb.y);
+                                    const float m2 = warp_max_relu_safe(__uint_as_float(v[32 * h + 4 * q + 2]) + bb.z);
+                                    const float m3 = warp_max_relu_safe(__uint_as_float(v[32 * h + 4 * q + 3]) + bb.w);
+                                    if (lane == 4 * q) mine = m0;
+                                    if (lane == 4 * q + 1) mine = m1;
+                                    if (lane == 4 * q + 2) mine = m2;
+                                    if (lane == 4 * q + 3) mine = m3;
+                                }
+                                atomicMax(p.pool + (long long)cloud * op.N + part * 128 + c0 + 32 * h + lane, __float_as_uint(fmaxf(mine, 0.f)));
                             }
-                            atomicMax(p.pool + (long long)cloud * op.N + part * 128 + c0 + lane, __float_as_uint(fmaxf(mine, 0.f)));
                         }
                     }
                     // accumulator reads and A-operand writes of this layer are done before the next MMA is issued
@@ -345,7 +411,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain32_kernel(const __grid_co
                 }
             }
         }
-        if ((warp & 7) == 0 && !w_ready) mbar_wait(wbar, 0);     // never leave with a bulk copy in flight
+        if (issuer_warp)                                           // never leave with a bulk copy in flight
+            for (int l = 0; l < p.n_ops; ++l)
+                if (!(w_ready & (1u << l))) mbar_wait_bounded(wbar0 + 8 * l, 0);
     }
     T32_PROF();                                                  // all tiles done
     if (prof) p.prof[255] = pi;
@@ -381,6 +449,29 @@ __global__ void t32_pack_kernel(const T32PackTable t, unsigned char* __restrict_
     }
 }
 
+// bmm + cat + conv_1 (pointnetAtt.py:85-90) folded into per-cloud conv_1 weights, BatchNorm scale applied, split and packed:
+//   W1eff[b][c][i] = W1[c][3 + i] + (i < 3 ? sum_j W1[c][j] * T[b][i][j] : 0),  i < 9 (K padded to 16)
+__global__ void t32_fold_w1_kernel(const float* __restrict__ W1, const float* __restrict__ T, const float* __restrict__ scale,
+                                   unsigned char* __restrict__ dst, long long dst_stride) {
+    pdl_sync();
+    const int b = blockIdx.x;
+    const float* t = T + b * 9;
+    unsigned char* out = dst + (long long)b * dst_stride;
+    for (int e = threadIdx.x; e < 64 * 16; e += blockDim.x) {
+        const int c = e >> 4, i = e & 15;
+        float v = 0.f;
+        if (i < 9) {
+            v = W1[c * 12 + 3 + i];
+            if (i < 3) v += W1[c * 12] * t[i * 3] + W1[c * 12 + 1] * t[i * 3 + 1] + W1[c * 12 + 2] * t[i * 3 + 2];
+            v *= scale[c];
+        }
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const int off = ((i >> 3) * 64 + c) * 16 + (i & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(out + off) = h;
+        *reinterpret_cast<__nv_bfloat16*>(out + 64 * 16 * 2 + off) = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
 __global__ void t32_bias_kernel(const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
                                 int n, int n_pad, float* __restrict__ dst) {
     pdl_sync();
@@ -396,6 +487,12 @@ int t32_affine_bias(const float* bias, const float* scale, const float* shift, i
     return check_launch("t32_bias_kernel");
 }
 
+int t32_fold_w1(const float* W1, const float* T, const float* scale, int n_clouds, unsigned char* dst, long long dst_stride, cudaStream_t st) {
+    launch_pdl(t32_fold_w1_kernel, dim3((unsigned)n_clouds), dim3(256), 0, st, W1, T, scale, dst, dst_stride);
+    count_launch();
+    return check_launch("t32_fold_w1_kernel");
+}
+
 int tc_chain32_launch(const T32Params& p, cudaStream_t st) {
     if (p.n_ops < 1 || p.n_ops > kT32MaxOps) return fail(AMP_E_BADARG, "tc_chain32: bad op count %d", p.n_ops);
     int stage_f32 = 0, stream = 0;
@@ -409,6 +506,8 @@ int tc_chain32_launch(const T32Params& p, cudaStream_t st) {
             return fail(AMP_E_BADARG, "tc_chain32: op %d cannot stream its weights", l);
         if (o.write_act && (l + 1 >= p.n_ops || p.op[l + 1].K != o.N)) return fail(AMP_E_BADARG, "tc_chain32: op %d does not feed op %d", l, l + 1);
         if (o.w_off % 128) return fail(AMP_E_BADARG, "tc_chain32: op %d weights are not 128-byte aligned", l);
+        if (!o.w_stream && o.w_off + o.N * o.K * 4 > (o.w_cloud ? p.wcloud_bytes : p.wblob_bytes))
+            return fail(AMP_E_BADARG, "tc_chain32: op %d weights lie outside the packed buffer", l);
         if (o.bias_off >= 0 && (o.bias_off % 4 || o.bias_off + o.N > p.n_bias || !p.bias))
             return fail(AMP_E_BADARG, "tc_chain32: op %d bias outside the table", l);
         if (o.store_logits && (!p.logits || p.n_classes < 1 || p.n_classes > o.N || p.n_classes > 32))
@@ -420,7 +519,7 @@ int tc_chain32_launch(const T32Params& p, cudaStream_t st) {
         stage_f32 |= o.store_f32; stream |= o.w_stream;
     }
     if (p.in_mode == 0) {
-        if (p.op[0].K != 16 || p.in_k < 1 || p.in_k > 16) return fail(AMP_E_BADARG, "tc_chain32: narrow input needs K = 16 and at most 16 columns");
+        if (p.op[0].K != 16 || p.in_k < 1 || p.in_k > 10) return fail(AMP_E_BADARG, "tc_chain32: narrow input needs K = 16 and at most 10 columns");
     } else if (p.op[0].K != 64 || p.in_ld % 4 || ((uintptr_t)p.in_x & 15)) {
         return fail(AMP_E_BADARG, "tc_chain32: wide input needs K = 64 and 16-byte aligned rows");
     }

@@ -39,7 +39,7 @@ struct T32Op {
 struct T32Params {
     int n_ops;
     T32Op op[kT32MaxOps];
-    // input stage: 0 = the first in_k (<= 16) columns of fp32 rows x[row * in_ld + k], zero-padded to K = 16;
+    // input stage: 0 = the first in_k (<= 10) columns of fp32 rows x[row * in_ld + k], zero-padded to K = 16;
     //              1 = 64 fp32 columns per row (in_ld % 4 == 0, 16-byte aligned rows)
     int in_mode;
     const float* in_x; long long in_ld; int in_k;
@@ -69,6 +69,9 @@ struct T32PackJob {
 struct T32PackTable { static constexpr int kMax = 16; int n; int n_clouds; T32PackJob job[kMax]; };
 int t32_pack_weights(const T32PackTable& t, unsigned char* dst, cudaStream_t st);
 inline int t32_packed_bytes(int Npad, int Kpad) { return Npad * Kpad * 4; }
+// per-cloud conv_1 weights with the 3 x 3 input transform folded in (fold_input_transform of nn_common.cuh), scaled by the
+// BatchNorm scale and packed: 64 x 16 hi + lo block at dst + cloud * dst_stride
+int t32_fold_w1(const float* W1, const float* T, const float* scale, int n_clouds, unsigned char* dst, long long dst_stride, cudaStream_t st);
 // dst[i] = scale[i] * bias[i] + shift[i] for i < n (null pointers: 1, 0, 0), zero for n <= i < n_pad: a bias-table entry
 int t32_affine_bias(const float* bias, const float* scale, const float* shift, int n, int n_pad, float* dst, cudaStream_t st);
 

@@ -56,7 +56,9 @@ def build(model, seed):
 
 
 def run_case(train_loop, collate, enc, seg, n_samples, seed, device="cpu", **kw):
-    """One training step then one eval step, as train_att() drives them (train_pointnet-attention.py:127-149, 180-274)."""
+    """One eval step (validation loop, :245-274) then one training step (:180-219) on the same batch, as train_att() drives
+    them (:127-149). Eval first: after the first Adam step every weight has moved by ~lr * sign(gradient), so a later
+    forward would compare update directions of near-zero gradients rather than forward arithmetic."""
     opt_e = torch.optim.Adam(enc.parameters(), lr=LR)
     opt_s = torch.optim.Adam(seg.parameters(), lr=LR)
     ce = torch.nn.CrossEntropyLoss(weight=torch.FloatTensor([1, 2, 2, 1, 1]).to(device), reduction="mean", ignore_index=-1)
@@ -65,13 +67,13 @@ def run_case(train_loop, collate, enc, seg, n_samples, seed, device="cpu", **kw)
     tlo.seed_all(seed)
     data = collate(tlo.synthetic_samples(n_samples, seed))
     out = {}
-    tlo.seed_all(seed + 1)
-    r = train_loop(data, opt_e, opt_s, ce, enc, seg, **kw, train=True)
-    out["train"] = r
     tlo.seed_all(seed + 2)
     with torch.no_grad():
         r = train_loop(data, opt_e, opt_s, ce, enc, seg, **kw, train=False)
     out["eval"] = r
+    tlo.seed_all(seed + 1)
+    r = train_loop(data, opt_e, opt_s, ce, enc, seg, **kw, train=True)
+    out["train"] = r
     return out
 
 
