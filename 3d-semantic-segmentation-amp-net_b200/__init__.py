@@ -11,5 +11,6 @@ from .clustering import (kmeans_clustering, split_kmeans, split_kmeans_array, km
                          kmeans_constrained_windows, regroup_windows, gather_feats, get_cluster_centroid)
 from .modules import BasePointNet, TransformationNet, SegmentationWithAttention, set_default_precision  # noqa: F401
 from .parallel import shard_windows, GradAllReduce  # noqa: F401
+from .dataprep import split_windows, filter_normalize_windows  # noqa: F401
 from .tensorcore import tc_linear, linear_wgrad  # noqa: F401
 

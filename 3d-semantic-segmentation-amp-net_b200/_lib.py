@@ -29,6 +29,12 @@ SIGNATURES = {
     "amp_kmeans_constrained_f32": (_c.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32,
                                               _dbl, _vp, _vp, _vp, _vp, _sz, _vp]),
     "amp_kmeans_regroup": (_c.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "amp_minmax_f64": (_c.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "amp_window_ids_f64": (_c.c_int, [_vp, _vp, _i64, _i64, _dbl, _dbl, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "amp_window_partition_workspace_bytes": (_sz, [_i64]),
+    "amp_window_partition": (_c.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "amp_filter_normalize_workspace_bytes": (_sz, [_i64]),
+    "amp_filter_normalize_f64": (_c.c_int, [_vp, _vp, _vp, _i64, _dbl, _dbl, _vp, _vp, _vp, _sz, _vp]),
     "amp_encoder_param_count": (_c.c_int, []),
     "amp_encoder_param_name": (_c.c_char_p, [_c.c_int]),
     "amp_encoder_saved_bytes": (_sz, [_i64, _i64, _i32]),

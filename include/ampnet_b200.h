@@ -115,6 +115,36 @@ int amp_kmeans_regroup(const int32_t* labels, const int64_t* offsets, const int3
                        int64_t* order, int32_t* counts, float* xy_mean, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Data preparation in front of the block split (float64, bit-exact to the reference's numpy arithmetic).
+ * Replaces the numerical core of data_proc/1_get_windows_split.py:53-80 (LAS tile -> W x W metre windows) and
+ * data_proc/2_preprocessing_filter_norm.py:40-104 (class / outlier filter, 13-column row, normalisation); LAS I/O and
+ * the md5-keyed NIR join stay on the host (the NIR value is an input column).
+ *   amp_minmax_f64            out4 = (min x, max x, min y, max y); x / y element i at x[i * stride]; workspace 32 bytes
+ *   amp_window_ids_f64        ids[i] = iy * nx + ix of the window (x0 + ix*wx, x0 + (ix+1)*wx) x (y0 + iy*wy, ...) that holds
+ *                             point i, bounds strict on both sides (:58-62), -1 when no window takes it; the host derives
+ *                             x0 = round(min x), nx = len(range(x0, round(max x), wx)) (Python semantics) from amp_minmax_f64
+ *   amp_window_partition      stable counting sort by window id: order[] = point indices, window w = order[offsets[w] ..
+ *                             offsets[w + 1]) in original order, dropped points behind offsets[n_bins]
+ *   amp_filter_normalize_f64  cols [P, 10] = (x, y, z, HeightAboveGround, class, intensity, red, green, blue, nir) float64;
+ *                             per window: drop classes 2, 7, 8, 13, 24, 30 and HAG outside [0, max_z], write rows
+ *                             (x', y', hag / max_z, class, clip(intensity / max_intensity), r, g, b / 65536, clip(nir / 65535),
+ *                             clip((ndvi + 1) / 2), x, y, z) with x', y' = 2 (v - min) / (max - min) - 1 over the kept rows;
+ *                             a window with no kept row or a zero x / y extent writes nothing (:56, :92).
+ *                             out [sum kept, 13] f64 (caller sizes it for P rows), out_offsets [n_windows + 1] int64 (device).
+ * ------------------------------------------------------------------------------------------ */
+int amp_minmax_f64(const double* x, const double* y, int64_t n, int64_t stride, double* out4, void* workspace,
+                   size_t workspace_bytes, void* stream);
+int amp_window_ids_f64(const double* x, const double* y, int64_t n, int64_t stride, double x0, double y0, int32_t wx, int32_t wy,
+                       int32_t nx, int32_t ny, int32_t* ids, void* stream);
+size_t amp_window_partition_workspace_bytes(int64_t n);
+int amp_window_partition(const int32_t* ids, int64_t n, int32_t n_bins, int64_t* order, int64_t* offsets, void* workspace,
+                         size_t workspace_bytes, void* stream);
+size_t amp_filter_normalize_workspace_bytes(int64_t n_windows);
+int amp_filter_normalize_f64(const double* cols, const int64_t* order, const int64_t* offsets, int64_t n_windows, double max_z,
+                             double max_intensity, double* out, int64_t* out_offsets, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * PointNet encoder.  Replaces BasePointNet.forward (pointNet/model/pointnetAtt.py:80-112, with its two
  * TransformationNets :28-47) as called by train_pointnet-attention.py:410 / test_pointnet_att_segmen.py:164,
  * and the autograd backward loss.backward() runs through it (train_pointnet-attention.py:467).
