@@ -12,5 +12,6 @@ from .clustering import (kmeans_clustering, split_kmeans, split_kmeans_array, km
 from .modules import BasePointNet, TransformationNet, SegmentationWithAttention, set_default_precision  # noqa: F401
 from .parallel import shard_windows, GradAllReduce  # noqa: F401
 from .dataprep import split_windows, filter_normalize_windows  # noqa: F401
+from .assembly import assemble_windows, draw_augmentation  # noqa: F401
 from .tensorcore import tc_linear, linear_wgrad  # noqa: F401
 

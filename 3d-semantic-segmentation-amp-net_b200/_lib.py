@@ -35,6 +35,7 @@ SIGNATURES = {
     "amp_window_partition": (_c.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "amp_filter_normalize_workspace_bytes": (_sz, [_i64]),
     "amp_filter_normalize_f64": (_c.c_int, [_vp, _vp, _vp, _i64, _dbl, _dbl, _vp, _vp, _vp, _sz, _vp]),
+    "amp_assemble_windows_f32": (_c.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _dbl, _dbl, _vp, _vp, _vp]),
     "amp_encoder_param_count": (_c.c_int, []),
     "amp_encoder_param_name": (_c.c_char_p, [_c.c_int]),
     "amp_encoder_saved_bytes": (_sz, [_i64, _i64, _i32]),

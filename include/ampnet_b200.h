@@ -145,6 +145,21 @@ int amp_filter_normalize_f64(const double* cols, const int64_t* order, const int
                              void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Training-batch assembly and augmentation on the device.  Replaces the host work of
+ * pointNet/self-attention/train_pointnet-attention.py:390-408 for one collated batch: shuffle_clusters (utils/utils.py:620-632),
+ * per-window rotate_point_cloud_z (:582-604) + shuffle_data (:607-617) and the W per-window host-to-device copies.
+ *   pc            [B, N, D, W] f32, the collate_seq_padd layout (collate_fns.py:4-55), D >= 3     targets [B, N, W] int64 | NULL
+ *   cluster_perm  [W] int32: output window w reads input window cluster_perm[w]
+ *   point_perm    [W, N] int32: output row i of window w reads input row point_perm[w][i]
+ *   rotate        != 0: columns 0:3 times [[c, s, 0], [-s, c, 0], [0, 0, 1]] in float64 (numpy's arithmetic), rounded to f32
+ *   x             [W, B, N, D] f32 out (one contiguous [B, N, D] encoder input per window)
+ *   targets_out   [B, W * N] int64 out (window-major concatenation of train_pointnet-attention.py:421) | NULL
+ * ------------------------------------------------------------------------------------------ */
+int amp_assemble_windows_f32(const float* pc, const int64_t* targets, const int32_t* cluster_perm, const int32_t* point_perm, int64_t B,
+                             int64_t N, int32_t D, int32_t W, int32_t rotate, double cos_a, double sin_a, float* x, int64_t* targets_out,
+                             void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * PointNet encoder.  Replaces BasePointNet.forward (pointNet/model/pointnetAtt.py:80-112, with its two
  * TransformationNets :28-47) as called by train_pointnet-attention.py:410 / test_pointnet_att_segmen.py:164,
  * and the autograd backward loss.backward() runs through it (train_pointnet-attention.py:467).

@@ -44,7 +44,8 @@ def filter_normalize(x, y, z, hag, cls, intensity, red, green, blue, nir, max_z=
     (empty after filtering, zero x / y extent, or fewer than n_points rows)   (2_preprocessing_filter_norm.py:40-123).
     `nir` is the per-point NIR value the reference looks up in its md5-keyed dictionary (:61-67)."""
     cls = np.asarray(cls)
-    keep = np.ones(len(cls), dtype=bool)
+    nir = np.asarray(nir).astype(np.int64)       # the reference rebuilds NIR from a dict of Python ints (:61-69): an int64 array,
+    keep = np.ones(len(cls), dtype=bool)         # so `nir - red` against the uint16 colour does not wrap
     for c in DROP_CLASSES:
         keep &= cls != c
     hag = np.asarray(hag, dtype=np.float64)
