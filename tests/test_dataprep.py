@@ -110,14 +110,14 @@ def test_window_split_and_filter_normalize_bit_exact(amp, cuda, n, seed, w, exte
     for wi in range(nx * ny):                                            # stable: original order inside every window
         assert np.array_equal(order[offsets[wi]:offsets[wi + 1]], np.flatnonzero(ids == wi))
     assert sorted(order.tolist()) == list(range(n))                      # a permutation: dropped points sit behind offsets[-1]
-    rows, oo, stored = amp.filter_normalize_windows(cols, sp["order"], sp["offsets"], 100.0, 5000, 64)
+    rows, oo, stored = amp.filter_normalize_windows(cols, sp["order"], sp["offsets"], 100.0, 5000, 8)
     assert amp._lib.launch_count() - n0 >= 10
     rows = rows.cpu().numpy()
     n_stored = 0
     for wi in range(nx * ny):
         m = ids == wi
         ref = dpo.filter_normalize(tile["x"][m], tile["y"][m], tile["z"][m], tile["HeightAboveGround"][m], tile["classification"][m],
-                                   tile["intensity"][m], tile["red"][m], tile["green"][m], tile["blue"][m], tile["nir"][m], 100.0, 5000, 64) if m.any() else None
+                                   tile["intensity"][m], tile["red"][m], tile["green"][m], tile["blue"][m], tile["nir"][m], 100.0, 5000, 8) if m.any() else None
         if ref is None:
             assert not stored[wi]
         else:
