@@ -73,6 +73,13 @@ def kmeans_constrained_windows(feats, offsets, ks, size_min=0, size_max=0, max_i
         raise ValueError("size_max * k < n")
     kmax = int(ks.max())
     dev = feats.device
+    # fixed-point sums (rint(x * 2^32) in int64, csrc/kmeans.cu): sum |x| and sum x^2 of a window must stay below 2^31. The
+    # reference clusters normalised columns ([-1, 1] coordinates, [0, 1] features); raw UTM coordinates would wrap silently.
+    amax = float(feats.abs().max()) if total else 0.0
+    if not np.isfinite(amax) or amax * amax * float(sizes.max()) >= 2.0 ** 31 or amax * float(sizes.max()) >= 2.0 ** 31:
+        raise ValueError("kmeans: clustering features must be finite and normalised (max |x| = %g over windows of up to %d points "
+                         "overflows the fixed-point centroid sums); normalise the columns first as "
+                         "data_proc/2_preprocessing_filter_norm.py does" % (amax, int(sizes.max())))
     d_off = torch.from_numpy(offsets).to(dev)
     d_ks = torch.from_numpy(ks).to(dev)
     labels = torch.empty((total,), dtype=torch.int32, device=dev)

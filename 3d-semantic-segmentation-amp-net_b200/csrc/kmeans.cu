@@ -378,6 +378,13 @@ kmeans_window_kernel(const float* __restrict__ feats, const long long* __restric
     int* labels = labels_all + off;
     int* prop = prop_all + off;
     float* pd = pd_all + off;
+    // a window the constraints cannot be met on (or with more clusters than points): labels -1, n_iter -1, no out-of-range write
+    if (k < 1 || k > kmax || k > n || (size_max > 0 && (long long)size_max * k < n) || (size_min > 0 && (long long)size_min * k > n)) {
+        for (int i = tid; i < n; i += kWinThreads) labels[i] = -1;
+        for (int i = tid; i < kmax * 3; i += kWinThreads) centroids[(long long)w * kmax * 3 + i] = 0.0f;
+        if (tid == 0) n_iter[w] = -1;
+        return;
+    }
 
     // ---- A. fixed-point moments -> tol_abs ----
     if (tid < 6) s.mom[tid] = 0ull;
@@ -438,6 +445,7 @@ kmeans_window_kernel(const float* __restrict__ feats, const long long* __restric
         __syncthreads();
         for (int i = tid; i < n; i += kWinThreads) {
             int l = labels[i];
+            if (l < 0) continue;
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 long long q = __double2ll_rn(__dmul_rn((double)x[3 * i + d], kFix));
@@ -498,6 +506,7 @@ kmeans_regroup_kernel(const int* __restrict__ labels_all, const long long* __res
     __syncthreads();
     for (int i = tid; i < n; i += kWinThreads) {
         int l = labels[i];
+        if (l < 0 || l >= kKMax) continue;                 // unassigned (infeasible window): belongs to no group
         atomicAdd(&s_cnt[l], 1);
         if (pc) {
             const float* p = pc + (off + i) * row_stride;
@@ -525,7 +534,8 @@ kmeans_regroup_kernel(const int* __restrict__ labels_all, const long long* __res
     __syncthreads();
     for (int base = 0; base < n; base += kWinThreads) {
         const int i = base + tid;
-        const int l = (i < n) ? labels[i] : -1;
+        int l = (i < n) ? labels[i] : -1;
+        if (l >= kKMax) l = -1;
         for (int j = tid; j < 32 * kKMax; j += kWinThreads) s_wcnt[j] = 0;
         __syncthreads();
         // rank among equal labels inside the warp, in lane (= index) order
@@ -549,6 +559,10 @@ kmeans_regroup_kernel(const int* __restrict__ labels_all, const long long* __res
 }
 
 }  // namespace
+// on-chip variant (kmeans_window.cu): 1 = launched, 0 = window too large, < 0 = error
+int kmeans_window_fast_try(const float* feats, const long long* offsets, const int* ks, long long W, long long max_window_points, int kmax,
+                           int size_min, int size_max, int max_iter, double tol, int* labels, float* centroids, int* n_iter,
+                           cudaStream_t st);
 }  // namespace amp
 
 extern "C" {
@@ -608,9 +622,16 @@ int amp_kmeans_constrained_f32(const float* feats, const int64_t* offsets, const
     if (W < 1 || total_points < 1) return amp::fail(AMP_E_BADARG, "kmeans_constrained: empty input");
     if (max_window_points >= (1LL << 31)) return amp::fail(AMP_E_BADARG, "kmeans_constrained: window too large");
     if (max_iter < 1) return amp::fail(AMP_E_BADARG, "kmeans_constrained: max_iter < 1");
+    if (size_min < 0 || size_max < 0 || (size_max > 0 && size_min > size_max))
+        return amp::fail(AMP_E_BADARG, "kmeans_constrained: size_min / size_max must be >= 0 and size_min <= size_max");
     size_t need = amp_kmeans_workspace_bytes(total_points, W, kmax);
     if (!workspace || workspace_bytes < need)
         return amp::fail(AMP_E_WORKSPACE, "kmeans_constrained: workspace %zu < %zu", workspace_bytes, need);
+    {
+        const int rc = amp::kmeans_window_fast_try(feats, reinterpret_cast<const long long*>(offsets), ks, W, max_window_points, kmax, size_min,
+                                                   size_max, max_iter, tol, labels, centroids, n_iter, (cudaStream_t)stream);
+        if (rc != 0) return rc < 0 ? rc : AMP_OK;
+    }
     int* prop = reinterpret_cast<int*>(workspace);
     float* pd = reinterpret_cast<float*>(prop + total_points);
     amp::kmeans_window_kernel<<<(unsigned)W, amp::kWinThreads, 0, (cudaStream_t)stream>>>(

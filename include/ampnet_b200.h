@@ -94,12 +94,16 @@ int amp_kmeans_assign_f32(const float* feats, const float* centroids, int64_t n,
 /* Column gather feats[i,:] = pc[i, cols[0..2]] (`in_pc[:, i_f]`, 3_kmeans.py:81-82). */
 int amp_kmeans_gather_feats_f32(const float* pc, int64_t n, int64_t row_stride,
                                 int32_t c0, int32_t c1, int32_t c2, float* feats, void* stream);
-/* Whole constrained k-means for W independent windows (one CTA cluster per window):
+/* Whole constrained k-means for W independent windows (one CTA per window, working state in shared memory):
  *   feats      [sum n_w, 3] f32, window w owns rows [offsets[w], offsets[w+1])
  *   offsets    [W+1] int64 (device)
  *   ks         [W] int32 (device), 1 <= k_w <= kmax <= 32
  *   size_min / size_max  0 = unconstrained on that side (3_kmeans.py:78: both 2048; utils.py:500: min only)
  *   labels     [sum n_w] int32 out; centroids [W, kmax, 3] f32 out; n_iter [W] int32 out
+ * A window whose constraints cannot be met (k_w > n_w, size_max * k_w < n_w, size_min * k_w > n_w, k_w outside [1, kmax]) gets
+ * labels -1, zero centroids and n_iter -1; the other windows of the call are unaffected.
+ * Sums are fixed point (rint(x * 2^32) in int64): coordinates must satisfy sum |x| < 2^31 per window (the reference's
+ * inputs are normalised to [-1, 1]; clustering.py checks the range).
  */
 size_t amp_kmeans_workspace_bytes(int64_t total_points, int64_t W, int32_t kmax);
 int amp_kmeans_constrained_f32(const float* feats, const int64_t* offsets, const int32_t* ks,

@@ -113,3 +113,71 @@ def test_regroup_and_reference_shaped_calls(amp, cuda):
     big = rng.random((2048 * 11, 13))
     assert amp.split_kmeans_array(big, 2048, 9).shape == (2048, 13, 9)
     assert amp.split_kmeans_array(rng.random((3000, 13)), 2048, 9).shape == (2048, 13, 1)
+
+
+def test_on_chip_window_kernel_equals_global_memory_kernel_and_oracle(amp, cuda):
+    """kmeans_window_fast_kernel (state in shared memory, warp-parallel radix select) against kmeans_window_kernel (state in
+    global memory) and the oracle: identical labels, centroids and iteration counts, for window sizes on both sides of the
+    "coordinates fit in shared memory" limit and for all three constraint modes."""
+    rng = np.random.default_rng(21)
+    cases = [([5 * 2048, 3 * 2048, 2048 * 2], [5, 3, 2], 2048, 2048),        # balanced split (3_kmeans.py:78), x in shared memory
+             ([9 * 2048, 7 * 2048], [9, 7], 2048, 2048),                     # 18 432 points: coordinates stay in global memory
+             ([9000, 5000], [4, 2], 2048, 0),                                # size_min only (utils.py:500)
+             ([6000], [3], 0, 0)]                                            # unconstrained
+    for sizes, ks, smin, smax in cases:
+        x = rng.random((sum(sizes), 3), dtype=np.float32)
+        x[::50] = x[1::50][: len(x[::50])]                                   # exact duplicates: ties in the radix select
+        offsets = np.concatenate([[0], np.cumsum(sizes)])
+        xd = torch.from_numpy(x).to(cuda)
+        n0 = amp._lib.path_count("kmeans_fast")
+        lab, cent, it = amp.kmeans_constrained_windows(xd, offsets, ks, smin, smax)
+        assert amp._lib.path_count("kmeans_fast") == n0 + 1
+        amp._lib.set_disabled(["kmeans_fast"])
+        try:
+            lab2, cent2, it2 = amp.kmeans_constrained_windows(xd, offsets, ks, smin, smax)
+        finally:
+            amp._lib.set_disabled(None)
+        assert torch.equal(lab, lab2) and torch.equal(cent, cent2) and torch.equal(it, it2)
+        w = 0
+        el, ec, eit = ko.kmeans_constrained(x[offsets[w]:offsets[w + 1]], ks[w], smin or None, smax or None)
+        assert (lab[offsets[w]:offsets[w + 1]].cpu().numpy() == el).all() and (cent[w, :ks[w]].cpu().numpy() == ec).all() and int(it[w]) == eit
+
+
+def test_infeasible_windows_are_flagged_not_corrupted(amp, cuda):
+    """The C ABI itself (no Python-side validation): a window whose constraints cannot be met gets labels -1 / n_iter -1 and
+    leaves the other windows of the call alone (out-of-bounds shared-memory atomics on label -1)."""
+    import ctypes
+    rng = np.random.default_rng(3)
+    sizes, ks = [4096, 3000, 4096], [2, 2, 2]                                # window 1: size_max * k = 4096 >= 3000 but size_min * k = 4096 > 3000
+    x = torch.from_numpy(rng.random((sum(sizes), 3), dtype=np.float32)).to(cuda)
+    offsets = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int64, device=cuda)
+    dks = torch.tensor(ks, dtype=torch.int32, device=cuda)
+    lib = amp._lib.lib()
+    for disabled in (None, ["kmeans_fast"]):
+        amp._lib.set_disabled(disabled)
+        try:
+            labels = torch.full((sum(sizes),), 77, dtype=torch.int32, device=cuda)
+            cent = torch.empty((3, 2, 3), dtype=torch.float32, device=cuda)
+            nit = torch.empty(3, dtype=torch.int32, device=cuda)
+            wsb = lib.amp_kmeans_workspace_bytes(sum(sizes), 3, 2)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=cuda)
+            amp._lib.check(lib.amp_kmeans_constrained_f32(x.data_ptr(), offsets.data_ptr(), dks.data_ptr(), 3, sum(sizes), max(sizes), 2, 2048, 2048,
+                                                          10, 1e-2, labels.data_ptr(), cent.data_ptr(), nit.data_ptr(), ws.data_ptr(), wsb,
+                                                          torch.cuda.current_stream().cuda_stream))
+            torch.cuda.synchronize()
+        finally:
+            amp._lib.set_disabled(None)
+        assert nit.tolist()[1] == -1 and nit.tolist()[0] > 0 and nit.tolist()[2] > 0
+        assert (labels[4096:7096] == -1).all()
+        for w, (a, b) in enumerate([(0, 4096), (7096, 11192)]):
+            cnt = torch.bincount(labels[a:b].long(), minlength=2)
+            assert cnt.tolist() == [2048, 2048]
+        # the regroup kernel skips unassigned rows instead of indexing with -1
+        order, counts, _ = amp.regroup_windows(labels, offsets.cpu().numpy(), ks)
+        assert counts.cpu().tolist() == [[2048, 2048], [0, 0], [2048, 2048]]
+
+
+def test_unnormalised_coordinates_are_refused(amp, cuda):
+    x = torch.rand(5000, 3, device=cuda) * 1000.0 + 431000.0                 # raw UTM metres: the fixed-point sums would wrap
+    with pytest.raises(ValueError, match="normalised"):
+        amp.kmeans_constrained_windows(x, [0, 5000], [2], 2048, 0)
