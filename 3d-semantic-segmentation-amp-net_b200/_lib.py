@@ -27,7 +27,7 @@ SIGNATURES = {
     "amp_kmeans_gather_feats_f32": (_c.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp]),
     "amp_kmeans_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "amp_kmeans_constrained_f32": (_c.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32,
-                                              _dbl, _vp, _vp, _vp, _vp, _sz, _vp]),
+                                              _dbl, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "amp_kmeans_regroup": (_c.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
     "amp_minmax_f64": (_c.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),
     "amp_window_ids_f64": (_c.c_int, [_vp, _vp, _i64, _i64, _dbl, _dbl, _i32, _i32, _i32, _i32, _vp, _vp]),

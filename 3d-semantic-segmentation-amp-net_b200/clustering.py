@@ -48,7 +48,10 @@ def gather_feats(pc, cols):
     return feats
 
 
-def kmeans_constrained_windows(feats, offsets, ks, size_min=0, size_max=0, max_iter=10, tol=1e-2):
+N_INIT = 5        # the reference's KMeansConstrained(n_init=5) (3_kmeans.py:78-80, utils.py:500-503)
+
+
+def kmeans_constrained_windows(feats, offsets, ks, size_min=0, size_max=0, max_iter=10, tol=1e-2, n_init=1):
     """Constrained k-means of W independent windows in one launch.
 
     feats [total,3] CUDA f32; offsets: W+1 ints (host list/array); ks: W ints (host).
@@ -91,7 +94,7 @@ def kmeans_constrained_windows(feats, offsets, ks, size_min=0, size_max=0, max_i
     with torch.cuda.device(dev):
         _lib.check(lib.amp_kmeans_constrained_f32(
             feats.data_ptr(), d_off.data_ptr(), d_ks.data_ptr(), W, total, int(sizes.max()), kmax,
-            int(size_min), int(size_max), int(max_iter), float(tol), labels.data_ptr(), cent.data_ptr(),
+            int(size_min), int(size_max), int(max_iter), float(tol), int(n_init), labels.data_ptr(), cent.data_ptr(),
             n_iter.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr()))
     return labels, cent, n_iter
 
@@ -126,12 +129,14 @@ def get_cluster_centroid(pc):
     return torch.stack([pc[:, 0].mean(0), pc[:, 1].mean(0)], dim=0)
 
 
-def cluster_window(pc_dev, k, cols, size_min, size_max, max_iter=10, tol=1e-2):
+def cluster_window(pc_dev, k, cols, size_min, size_max, max_iter=10, tol=1e-2, n_init=N_INIT):
     """One window on the device: returns (grouped rows [n, D] sorted by (label, index),
     counts [k] (host ints), xy_mean [k,2] device, labels device)."""
     feats = gather_feats(pc_dev, cols)
     n = pc_dev.shape[0]
-    labels, _, _ = kmeans_constrained_windows(feats, [0, n], [k], size_min, size_max, max_iter, tol)
+    if n > 28000:
+        n_init = 1                      # restarts need the on-chip kernel (include/ampnet_b200.h)
+    labels, _, _ = kmeans_constrained_windows(feats, [0, n], [k], size_min, size_max, max_iter, tol, n_init)
     order, counts, xy = regroup_windows(labels, [0, n], [k], pc_dev)
     grouped = pc_dev.index_select(0, order)
     return grouped, counts[0].cpu().tolist(), xy[0], labels

@@ -560,8 +560,9 @@ kmeans_regroup_kernel(const int* __restrict__ labels_all, const long long* __res
 
 }  // namespace
 // on-chip variant (kmeans_window.cu): 1 = launched, 0 = window too large, < 0 = error
+int kmeans_window_fast_cap(bool with_x);
 int kmeans_window_fast_try(const float* feats, const long long* offsets, const int* ks, long long W, long long max_window_points, int kmax,
-                           int size_min, int size_max, int max_iter, double tol, int* labels, float* centroids, int* n_iter,
+                           int size_min, int size_max, int max_iter, double tol, int n_init, int* labels, float* centroids, int* n_iter,
                            cudaStream_t st);
 }  // namespace amp
 
@@ -613,7 +614,7 @@ size_t amp_kmeans_workspace_bytes(int64_t total_points, int64_t W, int32_t kmax)
 
 int amp_kmeans_constrained_f32(const float* feats, const int64_t* offsets, const int32_t* ks, int64_t W,
                                int64_t total_points, int64_t max_window_points, int32_t kmax,
-                               int32_t size_min, int32_t size_max, int32_t max_iter, double tol,
+                               int32_t size_min, int32_t size_max, int32_t max_iter, double tol, int32_t n_init,
                                int32_t* labels, float* centroids, int32_t* n_iter, void* workspace,
                                size_t workspace_bytes, void* stream) {
     if (!feats || !offsets || !ks || !labels || !centroids || !n_iter)
@@ -621,7 +622,7 @@ int amp_kmeans_constrained_f32(const float* feats, const int64_t* offsets, const
     if (kmax < 1 || kmax > amp::kKMax) return amp::fail(AMP_E_BADARG, "kmeans_constrained: kmax=%d not in [1,%d]", kmax, amp::kKMax);
     if (W < 1 || total_points < 1) return amp::fail(AMP_E_BADARG, "kmeans_constrained: empty input");
     if (max_window_points >= (1LL << 31)) return amp::fail(AMP_E_BADARG, "kmeans_constrained: window too large");
-    if (max_iter < 1) return amp::fail(AMP_E_BADARG, "kmeans_constrained: max_iter < 1");
+    if (max_iter < 1 || n_init < 1 || n_init > 64) return amp::fail(AMP_E_BADARG, "kmeans_constrained: max_iter >= 1 and 1 <= n_init <= 64");
     if (size_min < 0 || size_max < 0 || (size_max > 0 && size_min > size_max))
         return amp::fail(AMP_E_BADARG, "kmeans_constrained: size_min / size_max must be >= 0 and size_min <= size_max");
     size_t need = amp_kmeans_workspace_bytes(total_points, W, kmax);
@@ -629,9 +630,12 @@ int amp_kmeans_constrained_f32(const float* feats, const int64_t* offsets, const
         return amp::fail(AMP_E_WORKSPACE, "kmeans_constrained: workspace %zu < %zu", workspace_bytes, need);
     {
         const int rc = amp::kmeans_window_fast_try(feats, reinterpret_cast<const long long*>(offsets), ks, W, max_window_points, kmax, size_min,
-                                                   size_max, max_iter, tol, labels, centroids, n_iter, (cudaStream_t)stream);
+                                                   size_max, max_iter, tol, n_init, labels, centroids, n_iter, (cudaStream_t)stream);
         if (rc != 0) return rc < 0 ? rc : AMP_OK;
     }
+    if (n_init > 1)
+        return amp::fail(AMP_E_BADARG, "kmeans_constrained: n_init > 1 needs windows of at most %d points (the on-chip kernel)",
+                         amp::kmeans_window_fast_cap(false));
     int* prop = reinterpret_cast<int*>(workspace);
     float* pd = reinterpret_cast<float*>(prop + total_points);
     amp::kmeans_window_kernel<<<(unsigned)W, amp::kWinThreads, 0, (cudaStream_t)stream>>>(

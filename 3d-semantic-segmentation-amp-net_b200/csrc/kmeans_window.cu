@@ -13,6 +13,7 @@
 //     atomic per (warp, cluster, dimension) instead of one 64-bit shared-memory atomic (a CAS loop) per point and dimension.
 // Replaces the solver call of data_proc/3_kmeans.py:78-82 / utils/utils.py:500-505 (see kmeans.cu).
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "amp_common.cuh"
 
@@ -21,13 +22,15 @@ namespace {
 
 constexpr int kKMax = 32;
 constexpr double kFix = 4294967296.0;  // 2^32
-constexpr int kT = 1024, kWarps = kT / 32;
+constexpr int kT = 1024;
 
 __device__ __forceinline__ float sqd3(float x0, float x1, float x2, float c0, float c1, float c2) {
     float d0 = __fsub_rn(x0, c0), d1 = __fsub_rn(x1, c1), d2 = __fsub_rn(x2, c2);
     return __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
 }
 
+// (The bins of a histogram row are read with scalar loads: a 16-byte vector load of `hist`, which the compiler emits when it
+// may assume the dynamic shared-memory window is 16-byte aligned, faulted with "misaligned address" on B200.)
 struct WS {
     float cent[kKMax * 3];
     unsigned long long sums[kKMax * 3];
@@ -42,7 +45,10 @@ struct WS {
     unsigned hist[kKMax * 256];
     int red_bits[32];
     unsigned red_idx[32];
-    int n_todo, n_open, flag, flag2, pick;
+    int n_todo, n_open, flag, flag2, pick, best_it;
+    float best_cent[kKMax * 3];
+    unsigned long long inertia;
+    long long best_inertia;
     double tol_abs, shift;
 };
 
@@ -147,7 +153,7 @@ __device__ void capacity_rounds(WS& s, const State& st, int n, int k) {
                 }
                 __syncthreads();
                 if (warp < k && s.over[warp] && !s.done[warp]) {        // one warp per cluster: lane owns 8 consecutive bins
-                    const unsigned* h = s.hist + warp * 256 + lane * 8;
+                    const volatile unsigned* h = s.hist + warp * 256 + lane * 8;     // (scalar loads: see the note at WS)
                     int c[8], tot = 0;
 #pragma unroll
                     for (int b = 0; b < 8; ++b) { c[b] = (int)h[b]; tot += c[b]; }
@@ -158,16 +164,20 @@ __device__ void capacity_rounds(WS& s, const State& st, int n, int k) {
                     // the lane whose bins hold the rk-th element: before < rk <= before + tot (first such lane)
                     const bool mine = before < rk && rk <= incl;
                     if (mine) {
-                        int cum = before, dgt = 0;
+                        // first bin b with before + c[0..b] >= rk; selects only (no dynamically indexed local array)
+                        int cum = before, dgt = 7, cdg = c[7], run = before;
+                        bool found = false;
 #pragma unroll
                         for (int b = 0; b < 8; ++b) {
-                            if (cum + c[b] >= rk) { dgt = b; break; }
-                            cum += c[b];
+                            const bool hit = !found && run + c[b] >= rk;
+                            if (hit) { dgt = b; cum = run; cdg = c[b]; }
+                            found = found || hit;
+                            run += c[b];
                         }
                         s.prefix[warp] = (s.prefix[warp] << 8) | (unsigned long long)(lane * 8 + dgt);
                         s.rank[warp] = rk - cum;
                         if (pass == 3) {                                 // distance fully determined
-                            if (rk - cum == c[dgt]) {                    // the whole group of equal distances fits: no tie at the cut
+                            if (rk - cum == cdg) {                       // the whole group of equal distances fits: no tie at the cut
                                 s.prefix[warp] = (s.prefix[warp] << 32) | 0xffffffffull;
                                 s.done[warp] = 1;
                             } else {
@@ -264,13 +274,14 @@ template <bool XS>
 __global__ void __launch_bounds__(kT, 1)
 kmeans_window_fast_kernel(const float* __restrict__ feats, const long long* __restrict__ offsets, const int* __restrict__ ks, int kmax,
                           int size_min, int size_max, int max_iter, double tol, int cap, int* __restrict__ labels_all,
-                          float* __restrict__ centroids, int* __restrict__ n_iter) {
-    extern __shared__ __align__(16) unsigned char smem[];
+                          float* __restrict__ centroids, int* __restrict__ n_iter, int n_init) {
+    extern __shared__ __align__(8) unsigned char smem[];
     WS& s = *reinterpret_cast<WS*>(smem);
     float* s_pd = reinterpret_cast<float*>(smem + ((sizeof(WS) + 15) & ~(size_t)15));
     float* s_x = s_pd + cap;                                   // [3 * cap] when XS
     signed char* s_lab = reinterpret_cast<signed char*>(XS ? s_x + 3 * (size_t)cap : s_x);
     signed char* s_prop = s_lab + cap;
+    signed char* s_best = s_prop + cap;                        // labels of the best restart so far (n_init > 1)
     const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const long long off = offsets[w];
     const int n = (int)(offsets[w + 1] - off);
@@ -318,10 +329,13 @@ kmeans_window_fast_kernel(const float* __restrict__ feats, const long long* __re
         s.tol_abs = __dmul_rn(__ddiv_rn(acc, 3.0), tol);
     }
 
-    // ---- B. init: farthest-point sampling of k rows, start row 0 (pd[] = running min distance) ----
-    for (int i = tid; i < n; i += kT) s_pd[i] = (i == 0) ? -1.0f : INFINITY;
-    int last = 0;
-    if (tid < 3) s.cent[tid] = st.x[tid];
+    if (n_init < 1) n_init = 1;
+    for (int restart = 0; restart < n_init; ++restart) {
+    // ---- B. init: farthest-point sampling of k rows from the restart's start row (pd[] = running min distance) ----
+    const int start = (int)(((long long)restart * n) / n_init);
+    for (int i = tid; i < n; i += kT) s_pd[i] = (i == start) ? -1.0f : INFINITY;
+    int last = start;
+    if (tid < 3) s.cent[tid] = st.x[3 * start + tid];
     __syncthreads();
     for (int c = 1; c < k; ++c) {
         const float lx = st.x[3 * last], ly = st.x[3 * last + 1], lz = st.x[3 * last + 2];
@@ -391,9 +405,38 @@ kmeans_window_fast_kernel(const float* __restrict__ feats, const long long* __re
     __syncthreads();
     // ---- D. final labels with the final centroids ----
     constrained_assign(s, st, n, k, size_min, size_max);
-    for (int i = tid; i < n; i += kT) labels[i] = (int)s_lab[i];
-    for (int i = tid; i < kmax * 3; i += kT) centroids[(long long)w * kmax * 3 + i] = (i < k * 3) ? s.cent[i] : 0.0f;
-    if (tid == 0) n_iter[w] = it;
+    if (n_init == 1) {
+        for (int i = tid; i < n; i += kT) labels[i] = (int)s_lab[i];
+        for (int i = tid; i < kmax * 3; i += kT) centroids[(long long)w * kmax * 3 + i] = (i < k * 3) ? s.cent[i] : 0.0f;
+        if (tid == 0) n_iter[w] = it;
+        return;
+    }
+    // ---- E. restarts: keep the run with the smallest fixed-point inertia (earliest on a tie) ----
+    if (tid == 0) s.inertia = 0ull;
+    __syncthreads();
+    {
+        long long a = 0;
+        for (int i = tid; i < n; i += kT) {
+            const int l = s_lab[i];
+            const float d = sqd3(st.x[3 * i], st.x[3 * i + 1], st.x[3 * i + 2], s.cent[3 * l], s.cent[3 * l + 1], s.cent[3 * l + 2]);
+            a += __double2ll_rn(__dmul_rn((double)d, kFix));
+        }
+        a = warp_sum_ll(a);
+        if (lane == 0) atomicAdd(&s.inertia, (unsigned long long)a);
+    }
+    __syncthreads();
+    const bool better = restart == 0 || (long long)s.inertia < s.best_inertia;     // block-uniform
+    __syncthreads();
+    if (better) {
+        for (int i = tid; i < n; i += kT) s_best[i] = s_lab[i];
+        for (int i = tid; i < k * 3; i += kT) s.best_cent[i] = s.cent[i];
+        if (tid == 0) { s.best_inertia = (long long)s.inertia; s.best_it = it; }
+    }
+    __syncthreads();
+    }   // restarts
+    for (int i = tid; i < n; i += kT) labels[i] = (int)s_best[i];
+    for (int i = tid; i < kmax * 3; i += kT) centroids[(long long)w * kmax * 3 + i] = (i < k * 3) ? s.best_cent[i] : 0.0f;
+    if (tid == 0) n_iter[w] = s.best_it;
 }
 
 constexpr size_t kMaxSmem = 232448;
@@ -403,19 +446,19 @@ inline size_t ws_bytes() { return (sizeof(WS) + 15) & ~(size_t)15; }
 
 // Largest window (points) the on-chip kernel takes: with the coordinates in shared memory, and without.
 int kmeans_window_fast_cap(bool with_x) {
-    const size_t per = with_x ? 18 : 6;
+    const size_t per = with_x ? 19 : 7;
     return (int)(((kMaxSmem - ws_bytes() - 64) / per) & ~(size_t)15);
 }
 
 // 1 = launched, 0 = window too large for the on-chip kernel (the caller runs kmeans_window_kernel), < 0 = error
 int kmeans_window_fast_try(const float* feats, const long long* offsets, const int* ks, long long W, long long max_window_points, int kmax,
-                           int size_min, int size_max, int max_iter, double tol, int* labels, float* centroids, int* n_iter,
+                           int size_min, int size_max, int max_iter, double tol, int n_init, int* labels, float* centroids, int* n_iter,
                            cudaStream_t st) {
     if (path_disabled("kmeans_fast")) return 0;
     const bool xs = max_window_points <= kmeans_window_fast_cap(true);
     if (!xs && max_window_points > kmeans_window_fast_cap(false)) return 0;
     const int cap = (int)((max_window_points + 15) & ~15LL);
-    const size_t smem = ws_bytes() + (size_t)cap * (xs ? 18 : 6) + 64;
+    const size_t smem = ws_bytes() + (size_t)cap * (xs ? 19 : 7) + 64;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kmeans_window_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
@@ -425,10 +468,10 @@ int kmeans_window_fast_try(const float* feats, const long long* offsets, const i
     }
     if (xs)
         kmeans_window_fast_kernel<true><<<(unsigned)W, kT, smem, st>>>(feats, offsets, ks, kmax, size_min, size_max, max_iter, tol, cap, labels,
-                                                                        centroids, n_iter);
+                                                                        centroids, n_iter, n_init);
     else
         kmeans_window_fast_kernel<false><<<(unsigned)W, kT, smem, st>>>(feats, offsets, ks, kmax, size_min, size_max, max_iter, tol, cap, labels,
-                                                                         centroids, n_iter);
+                                                                         centroids, n_iter, n_init);
     count_launch();
     count_path("kmeans_fast");
     const int rc = check_launch("kmeans_window_fast");

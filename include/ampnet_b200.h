@@ -99,6 +99,9 @@ int amp_kmeans_gather_feats_f32(const float* pc, int64_t n, int64_t row_stride,
  *   offsets    [W+1] int64 (device)
  *   ks         [W] int32 (device), 1 <= k_w <= kmax <= 32
  *   size_min / size_max  0 = unconstrained on that side (3_kmeans.py:78: both 2048; utils.py:500: min only)
+ *   n_init     restarts (3_kmeans.py:78-80 passes n_init=5): restart r seeds the farthest-point initialisation at row
+ *              (r * n_w) / n_init, the run with the smallest inertia (fixed-point sum of squared distances) wins, the
+ *              earliest on a tie; n_init > 1 needs windows that fit the on-chip kernel (<= ~28 000 points)
  *   labels     [sum n_w] int32 out; centroids [W, kmax, 3] f32 out; n_iter [W] int32 out
  * A window whose constraints cannot be met (k_w > n_w, size_max * k_w < n_w, size_min * k_w > n_w, k_w outside [1, kmax]) gets
  * labels -1, zero centroids and n_iter -1; the other windows of the call are unaffected.
@@ -108,7 +111,7 @@ int amp_kmeans_gather_feats_f32(const float* pc, int64_t n, int64_t row_stride,
 size_t amp_kmeans_workspace_bytes(int64_t total_points, int64_t W, int32_t kmax);
 int amp_kmeans_constrained_f32(const float* feats, const int64_t* offsets, const int32_t* ks,
                                int64_t W, int64_t total_points, int64_t max_window_points, int32_t kmax,
-                               int32_t size_min, int32_t size_max, int32_t max_iter, double tol,
+                               int32_t size_min, int32_t size_max, int32_t max_iter, double tol, int32_t n_init,
                                int32_t* labels, float* centroids, int32_t* n_iter,
                                void* workspace, size_t workspace_bytes, void* stream);
 /* Stable regroup by label (3_kmeans.py:88-101, utils.py:508-517): order[] lists the rows of each

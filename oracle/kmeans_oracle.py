@@ -144,16 +144,23 @@ def center_shift(c_new, c_old):
     return acc
 
 
-def init_centroids(x, k):
+def init_centroids(x, k, start_row=0):
     x = np.asarray(x, dtype=np.float32)
-    return x[fps_oracle.fps_indices(x, k)].copy()
+    return x[fps_oracle.fps_indices(x, k, start_row)].copy()
 
 
-def kmeans_constrained(x, k, size_min=None, size_max=None, max_iter=10, tol=1e-2):
-    """Returns (labels int32 [n], centroids float32 [k,3], n_iter)."""
-    x = np.ascontiguousarray(x, dtype=np.float32)
-    c = init_centroids(x, k)
-    ta = tol_abs(x, tol)
+def inertia_fixed(x, labels, c):
+    """Sum over the points of the float32 squared distance to their own centroid, as an order-independent fixed-point
+    integer (rint(float64(d^2) * 2^32) in int64): the score the restarts are compared on."""
+    x = np.asarray(x, dtype=np.float32)
+    d = x - np.asarray(c, dtype=np.float32)[labels]
+    d = d * d
+    d2 = (d[:, 0] + d[:, 1]) + d[:, 2]
+    return int(np.rint(d2.astype(np.float64) * FIX).astype(np.int64).sum())
+
+
+def _one_run(x, k, size_min, size_max, max_iter, ta, start_row):
+    c = init_centroids(x, k, start_row)
     it = 0
     for it in range(1, max_iter + 1):
         labels = constrained_assign(x, c, size_min, size_max)
@@ -164,6 +171,24 @@ def kmeans_constrained(x, k, size_min=None, size_max=None, max_iter=10, tol=1e-2
             break
     labels = constrained_assign(x, c, size_min, size_max)
     return labels, c, it
+
+
+def kmeans_constrained(x, k, size_min=None, size_max=None, max_iter=10, tol=1e-2, n_init=1):
+    """Returns (labels int32 [n], centroids float32 [k,3], n_iter).
+    n_init restarts (the reference passes n_init=5 with random k-means++ seeds, 3_kmeans.py:78-80): restart r seeds the
+    farthest-point initialisation at row (r * n) // n_init; the run with the smallest inertia_fixed() wins, the earliest
+    on a tie. n_init=1 is the single run seeded at row 0."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    ta = tol_abs(x, tol)
+    best = None
+    for r in range(max(1, int(n_init))):
+        labels, c, it = _one_run(x, k, size_min, size_max, max_iter, ta, (r * len(x)) // max(1, int(n_init)))
+        if n_init <= 1:
+            return labels, c, it
+        score = inertia_fixed(x, labels, c)
+        if best is None or score < best[0]:
+            best = (score, labels, c, it)
+    return best[1], best[2], best[3]
 
 
 def regroup(pc, labels, k):

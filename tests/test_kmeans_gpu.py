@@ -90,7 +90,7 @@ def test_regroup_and_reference_shaped_calls(amp, cuda):
     pc = rng.random((2048 * 4 + 300, 10), dtype=np.float32)
     t = torch.from_numpy(pc).unsqueeze(0)                      # reference passes a CPU tensor [1,P,10]
     clusters, cents = amp.kmeans_clustering(t, n_points=2048, max_clusters=18)
-    el, _, _ = ko.kmeans_constrained(pc[:, [0, 1, 8]], 4, 2048, None)
+    el, _, _ = ko.kmeans_constrained(pc[:, [0, 1, 8]], 4, 2048, None, n_init=5)      # the drop-ins restart 5 times like the reference
     groups = ko.regroup(pc, el, 4)
     assert len(clusters) == len(groups) == 4
     for a, b in zip(clusters, groups):
@@ -181,3 +181,24 @@ def test_unnormalised_coordinates_are_refused(amp, cuda):
     x = torch.rand(5000, 3, device=cuda) * 1000.0 + 431000.0                 # raw UTM metres: the fixed-point sums would wrap
     with pytest.raises(ValueError, match="normalised"):
         amp.kmeans_constrained_windows(x, [0, 5000], [2], 2048, 0)
+
+
+def test_restarts_keep_the_lowest_inertia_and_match_the_oracle(amp, cuda):
+    """n_init = 5 (3_kmeans.py:78-80): restart r seeds the FPS initialisation at row (r * n) // 5; the run with the smallest
+    fixed-point inertia wins. Labels / centroids bit-exact against the oracle, and never worse than the single run."""
+    rng = np.random.default_rng(31)
+    sizes, ks = [5 * 2048, 3 * 2048], [5, 3]
+    x = rng.random((sum(sizes), 3), dtype=np.float32)
+    offsets = np.concatenate([[0], np.cumsum(sizes)])
+    xd = torch.from_numpy(x).to(cuda)
+    lab5, cent5, it5 = amp.kmeans_constrained_windows(xd, offsets, ks, 2048, 2048, n_init=5)
+    lab1, cent1, _ = amp.kmeans_constrained_windows(xd, offsets, ks, 2048, 2048, n_init=1)
+    for w in range(2):
+        xs = x[offsets[w]:offsets[w + 1]]
+        el, ec, eit = ko.kmeans_constrained(xs, ks[w], 2048, 2048, n_init=5)
+        got = lab5[offsets[w]:offsets[w + 1]].cpu().numpy()
+        assert (got == el).all() and (cent5[w, :ks[w]].cpu().numpy() == ec).all() and int(it5[w]) == eit
+        assert np.bincount(got, minlength=ks[w]).tolist() == [2048] * ks[w]
+        i5 = ko.inertia_fixed(xs, got, cent5[w, :ks[w]].cpu().numpy())
+        i1 = ko.inertia_fixed(xs, lab1[offsets[w]:offsets[w + 1]].cpu().numpy(), cent1[w, :ks[w]].cpu().numpy())
+        assert i5 <= i1
