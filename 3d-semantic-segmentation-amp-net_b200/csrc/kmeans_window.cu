@@ -149,7 +149,10 @@ __device__ void capacity_rounds(WS& s, const State& st, int n, int k) {
                             slot = j * 256 + (int)((key >> shift) & 255ull);
                         }
                     }
-                    agg_inc(s.hist, slot, act);
+                    // top byte (sign + exponent): a handful of distinct digits per warp -> one aggregated atomic per digit;
+                    // lower bytes are spread over the bins: plain atomics (match_any loops once per distinct value)
+                    if (pass == 0) agg_inc(s.hist, slot, act);
+                    else if (act) atomicAdd(s.hist + slot, 1u);
                 }
                 __syncthreads();
                 if (warp < k && s.over[warp] && !s.done[warp]) {        // one warp per cluster: lane owns 8 consecutive bins

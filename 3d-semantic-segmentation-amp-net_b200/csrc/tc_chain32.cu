@@ -34,7 +34,7 @@ constexpr int kMinSmem = 120 * 1024;                      // more than half an S
 
 __host__ __device__ inline int align_i(int v, int a) { return (v + a - 1) / a * a; }
 
-struct Plan { int w, wc, bias, stage, ring, bar, total; };
+struct Plan { int w, wc, bias, stage, ring, bar, gb, total; };
 __host__ __device__ inline Plan plan_of(int wblob_bytes, int wcloud_bytes, int n_bias, int stage_f32, int stream) {
     Plan s;
     s.w = 0;
@@ -43,7 +43,8 @@ __host__ __device__ inline Plan plan_of(int wblob_bytes, int wcloud_bytes, int n
     s.stage = s.bias + align_i(n_bias * 4, 128);
     s.ring = s.stage + (stage_f32 ? 2 * kStageBytes : 0);
     s.bar = s.ring + (stream ? 2 * kT32ChunkBytes : 0);
-    s.total = s.bar + 256;
+    s.gb = s.bar + 256;                                       // per slot: the tile's grouped-bias row (128 floats)
+    s.total = s.gb + 2 * 512;
     return s;
 }
 
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain32_kernel(const __grid_co
         const uint32_t wc_addr0 = smem_u32(smem + sp.wc + slot * 2 * wc_bytes);
         const uint32_t cbar0 = smem_u32(&s_bar[16 + 2 * slot]);
         float4* s_stage = reinterpret_cast<float4*>(smem + sp.stage + slot * kStageBytes);
+        float* s_gb = reinterpret_cast<float*>(smem + sp.gb + slot * 512);
         const uint32_t w_addr = smem_u32(smem + sp.w), ring_addr = smem_u32(smem + sp.ring);
         const bool issuer_warp = (warp & 3) == 0;
         uint32_t phase = 0;
@@ -233,11 +235,24 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain32_kernel(const __grid_co
                 __syncwarp();
             }
             fetch_rows(r + 1);
-            // group of this row (per-block bias of the segmentation head)
+            // group of this row (per-block bias of the segmentation head); when the whole tile lies in one block (the usual
+            // case: blocks of 2048 points, tiles of 128) its bias row goes to shared memory once and the first layer's epilogue
+            // reads it like an ordinary bias table instead of 32 global loads per thread
             int group = 0;
-            if (p.n_groups > 1) {
-                const int rr = row0 + (row_ok ? row : valid - 1);
-                for (int g = 1; g < p.n_groups; ++g) group += (rr >= __ldg(p.group_rows + g)) ? 1 : 0;
+            bool gb_uniform = false;
+            if (p.gbias) {
+                int g_first = 0, g_last = 0;
+                if (p.n_groups > 1) {
+                    const int rr = row0 + (row_ok ? row : valid - 1);
+                    for (int g = 1; g < p.n_groups; ++g) {
+                        const int start = __ldg(p.group_rows + g);
+                        group += (rr >= start) ? 1 : 0;
+                        g_first += (row0 >= start) ? 1 : 0;
+                        g_last += (row0 + valid - 1 >= start) ? 1 : 0;
+                    }
+                }
+                gb_uniform = g_first == g_last;                          // computed alike by every thread of the slot
+                if (gb_uniform && stid < p.op[0].N) s_gb[stid] = __ldg(p.gbias + ((long long)cloud * p.n_groups + g_first) * p.op[0].N + stid);
             }
             tmem_wait_st();
             tc_fence_before();
@@ -289,7 +304,43 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain32_kernel(const __grid_co
 
                     if (!op.pool) {
                         const float* gb = op.bias_grouped ? p.gbias + ((long long)cloud * p.n_groups + group) * op.N : nullptr;
-                        // a thread owns a whole row: 64 accumulator columns per pass, both TMEM loads in flight before the wait
+                        // a thread owns a whole row: 64 accumulator columns per pass, both TMEM loads in flight before the wait.
+                        // The common layer (bias + ReLU + hand-over, N a multiple of 64) gets a branch-free pass: with one
+                        // epilogue warp per scheduler every uniform branch of the generic pass below (5 per 16 columns) is
+                        // exposed latency (measured: 1.4 k cycles for the bias / ReLU section of 64 columns)
+                        const bool gb_plain = op.bias_grouped && gb_uniform && l == 0 && op.bias_off < 0;
+                        const bool plain = (gb_plain || (op.bias_off >= 0 && !op.bias_grouped)) && op.relu && op.write_act &&
+                                           !op.store_logits && !op.store_f32 && (op.N & 63) == 0;
+                        if (plain) {
+                            for (int c0 = 0; c0 < op.N; c0 += 64) {
+                                uint32_t v[64];
+                                tmem_ld32(tcol + lane_addr + kAcc + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                                tmem_ld32(tcol + lane_addr + kAcc + (uint32_t)(c0 + 32), *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+                                tmem_wait_ld();
+                                T32_PROF();                      // (epilogue detail) accumulator columns in registers
+                                const float4* b4 = reinterpret_cast<const float4*>((gb_plain ? s_gb : s_bias + op.bias_off) + c0);
+#pragma unroll
+                                for (int q = 0; q < 16; ++q) {
+                                    const float4 bb = b4[q];
+                                    v[4 * q] = __float_as_uint(fmaxf(__uint_as_float(v[4 * q]) + bb.x, 0.f));
+                                    v[4 * q + 1] = __float_as_uint(fmaxf(__uint_as_float(v[4 * q + 1]) + bb.y, 0.f));
+                                    v[4 * q + 2] = __float_as_uint(fmaxf(__uint_as_float(v[4 * q + 2]) + bb.z, 0.f));
+                                    v[4 * q + 3] = __float_as_uint(fmaxf(__uint_as_float(v[4 * q + 3]) + bb.w, 0.f));
+                                }
+                                T32_PROF();                      // (epilogue detail) bias / ReLU done
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                    uint32_t hi[16], lo[16];
+#pragma unroll
+                                    for (int q = 0; q < 16; ++q)
+                                        split_pair(__uint_as_float(v[32 * h + 2 * q]), __uint_as_float(v[32 * h + 2 * q + 1]), hi[q], lo[q]);
+                                    tmem_st16(tcol + lane_addr + kAhi + (uint32_t)((c0 >> 1) + 16 * h), hi);
+                                    tmem_st16(tcol + lane_addr + kAlo + (uint32_t)((c0 >> 1) + 16 * h), lo);
+                                }
+                            }
+                            T32_PROF();                          // (epilogue detail) split + tcgen05.st issued
+                            tmem_wait_st();
+                        } else {
                         for (int c0 = 0; c0 < op.N; c0 += 64) {
                             const int nc = min(64, op.N - c0);           // 16, 32 or 64
                             uint32_t v[64];
@@ -375,6 +426,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain32_kernel(const __grid_co
                                 const int rr = i >> 4, piece = i & 15;
                                 if (rr < valid) *reinterpret_cast<float4*>(ob + (long long)rr * p.out_ld + piece * 4) = s_stage[rr * 16 + (piece ^ (rr & 15))];
                             }
+                        }
                         }
                     } else {
                         // max over the 128 rows of the tile, 32 rows per warp by redux; lane j keeps channels j, 32 + j, 64 + j, 96 + j

@@ -207,6 +207,84 @@ def bench_train(dist, amp, steps, warmup, with_cpu):
     return res
 
 
+def bench_train_w9(dist, amp, steps, warmup, with_cpu):
+    """The training step at the shape the script really runs (train_pointnet-attention.py:337-475 on a collate_seq_padd batch):
+    W = 9 windows of 2048 points per sample, batch 32: device-side batch assembly + augmentation (one H2D, one kernel), 9 encoder
+    calls (one BatchNorm group each), attention + head over 9 x 2048 points per sample, CE(ignore -1) + reg, backward, 2 x Adam.
+    Both the device-timed value and e2e start from the collated batch in pinned HOST memory (the assembly is part of the step)."""
+    dev = dist.device
+    W, B, N = 9, NN_BATCH, NN_POINTS
+    enc, seg = build_modules(amp, dev)
+    enc.train(); seg.train()
+    params = list(enc.parameters()) + list(seg.parameters())
+    if dist.pg:
+        for p in params:
+            torch.distributed.broadcast(p.data, 0)
+    opt_e = torch.optim.Adam(enc.parameters(), lr=1e-3, fused=True)
+    opt_s = torch.optim.Adam(seg.parameters(), lr=1e-3, fused=True)
+    ce = torch.nn.CrossEntropyLoss(weight=torch.tensor([1., 2., 2., 1., 1.], device=dev), reduction="mean", ignore_index=-1)
+    rng = np.random.default_rng(5000 + dist.rank)
+    pc = rng.random((B, N, NN_DIMS, W), dtype=np.float32)
+    pc[:, :, :2, :] = pc[:, :, :2, :] * 2 - 1
+    pc[:, :, 2, :] *= 0.3
+    tg = rng.integers(0, NN_CLASSES, (B, N, W)).astype(np.int64)
+    real = rng.integers(3, W + 1, B)                                 # trailing windows: replicas with targets -1 (collate_fns.py:42-44)
+    for b in range(B):
+        pc[b, :, :, real[b]:] = pc[b, :, :, real[b] - 1:real[b]]
+        tg[b, :, real[b]:] = -1
+    pc_host, tg_host = torch.from_numpy(pc).pin_memory(), torch.from_numpy(tg).pin_memory()
+    cent = torch.from_numpy(pc[:, :, :2, :].mean(1).transpose(0, 2, 1).copy()).to(dev)      # [B, W, 2]
+    eye = torch.eye(64, device=dev)
+    flush = _Flush(dev)
+    keep = {}
+    flat = amp.GradAllReduce(params, dist.world, zero_copy=True) if dist.pg else None
+    np.random.seed(7)
+
+    def train_step():
+        opt_e.zero_grad(set_to_none=True); opt_s.zero_grad(set_to_none=True)      # as the script does (:372-373)
+        x, targets_pc = amp.assemble_windows(pc_host, tg_host, train=True, device=dev)
+        lo, gl, npc, ft = [], [], [], None
+        for w in range(W):
+            out, ft = enc(x[w])
+            lo.append(out[:, :, -64:]); gl.append(out[:, 0, :-64].view(-1, 1, 256)); npc.append(N)
+        logits, _ = seg(torch.transpose(torch.cat(gl, 1), 0, 1), torch.cat(lo, 1), cent, npc, None)
+        loss = ce(logits, targets_pc) + 0.001 * torch.norm(eye - torch.bmm(ft, ft.transpose(2, 1)))
+        loss.backward()
+        if flat is not None:
+            flat.all_reduce()
+        opt_e.step(); opt_s.step()
+        keep["loss"] = loss.detach()
+
+    n0 = amp._lib.launch_count()
+    ms = _timed(dist, train_step, steps, warmup, flush)
+    launches = (amp._lib.launch_count() - n0) // (steps + warmup) * steps
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        train_step()
+        loss_host.copy_(keep["loss"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e_ms = _timed(dist, step_e2e, steps, warmup, flush)
+    pts = B * W * N * dist.world * steps
+    peak, src = _peaks()
+    ach = (B * W * N * TRAIN_FLOP_PER_POINT) / (ms / steps * 1e-3) / 1e12
+    res = {
+        "value": pts / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms / steps, "gpu_launches": int(launches),
+        "e2e": {"value": pts / (e_ms * 1e-3), "unit": "points/s",
+                "h2d_bytes_per_step": int(pc_host.numel() * 4 + tg_host.numel() * 8 + W * N * 4 + W * 4), "d2h_bytes_per_step": 4},
+        "roofline": {"bound": "tensor", "kernel": "whole step", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                     "traffic": None, "peak_source": src, "model": "3 x 413 143 FLOP per point x 589 824 points / step time"},
+        "config": {"workload": "train_w9: training step on a collated batch, 32 samples x 9 windows x 2048 points per GPU"},
+        "notes": {"l2": "flushed between steps (256 MiB write)", "h2d": "the collated batch is copied from pinned host memory inside the timed step"},
+        "dtype": "f32", "final_loss": float(keep["loss"]),
+    }
+    if with_cpu:
+        from oracle import nn_bench as onb
+        res["cpu_baseline"] = onb.cpu_train_w9()
+    return res
+
+
 def bench_fwd_bf16(dist, amp, steps, warmup, with_cpu):
     return bench_fwd(dist, amp, steps, warmup, with_cpu, precision="bf16")
 
@@ -336,4 +414,4 @@ def bench_tile(dist, amp, steps, warmup, with_cpu, precision="fp32"):
 
 
 def hooks():
-    return {"fwd": bench_fwd, "fwd_bf16": bench_fwd_bf16, "train": bench_train, "tile": bench_tile}
+    return {"fwd": bench_fwd, "fwd_bf16": bench_fwd_bf16, "train": bench_train, "train_w9": bench_train_w9, "tile": bench_tile}

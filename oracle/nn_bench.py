@@ -68,6 +68,43 @@ def cpu_train(sample_steps=2):
                       "best %.3f s" % (sample_steps, cores, best), "seconds": ts}
 
 
+def cpu_train_w9(B=4, W=9):
+    """CPU arm of train_w9 on a bounded sample: ONE training step of B samples x 9 windows x 2048 points (host augmentation as the
+    reference loop does it, oracle forward / autograd backward, Adam), all host threads."""
+    from . import train_loop_oracle as tlo
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rng = np.random.default_rng(0)
+    pc = torch.from_numpy(rng.random((B, N, 9, W), dtype=np.float32))
+    tg = torch.from_numpy(rng.integers(0, 5, (B, N, W)).astype(np.int64))
+    sd_e = nn_params.synthetic_state_dict(nn_params.encoder_shapes(), 0, trained_bn=False)
+    sd_s = nn_params.synthetic_state_dict(nn_params.seg_shapes(), 1, trained_bn=False)
+    leaves = []
+    for sd in (sd_e, sd_s):
+        for k, v in sd.items():
+            if v.is_floating_point() and "running" not in k:
+                v.requires_grad_(True); leaves.append(v)
+    opt = torch.optim.Adam(leaves, lr=1e-3)
+    t0 = time.perf_counter()
+    pcs, tgs = tlo.shuffle_clusters(pc, tg)
+    ang = np.random.uniform() * 2 * np.pi
+    xs, ts = [], []
+    for w in range(W):
+        a = pcs[:, :, :, w].numpy().copy()
+        a[:, :, :3] = tlo.rotate_point_cloud_z(a[:, :, :3], rotation_angle=ang)
+        a, t, _ = tlo.shuffle_data(a, tgs[:, :, w])
+        xs.append(torch.Tensor(a)); ts.append(torch.LongTensor(t))
+    cent = torch.stack([x[:, :, :2].mean(1) for x in xs], 1)
+    opt.zero_grad()
+    logits, ft = nn_oracle.forward_windows(sd_e, sd_s, xs, cent, training=True, stats_enc={}, stats_seg={})
+    loss, _, _ = nn_oracle.train_step_loss(logits, torch.cat(ts, 1), ft)
+    loss.backward()
+    opt.step()
+    dt = time.perf_counter() - t0
+    return {"value": B * W * N / dt, "unit": "points/s", "cores": cores, "kind": "port",
+            "sample": "1 step of %d samples x %d windows x %d points (oracle port, %d threads), %.1f s" % (B, W, N, cores, dt)}
+
+
 def cpu_tile(wins, ks):
     """CPU arm of the tile workload on a bounded sample: the oracle's constrained k-means (numpy restatement; the reference's
     third-party solver is not installable) + regroup + the oracle forward of the resulting blocks, for the given windows."""
@@ -95,6 +132,14 @@ def cpu_tile(wins, ks):
 
 
 def reference_line(workload, args):
+    if workload == "train_w9":
+        r = cpu_train_w9()
+        v = r["value"]
+        return {"impl": "reference", "metric": "train pts/sec (9 windows per sample)", "value": v, "unit": "points/s", "n_gpus": args.gpus,
+                "steps": 1, "warmup": 0, "ms_per_step": 1e3 * 32 * 9 * N / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "train_w9: training step on a collated batch, 32 samples x 9 windows x 2048 points per GPU"},
+                "cpu_baseline": r, "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     fn = cpu_forward if workload == "fwd" else cpu_train
     for _ in range(min(args.warmup, 1)):
         fn(1)

@@ -162,7 +162,7 @@ def test_infeasible_windows_are_flagged_not_corrupted(amp, cuda):
             wsb = lib.amp_kmeans_workspace_bytes(sum(sizes), 3, 2)
             ws = torch.empty(wsb, dtype=torch.uint8, device=cuda)
             amp._lib.check(lib.amp_kmeans_constrained_f32(x.data_ptr(), offsets.data_ptr(), dks.data_ptr(), 3, sum(sizes), max(sizes), 2, 2048, 2048,
-                                                          10, 1e-2, labels.data_ptr(), cent.data_ptr(), nit.data_ptr(), ws.data_ptr(), wsb,
+                                                          10, 1e-2, 1, labels.data_ptr(), cent.data_ptr(), nit.data_ptr(), ws.data_ptr(), wsb,
                                                           torch.cuda.current_stream().cuda_stream))
             torch.cuda.synchronize()
         finally:
