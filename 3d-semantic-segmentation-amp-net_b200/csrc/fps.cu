@@ -1,6 +1,6 @@
 // Farthest-point sampling for sm_100a: one thread-block CLUSTER per cloud, the cloud resident
 // on chip for the whole run (coordinates in registers + shared memory, running min-distance in
-// registers), one cluster barrier per pick.
+// registers), no block-wide or cluster-wide barrier inside a pick.
 //
 // Replaces utils/utils.py:889-933 `fps` (reference). Semantics are those pinned by
 // oracle/fps_oracle.py: start index given, picked points leave the candidate set, lowest index
@@ -9,13 +9,21 @@
 // Data placement for a cloud of P points on a cluster of C CTAs x THREADS threads
 // (TT = C*THREADS): point i belongs to cluster-thread g = i % TT, slot j = i / TT.
 //   slots [0, RS)         x,y,z and min-dist in registers
-//   slots [RS, RS+DS)     x,y,z in shared memory (SoA, conflict-free), min-dist in registers
+//   slots [RS, RS+DS)     x,y,z in shared memory (xy pairs + z, conflict-free), min-dist in registers
 //   slots >= RS+DS        x,y,z,min-dist in a global workspace (only for P > 8 * capacity)
-// Each pick: every thread updates its slots against the last pick and keeps its best; warp
-// argmax by redux.sync; per-CTA argmax through shared memory; every CTA posts its candidate
-// (with coordinates) into every peer's shared memory (DSMEM); one cluster barrier; everybody
-// reduces the C candidates locally. Candidate slots are double-buffered so one barrier per pick
-// is enough.
+// A pick, per thread: one subtract-square-add chain, one min and one max per slot (FMNMX: the
+// slot of the maximum is NOT tracked in the loop). Per warp: redux argmax of the value; the
+// lane(s) that hold it rescan their slots for the lowest one, a second redux takes the lowest
+// index; the winning lane posts (d, index, x, y, z) into the candidate table of EVERY CTA of the
+// cluster, its own included, with st.async -- a remote shared-memory store that completes
+// transaction bytes on the receiver's mbarrier. Every warp then waits on its CTA's mbarrier and
+// reduces the NW * C candidates itself (lanes = candidates, redux again). There is no
+// __syncthreads and no barrier.cluster in the loop (round 1 had one of each per pick; the cluster
+// barrier alone carried a MEMBAR.ALL.GPU). The candidate tables and mbarriers are double
+// buffered by pick parity: a CTA can only post pick s + 2 after it has seen all posts of pick
+// s + 1, which every warp of every peer sends after it has finished reading pick s.
+// The thread that owns the picked point retires it (d = -1) before the next pick, outside the
+// slot loop.
 #include <cooperative_groups.h>
 
 #include "amp_common.cuh"
@@ -27,13 +35,6 @@ namespace {
 
 constexpr unsigned kNoIdx = 0xffffffffu;
 
-template <typename T>
-struct Cand {
-    T d;
-    unsigned idx;
-    T x, y, z;
-};
-
 __device__ __forceinline__ float sqd(float lx, float ly, float lz, float x, float y, float z) {
     float dx = __fsub_rn(lx, x), dy = __fsub_rn(ly, y), dz = __fsub_rn(lz, z);
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
@@ -42,6 +43,11 @@ __device__ __forceinline__ double sqd(double lx, double ly, double lz, double x,
     double dx = __dsub_rn(lx, x), dy = __dsub_rn(ly, y), dz = __dsub_rn(lz, z);
     return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
+// min that keeps d when nd is NaN (non-finite input rows are reported through `status`), max likewise
+__device__ __forceinline__ float keep_min(float d, float nd) { return fminf(d, nd); }
+__device__ __forceinline__ double keep_min(double d, double nd) { return (nd < d) ? nd : d; }
+__device__ __forceinline__ float keep_max(float b, float d) { return fmaxf(b, d); }
+__device__ __forceinline__ double keep_max(double b, double d) { return (d > b) ? d : b; }
 
 // Warp-wide argmax of (d desc, idx asc). On return every lane holds the winner.
 // All real distances are >= +0, picked / padded slots carry -1, so for float the IEEE bit
@@ -61,11 +67,60 @@ __device__ __forceinline__ void warp_argmax(double& d, unsigned& idx) {
         if (od > d || (od == d && oi < idx)) { d = od; idx = oi; }
     }
 }
+// warp-wide maximum of the value alone
+__device__ __forceinline__ float warp_max(float d) {
+    return __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(d)));
+}
+__device__ __forceinline__ double warp_max(double d) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double od = __shfl_xor_sync(0xffffffffu, d, o);
+        d = (od > d) ? od : d;
+    }
+    return d;
+}
 
 template <typename T>
 __device__ __forceinline__ bool is_finite3(T x, T y, T z) {
     return isfinite(x) && isfinite(y) && isfinite(z);
 }
+
+// ---- st.async: remote shared-memory store that completes bytes on the receiver's mbarrier ----
+__device__ __forceinline__ uint32_t fps_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, int rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_async(uint32_t addr, unsigned v, uint32_t bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr), "r"(v), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void st_async(uint32_t addr, float v, uint32_t bar) { st_async(addr, __float_as_uint(v), bar); }
+__device__ __forceinline__ void st_async(uint32_t addr, double v, uint32_t bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(addr), "l"(__double_as_longlong(v)), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void st_async_v4(uint32_t addr, unsigned a, unsigned b, unsigned c, unsigned d, uint32_t bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr), "r"(a),
+                 "r"(b), "r"(c), "r"(d), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fps_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fps_mbar_expect(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fps_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "FPS_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra FPS_DONE_%=;\n\t"
+        "bra FPS_WAIT_%=;\n\t"
+        "FPS_DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// bytes one candidate adds to a receiver's transaction count: d, idx, x, y, z
+template <typename T> struct CandBytes { static constexpr unsigned v = 4 * sizeof(T) + 4; };
 
 template <typename T, int THREADS, int RS, int DS>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -73,21 +128,43 @@ fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S,
                    long long* __restrict__ out_idx, int* __restrict__ status,
                    T* __restrict__ ovf, int ovf_slots, int log2C) {
     constexpr int NW = THREADS / 32;
+    struct XY { T x, y; };
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* sx = reinterpret_cast<T*>(smem_raw);
-    T* sy = sx + DS * THREADS;
-    T* sz = sy + DS * THREADS;
-    Cand<T>* s_warp = reinterpret_cast<Cand<T>*>(sz + DS * THREADS);   // [NW]
-    Cand<T>* s_clu = s_warp + NW;                                       // [2][8]
+    XY* sxy = reinterpret_cast<XY*>(smem_raw);
+    T* sz = reinterpret_cast<T*>(sxy + DS * THREADS);
+    const int C = 1 << log2C;
+    const int NC = NW << log2C;                                  // candidates per pick
+    // candidate tables [2][NC], two mbarriers behind them. float: {d, idx, x, y} as one 16-byte entry (one st.async.v4
+    // per receiver, one 8-byte read per candidate in the reduction) + z; double: one array per field
+    constexpr bool kF32 = sizeof(T) == 4;
+    unsigned char* c_base = reinterpret_cast<unsigned char*>(sz + DS * THREADS);
+    uint4* c_a = reinterpret_cast<uint4*>(c_base);                       // float only
+    float* c_zf = reinterpret_cast<float*>(c_a + 2 * NC);                 // float only
+    T* c_d = reinterpret_cast<T*>(c_base);                                // double only from here
+    T* c_x = c_d + 2 * NC;
+    T* c_y = c_x + 2 * NC;
+    T* c_z = c_y + 2 * NC;
+    unsigned* c_i = reinterpret_cast<unsigned*>(c_z + 2 * NC);
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(c_base + (size_t)2 * NC * CandBytes<T>::v);
 
     cg::cluster_group cluster = cg::this_cluster();
-    const int C = 1 << log2C;
     const int r = (int)cluster.block_rank();
     const int b = blockIdx.x >> log2C;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int TT = THREADS << log2C;
     const int log2TT = log2C + 31 - __clz(THREADS);
     const int g = r * THREADS + tid;
+    const uint32_t bar0 = fps_smem_u32(&s_bar[0]);
+    const uint32_t pick_bytes = (uint32_t)NC * CandBytes<T>::v;
+    const int my_cand = r * NW + warp;                          // this warp's entry in every CTA's candidate table
+
+    if (tid == 0) {
+        fps_mbar_init(bar0, 1);
+        fps_mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fps_mbar_expect(bar0 + 8, pick_bytes);                   // pick 1 (parity 1), then pick 2 (parity 0)
+        fps_mbar_expect(bar0, pick_bytes);
+    }
 
     const T* cloud = pc + (long long)b * P * row_stride;
     T* my_ovf = ovf ? ovf + ((long long)(b * C + r) * ovf_slots) * (4 * THREADS) : nullptr;
@@ -116,7 +193,8 @@ fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S,
             x = p[0]; y = p[1]; z = p[2]; dd[j] = kInf;
             bad |= !is_finite3(x, y, z);
         }
-        sx[j * THREADS + tid] = x; sy[j * THREADS + tid] = y; sz[j * THREADS + tid] = z;
+        XY v; v.x = x; v.y = y;
+        sxy[j * THREADS + tid] = v; sz[j * THREADS + tid] = z;
     }
     for (int j = 0; j < ovf_slots; ++j) {
         int i = (RS + DS + j) * TT + g;
@@ -138,46 +216,57 @@ fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S,
         lx = p[0]; ly = p[1]; lz = p[2];
     }
     if (g == 0) out_idx[(long long)b * S] = last;
+    // every mbarrier of the cluster is initialised and armed before anybody posts into it
+    if (C > 1) cluster.sync(); else __syncthreads();
 
     for (int s = 1; s < S; ++s) {
         const int par = s & 1;
-        const bool own_last = (last & (TT - 1)) == g;
-        const int lslot = last >> log2TT;
+        // ---- the owner of the last pick retires it: d = -1 stays -1 under min() and never wins ----
+        if ((last & (TT - 1)) == g) {
+            const int lslot = last >> log2TT;
+#pragma unroll
+            for (int j = 0; j < RS; ++j)
+                if (lslot == j) rd[j] = (T)-1;
+#pragma unroll
+            for (int j = 0; j < DS; ++j)
+                if (lslot == RS + j) dd[j] = (T)-1;
+            if (lslot >= RS + DS) my_ovf[(long long)(lslot - RS - DS) * (4 * THREADS) + 3 * THREADS + tid] = (T)-1;
+        }
         T bd = (T)-1;
-        int bslot = 0;
 #pragma unroll
         for (int j = 0; j < RS; ++j) {
-            T d = rd[j];
-            T nd = sqd(lx, ly, lz, rx[j], ry[j], rz[j]);
-            d = (nd < d) ? nd : d;                // picked / absent slots hold -1 and stay -1
-            if (own_last && lslot == j) d = (T)-1;
-            rd[j] = d;
-            if (d > bd) { bd = d; bslot = j; }    // strict: lowest slot (= lowest index) wins
+            rd[j] = keep_min(rd[j], sqd(lx, ly, lz, rx[j], ry[j], rz[j]));
+            bd = keep_max(bd, rd[j]);
         }
 #pragma unroll
         for (int j = 0; j < DS; ++j) {
-            T d = dd[j];
-            T nd = sqd(lx, ly, lz, sx[j * THREADS + tid], sy[j * THREADS + tid], sz[j * THREADS + tid]);
-            d = (nd < d) ? nd : d;
-            if (own_last && lslot == RS + j) d = (T)-1;
-            dd[j] = d;
-            if (d > bd) { bd = d; bslot = RS + j; }
+            const XY v = sxy[j * THREADS + tid];
+            dd[j] = keep_min(dd[j], sqd(lx, ly, lz, v.x, v.y, sz[j * THREADS + tid]));
+            bd = keep_max(bd, dd[j]);
         }
         for (int j = 0; j < ovf_slots; ++j) {
             T* o = my_ovf + (long long)j * (4 * THREADS);
-            T d = o[3 * THREADS + tid];
-            T nd = sqd(lx, ly, lz, o[tid], o[THREADS + tid], o[2 * THREADS + tid]);
-            d = (nd < d) ? nd : d;
-            if (own_last && lslot == RS + DS + j) d = (T)-1;
+            const T d = keep_min(o[3 * THREADS + tid], sqd(lx, ly, lz, o[tid], o[THREADS + tid], o[2 * THREADS + tid]));
             o[3 * THREADS + tid] = d;
-            if (d > bd) { bd = d; bslot = RS + DS + j; }
+            bd = keep_max(bd, d);
         }
 
-        // ---- warp argmax; the winning lane publishes (d, idx, coords) ----
-        const unsigned my_idx = (bd >= (T)0) ? (unsigned)(bslot * TT + g) : kNoIdx;
-        T wd = bd;
-        unsigned wi = my_idx;
-        warp_argmax(wd, wi);
+        // ---- warp argmax: value by redux, then only the lanes that hold it look for their lowest slot ----
+        const T wd = warp_max(bd);
+        unsigned my_idx = kNoIdx;
+        int bslot = 0;
+        if (bd == wd && wd >= (T)0) {
+            for (int j = ovf_slots - 1; j >= 0; --j)
+                if (my_ovf[(long long)j * (4 * THREADS) + 3 * THREADS + tid] == wd) bslot = RS + DS + j;
+#pragma unroll
+            for (int j = DS - 1; j >= 0; --j)
+                if (dd[j] == wd) bslot = RS + j;
+#pragma unroll
+            for (int j = RS - 1; j >= 0; --j)
+                if (rd[j] == wd) bslot = j;
+            my_idx = (unsigned)(bslot * TT + g);
+        }
+        const unsigned wi = __reduce_min_sync(0xffffffffu, my_idx);
         const bool lane_wins = (wi == kNoIdx) ? (lane == 0) : (my_idx == wi);
         if (lane_wins) {
             T x = 0, y = 0, z = 0;
@@ -187,42 +276,67 @@ fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S,
                     for (int j = 0; j < RS; ++j)
                         if (j == bslot) { x = rx[j]; y = ry[j]; z = rz[j]; }
                 } else if (bslot < RS + DS) {
-                    int o = (bslot - RS) * THREADS + tid;
-                    x = sx[o]; y = sy[o]; z = sz[o];
+                    const int o = (bslot - RS) * THREADS + tid;
+                    const XY v = sxy[o];
+                    x = v.x; y = v.y; z = sz[o];
                 } else {
                     T* o = my_ovf + (long long)(bslot - RS - DS) * (4 * THREADS);
                     x = o[tid]; y = o[THREADS + tid]; z = o[2 * THREADS + tid];
                 }
             }
-            Cand<T> c; c.d = wd; c.idx = wi; c.x = x; c.y = y; c.z = z;
-            s_warp[warp] = c;
-        }
-        __syncthreads();
-        // ---- CTA argmax by warp 0; post the CTA candidate into every peer's slot ----
-        if (warp == 0) {
-            Cand<T> c;
-            c.d = (T)-1; c.idx = kNoIdx; c.x = c.y = c.z = (T)0;
-            if (lane < NW) c = s_warp[lane];
-            T d2 = c.d;
-            unsigned i2 = c.idx;
-            warp_argmax(d2, i2);
-            const bool wins = (i2 == kNoIdx) ? (lane == 0) : (c.idx == i2);
-            if (wins) {
+            const int slot = par * NC + my_cand;
+            const uint32_t a_b = bar0 + 8u * (uint32_t)par;
+            if constexpr (kF32) {
+                const uint32_t a_a = fps_smem_u32(&c_a[slot]), a_z = fps_smem_u32(&c_zf[slot]);
                 for (int p = 0; p < C; ++p) {
-                    Cand<T>* dst = cluster.map_shared_rank(&s_clu[par * 8 + r], p);
-                    *dst = c;
+                    // a CTA's shared window is contiguous in the cluster address space: one mapa, then plain offsets
+                    const uint32_t off = map_to_cta(bar0, p) - bar0;
+                    st_async_v4(off + a_a, __float_as_uint(wd), wi, __float_as_uint(x), __float_as_uint(y), off + a_b);
+                    st_async(off + a_z, z, off + a_b);
+                }
+            } else {
+                const uint32_t a_d = fps_smem_u32(&c_d[slot]), a_x = fps_smem_u32(&c_x[slot]), a_y = fps_smem_u32(&c_y[slot]),
+                               a_z = fps_smem_u32(&c_z[slot]), a_i = fps_smem_u32(&c_i[slot]);
+                for (int p = 0; p < C; ++p) {
+                    const uint32_t off = map_to_cta(bar0, p) - bar0;
+                    const uint32_t pb = off + a_b;
+                    st_async(off + a_d, wd, pb);
+                    st_async(off + a_i, wi, pb);
+                    st_async(off + a_x, x, pb);
+                    st_async(off + a_y, y, pb);
+                    st_async(off + a_z, z, pb);
                 }
             }
         }
-        if (C > 1) cluster.sync(); else __syncthreads();
-        // ---- everybody reduces the C CTA candidates ----
-        Cand<T> best = s_clu[par * 8];
-        for (int p = 1; p < C; ++p) {
-            Cand<T> c = s_clu[par * 8 + p];
-            if (c.d > best.d || (c.d == best.d && c.idx < best.idx)) best = c;
+        // ---- wait for the NC candidates of this pick; every warp reduces them on its own ----
+        fps_mbar_wait(bar0 + 8u * (uint32_t)par, (uint32_t)(((s - 1) >> 1) & 1));   // k-th use of this barrier: picks 2k+1 / 2k+2
+        if (tid == 0 && s + 2 < S) fps_mbar_expect(bar0 + 8u * (uint32_t)par, pick_bytes);   // re-arm for pick s + 2
+        T cd = (T)-1;
+        unsigned ci = kNoIdx;
+        int cs = par * NC + lane;
+        for (int c = par * NC + lane; c < (par + 1) * NC; c += 32) {
+            T d;
+            unsigned i2;
+            if constexpr (kF32) {
+                const uint2 v = *reinterpret_cast<const uint2*>(&c_a[c]);
+                d = __uint_as_float(v.x); i2 = v.y;
+            } else {
+                d = c_d[c]; i2 = c_i[c];
+            }
+            if (d > cd || (d == cd && i2 < ci)) { cd = d; ci = i2; cs = c; }
         }
-        last = (int)best.idx;
-        lx = best.x; ly = best.y; lz = best.z;
+        T gd = cd;
+        unsigned gi = ci;
+        warp_argmax(gd, gi);
+        const unsigned holders = __ballot_sync(0xffffffffu, ci == gi && cd == gd);
+        cs = __shfl_sync(0xffffffffu, cs, __ffs(holders) - 1);
+        last = (int)gi;
+        if constexpr (kF32) {
+            const uint2 v = *(reinterpret_cast<const uint2*>(&c_a[cs]) + 1);
+            lx = __uint_as_float(v.x); ly = __uint_as_float(v.y); lz = c_zf[cs];
+        } else {
+            lx = c_x[cs]; ly = c_y[cs]; lz = c_z[cs];
+        }
         if (g == 0) out_idx[(long long)b * S + s] = last;
     }
     if (C > 1) cluster.sync();   // no CTA may exit while a peer could still write into it
@@ -250,7 +364,8 @@ int launch_variant(const T* pc, int64_t B, int P, int64_t row_stride, int S, int
                    int64_t* out_idx, int32_t* status, T* ovf, int ovf_slots, int log2C,
                    cudaStream_t st) {
     auto kern = fps_cluster_kernel<T, kThreads, kRS, DS>;
-    size_t smem = (size_t)3 * DS * kThreads * sizeof(T) + sizeof(Cand<T>) * (kThreads / 32 + 16);
+    const size_t n_cand = (size_t)(kThreads / 32) << log2C;
+    size_t smem = (size_t)3 * DS * kThreads * sizeof(T) + 2 * n_cand * (4 * sizeof(T) + 4) + 8 + 16;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(AMP_E_CUDA, "fps: smem attribute: %s", cudaGetErrorString(e));
     cudaLaunchConfig_t cfg{};
