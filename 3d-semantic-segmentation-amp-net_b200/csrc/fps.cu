@@ -9,10 +9,10 @@
 // Data placement for a cloud of P points on a cluster of C CTAs x THREADS threads
 // (TT = C*THREADS): point i belongs to cluster-thread g = i % TT, slot j = i / TT.
 //   slots [0, RS)         x,y,z and min-dist in registers
-//   slots [RS, RS+DS)     x,y,z in shared memory (xy pairs + z, conflict-free), min-dist in registers
+//   slots [RS, RS+DS)     x,y,z in shared memory (pairs of slots per 8-byte entry, conflict-free), min-dist in registers
 //   slots >= RS+DS        x,y,z,min-dist in a global workspace (only for P > 8 * capacity)
-// A pick, per thread: one subtract-square-add chain, one min and one max per slot (FMNMX: the
-// slot of the maximum is NOT tracked in the loop). Per warp: redux argmax of the value; the
+// A pick, per thread: the subtract-square-add chain of TWO slots at a time on packed fp32 pairs (FFMA2, bit-identical
+// to the scalar operations), one min and one max per slot (FMNMX: the slot of the maximum is NOT tracked in the loop). Per warp: redux argmax of the value; the
 // lane(s) that hold it rescan their slots for the lowest one, a second redux takes the lowest
 // index; the winning lane posts (d, index, x, y, z) into the candidate table of EVERY CTA of the
 // cluster, its own included, with st.async -- a remote shared-memory store that completes
@@ -49,24 +49,8 @@ __device__ __forceinline__ double keep_min(double d, double nd) { return (nd < d
 __device__ __forceinline__ float keep_max(float b, float d) { return fmaxf(b, d); }
 __device__ __forceinline__ double keep_max(double b, double d) { return (d > b) ? d : b; }
 
-// Warp-wide argmax of (d desc, idx asc). On return every lane holds the winner.
-// All real distances are >= +0, picked / padded slots carry -1, so for float the IEEE bit
-// pattern ordered as a signed int is the distance order.
-__device__ __forceinline__ void warp_argmax(float& d, unsigned& idx) {
-    int kb = __float_as_int(d);
-    int m = __reduce_max_sync(0xffffffffu, kb);
-    unsigned c = (kb == m) ? idx : kNoIdx;
-    idx = __reduce_min_sync(0xffffffffu, c);
-    d = __int_as_float(m);
-}
-__device__ __forceinline__ void warp_argmax(double& d, unsigned& idx) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        double od = __shfl_xor_sync(0xffffffffu, d, o);
-        unsigned oi = __shfl_xor_sync(0xffffffffu, idx, o);
-        if (od > d || (od == d && oi < idx)) { d = od; idx = oi; }
-    }
-}
+// All real distances are >= +0, picked / padded slots carry -1, so for float the IEEE bit pattern ordered as a signed int
+// is the distance order.
 // warp-wide maximum of the value alone
 __device__ __forceinline__ float warp_max(float d) {
     return __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(d)));
@@ -78,6 +62,32 @@ __device__ __forceinline__ double warp_max(double d) {
         d = (od > d) ? od : d;
     }
     return d;
+}
+
+// Packed fp32 pairs (sm_100 FFMA2): two slots per instruction, each half rounded exactly like the scalar operation.
+// Products and sums are written as fused multiply-adds that restate the unfused operations exactly,
+//   rn(a - b) = fma(b, -1, a),  rn(a * a) = fma(a, a, -0),  rn(a + b) = fma(a, 1, b),
+// with the constants arriving as kernel arguments (opaque to ptxas, which would otherwise contract a packed multiply
+// and a packed add into one fused operation and change the rounding).
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+struct FpsConsts { float one, neg_one, neg_zero; };
+// squared distances of two slots to the last pick, each half bit-identical to sqd(float...)
+__device__ __forceinline__ f32x2_t sqd2(f32x2_t lx, f32x2_t ly, f32x2_t lz, f32x2_t x, f32x2_t y, f32x2_t z, f32x2_t one, f32x2_t neg_one,
+                                        f32x2_t neg_zero) {
+    const f32x2_t dx = fma2(x, neg_one, lx), dy = fma2(y, neg_one, ly), dz = fma2(z, neg_one, lz);
+    const f32x2_t xx = fma2(dx, dx, neg_zero), yy = fma2(dy, dy, neg_zero), zz = fma2(dz, dz, neg_zero);
+    return fma2(fma2(xx, one, yy), one, zz);
 }
 
 template <typename T>
@@ -113,31 +123,46 @@ __device__ __forceinline__ void fps_mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "FPS_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra FPS_DONE_%=;\n\t"
         "bra FPS_WAIT_%=;\n\t"
-        "FPS_DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+        "FPS_DONE_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(4000u) : "memory");   // suspend-time hint (ns): wake on completion, not by polling
 }
 
 // bytes one candidate adds to a receiver's transaction count: d, idx, x, y, z
 template <typename T> struct CandBytes { static constexpr unsigned v = 4 * sizeof(T) + 4; };
 
-template <typename T, int THREADS, int RS, int DS>
+#ifdef AMP_FPS_PROF
+__device__ long long g_fps_prof[3 * 8 * 6];
+#define FPS_PROF(k) do { if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 15 || warp == 31) && s >= 100 && s < 108) \
+    g_fps_prof[((warp == 0 ? 0 : warp == 15 ? 1 : 2) * 8 + (s - 100)) * 6 + (k)] = clock64(); } while (0)
+#else
+#define FPS_PROF(k) do { } while (0)
+#endif
+
+// LC >= 0: cluster size 2^LC known at compile time (the float variants: every table offset of the exchange folds into
+// an immediate); LC < 0: taken from the argument.
+template <typename T, int THREADS, int RS, int DS, int LC>
 __global__ void __launch_bounds__(THREADS, 1)
 fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S, int start_idx,
                    long long* __restrict__ out_idx, int* __restrict__ status,
-                   T* __restrict__ ovf, int ovf_slots, int log2C) {
+                   T* __restrict__ ovf, int ovf_slots, int log2C_arg, const FpsConsts kc) {
+    const int log2C = LC >= 0 ? LC : log2C_arg;
     constexpr int NW = THREADS / 32;
-    struct XY { T x, y; };
+    static_assert(RS % 2 == 0 && DS % 2 == 0, "slots are processed in pairs");
+    // shared-memory slots as PAIRS: entry [j / 2][tid] holds slots j and j + 1 of this thread (8-byte reads feed the packed
+    // arithmetic directly; conflict-free)
+    struct Pair { T a, b; };
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    XY* sxy = reinterpret_cast<XY*>(smem_raw);
-    T* sz = reinterpret_cast<T*>(sxy + DS * THREADS);
+    Pair* sx = reinterpret_cast<Pair*>(smem_raw);
+    Pair* sy = sx + (DS / 2) * THREADS;
+    Pair* sz = sy + (DS / 2) * THREADS;
     const int C = 1 << log2C;
     const int NC = NW << log2C;                                  // candidates per pick
     // candidate tables [2][NC], two mbarriers behind them. float: {d, idx, x, y} as one 16-byte entry (one st.async.v4
     // per receiver, one 8-byte read per candidate in the reduction) + z; double: one array per field
     constexpr bool kF32 = sizeof(T) == 4;
-    unsigned char* c_base = reinterpret_cast<unsigned char*>(sz + DS * THREADS);
+    unsigned char* c_base = reinterpret_cast<unsigned char*>(sz + (DS / 2) * THREADS);
     uint4* c_a = reinterpret_cast<uint4*>(c_base);                       // float only
     float* c_zf = reinterpret_cast<float*>(c_a + 2 * NC);                 // float only
     T* c_d = reinterpret_cast<T*>(c_base);                                // double only from here
@@ -193,8 +218,8 @@ fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S,
             x = p[0]; y = p[1]; z = p[2]; dd[j] = kInf;
             bad |= !is_finite3(x, y, z);
         }
-        XY v; v.x = x; v.y = y;
-        sxy[j * THREADS + tid] = v; sz[j * THREADS + tid] = z;
+        const int o = (j >> 1) * THREADS + tid;
+        (&sx[o].a)[j & 1] = x; (&sy[o].a)[j & 1] = y; (&sz[o].a)[j & 1] = z;
     }
     for (int j = 0; j < ovf_slots; ++j) {
         int i = (RS + DS + j) * TT + g;
@@ -221,6 +246,7 @@ fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S,
 
     for (int s = 1; s < S; ++s) {
         const int par = s & 1;
+        FPS_PROF(0);
         // ---- the owner of the last pick retires it: d = -1 stays -1 under min() and never wins ----
         if ((last & (TT - 1)) == g) {
             const int lslot = last >> log2TT;
@@ -233,16 +259,37 @@ fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S,
             if (lslot >= RS + DS) my_ovf[(long long)(lslot - RS - DS) * (4 * THREADS) + 3 * THREADS + tid] = (T)-1;
         }
         T bd = (T)-1;
+        if constexpr (kF32) {
+            const f32x2_t one = pack2(kc.one, kc.one), neg_one = pack2(kc.neg_one, kc.neg_one), neg_zero = pack2(kc.neg_zero, kc.neg_zero);
+            const f32x2_t lx2 = pack2(lx, lx), ly2 = pack2(ly, ly), lz2 = pack2(lz, lz);
 #pragma unroll
-        for (int j = 0; j < RS; ++j) {
-            rd[j] = keep_min(rd[j], sqd(lx, ly, lz, rx[j], ry[j], rz[j]));
-            bd = keep_max(bd, rd[j]);
-        }
+            for (int j = 0; j < RS; j += 2) {
+                float na, nb;
+                unpack2(sqd2(lx2, ly2, lz2, pack2(rx[j], rx[j + 1]), pack2(ry[j], ry[j + 1]), pack2(rz[j], rz[j + 1]), one, neg_one, neg_zero), na, nb);
+                rd[j] = keep_min(rd[j], na); rd[j + 1] = keep_min(rd[j + 1], nb);
+                bd = keep_max(bd, rd[j]); bd = keep_max(bd, rd[j + 1]);
+            }
 #pragma unroll
-        for (int j = 0; j < DS; ++j) {
-            const XY v = sxy[j * THREADS + tid];
-            dd[j] = keep_min(dd[j], sqd(lx, ly, lz, v.x, v.y, sz[j * THREADS + tid]));
-            bd = keep_max(bd, dd[j]);
+            for (int j = 0; j < DS; j += 2) {
+                const int o = (j >> 1) * THREADS + tid;
+                float na, nb;
+                unpack2(sqd2(lx2, ly2, lz2, *reinterpret_cast<const f32x2_t*>(&sx[o]), *reinterpret_cast<const f32x2_t*>(&sy[o]),
+                             *reinterpret_cast<const f32x2_t*>(&sz[o]), one, neg_one, neg_zero), na, nb);
+                dd[j] = keep_min(dd[j], na); dd[j + 1] = keep_min(dd[j + 1], nb);
+                bd = keep_max(bd, dd[j]); bd = keep_max(bd, dd[j + 1]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < RS; ++j) {
+                rd[j] = keep_min(rd[j], sqd(lx, ly, lz, rx[j], ry[j], rz[j]));
+                bd = keep_max(bd, rd[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < DS; ++j) {
+                const int o = (j >> 1) * THREADS + tid;
+                dd[j] = keep_min(dd[j], sqd(lx, ly, lz, (&sx[o].a)[j & 1], (&sy[o].a)[j & 1], (&sz[o].a)[j & 1]));
+                bd = keep_max(bd, dd[j]);
+            }
         }
         for (int j = 0; j < ovf_slots; ++j) {
             T* o = my_ovf + (long long)j * (4 * THREADS);
@@ -252,6 +299,7 @@ fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S,
         }
 
         // ---- warp argmax: value by redux, then only the lanes that hold it look for their lowest slot ----
+        FPS_PROF(1);
         const T wd = warp_max(bd);
         unsigned my_idx = kNoIdx;
         int bslot = 0;
@@ -267,6 +315,7 @@ fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S,
             my_idx = (unsigned)(bslot * TT + g);
         }
         const unsigned wi = __reduce_min_sync(0xffffffffu, my_idx);
+        FPS_PROF(2);
         const bool lane_wins = (wi == kNoIdx) ? (lane == 0) : (my_idx == wi);
         if (lane_wins) {
             T x = 0, y = 0, z = 0;
@@ -276,9 +325,8 @@ fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S,
                     for (int j = 0; j < RS; ++j)
                         if (j == bslot) { x = rx[j]; y = ry[j]; z = rz[j]; }
                 } else if (bslot < RS + DS) {
-                    const int o = (bslot - RS) * THREADS + tid;
-                    const XY v = sxy[o];
-                    x = v.x; y = v.y; z = sz[o];
+                    const int q = bslot - RS, o = (q >> 1) * THREADS + tid;
+                    x = (&sx[o].a)[q & 1]; y = (&sy[o].a)[q & 1]; z = (&sz[o].a)[q & 1];
                 } else {
                     T* o = my_ovf + (long long)(bslot - RS - DS) * (4 * THREADS);
                     x = o[tid]; y = o[THREADS + tid]; z = o[2 * THREADS + tid];
@@ -288,6 +336,7 @@ fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S,
             const uint32_t a_b = bar0 + 8u * (uint32_t)par;
             if constexpr (kF32) {
                 const uint32_t a_a = fps_smem_u32(&c_a[slot]), a_z = fps_smem_u32(&c_zf[slot]);
+#pragma unroll
                 for (int p = 0; p < C; ++p) {
                     // a CTA's shared window is contiguous in the cluster address space: one mapa, then plain offsets
                     const uint32_t off = map_to_cta(bar0, p) - bar0;
@@ -297,6 +346,7 @@ fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S,
             } else {
                 const uint32_t a_d = fps_smem_u32(&c_d[slot]), a_x = fps_smem_u32(&c_x[slot]), a_y = fps_smem_u32(&c_y[slot]),
                                a_z = fps_smem_u32(&c_z[slot]), a_i = fps_smem_u32(&c_i[slot]);
+#pragma unroll
                 for (int p = 0; p < C; ++p) {
                     const uint32_t off = map_to_cta(bar0, p) - bar0;
                     const uint32_t pb = off + a_b;
@@ -308,27 +358,36 @@ fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S,
                 }
             }
         }
+        FPS_PROF(3);
         // ---- wait for the NC candidates of this pick; every warp reduces them on its own ----
         fps_mbar_wait(bar0 + 8u * (uint32_t)par, (uint32_t)(((s - 1) >> 1) & 1));   // k-th use of this barrier: picks 2k+1 / 2k+2
+        FPS_PROF(4);
         if (tid == 0 && s + 2 < S) fps_mbar_expect(bar0 + 8u * (uint32_t)par, pick_bytes);   // re-arm for pick s + 2
+        // value first (max), then the lowest index among the candidates that carry it, then the entry that holds it
+        const int c_lane = par * NC + lane;
         T cd = (T)-1;
+#pragma unroll
+        for (int k = 0; k < (LC >= 0 ? (1 << LC) : C); ++k) {
+            if constexpr (kF32) cd = keep_max(cd, __uint_as_float(c_a[c_lane + 32 * k].x));
+            else cd = keep_max(cd, c_d[c_lane + 32 * k]);
+        }
+        const T gd = warp_max(cd);
         unsigned ci = kNoIdx;
-        int cs = par * NC + lane;
-        for (int c = par * NC + lane; c < (par + 1) * NC; c += 32) {
+        int cs = c_lane;
+#pragma unroll
+        for (int k = 0; k < (LC >= 0 ? (1 << LC) : C); ++k) {
             T d;
             unsigned i2;
             if constexpr (kF32) {
-                const uint2 v = *reinterpret_cast<const uint2*>(&c_a[c]);
+                const uint2 v = *reinterpret_cast<const uint2*>(&c_a[c_lane + 32 * k]);
                 d = __uint_as_float(v.x); i2 = v.y;
             } else {
-                d = c_d[c]; i2 = c_i[c];
+                d = c_d[c_lane + 32 * k]; i2 = c_i[c_lane + 32 * k];
             }
-            if (d > cd || (d == cd && i2 < ci)) { cd = d; ci = i2; cs = c; }
+            if (d == gd && i2 < ci) { ci = i2; cs = c_lane + 32 * k; }
         }
-        T gd = cd;
-        unsigned gi = ci;
-        warp_argmax(gd, gi);
-        const unsigned holders = __ballot_sync(0xffffffffu, ci == gi && cd == gd);
+        const unsigned gi = __reduce_min_sync(0xffffffffu, ci);
+        const unsigned holders = __ballot_sync(0xffffffffu, ci == gi);
         cs = __shfl_sync(0xffffffffu, cs, __ffs(holders) - 1);
         last = (int)gi;
         if constexpr (kF32) {
@@ -338,6 +397,7 @@ fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S,
             lx = c_x[cs]; ly = c_y[cs]; lz = c_z[cs];
         }
         if (g == 0) out_idx[(long long)b * S + s] = last;
+        FPS_PROF(5);
     }
     if (C > 1) cluster.sync();   // no CTA may exit while a peer could still write into it
 }
@@ -359,11 +419,11 @@ constexpr int kRS = 2;
 template <typename T> struct MaxDS { static constexpr int v = 18; };
 template <> struct MaxDS<double> { static constexpr int v = 8; };
 
-template <typename T, int DS>
-int launch_variant(const T* pc, int64_t B, int P, int64_t row_stride, int S, int start_idx,
-                   int64_t* out_idx, int32_t* status, T* ovf, int ovf_slots, int log2C,
-                   cudaStream_t st) {
-    auto kern = fps_cluster_kernel<T, kThreads, kRS, DS>;
+template <typename T, int DS, int LC>
+int launch_kernel(const T* pc, int64_t B, int P, int64_t row_stride, int S, int start_idx,
+                  int64_t* out_idx, int32_t* status, T* ovf, int ovf_slots, int log2C,
+                  cudaStream_t st) {
+    auto kern = fps_cluster_kernel<T, kThreads, kRS, DS, LC>;
     const size_t n_cand = (size_t)(kThreads / 32) << log2C;
     size_t smem = (size_t)3 * DS * kThreads * sizeof(T) + 2 * n_cand * (4 * sizeof(T) + 4) + 8 + 16;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -381,11 +441,29 @@ int launch_variant(const T* pc, int64_t B, int P, int64_t row_stride, int S, int
     cfg.attrs = at;
     cfg.numAttrs = 1;
     long long* oi = reinterpret_cast<long long*>(out_idx);
+    FpsConsts kc;
+    kc.one = 1.f; kc.neg_one = -1.f; kc.neg_zero = -0.f;
     e = cudaLaunchKernelEx(&cfg, kern, pc, P, (long long)row_stride, S, start_idx, oi, status, ovf,
-                           ovf_slots, log2C);
+                           ovf_slots, log2C, kc);
     if (e != cudaSuccess) return fail(AMP_E_CUDA, "fps launch: %s", cudaGetErrorString(e));
     count_launch();
     return AMP_OK;
+}
+
+template <typename T, int DS>
+int launch_variant(const T* pc, int64_t B, int P, int64_t row_stride, int S, int start_idx,
+                   int64_t* out_idx, int32_t* status, T* ovf, int ovf_slots, int log2C,
+                   cudaStream_t st) {
+    if constexpr (sizeof(T) == 4) {
+        switch (log2C) {
+            case 0: return launch_kernel<T, DS, 0>(pc, B, P, row_stride, S, start_idx, out_idx, status, ovf, ovf_slots, log2C, st);
+            case 1: return launch_kernel<T, DS, 1>(pc, B, P, row_stride, S, start_idx, out_idx, status, ovf, ovf_slots, log2C, st);
+            case 2: return launch_kernel<T, DS, 2>(pc, B, P, row_stride, S, start_idx, out_idx, status, ovf, ovf_slots, log2C, st);
+            default: return launch_kernel<T, DS, 3>(pc, B, P, row_stride, S, start_idx, out_idx, status, ovf, ovf_slots, log2C, st);
+        }
+    } else {
+        return launch_kernel<T, DS, -1>(pc, B, P, row_stride, S, start_idx, out_idx, status, ovf, ovf_slots, log2C, st);
+    }
 }
 
 template <typename T>
@@ -445,6 +523,12 @@ int fps_impl(const T* pc, int64_t B, int64_t P, int64_t row_stride, int32_t S, i
 
 }  // namespace
 }  // namespace amp
+
+#ifdef AMP_FPS_PROF
+extern "C" int amp_fps_prof_dump(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, amp::g_fps_prof, sizeof(long long) * 3 * 8 * 6);
+}
+#endif
 
 extern "C" {
 
