@@ -158,19 +158,21 @@ fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S,
     Pair* sy = sx + (DS / 2) * THREADS;
     Pair* sz = sy + (DS / 2) * THREADS;
     const int C = 1 << log2C;
-    const int NC = NW << log2C;                                  // candidates per pick
-    // candidate tables [2][NC], two mbarriers behind them. float: {d, idx, x, y} as one 16-byte entry (one st.async.v4
-    // per receiver, one 8-byte read per candidate in the reduction) + z; double: one array per field
+    // candidate tables [2][C] (one entry per CTA of the cluster and pick parity), then two mbarriers, the warp maxima
+    // [2][NW] and the tie cells [2]. float: {d, idx, x, y} as one 16-byte entry (one st.async.v4 per receiver) + z;
+    // double: one array per field
     constexpr bool kF32 = sizeof(T) == 4;
     unsigned char* c_base = reinterpret_cast<unsigned char*>(sz + (DS / 2) * THREADS);
     uint4* c_a = reinterpret_cast<uint4*>(c_base);                       // float only
-    float* c_zf = reinterpret_cast<float*>(c_a + 2 * NC);                 // float only
+    float* c_zf = reinterpret_cast<float*>(c_a + 2 * C);                  // float only
     T* c_d = reinterpret_cast<T*>(c_base);                                // double only from here
-    T* c_x = c_d + 2 * NC;
-    T* c_y = c_x + 2 * NC;
-    T* c_z = c_y + 2 * NC;
-    unsigned* c_i = reinterpret_cast<unsigned*>(c_z + 2 * NC);
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(c_base + (size_t)2 * NC * CandBytes<T>::v);
+    T* c_x = c_d + 2 * C;
+    T* c_y = c_x + 2 * C;
+    T* c_z = c_y + 2 * C;
+    unsigned* c_i = reinterpret_cast<unsigned*>(c_z + 2 * C);
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(c_base + ((size_t)2 * C * CandBytes<T>::v + 15) / 16 * 16);
+    T* s_wmax = reinterpret_cast<T*>(s_bar + 2);
+    unsigned* s_tie = reinterpret_cast<unsigned*>(s_wmax + 2 * NW);
 
     cg::cluster_group cluster = cg::this_cluster();
     const int r = (int)cluster.block_rank();
@@ -180,8 +182,7 @@ fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S,
     const int log2TT = log2C + 31 - __clz(THREADS);
     const int g = r * THREADS + tid;
     const uint32_t bar0 = fps_smem_u32(&s_bar[0]);
-    const uint32_t pick_bytes = (uint32_t)NC * CandBytes<T>::v;
-    const int my_cand = r * NW + warp;                          // this warp's entry in every CTA's candidate table
+    const uint32_t pick_bytes = (uint32_t)C * CandBytes<T>::v;  // one candidate per CTA and pick
 
     if (tid == 0) {
         fps_mbar_init(bar0, 1);
@@ -189,6 +190,7 @@ fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S,
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fps_mbar_expect(bar0 + 8, pick_bytes);                   // pick 1 (parity 1), then pick 2 (parity 0)
         fps_mbar_expect(bar0, pick_bytes);
+        s_tie[0] = kNoIdx; s_tie[1] = kNoIdx;
     }
 
     const T* cloud = pc + (long long)b * P * row_stride;
@@ -298,26 +300,44 @@ fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S,
             bd = keep_max(bd, d);
         }
 
-        // ---- warp argmax: value by redux, then only the lanes that hold it look for their lowest slot ----
+        // ---- CTA maximum: warp maxima by redux -> shared memory -> one block barrier -> every warp reduces the NW values ----
         FPS_PROF(1);
         const T wd = warp_max(bd);
-        unsigned my_idx = kNoIdx;
+        if (lane == 0) s_wmax[par * NW + warp] = wd;
+        __syncthreads();
+        const T wm = s_wmax[par * NW + lane];
+        const T cm = warp_max(wm);
+        const int n_tied = __popc(__ballot_sync(0xffffffffu, wm == cm));     // warps that carry the CTA maximum (uniform over the CTA)
+        if (tid == 0) s_tie[par ^ 1] = kNoIdx;                               // the other parity's cell: nobody reads or writes it now
+        // Only a warp that carries the CTA maximum looks for the slot (the rescan is 2 ALU instructions per slot, and the ALU
+        // pipe is the busiest one of this kernel): lowest slot per lane, lowest index over the lanes by a second redux.
+        unsigned my_idx = kNoIdx, wi = kNoIdx;
         int bslot = 0;
-        if (bd == wd && wd >= (T)0) {
-            for (int j = ovf_slots - 1; j >= 0; --j)
-                if (my_ovf[(long long)j * (4 * THREADS) + 3 * THREADS + tid] == wd) bslot = RS + DS + j;
+        bool poster = false;
+        if (cm < (T)0) {
+            poster = warp == 0 && lane == 0;                                 // nothing left in this CTA: an empty candidate
+        } else if (wd == cm) {
+            if (bd == wd) {
+                for (int j = ovf_slots - 1; j >= 0; --j)
+                    if (my_ovf[(long long)j * (4 * THREADS) + 3 * THREADS + tid] == wd) bslot = RS + DS + j;
 #pragma unroll
-            for (int j = DS - 1; j >= 0; --j)
-                if (dd[j] == wd) bslot = RS + j;
+                for (int j = DS - 1; j >= 0; --j)
+                    if (dd[j] == wd) bslot = RS + j;
 #pragma unroll
-            for (int j = RS - 1; j >= 0; --j)
-                if (rd[j] == wd) bslot = j;
-            my_idx = (unsigned)(bslot * TT + g);
+                for (int j = RS - 1; j >= 0; --j)
+                    if (rd[j] == wd) bslot = j;
+                my_idx = (unsigned)(bslot * TT + g);
+            }
+            wi = __reduce_min_sync(0xffffffffu, my_idx);
+            if (n_tied == 1) poster = my_idx == wi;
+            else if (lane == 0) atomicMin(&s_tie[par], wi);
         }
-        const unsigned wi = __reduce_min_sync(0xffffffffu, my_idx);
+        if (cm >= (T)0 && n_tied > 1) {                                      // rare: equal distances in different warps
+            __syncthreads();
+            poster = wd == cm && my_idx == wi && s_tie[par] == wi;
+        }
         FPS_PROF(2);
-        const bool lane_wins = (wi == kNoIdx) ? (lane == 0) : (my_idx == wi);
-        if (lane_wins) {
+        if (poster) {
             T x = 0, y = 0, z = 0;
             if (wi != kNoIdx) {
                 if (bslot < RS) {
@@ -332,7 +352,7 @@ fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S,
                     x = o[tid]; y = o[THREADS + tid]; z = o[2 * THREADS + tid];
                 }
             }
-            const int slot = par * NC + my_cand;
+            const int slot = par * C + r;
             const uint32_t a_b = bar0 + 8u * (uint32_t)par;
             if constexpr (kF32) {
                 const uint32_t a_a = fps_smem_u32(&c_a[slot]), a_z = fps_smem_u32(&c_zf[slot]);
@@ -340,7 +360,7 @@ fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S,
                 for (int p = 0; p < C; ++p) {
                     // a CTA's shared window is contiguous in the cluster address space: one mapa, then plain offsets
                     const uint32_t off = map_to_cta(bar0, p) - bar0;
-                    st_async_v4(off + a_a, __float_as_uint(wd), wi, __float_as_uint(x), __float_as_uint(y), off + a_b);
+                    st_async_v4(off + a_a, __float_as_uint(cm), wi, __float_as_uint(x), __float_as_uint(y), off + a_b);
                     st_async(off + a_z, z, off + a_b);
                 }
             } else {
@@ -350,7 +370,7 @@ fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S,
                 for (int p = 0; p < C; ++p) {
                     const uint32_t off = map_to_cta(bar0, p) - bar0;
                     const uint32_t pb = off + a_b;
-                    st_async(off + a_d, wd, pb);
+                    st_async(off + a_d, cm, pb);
                     st_async(off + a_i, wi, pb);
                     st_async(off + a_x, x, pb);
                     st_async(off + a_y, y, pb);
@@ -359,42 +379,26 @@ fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S,
             }
         }
         FPS_PROF(3);
-        // ---- wait for the NC candidates of this pick; every warp reduces them on its own ----
+        // ---- wait for the C candidates of this pick (one per CTA); every thread reduces them itself ----
         fps_mbar_wait(bar0 + 8u * (uint32_t)par, (uint32_t)(((s - 1) >> 1) & 1));   // k-th use of this barrier: picks 2k+1 / 2k+2
         FPS_PROF(4);
         if (tid == 0 && s + 2 < S) fps_mbar_expect(bar0 + 8u * (uint32_t)par, pick_bytes);   // re-arm for pick s + 2
-        // value first (max), then the lowest index among the candidates that carry it, then the entry that holds it
-        const int c_lane = par * NC + lane;
-        T cd = (T)-1;
+        {
+            T gd = (T)-2;
+            unsigned gi = kNoIdx;
 #pragma unroll
-        for (int k = 0; k < (LC >= 0 ? (1 << LC) : C); ++k) {
-            if constexpr (kF32) cd = keep_max(cd, __uint_as_float(c_a[c_lane + 32 * k].x));
-            else cd = keep_max(cd, c_d[c_lane + 32 * k]);
-        }
-        const T gd = warp_max(cd);
-        unsigned ci = kNoIdx;
-        int cs = c_lane;
-#pragma unroll
-        for (int k = 0; k < (LC >= 0 ? (1 << LC) : C); ++k) {
-            T d;
-            unsigned i2;
-            if constexpr (kF32) {
-                const uint2 v = *reinterpret_cast<const uint2*>(&c_a[c_lane + 32 * k]);
-                d = __uint_as_float(v.x); i2 = v.y;
-            } else {
-                d = c_d[c_lane + 32 * k]; i2 = c_i[c_lane + 32 * k];
+            for (int p = 0; p < C; ++p) {
+                T d, x, y, z;
+                unsigned i2;
+                if constexpr (kF32) {
+                    const uint4 v = c_a[par * C + p];
+                    d = __uint_as_float(v.x); i2 = v.y; x = __uint_as_float(v.z); y = __uint_as_float(v.w); z = c_zf[par * C + p];
+                } else {
+                    d = c_d[par * C + p]; i2 = c_i[par * C + p]; x = c_x[par * C + p]; y = c_y[par * C + p]; z = c_z[par * C + p];
+                }
+                if (d > gd || (d == gd && i2 < gi)) { gd = d; gi = i2; lx = x; ly = y; lz = z; }
             }
-            if (d == gd && i2 < ci) { ci = i2; cs = c_lane + 32 * k; }
-        }
-        const unsigned gi = __reduce_min_sync(0xffffffffu, ci);
-        const unsigned holders = __ballot_sync(0xffffffffu, ci == gi);
-        cs = __shfl_sync(0xffffffffu, cs, __ffs(holders) - 1);
-        last = (int)gi;
-        if constexpr (kF32) {
-            const uint2 v = *(reinterpret_cast<const uint2*>(&c_a[cs]) + 1);
-            lx = __uint_as_float(v.x); ly = __uint_as_float(v.y); lz = c_zf[cs];
-        } else {
-            lx = c_x[cs]; ly = c_y[cs]; lz = c_z[cs];
+            last = (int)gi;
         }
         if (g == 0) out_idx[(long long)b * S + s] = last;
         FPS_PROF(5);
