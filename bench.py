@@ -39,7 +39,8 @@ PKG = "3d-semantic-segmentation-amp-net_b200"
 
 FPS_CLOUDS, FPS_POINTS, FPS_DIMS, FPS_SAMPLES = 64, 40000, 11, 2048
 # fps_cluster_kernel as built: thread instructions per (candidate, pick) and DRAM bytes per 64-cloud launch, from ncu
-FPS_WARP_INST_PER_UPDATE, FPS_DRAM_BYTES_PER_LAUNCH, FPS_NCU_SOURCE = 24.4, 127.5e6, "profiles/r01_fps_ncu_full.txt"
+FPS_WARP_INST_PER_UPDATE, FPS_DRAM_BYTES_PER_LAUNCH, FPS_NCU_SOURCE = 14.8, 122.3e6, "profiles/r02_fps_ncu_full.txt"
+FPS_SMEM_SLOT_FRACTION = 18.0 / 20.0        # configs[1]: 20 slots per thread, 18 of them in shared memory (2 in registers)
 NN_BATCH, NN_POINTS, NN_DIMS = 32, 2048, 9
 
 
@@ -213,23 +214,28 @@ def bench_fps(dist, amp, steps, warmup, with_cpu):
 
     e_ms, _ = timed_steps(dist, step_e2e, steps, warmup, flush)
     clouds = FPS_CLOUDS * dist.world * steps
-    # Roofline of fps_cluster_kernel: the whole cloud lives on chip (registers + shared memory; ncu: dram bytes = 0.3 % of the
-    # HBM model's), so the bound is the instruction issue rate: executed warp instructions (smsp__inst_executed.sum of one
-    # launch, a property of the build, from the ncu capture named below) / kernel time, against 4 issue slots per SM per clock.
+    # Roofline of fps_cluster_kernel: the whole cloud lives on chip (registers + shared memory; ncu: dram bytes = 0.2 % of the
+    # HBM model's), so HBM bounds nothing. The binding resource is the shared-memory read port: every pick reads the 12-byte
+    # coordinates of every shared-memory-resident candidate once (ncu: the LSU shared pipe is 68 % busy over the active
+    # cycles, the issue slots 56 %). achieved = algorithmic shared-memory bytes / kernel time, peak = 128 B per clock per SM.
     sm_mhz = clock_mhz()
+    smem_bytes = 12.0 * FPS_SMEM_SLOT_FRACTION * (FPS_SAMPLES - 1) * FPS_POINTS * FPS_CLOUDS
+    ach = smem_bytes / (k_ms / steps * 1e-3) / 1e9
+    peak = 128.0 * 148 * sm_mhz * 1e-3
     warp_inst = FPS_WARP_INST_PER_UPDATE * (FPS_SAMPLES - 1) * FPS_POINTS * FPS_CLOUDS / 32.0
-    ach = warp_inst / (k_ms / steps * 1e-3) / 1e9
-    peak = 4.0 * 148 * sm_mhz * 1e-3
+    issue_frac = warp_inst / (k_ms / steps * 1e-3) / 1e9 / (4.0 * 148 * sm_mhz * 1e-3)
     res = {
         "value": clouds / (total_ms * 1e-3), "unit": "clouds/s", "ms_per_step": total_ms / steps,
         "gpu_launches": int(launches),
         "e2e": {"value": clouds / (e_ms * 1e-3), "unit": "clouds/s",
                 "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": int(rows_host.numel() * 4)},
-        "roofline": {"bound": "issue", "kernel": "fps_cluster_kernel", "achieved": ach, "peak": peak, "unit": "Gwarp-inst/s",
+        "roofline": {"bound": "smem", "kernel": "fps_cluster_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
                      "frac": ach / peak, "traffic": FPS_DRAM_BYTES_PER_LAUNCH,
-                     "model": "%.1f thread instructions per candidate update (ncu, %s) x (S-1) x P x clouds / 32 per launch; "
-                              "peak = 4 issue slots x 148 SMs x %.0f MHz; HBM is idle (cloud on chip)"
-                              % (FPS_WARP_INST_PER_UPDATE, FPS_NCU_SOURCE, sm_mhz),
+                     "model": "12 B of coordinates per shared-memory-resident candidate (%.0f %% of the slots) per pick x (S-1) x P x "
+                              "clouds / kernel time; peak = 128 B/clk x 148 SMs x %.0f MHz (the launch occupies 128 SMs: 64 clouds x "
+                              "2 CTAs). Issue slots: %.1f thread instructions per candidate update (ncu, %s) = %.2f of 4 per SM per "
+                              "clock; traffic = DRAM bytes per launch (ncu): HBM is idle, the cloud is on chip"
+                              % (100 * FPS_SMEM_SLOT_FRACTION, sm_mhz, FPS_WARP_INST_PER_UPDATE, FPS_NCU_SOURCE, issue_frac),
                      "kernel_ms": k_ms / steps},
         "config": {"workload": "configs[1]: FPS %d windows x %d pts -> %d per GPU, float32 rows of %d columns"
                                % (FPS_CLOUDS, FPS_POINTS, FPS_SAMPLES, FPS_DIMS)},
