@@ -15,4 +15,5 @@ from .dataprep import split_windows, filter_normalize_windows  # noqa: F401
 from .assembly import assemble_windows, draw_augmentation  # noqa: F401
 from .blockstore import BlockStore, BlockStoreWriter, convert_kmeans_pt_files  # noqa: F401
 from .tensorcore import tc_linear, linear_wgrad  # noqa: F401
+from .graphstep import GraphedStep  # noqa: F401
 

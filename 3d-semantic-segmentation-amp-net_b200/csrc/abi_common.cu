@@ -39,6 +39,11 @@ bool path_disabled(const char* name) {
     return list && strstr(list, name) != nullptr;
 }
 
+// process-wide, not thread-local: autograd runs the backward (amp_seg_bwd) on its own worker thread
+static std::atomic<const unsigned long long*> g_drop_off{nullptr};
+const unsigned long long* dropout_offset() { return g_drop_off.load(std::memory_order_acquire); }
+void set_dropout_offset(const unsigned long long* p) { g_drop_off.store(p, std::memory_order_release); }
+
 // per-path launch counters (amp_path_count): which kernel family actually served a call
 struct PathCounter { char name[32]; long long n; };
 static PathCounter g_paths[48];
@@ -73,6 +78,10 @@ int64_t amp_path_count(const char* name) {
     for (int i = 0; i < amp::g_n_paths; ++i)
         if (strcmp(amp::g_paths[i].name, name) == 0) return (int64_t)amp::g_paths[i].n;
     return 0;
+}
+int amp_set_dropout_offset(const void* device_u64) {
+    amp::set_dropout_offset(reinterpret_cast<const unsigned long long*>(device_u64));
+    return AMP_OK;
 }
 int amp_debug_set_disabled(const char* csv) {
     std::lock_guard<std::mutex> lk(amp::g_dbg_mu);

@@ -64,6 +64,8 @@ struct StrictScope {                    // RAII: calls of this thread avoid the 
     ~StrictScope();
     bool prev;
 };
+// device word added to every dropout seed (amp_set_dropout_offset; null = none)
+const unsigned long long* dropout_offset();
 // per-path launch counter behind amp_path_count() (tests assert which kernel family served a call)
 void count_path(const char* name, int n = 1);
 

@@ -24,6 +24,9 @@ struct PwParams {
     //                dy = c1 * dz + c3 + c2 * (y - mean)  with X = dz, X2 = y
     const float* in_a; const float* in_b; const float* in_c; const float* in_m; const float* X2; int in_relu;
     float in_drop_p; unsigned long long in_drop_seed;
+    // optional device word added to every dropout seed of the call when non-null (amp_set_dropout_offset: a training step
+    // captured in a CUDA graph draws a new mask per replay by bumping that word on the device)
+    const unsigned long long* drop_off;
     // weights: w_kn == 0: W[n * ldw + k] (PyTorch [out, in]);  w_kn == 1: W[k * ldw + n] ([in, out]);
     // per-cloud weights when w_cloud_stride != 0
     const float* W; long long ldw; long long w_cloud_stride; int w_kn;
@@ -81,6 +84,7 @@ struct WgParams {
     // A operand with the forward prologue: a = (A - a_m[k]) * a_a[k] + a_b[k]; ReLU if a_relu; dropout if a_drop_p > 0
     const float* A; long long lda; int K; const float* a_a; const float* a_b; const float* a_m; int a_relu;
     float a_drop_p; unsigned long long a_drop_seed;
+    const unsigned long long* drop_off;          // see PwParams
     int n_clouds; int rows_per_cloud;
     int per_cloud;                      // 1: one dW per cloud (bmm weights), dW[cloud][n * ldw + k]
     int w_kn;                           // 0: dW[n * ldw + k]; 1: dW[k * ldw + n]
@@ -118,6 +122,10 @@ __host__ __device__ inline float unordered_bits(unsigned int u) {
 #endif
 }
 
+// seed of a dropout site: the by-value seed of the call plus the optional device-side offset (see PwParams::drop_off)
+__device__ __forceinline__ unsigned long long eff_seed(unsigned long long seed, const unsigned long long* off) {
+    return off ? seed + __ldg(off) : seed;
+}
 // Counter-based dropout: keep-scale (0 or 1/(1-p)) of element `idx` of a tensor under `seed`.
 // Forward and backward call it with the same (seed, idx), so no mask is stored.
 __device__ __forceinline__ float dropout_keep(unsigned long long seed, unsigned long long idx, float p) {

@@ -17,64 +17,84 @@ __global__ void bn_fold_eval_kernel(const BnTable table, float eps) {
     }
 }
 
-__global__ void bn_finalize_train_kernel(const float* __restrict__ part_sum, const float* __restrict__ part_m2, int tiles,
-                                         int tiles_per_cloud, int rows_per_cloud, long long count, int C,
-                                         const float* __restrict__ gamma, float* running_mean, float* running_var,
-                                         long long* nbt, float momentum, float eps, float* __restrict__ scale,
-                                         float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+// The two BatchNorm finalize kernels sit between every pair of layer kernels of a training step (~ 45 launches per
+// step): they are pure latency. 128 threads per channel, two channels per CTA (32 .. 128 CTAs instead of 8 .. 32 with one
+// warp per channel): a thread keeps 4 tiles in registers (one round of loads), fixed-order double sums through shuffles
+// and shared memory (deterministic), no integer division per tile.
+constexpr int BF_TPC = 128, BF_CH = 2, BF_REG = 4;
+
+__device__ __forceinline__ double bf_channel_sum(double v, double* s_red, int ch, int li) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((li & 31) == 0) s_red[ch * (BF_TPC / 32) + (li >> 5)] = v;
+    __syncthreads();
+    double r = 0.0;
+#pragma unroll
+    for (int w = 0; w < BF_TPC / 32; ++w) r += s_red[ch * (BF_TPC / 32) + w];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(BF_TPC * BF_CH)
+bn_finalize_train_kernel(const float* __restrict__ part_sum, const float* __restrict__ part_m2, int tiles,
+                         int tiles_per_cloud, int rows_per_cloud, long long count, int C,
+                         const float* __restrict__ gamma, float* running_mean, float* running_var,
+                         long long* nbt, float momentum, float eps, float* __restrict__ scale,
+                         float* __restrict__ save_mean, float* __restrict__ save_invstd) {
     pdl_sync();
-    // one warp per channel, fixed lane-strided order, double accumulation; the per-tile (sum, M2) pairs are
-    // combined exactly (Chan et al.): M2 = sum_t [ M2_t + n_t (mean_t - mean)^2 ]
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (c < C) {
-        // up to 16 tiles per lane are kept in registers: one pass over global memory, all loads in flight together
-        constexpr int kReg = 16;
-        float ps[kReg], pq[kReg];
+    // the per-tile (sum, M2) pairs are combined exactly (Chan et al.): M2 = sum_t [ M2_t + n_t (mean_t - mean)^2 ]
+    __shared__ double s_red[BF_CH * (BF_TPC / 32)];
+    const int ch = threadIdx.x / BF_TPC, li = threadIdx.x - ch * BF_TPC;
+    const int c = blockIdx.x * BF_CH + ch;
+    const bool ok = c < C;
+    float ps[BF_REG], pq[BF_REG];
 #pragma unroll
-        for (int i = 0; i < kReg; ++i) {
-            const int t = lane + 32 * i;
-            ps[i] = t < tiles ? part_sum[(long long)t * C + c] : 0.f;
-            pq[i] = t < tiles ? part_m2[(long long)t * C + c] : 0.f;
+    for (int i = 0; i < BF_REG; ++i) {
+        const int t = li + BF_TPC * i;
+        ps[i] = (ok && t < tiles) ? part_sum[(long long)t * C + c] : 0.f;
+        pq[i] = (ok && t < tiles) ? part_m2[(long long)t * C + c] : 0.f;
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < BF_REG; ++i) s += (double)ps[i];
+    if (ok)
+        for (int t = li + BF_TPC * BF_REG; t < tiles; t += BF_TPC) s += (double)part_sum[(long long)t * C + c];
+    s = bf_channel_sum(s, s_red, ch, li);
+    const double n = (double)count;
+    const double mean = s / n;
+    const int nt_last = rows_per_cloud - (tiles_per_cloud - 1) * 128;        // rows of the last tile of a cloud
+    const double inv_full = 1.0 / 128.0, inv_last = 1.0 / (double)nt_last;     // (no fp64 divide per tile)
+    // position of this thread's first tile inside its cloud, advanced by BF_TPC tiles per step (no division per tile)
+    int pos = li % tiles_per_cloud;
+    const int step = BF_TPC % tiles_per_cloud;
+    double m2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < BF_REG; ++i) {
+        const int t = li + BF_TPC * i;
+        if (ok && t < tiles) {
+            const bool last = pos == tiles_per_cloud - 1;
+            const double d = (double)ps[i] * (last ? inv_last : inv_full) - mean;
+            m2 += (double)pq[i] + (double)(last ? nt_last : 128) * d * d;
         }
-        double s = 0.0;
-#pragma unroll
-        for (int i = 0; i < kReg; ++i) s += (double)ps[i];
-        for (int t = lane + 32 * kReg; t < tiles; t += 32) s += (double)part_sum[(long long)t * C + c];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        const double n = (double)count;
-        const double mean = s / n;
-        double m2 = 0.0;
-        const int nt_last = rows_per_cloud - (tiles_per_cloud - 1) * 128;        // rows of the last tile of a cloud
-        const double inv_full = 1.0 / 128.0, inv_last = 1.0 / (double)nt_last;     // (no fp64 divide per tile)
-#pragma unroll
-        for (int i = 0; i < kReg; ++i) {
-            const int t = lane + 32 * i;
-            if (t < tiles) {
-                const bool last = (t % tiles_per_cloud) == tiles_per_cloud - 1;
-                const int nt = last ? nt_last : 128;
-                const double d = (double)ps[i] * (last ? inv_last : inv_full) - mean;
-                m2 += (double)pq[i] + nt * d * d;
-            }
+        pos += step; if (pos >= tiles_per_cloud) pos -= tiles_per_cloud;
+    }
+    if (ok)
+        for (int t = li + BF_TPC * BF_REG; t < tiles; t += BF_TPC) {
+            const bool last = pos == tiles_per_cloud - 1;
+            const double d = (double)part_sum[(long long)t * C + c] * (last ? inv_last : inv_full) - mean;
+            m2 += (double)part_m2[(long long)t * C + c] + (double)(last ? nt_last : 128) * d * d;
+            pos += step; if (pos >= tiles_per_cloud) pos -= tiles_per_cloud;
         }
-        for (int t = lane + 32 * kReg; t < tiles; t += 32) {
-            const int nt = min(128, rows_per_cloud - (t % tiles_per_cloud) * 128);
-            const double d = (double)part_sum[(long long)t * C + c] / nt - mean;
-            m2 += (double)part_m2[(long long)t * C + c] + nt * d * d;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, o);
-        if (lane == 0) {
-            const double var = m2 / n;
-            const float invstd = (float)(1.0 / sqrt(var + (double)eps));
-            scale[c] = gamma[c] * invstd;
-            if (save_mean) { save_mean[c] = (float)mean; save_invstd[c] = invstd; }
-            if (running_mean) {
-                const double unbiased = count > 1 ? m2 / (n - 1.0) : var;
-                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
-                running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
-            }
+    m2 = bf_channel_sum(m2, s_red, ch, li);
+    if (ok && li == 0) {
+        const double var = m2 / n;
+        const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+        scale[c] = gamma[c] * invstd;
+        if (save_mean) { save_mean[c] = (float)mean; save_invstd[c] = invstd; }
+        if (running_mean) {
+            const double unbiased = count > 1 ? m2 / (n - 1.0) : var;
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
         }
     }
     if (nbt && blockIdx.x == 0 && threadIdx.x == 0) *nbt += 1;
@@ -165,9 +185,11 @@ __global__ void posenc_add_kernel(const float* __restrict__ gl, long long gl_ld,
 
 // one warp per (cloud, head, query token); lanes own head-dim elements (hd = 32 for E = 256, 8 heads)
 __global__ void attention_core_kernel(const float* __restrict__ qkv, const unsigned char* __restrict__ key_mask,
-                                      float drop_p, unsigned long long drop_seed, int n_clouds, int L, int E,
+                                      float drop_p, unsigned long long drop_seed_arg, const unsigned long long* drop_off,
+                                      int n_clouds, int L, int E,
                                       int heads, float* __restrict__ out, float* __restrict__ probs) {
     pdl_sync();
+    const unsigned long long drop_seed = eff_seed(drop_seed_arg, drop_off);
     const int hd = E / heads;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int total = n_clouds * heads * L;
@@ -216,47 +238,46 @@ __global__ void attention_core_kernel(const float* __restrict__ qkv, const unsig
 
 
 // BatchNorm backward: per-channel sums -> dgamma, dbeta and the coefficients of dy = c1 dz + c2 y + c3
-__global__ void bn_backward_finalize_kernel(const float* __restrict__ part_sum, const float* __restrict__ part_sq, int tiles,
-                                            long long count, int C, const float* __restrict__ gamma,
-                                            const float* __restrict__ mean, const float* __restrict__ invstd,
-                                            float* dgamma, float* dbeta, int accumulate, float* __restrict__ c1,
-                                            float* __restrict__ c2, float* __restrict__ c3) {
+__global__ void __launch_bounds__(BF_TPC * BF_CH)
+bn_backward_finalize_kernel(const float* __restrict__ part_sum, const float* __restrict__ part_sq, int tiles,
+                            long long count, int C, const float* __restrict__ gamma,
+                            const float* __restrict__ mean, const float* __restrict__ invstd,
+                            float* dgamma, float* dbeta, int accumulate, float* __restrict__ c1,
+                            float* __restrict__ c2, float* __restrict__ c3) {
     pdl_sync();
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (c >= C) return;
+    __shared__ double s_red[BF_CH * (BF_TPC / 32)];
+    const int ch = threadIdx.x / BF_TPC, li = threadIdx.x - ch * BF_TPC;
+    const int c = blockIdx.x * BF_CH + ch;
+    const bool ok = c < C;
     double s = 0.0, q = 0.0;
     {
-        constexpr int kReg = 16;                  // all loads of the first 512 tiles in flight together
-        float ps[kReg], pq[kReg];
+        float ps[BF_REG], pq[BF_REG];             // all loads of the first 512 tiles in flight together
 #pragma unroll
-        for (int i = 0; i < kReg; ++i) {
-            const int t = lane + 32 * i;
-            ps[i] = t < tiles ? part_sum[(long long)t * C + c] : 0.f;
-            pq[i] = t < tiles ? part_sq[(long long)t * C + c] : 0.f;
+        for (int i = 0; i < BF_REG; ++i) {
+            const int t = li + BF_TPC * i;
+            ps[i] = (ok && t < tiles) ? part_sum[(long long)t * C + c] : 0.f;
+            pq[i] = (ok && t < tiles) ? part_sq[(long long)t * C + c] : 0.f;
         }
 #pragma unroll
-        for (int i = 0; i < kReg; ++i) { s += (double)ps[i]; q += (double)pq[i]; }
-        for (int t = lane + 32 * kReg; t < tiles; t += 32) {
-            s += (double)part_sum[(long long)t * C + c];
-            q += (double)part_sq[(long long)t * C + c];
-        }
+        for (int i = 0; i < BF_REG; ++i) { s += (double)ps[i]; q += (double)pq[i]; }
+        if (ok)
+            for (int t = li + BF_TPC * BF_REG; t < tiles; t += BF_TPC) {
+                s += (double)part_sum[(long long)t * C + c];
+                q += (double)part_sq[(long long)t * C + c];
+            }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        q += __shfl_xor_sync(0xffffffffu, q, o);
-    }
-    if (lane == 0) {
+    s = bf_channel_sum(s, s_red, ch, li);
+    q = bf_channel_sum(q, s_red, ch, li);
+    if (ok && li == 0) {
         const double n = (double)count;
-        const double g = gamma[c], mu = mean[c], is = invstd[c];
+        const double g = gamma[c], is = invstd[c];
         if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)q : (float)q;
         if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s;
         const double a = g * is;
         c1[c] = (float)a;                       // dy = c1 dz + c2 (y - mean) + c3
         c2[c] = (float)(-a * is * q / n);
         c3[c] = (float)(-a * s / n);
-        (void)mu;
+        (void)mean;
     }
 }
 
@@ -390,9 +411,10 @@ __global__ void posenc_bwd_param_kernel(const float* __restrict__ dtok, const fl
 
 // one block per (cloud, head): dS / Pd in shared memory, then dQ, dK, dV
 __global__ void attention_core_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ qkv,
-                                          const float* __restrict__ probs, float drop_p, unsigned long long drop_seed,
-                                          int L, int E, int heads, float* __restrict__ dqkv) {
+                                          const float* __restrict__ probs, float drop_p, unsigned long long drop_seed_arg,
+                                          const unsigned long long* drop_off, int L, int E, int heads, float* __restrict__ dqkv) {
     pdl_sync();
+    const unsigned long long drop_seed = eff_seed(drop_seed_arg, drop_off);
     extern __shared__ float sm[];
     float* dS = sm;            // [L][L]
     float* Pd = sm + L * L;    // [L][L]
@@ -448,7 +470,7 @@ int bn_finalize_train(const float* part_sum, const float* part_m2, int n_clouds,
                       const float* gamma, float* running_mean, float* running_var, long long* nbt, float momentum,
                       float eps, float* scale, float* save_mean, float* save_invstd, cudaStream_t st) {
     const int tpc = (rows_per_cloud + 127) / 128;
-    launch_pdl(bn_finalize_train_kernel, dim3((unsigned)((C + 7) / 8)), dim3(256), 0, st, part_sum, part_m2, n_clouds * tpc, tpc, rows_per_cloud,
+    launch_pdl(bn_finalize_train_kernel, dim3((unsigned)((C + BF_CH - 1) / BF_CH)), dim3(BF_TPC * BF_CH), 0, st, part_sum, part_m2, n_clouds * tpc, tpc, rows_per_cloud,
                                                          (long long)n_clouds * rows_per_cloud, C, gamma, running_mean,
                                                          running_var, nbt, momentum, eps, scale, save_mean, save_invstd);
     count_launch();
@@ -458,7 +480,7 @@ int bn_finalize_train(const float* part_sum, const float* part_m2, int n_clouds,
 int bn_backward_finalize(const float* part_sum, const float* part_sq, int tiles, long long count, int C,
                          const float* gamma, const float* mean, const float* invstd, float* dgamma, float* dbeta,
                          int accumulate, float* c1, float* c2, float* c3, cudaStream_t st) {
-    launch_pdl(bn_backward_finalize_kernel, dim3((unsigned)((C + 7) / 8)), dim3(256), 0, st, part_sum, part_sq, tiles, count, C, gamma, mean, invstd,
+    launch_pdl(bn_backward_finalize_kernel, dim3((unsigned)((C + BF_CH - 1) / BF_CH)), dim3(BF_TPC * BF_CH), 0, st, part_sum, part_sq, tiles, count, C, gamma, mean, invstd,
                                                             dgamma, dbeta, accumulate, c1, c2, c3);
     count_launch();
     return check_launch("bn_backward_finalize");
@@ -561,7 +583,7 @@ int attention_core(const float* qkv, const unsigned char* key_mask, float drop_p
     const int warps = n_clouds * heads * n_tokens;
     const int wpb = 4;
     launch_pdl(attention_core_kernel, dim3((unsigned)((warps + wpb - 1) / wpb)), dim3(wpb * 32), wpb * n_tokens * sizeof(float), st, 
-        qkv, key_mask, drop_p, drop_seed, n_clouds, n_tokens, E, heads, out, probs);
+        qkv, key_mask, drop_p, drop_seed, dropout_offset(), n_clouds, n_tokens, E, heads, out, probs);
     count_launch();
     return check_launch("attention_core");
 }
@@ -571,7 +593,7 @@ int attention_core_bwd(const float* dout, const float* qkv, const float* probs, 
                        cudaStream_t st) {
     if (n_tokens > 64) return fail(AMP_E_BADARG, "attention_core_bwd: more than 64 tokens per cloud");
     launch_pdl(attention_core_bwd_kernel, dim3((unsigned)(n_clouds * heads)), dim3(128), 2 * n_tokens * n_tokens * sizeof(float), st, 
-        dout, qkv, probs, drop_p, drop_seed, n_tokens, E, heads, dqkv);
+        dout, qkv, probs, drop_p, drop_seed, dropout_offset(), n_tokens, E, heads, dqkv);
     count_launch();
     return check_launch("attention_core_bwd");
 }

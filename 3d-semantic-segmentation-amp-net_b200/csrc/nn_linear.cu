@@ -61,7 +61,7 @@ pw_linear_kernel(const PwParams p) {
                 else if (p.in_a) v = fmaf(v - m, __ldg(p.in_a + k0 + k), __ldg(p.in_b + k0 + k));
                 if (p.in_relu) v = fmaxf(v, 0.f);
                 if (p.in_drop_p > 0.f)
-                    v *= dropout_keep(p.in_drop_seed, (unsigned long long)(row_base + r) * K + k0 + k, p.in_drop_p);
+                    v *= dropout_keep(eff_seed(p.in_drop_seed, p.drop_off), (unsigned long long)(row_base + r) * K + k0 + k, p.in_drop_p);
             }
             xr[i] = v;
         }
@@ -261,7 +261,7 @@ pw_linear_kernel(const PwParams p) {
                         const float y = My[(long long)r * p.ld_mask + col[j]];
                         dz = acc[i][j];
                         if (p.out_drop_p > 0.f)
-                            dz *= dropout_keep(p.out_drop_seed, (unsigned long long)(row_base + r) * p.Nout + col[j], p.out_drop_p);
+                            dz *= dropout_keep(eff_seed(p.out_drop_seed, p.drop_off), (unsigned long long)(row_base + r) * p.Nout + col[j], p.out_drop_p);
                         dz = (fmaf(y - mu, ms, mt) > 0.f) ? dz : 0.f;
                         s += dz;
                         q = fmaf(dz, (y - mu) * is, q);

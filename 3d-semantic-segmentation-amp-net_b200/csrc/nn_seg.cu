@@ -314,7 +314,7 @@ int amp_seg_fwd(const void* const* params, const float* gl_feats, int64_t gl_ld,
     {
         PwParams p{};
         p.X = S.y2; p.ldx = hid; p.K = hid;
-        if (train) { p.in_a = S.scale + kSegBn2; p.in_b = pf(params, S_BN2 + BN_B); p.in_m = S.mean + kSegBn2; p.in_relu = 1; p.in_drop_p = dp; p.in_drop_seed = seed + 2; }
+        if (train) { p.in_a = S.scale + kSegBn2; p.in_b = pf(params, S_BN2 + BN_B); p.in_m = S.mean + kSegBn2; p.in_relu = 1; p.in_drop_p = dp; p.drop_off = dropout_offset(); p.in_drop_seed = seed + 2; }
         p.W = pf(params, S_C3W); p.ldw = hid; p.bias = pf(params, S_C3B); p.n_groups = 1;
         p.fp16_split = train ? 1 : 0;
         p.Y = S.y3; p.ldy = 64; p.n_clouds = Bi; p.rows_per_cloud = Ri; p.Nout = 64;
@@ -327,7 +327,7 @@ int amp_seg_fwd(const void* const* params, const float* gl_feats, int64_t gl_ld,
     {
         PwParams p{};
         p.X = S.y3; p.ldx = 64; p.K = 64;
-        if (train) { p.in_a = S.scale + kSegBn3; p.in_b = pf(params, S_BN3 + BN_B); p.in_m = S.mean + kSegBn3; p.in_relu = 1; p.in_drop_p = dp; p.in_drop_seed = seed + 3; }
+        if (train) { p.in_a = S.scale + kSegBn3; p.in_b = pf(params, S_BN3 + BN_B); p.in_m = S.mean + kSegBn3; p.in_relu = 1; p.in_drop_p = dp; p.drop_off = dropout_offset(); p.in_drop_seed = seed + 3; }
         p.W = pf(params, S_C4W); p.ldw = 64; p.bias = pf(params, S_C4B); p.n_groups = 1;
         p.Y = logits; p.y_transposed = 1; p.n_clouds = Bi; p.rows_per_cloud = Ri; p.Nout = num_classes;
         AMP_TRY(pw_linear(p, st));
@@ -373,14 +373,14 @@ int amp_seg_bwd(const void* const* params, void* const* grads, const float* lo_f
         WgParams g{};
         g.dY = d_logits; g.Nout = C; g.dy_transposed = 1;
         g.A = S.y3; g.lda = 64; g.K = 64; g.a_a = S.scale + kSegBn3; g.a_b = pf(params, S_BN3 + BN_B); g.a_m = S.mean + kSegBn3; g.a_relu = 1;
-        g.a_drop_p = dp; g.a_drop_seed = seed + 3;
+        g.a_drop_p = dp; g.drop_off = dropout_offset(); g.a_drop_seed = seed + 3;
         g.n_clouds = Bi; g.rows_per_cloud = Ri; g.dW = gf(grads, S_C4W); g.ldw = 64; g.db = gf(grads, S_C4B);
         g.partials = ws.wg; g.partial_floats = ws.wg_floats;
         AMP_TRY(wgrad(g, st));
         PwParams p{};
         p.X = d_logits; p.K = C; p.x_transposed = 1; p.W = pf(params, S_C4W); p.ldw = 64; p.w_kn = 1; p.n_groups = 1;
         p.mask_y = S.y3; p.ld_mask = 64; p.mask_scale = S.scale + kSegBn3; p.mask_shift = pf(params, S_BN3 + BN_B);
-        p.mask_mean = S.mean + kSegBn3; p.mask_invstd = S.invstd + kSegBn3; p.out_drop_p = dp; p.out_drop_seed = seed + 3;
+        p.mask_mean = S.mean + kSegBn3; p.mask_invstd = S.invstd + kSegBn3; p.out_drop_p = dp; p.drop_off = dropout_offset(); p.out_drop_seed = seed + 3;
         p.part_sum = ws.part_sum; p.part_sq = ws.part_sq;
         p.Y = ws.dz3; p.ldy = 64; p.n_clouds = Bi; p.rows_per_cloud = Ri; p.Nout = 64;
         AMP_TRY(pw_linear(p, st));
@@ -393,7 +393,7 @@ int amp_seg_bwd(const void* const* params, void* const* grads, const float* lo_f
         WgParams g{};
         g.dY = ws.dz3; g.lddy = 64; g.Nout = 64; g.y_a = ws.k1 + kSegBn3; g.y_b = ws.k3 + kSegBn3; g.y_c = ws.k2 + kSegBn3; g.y_m = S.mean + kSegBn3; g.Y2 = S.y3;
         g.A = S.y2; g.lda = hid; g.K = hid; g.a_a = S.scale + kSegBn2; g.a_b = pf(params, S_BN2 + BN_B); g.a_m = S.mean + kSegBn2; g.a_relu = 1;
-        g.a_drop_p = dp; g.a_drop_seed = seed + 2;
+        g.a_drop_p = dp; g.drop_off = dropout_offset(); g.a_drop_seed = seed + 2;
         g.n_clouds = Bi; g.rows_per_cloud = Ri; g.dW = gf(grads, S_C3W); g.ldw = hid; g.db = gf(grads, S_C3B);
         g.partials = ws.wg; g.partial_floats = ws.wg_floats;
         AMP_TRY(wgrad(g, st));
@@ -401,7 +401,7 @@ int amp_seg_bwd(const void* const* params, void* const* grads, const float* lo_f
         p.X = ws.dz3; p.ldx = 64; p.K = 64; p.in_a = ws.k1 + kSegBn3; p.in_b = ws.k3 + kSegBn3; p.in_c = ws.k2 + kSegBn3; p.in_m = S.mean + kSegBn3; p.X2 = S.y3;
         p.W = pf(params, S_C3W); p.ldw = hid; p.w_kn = 1; p.n_groups = 1;
         p.mask_y = S.y2; p.ld_mask = hid; p.mask_scale = S.scale + kSegBn2; p.mask_shift = pf(params, S_BN2 + BN_B);
-        p.mask_mean = S.mean + kSegBn2; p.mask_invstd = S.invstd + kSegBn2; p.out_drop_p = dp; p.out_drop_seed = seed + 2;
+        p.mask_mean = S.mean + kSegBn2; p.mask_invstd = S.invstd + kSegBn2; p.out_drop_p = dp; p.drop_off = dropout_offset(); p.out_drop_seed = seed + 2;
         p.part_sum = ws.part_sum; p.part_sq = ws.part_sq;
         p.Y = ws.dz2; p.ldy = hid; p.n_clouds = Bi; p.rows_per_cloud = Ri; p.Nout = hid;
         AMP_TRY(pw_linear(p, st));

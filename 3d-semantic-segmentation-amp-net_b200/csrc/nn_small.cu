@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(256) narrow_out_fwd_kernel(const PwParams p) {
         if (p.in_drop_p > 0.f) {
             const unsigned long long di = (unsigned long long)(row_base + r) * 64 + k;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) a[j] *= dropout_keep(p.in_drop_seed, di + j, p.in_drop_p);
+            for (int j = 0; j < 4; ++j) a[j] *= dropout_keep(eff_seed(p.in_drop_seed, p.drop_off), di + j, p.in_drop_p);
         }
 #pragma unroll
         for (int n = 0; n < NOF_MAXN; ++n) {
@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(256) narrow_out_wgrad_kernel(const WgParams p,
                 if (p.a_drop_p > 0.f) {
                     const unsigned long long di = (unsigned long long)(cloud_row + r) * K + k;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) a[j] *= dropout_keep(p.a_drop_seed, di + j, p.a_drop_p);
+                    for (int j = 0; j < 4; ++j) a[j] *= dropout_keep(eff_seed(p.a_drop_seed, p.drop_off), di + j, p.a_drop_p);
                 }
                 const float* dyr = dys + (r - r_begin) * NO_MAXN;
 #pragma unroll

@@ -23,6 +23,8 @@
 
 #include <cuda_fp16.h>
 
+#include <algorithm>
+
 #include "nn_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -94,7 +96,7 @@ __device__ __noinline__ float dropout_keep_ool(unsigned long long seed, unsigned
 enum { TL_STATS = 1, TL_POOL2 = 2, TL_AFFINE = 4, TL_POOL1 = 8, TL_MASK = 16, TL_DROP = 32, TL_ACC = 64, TL_FP16 = 128 };
 
 template <int MODE>
-__global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_constant__ PwParams p, const int Mpad, const int kcw, long long* prof_buf) {
+__global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_constant__ PwParams p, const int Mpad, const int kcw, const int cloud_split, long long* prof_buf) {
     pdl_trigger();
     extern __shared__ __align__(1024) unsigned char smem[];
     // two slots of 256 threads (two warpgroups each): `wg` = slot, `sub` = which warpgroup of the slot, `wtid` = thread in slot
@@ -285,7 +287,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
                         if (p.in_drop_p > 0.f) {
                             const unsigned long long di = (unsigned long long)(row_base + r) * K + k;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] *= dropout_keep_ool(p.in_drop_seed, di + j, p.in_drop_p);
+                            for (int j = 0; j < 8; ++j) v[j] *= dropout_keep_ool(eff_seed(p.in_drop_seed, p.drop_off), di + j, p.in_drop_p);
                         }
                         if (r >= valid) {
 #pragma unroll
@@ -410,7 +412,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
                     if (MODE & TL_MASK) {
                         float dz = x;
                         if (MODE & TL_DROP)
-                            dz *= dropout_keep_ool(p.out_drop_seed, (unsigned long long)(row_base + r) * Nout + n, p.out_drop_p);
+                            dz *= dropout_keep_ool(eff_seed(p.out_drop_seed, p.drop_off), (unsigned long long)(row_base + r) * Nout + n, p.out_drop_p);
                         dz = (ok && fmaf(ym[j] - mmu, msc, msh) > 0.f) ? dz : 0.f;
                         s2 += dz;
                         q2 = fmaf(dz, (ym[j] - mmu) * mis, q2);
@@ -476,18 +478,23 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
     };
 
     // One loop, one call site of stage_weights / process (they are big: a second inlined copy doubles the cold-start
-    // instruction fetch). Shared weights: tiles strided over (CTA, slot). Per-cloud weights: clouds strided over CTAs, the
-    // two slots take alternating tiles of the cloud and both pass the CTA barriers around the weight restaging.
+    // instruction fetch). Shared weights: tiles strided over (CTA, slot). Per-cloud weights: a cloud is cut into cloud_split
+    // units of consecutive tile pairs, units strided over CTAs (32 clouds fill 128 SMs instead of 32); the two slots take
+    // alternating tiles of the unit and both pass the CTA barriers around the weight restaging.
     const int n_tiles = p.n_clouds * tpc;
     const int tps = (tpc + 1) >> 1;
-    const int n_it = per_cloud_w ? ((p.n_clouds - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * tps
+    const int tpu = (tps + cloud_split - 1) / cloud_split;     // tile pairs per unit
+    const int n_units = p.n_clouds * cloud_split;
+    const int n_it = per_cloud_w ? ((n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * tpu
                                  : (n_tiles - (int)blockIdx.x * 2 + (int)gridDim.x * 2 - 1) / ((int)gridDim.x * 2);
     auto work = [&](int it, int& cloud, int& t) -> bool {
         if (per_cloud_w) {
-            const int ci = it / tps, j = it - ci * tps;
-            cloud = blockIdx.x + ci * gridDim.x;
-            t = j * 2 + wg;
-            return cloud < p.n_clouds && t < tpc;
+            const int ci = it / tpu, j = it - ci * tpu;
+            const int u = blockIdx.x + ci * gridDim.x;
+            cloud = u / cloud_split;
+            const int jj = (u - cloud * cloud_split) * tpu + j;
+            t = jj * 2 + wg;
+            return u < n_units && jj < tps && t < tpc;
         }
         const int tile = blockIdx.x * 2 + wg + it * gridDim.x * 2;
         cloud = tile / tpc;
@@ -500,7 +507,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
         int cloud, t, cn = 0, tn = 0;
         const bool have = work(it, cloud, t);
         if (have && !pending) issue_chunk(cloud, t, 0);
-        if (per_cloud_w ? (it % tps == 0) : (it == 0)) {
+        if (per_cloud_w ? (it % tpu == 0) : (it == 0)) {
             __syncthreads();                  // every MMA that read the previous weights has been waited for
             stage_weights(per_cloud_w ? cloud : 0);
             __syncthreads();
@@ -546,7 +553,11 @@ int tc_layer_try(const PwParams& p, cudaStream_t st) {
     PwParams q = p;
     if (q.n_groups < 1) q.n_groups = 1;
     const long long n_tiles = (long long)p.n_clouds * ((p.rows_per_cloud + TL_ROWS - 1) / TL_ROWS);
-    long long grid = p.w_cloud_stride ? p.n_clouds : (n_tiles + 1) / 2;
+    // per-cloud weights: cut every cloud into units of tile pairs until the units fill the machine
+    const int tpc_h = (p.rows_per_cloud + TL_ROWS - 1) / TL_ROWS, tps_h = (tpc_h + 1) / 2;
+    int cloud_split = 1;
+    if (p.w_cloud_stride) cloud_split = (int)std::max(1LL, std::min((long long)tps_h, (long long)kNumSMs / p.n_clouds));
+    long long grid = p.w_cloud_stride ? (long long)p.n_clouds * cloud_split : (n_tiles + 1) / 2;
     if (grid > kNumSMs) grid = kNumSMs;
     const int smem_bytes = sp.total < TL_MIN_SMEM ? TL_MIN_SMEM : sp.total;
     static const bool want_prof = getenv("AMP_LAYER_PROF") != nullptr;       // debugging aid: phase timeline of CTA 0 / thread 0
@@ -561,7 +572,7 @@ int tc_layer_try(const PwParams& p, cudaStream_t st) {
             if (e != cudaSuccess) return fail(AMP_E_CUDA, "tc_layer: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); \
             attr_set = true; \
         } \
-        launch_pdl(tc_layer_kernel<M>, dim3((unsigned)((int)grid)), dim3(TL_THREADS), smem_bytes, st, q, Mpad, kcw, want_prof ? dprof : nullptr); \
+        launch_pdl(tc_layer_kernel<M>, dim3((unsigned)((int)grid)), dim3(TL_THREADS), smem_bytes, st, q, Mpad, kcw, cloud_split, want_prof ? dprof : nullptr); \
         break; }
         TL_CASE(0) TL_CASE(TL_ACC) TL_CASE(TL_STATS) TL_CASE(TL_STATS | TL_POOL2) TL_CASE(TL_AFFINE) TL_CASE(TL_AFFINE | TL_POOL1)
         TL_CASE(TL_MASK) TL_CASE(TL_MASK | TL_ACC) TL_CASE(TL_MASK | TL_DROP)

@@ -205,7 +205,7 @@ tc_wgrad_kernel(const __grid_constant__ WgParams p, const int Mpad, const int Kp
                                 if (p.a_drop_p > 0.f) {
 #pragma unroll
                                     for (int j = 0; j < 8; ++j)
-                                        v[j] *= dropout_keep(p.a_drop_seed, (unsigned long long)grow * K + k + j, p.a_drop_p);
+                                        v[j] *= dropout_keep(eff_seed(p.a_drop_seed, p.drop_off), (unsigned long long)grow * K + k + j, p.a_drop_p);
                                 }
 #pragma unroll
                                 for (int j = 0; j < 8; ++j)

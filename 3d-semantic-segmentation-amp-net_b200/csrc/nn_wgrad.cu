@@ -61,7 +61,7 @@ wgrad_partial_kernel(const WgParams p, int n_tiles, int k_tiles, int slabs, int 
                 if (p.a_a) v = fmaf(v - (p.a_m ? __ldg(p.a_m + k0 + k) : 0.f), __ldg(p.a_a + k0 + k), __ldg(p.a_b + k0 + k));
                 if (p.a_relu) v = fmaxf(v, 0.f);
                 if (p.a_drop_p > 0.f)
-                    v *= dropout_keep(p.a_drop_seed, (unsigned long long)(cloud_row + r) * p.K + k0 + k, p.a_drop_p);
+                    v *= dropout_keep(eff_seed(p.a_drop_seed, p.drop_off), (unsigned long long)(cloud_row + r) * p.K + k0 + k, p.a_drop_p);
             }
             ar[i] = v;
         }

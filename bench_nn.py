@@ -11,6 +11,7 @@ torch.manual_seed), inputs are the synthetic blocks of SURVEY 8(d) generated her
 """
 import json
 import os
+import sys
 
 import numpy as np
 import torch
@@ -150,8 +151,8 @@ def bench_train(dist, amp, steps, warmup, with_cpu):
         for p in params:
             torch.distributed.broadcast(p.data, 0)
     # the script's two Adam optimizers (train_pointnet-attention.py:141-142), torch's fused multi-tensor implementation
-    opt_e = torch.optim.Adam(enc.parameters(), lr=1e-3, fused=True)
-    opt_s = torch.optim.Adam(seg.parameters(), lr=1e-3, fused=True)
+    opt_e = torch.optim.Adam(enc.parameters(), lr=1e-3, fused=True, capturable=True)
+    opt_s = torch.optim.Adam(seg.parameters(), lr=1e-3, fused=True, capturable=True)
     ce = torch.nn.CrossEntropyLoss(weight=torch.tensor([1., 2., 2., 1., 1.], device=dev), reduction="mean", ignore_index=-1)
     x_np, c_np, t_np = synthetic_blocks(dist.rank)
     x_host, c_host, t_host = (torch.from_numpy(a).pin_memory() for a in (x_np, c_np, t_np))
@@ -176,16 +177,33 @@ def bench_train(dist, amp, steps, warmup, with_cpu):
         keep["loss"] = loss.detach()
 
     n0 = amp._lib.launch_count()
-    ms = _timed(dist, lambda: train_step(x, cent, tg), steps, warmup, flush)
+    eager_ms = _timed(dist, lambda: train_step(x, cent, tg), steps, warmup, flush)
     launches = (amp._lib.launch_count() - n0) // (steps + warmup) * steps
+    # The step is ~180 short dependent kernels: capture zero_grad + forward + loss + backward + (all-reduce) + 2 x Adam once
+    # in a CUDA graph (amp.GraphedStep: static tensors, a device-side dropout offset so that every replay draws a new mask)
+    # and replay it. The eager step -- what the reference's train_loop does -- is measured next to it.
+    graphed, ms = None, eager_ms
+    if os.environ.get("AMP_BENCH_EAGER_TRAIN") != "1":
+        try:
+            graphed = amp.GraphedStep(lambda: train_step(x, cent, tg), device=dev)
+            ms = _timed(dist, graphed, steps, warmup, flush)
+        except Exception as e:                                   # capture refused (e.g. a collective that cannot be captured)
+            sys.stderr.write("bench_train: CUDA graph capture failed (%s); eager numbers\n" % (str(e).splitlines()[0],))
+            graphed, ms = None, eager_ms
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
     def step_e2e():
-        train_step(x_host.to(dev, non_blocking=True), c_host.to(dev, non_blocking=True), t_host.to(dev, non_blocking=True))
+        if graphed is not None:                                      # pinned host inputs -> the graph's static tensors -> replay
+            x.copy_(x_host, non_blocking=True); cent.copy_(c_host, non_blocking=True); tg.copy_(t_host, non_blocking=True)
+            graphed()
+        else:
+            train_step(x_host.to(dev, non_blocking=True), c_host.to(dev, non_blocking=True), t_host.to(dev, non_blocking=True))
         loss_host.copy_(keep["loss"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     e_ms = _timed(dist, step_e2e, steps, warmup, flush)
+    if graphed is not None:
+        graphed.close()
     pts = NN_BATCH * NN_POINTS * dist.world * steps
     peak, src = _peaks()
     ach = (NN_BATCH * NN_POINTS * TRAIN_FLOP_PER_POINT) / (ms / steps * 1e-3) / 1e12
@@ -198,6 +216,8 @@ def bench_train(dist, amp, steps, warmup, with_cpu):
                      "model": "3 x 413 143 algorithmic FLOP per point (SURVEY 8d) x 65 536 points / step time"},
         "config": {"workload": "configs[2]: training step fwd+loss+bwd+2xAdam, batch %d x %d points per GPU" % (NN_BATCH, NN_POINTS)},
         "notes": {"l2": "flushed between steps (256 MiB write)", "precision": "fp32", "dropout": 0.3, "adam": "torch fused",
+                  "launch": ("CUDA graph replay of the whole step (eager: %.3f ms per step)" % (eager_ms / steps)) if graphed is not None
+                            else "eager",
                   "collective": "NCCL gradient all-reduce (AVG, one flat buffer)" if dist.pg else "none (1 GPU)"},
         "dtype": "f32", "final_loss": float(keep["loss"]),
     }

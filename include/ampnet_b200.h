@@ -60,6 +60,13 @@ int64_t amp_launch_count(void);
  *                               The generic kernels then serve the call: tests compare both on the same inputs. */
 int64_t amp_path_count(const char* name);
 int amp_debug_set_disabled(const char* csv);
+/* Dropout seed offset on the device (no reference counterpart; the reference draws its masks from torch's generator on
+ * every call, pointNet/model/pointnetAtt.py:167,188). amp_seg_fwd / amp_seg_bwd take their dropout seed BY VALUE, which a
+ * captured CUDA graph would replay unchanged. When `device_u64` is non-null, every dropout site of the following calls (of
+ * any thread: autograd runs the backward on a worker thread) uses seed + *device_u64, read on the device at execution time: a graph-captured training step bumps that
+ * word inside the graph and draws a fresh mask per replay. The word must stay valid while such work is enqueued or
+ * captured; forward and backward of one step must see the same value. NULL switches the offset off. */
+int amp_set_dropout_offset(const void* device_u64);
 
 /* ------------------------------------------------------------------------------------------
  * Farthest-point sampling.  Replaces utils/utils.py:889-933 `fps(pc, n_samples)` and its

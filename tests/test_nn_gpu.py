@@ -458,3 +458,85 @@ def test_zero_copy_gradient_sinks_match_autograd_gradients(amp, cuda):
 
     for a, b in zip(run(False), run(True)):
         assert _rel(a, b) < 1e-6
+
+
+def _grads(mods):
+    return {"%d.%s" % (i, k): p.grad.detach().clone() for i, m in enumerate(mods) for k, p in m.named_parameters()}
+
+
+def test_device_dropout_offset_shifts_every_dropout_seed(amp, cuda):
+    """amp_set_dropout_offset: seed_by_value + *device_word must be what every dropout site of forward AND backward uses.
+    (seed a, offset b - a) has to reproduce (seed b, no offset) bit for bit, at a shape served by the tensor-core kernels."""
+    B, N, W, seed = 4, 1024, 2, 63
+    enc, seg, _, _ = _build(amp, seed, cuda, dropout=0.3)
+    xs, cent = nn_params.synthetic_blocks(B, N, W, seed)
+    enc.train(); seg.train()
+
+    def draw(s):                                             # the by-value seed SegmentationWithAttention.forward will draw
+        torch.manual_seed(s)
+        return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+    def run(s):
+        for m in (enc, seg):
+            m.zero_grad(set_to_none=True)
+        torch.manual_seed(s)
+        logits, ft, _ = _run(enc, seg, xs, cent, None, cuda)
+        (logits.square().mean() + ft.sum() * 1e-3).backward()
+        return logits.detach().clone(), _grads((enc, seg))
+
+    sa, sb = draw(11), draw(12)
+    word = torch.tensor([(sb - sa) % (1 << 63)], dtype=torch.int64, device=cuda)
+    assert (sa + int(word.item())) % (1 << 64) == sb % (1 << 64) or sb < sa
+    if sb < sa:                                              # keep the sum free of 64-bit wrap-around games: swap the roles
+        sa, sb = sb, sa
+        word = torch.tensor([sb - sa], dtype=torch.int64, device=cuda)
+        first, second = 12, 11
+    else:
+        first, second = 11, 12
+    lb, gb = run(second)
+    la0, _ = run(first)
+    assert _rel(la0, lb) > 1e-3                              # different seeds, different masks
+    amp._lib.check(amp._lib.lib().amp_set_dropout_offset(word.data_ptr()))
+    try:
+        la, ga = run(first)
+    finally:
+        amp._lib.check(amp._lib.lib().amp_set_dropout_offset(None))
+    assert torch.equal(la, lb)
+    for k in gb:
+        assert torch.equal(ga[k], gb[k]), k
+
+
+def test_graphed_training_step_redraws_dropout_and_trains(amp, cuda):
+    """amp.GraphedStep: zero_grad + forward + loss + backward + 2 x Adam as one CUDA graph; every replay draws new masks."""
+    B, N, seed = 8, 1024, 65
+    enc, seg, _, _ = _build(amp, seed, cuda, dropout=0.3)
+    xs, cent = nn_params.synthetic_blocks(B, N, 1, seed)
+    x, cent = xs[0].to(cuda), cent.to(cuda)
+    tg = torch.randint(0, 5, (B, N), device=cuda)
+    enc.train(); seg.train()
+    opt_e = torch.optim.Adam(enc.parameters(), lr=1e-3, fused=True, capturable=True)
+    opt_s = torch.optim.Adam(seg.parameters(), lr=1e-3, fused=True, capturable=True)
+    keep = {}
+
+    def step():
+        opt_e.zero_grad(set_to_none=True); opt_s.zero_grad(set_to_none=True)
+        logits, ft, _ = _run(enc, seg, [x], cent, None, cuda)
+        loss = torch.nn.functional.cross_entropy(logits, tg) + 0.001 * torch.norm(torch.eye(64, device=cuda) - torch.bmm(ft, ft.transpose(2, 1)))
+        loss.backward()
+        opt_e.step(); opt_s.step()
+        keep["loss"] = loss.detach(); keep["logits"] = logits.detach()
+
+    g = amp.GraphedStep(step, device=cuda)
+    try:
+        w0 = seg.conv_3.weight.detach().clone()
+        seen = []
+        for _ in range(4):
+            g()
+            seen.append((float(keep["loss"]), keep["logits"].clone()))
+        torch.cuda.synchronize()
+    finally:
+        g.close()
+    assert all(np.isfinite(l) for l, _ in seen)
+    assert _rel(seen[0][1], seen[1][1]) > 1e-3               # consecutive replays: different dropout masks
+    assert not torch.equal(w0, seg.conv_3.weight)            # the optimizers ran inside the graph
+    assert seen[-1][0] < seen[0][0] * 1.5                    # and did not blow the loss up
