@@ -9,8 +9,10 @@
 // thread owns one row r and writes 16-byte pieces (8 consecutive channels) -- conflict-free, no transpose.
 //
 // Work unit = one (cloud, slab of SLAB rows) = one partial of wgrad_reduce_kernel (fixed-order, deterministic sum).
-// One CTA per unit; its two warpgroups split the 64-row blocks of the slab and accumulate into separate TMEM
-// regions (D[n, k], lanes = n, columns = k), which the epilogue adds in a fixed order. The bias gradient
+// One CTA per unit; its two slots (8 warps each) split the 64-row blocks of the slab and accumulate into separate TMEM
+// regions (D[n, k], lanes = n, columns = k), which the epilogue adds in a fixed order. The kernel is bound by the latency
+// of the staging loads (one CTA per SM: the 512 TMEM columns), so it runs 16 warps, every one with a single batch of
+// dY / Y2 loads and one of A loads per block (8 warps with two row groups each took 58 us per launch on average). The bias gradient
 // db[n] = sum_r dy'[r, n] is one more accumulator column: the B operand carries a constant column of ones.
 #include "nn_common.cuh"
 #include "tc_ptx.cuh"
@@ -19,7 +21,7 @@ namespace amp {
 namespace {
 using namespace tcx;
 
-constexpr int TW_THREADS = 256, TW_RB = 64;
+constexpr int TW_THREADS = 512, TW_RB = 64;          // two slots of 8 warps: a warp stages one 8-row group of a block
 constexpr int TW_MAX_SMEM = 232448, TW_MIN_SMEM = 120 * 1024;
 
 struct TwPlan { int a_lo, b_hi, b_lo, slot, tab, bar, total; };
@@ -45,6 +47,7 @@ __device__ __forceinline__ void split_store8_w(const float (&v)[8], uint4* hi_ds
     split_pair_w(v[4], v[5], h.z, l.z); split_pair_w(v[6], v[7], h.w, l.w);
     *hi_dst = h; *lo_dst = l;
 }
+__device__ __forceinline__ void slot_bar_sync256(int slot) { asm volatile("bar.sync %0, 256;" ::"r"(slot + 1) : "memory"); }
 // instruction descriptor with both operands MN-major
 __device__ __forceinline__ uint32_t umma_idesc_mn(int M, int N) { return umma_idesc(M, N) | (1u << 15) | (1u << 16); }
 
@@ -53,7 +56,7 @@ tc_wgrad_kernel(const __grid_constant__ WgParams p, const int Mpad, const int Kp
                 const int a_vec, const int out_vec) {
     pdl_trigger();
     extern __shared__ __align__(1024) unsigned char smem[];
-    const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31, wg = warp >> 2, wtid = tid & 127;
+    const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31, wg = warp >> 3, wtid = tid & 255;   // wg = slot
     const int K = p.K, Nout = p.Nout, rows = p.rows_per_cloud;
     const TwPlan sp = tw_plan(Mpad, Kext, Nout, K);
     unsigned char* s_slot = smem + wg * sp.slot;
@@ -84,7 +87,7 @@ tc_wgrad_kernel(const __grid_constant__ WgParams p, const int Mpad, const int Kp
     }
     const int a_groups = Mpad >> 3, b_groups = Kext >> 3;       // 16-byte pieces per row
     // constant part of the B operand: columns K .. Kext-1 (a column of ones for the bias gradient, then zeros)
-    if (Kext > Kp) {
+    if (Kext > Kp && wtid < 128) {
         const int r = wtid & 63, half = wtid >> 6;
         const int g = (Kp >> 3) + half;                         // two extra groups of 8 columns
         s_bhi[g * 8 + (r >> 3) * (b_groups * 8) + (r & 7)] = make_uint4(half == 0 ? 0x00003f80u : 0u, 0u, 0u, 0u);   // bf16 1.0 at column K
@@ -117,11 +120,11 @@ tc_wgrad_kernel(const __grid_constant__ WgParams p, const int Mpad, const int Kp
             // Coalesced staging: within a warp, 8 lanes = the 8 rows of one row group, 4 lane groups = 4 consecutive
             // 8-channel pieces: a warp load touches 8 rows x 128 contiguous bytes (not 32 separate lines) and a warp store
             // writes 4 whole core matrices (conflict-free). Each thread keeps 4 pieces (8 + 8 float4 loads) in flight.
-            const int rr = lane & 7, gq = lane >> 3, wq = warp & 3;
+            const int rr = lane & 7, gq = lane >> 3, wq = warp & 7;
             const int blk_row0 = r_begin + blk * TW_RB;
             const int kgd = Kp >> 3;                                  // B groups that carry data
 #pragma unroll 1
-            for (int rg = wq; rg < TW_RB / 8; rg += 4) {
+            for (int rg = wq; rg < TW_RB / 8; rg += 8) {
                 const int rl = rg * 8 + rr, r = blk_row0 + rl;
                 const bool row_ok = r < r_end;
                 const long long grow = cloud_row + r;
@@ -219,8 +222,8 @@ tc_wgrad_kernel(const __grid_constant__ WgParams p, const int Mpad, const int Kp
             }
             fence_proxy_async();
             tc_fence_before();
-            wg_bar_sync(wg);
-            if ((warp & 3) == 0) {                         // first warp of the slot; one elected lane issues (uniform descriptors)
+            slot_bar_sync256(wg);
+            if ((warp & 7) == 0) {                         // first warp of the slot; one elected lane issues (uniform descriptors)
                 tc_fence_after();
                 if (elect_one_sync()) {
                 for (int mt = 0; mt < n_mt; ++mt) {
@@ -257,7 +260,7 @@ tc_wgrad_kernel(const __grid_constant__ WgParams p, const int Mpad, const int Kp
                 const uint32_t c_base = tmem_base + lane_addr + (uint32_t)(mt * Kext);
                 int ci = 0;
                 for (int c0 = 0; c0 < Kext; c0 += 32, ++ci) {
-                    if ((ci & 1) != wg) continue;
+                    if ((ci & 3) != (warp >> 2)) continue;       // the four warps of a TMEM lane quadrant take alternating chunks
                     uint32_t v0[32], v1[32];
                     tmem_ld32(c_base + (uint32_t)c0, v0);
                     if (two) tmem_ld32(c_base + 256u + (uint32_t)c0, v1);

@@ -1,13 +1,18 @@
+# One gpurun call: tests, smoke, default bench, reference arm, ncu launch lists and full captures -> gpurun_out/final/
 set -x
-mkdir -p gpurun_out/final
-timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -3 > gpurun_out/final/pytest_gpu.txt
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" > gpurun_out/final/smoke.txt 2>&1
-timeout 900 python bench.py > gpurun_out/final/bench_default.json 2> gpurun_out/final/bench_default.err
-timeout 600 python bench.py --impl reference > gpurun_out/final/bench_reference.json 2> gpurun_out/final/bench_reference.err
-for w in fwd fwd_bf16 train; do
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/final/l_$w.csv python bench.py --workload $w --only --no-cpu --steps 2 --warmup 1 > gpurun_out/final/ncu_$w.log 2>&1
+O=gpurun_out/final
+mkdir -p $O
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -3 > $O/pytest_gpu.txt
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" > $O/smoke.txt 2>&1
+timeout 900 python bench.py > $O/bench_default.json 2> $O/bench_default.err
+cp gpurun_out/bench_detail_n1.json $O/bench_detail_n1.json 2>/dev/null
+timeout 600 python bench.py --impl reference > $O/bench_reference.json 2> $O/bench_reference.err
+for w in fwd train fps; do
+  AMP_BENCH_EAGER_TRAIN=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $O/l_$w.csv python bench.py --workload $w --only --no-cpu --steps 2 --warmup 1 > $O/ncu_$w.log 2>&1
 done
-ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:tc_layer_kernelILi1E -s 9 -c 1 -o gpurun_out/final/prof_tc_layer_m1 python bench.py --workload train --only --no-cpu --steps 1 --warmup 1 > gpurun_out/final/ncu_tl.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:kmeans_assign -c 1 -o gpurun_out/final/prof_kmeans python bench.py --workload kmeans --only --no-cpu --steps 2 --warmup 1 > gpurun_out/final/ncu_km.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:tc_chain_kernel -s 8 -c 4 -o gpurun_out/final/prof_tc_chain python bench.py --workload fwd_bf16 --only --no-cpu --steps 1 --warmup 1 > gpurun_out/final/ncu_chain.log 2>&1
-tail -2 gpurun_out/final/pytest_gpu.txt; tail -1 gpurun_out/final/smoke.txt; wc -c gpurun_out/final/*.json
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:tc_chain32_kernel -s 10 -c 5 -o $O/prof_tc_chain32 python bench.py --workload fwd --only --no-cpu --steps 1 --warmup 1 > $O/ncu_chain32.log 2>&1
+AMP_BENCH_EAGER_TRAIN=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:tc_wgrad_kernel -s 15 -c 1 -o $O/prof_tc_wgrad python bench.py --workload train --only --no-cpu --steps 1 --warmup 1 > $O/ncu_wgrad.log 2>&1
+AMP_BENCH_EAGER_TRAIN=1 timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:tc_layer_kernelILi16E -s 10 -c 1 -o $O/prof_tc_layer_dgrad python bench.py --workload train --only --no-cpu --steps 1 --warmup 1 > $O/ncu_tl.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:kmeans_assign -c 1 -o $O/prof_kmeans python bench.py --workload kmeans --only --no-cpu --steps 2 --warmup 1 > $O/ncu_km.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:kmeans_window_fast -c 1 -o $O/prof_kmeans_window python bench.py --workload tile --only --no-cpu --steps 1 --warmup 1 > $O/ncu_kw.log 2>&1
+tail -2 $O/pytest_gpu.txt; tail -1 $O/smoke.txt; wc -c $O/*.json; ls -la $O

@@ -1,7 +1,7 @@
 import importlib, os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 amp = importlib.import_module("3d-semantic-segmentation-amp-net_b200")
-nb = importlib.import_module("3d-semantic-segmentation-amp-net_b200.nn_bench")
+import bench_nn as nb
 dev = torch.device("cuda:0")
 enc, seg = nb.build_modules(amp, dev, dropout=0.0); enc.train(); seg.train()
 x_np, c_np, t_np = nb.synthetic_blocks(0)

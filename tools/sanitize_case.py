@@ -2,7 +2,7 @@
 import importlib, os, sys, torch, numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 amp = importlib.import_module("3d-semantic-segmentation-amp-net_b200")
-nb = importlib.import_module("3d-semantic-segmentation-amp-net_b200.nn_bench")
+import bench_nn as nb
 dev = torch.device("cuda:0")
 rng = np.random.default_rng(0)
 pc = torch.from_numpy(rng.random((2, 3000, 11), dtype=np.float32)).to(dev)
