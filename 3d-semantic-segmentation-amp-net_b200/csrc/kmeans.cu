@@ -560,7 +560,7 @@ kmeans_regroup_kernel(const int* __restrict__ labels_all, const long long* __res
 
 }  // namespace
 // on-chip variant (kmeans_window.cu): 1 = launched, 0 = window too large, < 0 = error
-int kmeans_window_fast_cap(bool with_x);
+int kmeans_window_fast_cap(bool with_x, int kmax);
 int kmeans_window_fast_try(const float* feats, const long long* offsets, const int* ks, long long W, long long max_window_points, int kmax,
                            int size_min, int size_max, int max_iter, double tol, int n_init, int* labels, float* centroids, int* n_iter,
                            cudaStream_t st);
@@ -635,7 +635,7 @@ int amp_kmeans_constrained_f32(const float* feats, const int64_t* offsets, const
     }
     if (n_init > 1)
         return amp::fail(AMP_E_BADARG, "kmeans_constrained: n_init > 1 needs windows of at most %d points (the on-chip kernel)",
-                         amp::kmeans_window_fast_cap(false));
+                         amp::kmeans_window_fast_cap(false, kmax));
     int* prop = reinterpret_cast<int*>(workspace);
     float* pd = reinterpret_cast<float*>(prop + total_points);
     amp::kmeans_window_kernel<<<(unsigned)W, amp::kWinThreads, 0, (cudaStream_t)stream>>>(

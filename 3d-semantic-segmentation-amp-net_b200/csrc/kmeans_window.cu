@@ -42,7 +42,6 @@ struct WS {
     int done[kKMax];
     unsigned long long prefix[kKMax];
     int rank[kKMax];
-    unsigned hist[kKMax * 256];
     int red_bits[32];
     unsigned red_idx[32];
     int n_todo, n_open, flag, flag2, pick, best_it;
@@ -54,6 +53,8 @@ struct WS {
 
 struct State {                      // per-point state in shared memory
     float* pd; signed char* lab; signed char* prop; const float* x;   // x: shared copy (XS) or the global rows
+    unsigned* hist;                 // [kmax][256] radix histogram rows (sized by the launch's largest k, not by kKMax: 27 KB
+                                    // more for the points, which keeps 10 k-point windows' coordinates on chip)
 };
 
 __device__ __forceinline__ long long warp_sum_ll(long long v) {
@@ -134,7 +135,7 @@ __device__ void capacity_rounds(WS& s, const State& st, int n, int k) {
             // half run only if some cluster's cut falls inside a group of equal distances
             for (int pass = 0; pass < 8; ++pass) {
                 const int shift = 56 - 8 * pass;
-                for (int i = tid; i < k * 256; i += kT) s.hist[i] = 0u;
+                for (int i = tid; i < k * 256; i += kT) st.hist[i] = 0u;
                 if (tid == 0) s.flag2 = 0;
                 __syncthreads();
                 for (int i0 = 0; i0 < n; i0 += kT) {
@@ -151,12 +152,12 @@ __device__ void capacity_rounds(WS& s, const State& st, int n, int k) {
                     }
                     // top byte (sign + exponent): a handful of distinct digits per warp -> one aggregated atomic per digit;
                     // lower bytes are spread over the bins: plain atomics (match_any loops once per distinct value)
-                    if (pass == 0) agg_inc(s.hist, slot, act);
-                    else if (act) atomicAdd(s.hist + slot, 1u);
+                    if (pass == 0) agg_inc(st.hist, slot, act);
+                    else if (act) atomicAdd(st.hist + slot, 1u);
                 }
                 __syncthreads();
                 if (warp < k && s.over[warp] && !s.done[warp]) {        // one warp per cluster: lane owns 8 consecutive bins
-                    const volatile unsigned* h = s.hist + warp * 256 + lane * 8;     // (scalar loads: see the note at WS)
+                    const volatile unsigned* h = st.hist + warp * 256 + lane * 8;     // (scalar loads: see the note at WS)
                     int c[8], tot = 0;
 #pragma unroll
                     for (int b = 0; b < 8; ++b) { c[b] = (int)h[b]; tot += c[b]; }
@@ -280,7 +281,8 @@ kmeans_window_fast_kernel(const float* __restrict__ feats, const long long* __re
                           float* __restrict__ centroids, int* __restrict__ n_iter, int n_init) {
     extern __shared__ __align__(8) unsigned char smem[];
     WS& s = *reinterpret_cast<WS*>(smem);
-    float* s_pd = reinterpret_cast<float*>(smem + ((sizeof(WS) + 15) & ~(size_t)15));
+    unsigned* s_hist = reinterpret_cast<unsigned*>(smem + ((sizeof(WS) + 15) & ~(size_t)15));
+    float* s_pd = reinterpret_cast<float*>(s_hist + (size_t)kmax * 256);
     float* s_x = s_pd + cap;                                   // [3 * cap] when XS
     signed char* s_lab = reinterpret_cast<signed char*>(XS ? s_x + 3 * (size_t)cap : s_x);
     signed char* s_prop = s_lab + cap;
@@ -299,7 +301,7 @@ kmeans_window_fast_kernel(const float* __restrict__ feats, const long long* __re
         return;
     }
     if (XS) for (int i = tid; i < 3 * n; i += kT) s_x[i] = gx[i];
-    State st{s_pd, s_lab, s_prop, XS ? s_x : gx};
+    State st{s_pd, s_lab, s_prop, XS ? s_x : gx, s_hist};
 
     // ---- A. fixed-point moments -> tol_abs ----
     if (tid < 6) s.mom[tid] = 0ull;
@@ -443,14 +445,14 @@ kmeans_window_fast_kernel(const float* __restrict__ feats, const long long* __re
 }
 
 constexpr size_t kMaxSmem = 232448;
-inline size_t ws_bytes() { return (sizeof(WS) + 15) & ~(size_t)15; }
+inline size_t ws_bytes(int kmax) { return ((sizeof(WS) + 15) & ~(size_t)15) + (size_t)kmax * 256 * sizeof(unsigned); }
 
 }  // namespace
 
 // Largest window (points) the on-chip kernel takes: with the coordinates in shared memory, and without.
-int kmeans_window_fast_cap(bool with_x) {
+int kmeans_window_fast_cap(bool with_x, int kmax) {
     const size_t per = with_x ? 19 : 7;
-    return (int)(((kMaxSmem - ws_bytes() - 64) / per) & ~(size_t)15);
+    return (int)(((kMaxSmem - ws_bytes(kmax) - 64) / per) & ~(size_t)15);
 }
 
 // 1 = launched, 0 = window too large for the on-chip kernel (the caller runs kmeans_window_kernel), < 0 = error
@@ -458,10 +460,11 @@ int kmeans_window_fast_try(const float* feats, const long long* offsets, const i
                            int size_min, int size_max, int max_iter, double tol, int n_init, int* labels, float* centroids, int* n_iter,
                            cudaStream_t st) {
     if (path_disabled("kmeans_fast")) return 0;
-    const bool xs = max_window_points <= kmeans_window_fast_cap(true);
-    if (!xs && max_window_points > kmeans_window_fast_cap(false)) return 0;
+    if (kmax < 1 || kmax > kKMax) return 0;
+    const bool xs = max_window_points <= kmeans_window_fast_cap(true, kmax);
+    if (!xs && max_window_points > kmeans_window_fast_cap(false, kmax)) return 0;
     const int cap = (int)((max_window_points + 15) & ~15LL);
-    const size_t smem = ws_bytes() + (size_t)cap * (xs ? 19 : 7) + 64;
+    const size_t smem = ws_bytes(kmax) + (size_t)cap * (xs ? 19 : 7) + 64;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kmeans_window_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);

@@ -56,6 +56,9 @@ struct PwParams {
     // from the TILE mean (combined exactly by bn_finalize_train: no E[x^2] - mean^2 cancellation);
     // backward (mask_y given) = sum of dz and of dz * xhat
     float* part_sum; float* part_sq;
+    // optional scratch for the split-K path of the few-row kernels (long reductions, e.g. the 4096-wide gradient of the
+    // 64 x 64 transform's fc_3): (K / 32) * Nout * 32 floats
+    float* splitk_ws; size_t splitk_floats;
 };
 
 int pw_linear(const PwParams& p, cudaStream_t st);

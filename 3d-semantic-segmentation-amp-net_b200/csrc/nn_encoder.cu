@@ -213,6 +213,7 @@ int bwd_step(EncCtx& c, const float* dz, int Nout, int L_out, const float* y_out
     p.n_groups = 1;
     p.accumulate = accumulate;
     p.Y = dA; p.ldy = ldda; p.n_clouds = clouds; p.rows_per_cloud = rows; p.Nout = K;
+    p.splitk_ws = c.wg; p.splitk_floats = c.wg_floats;         // (the weight-gradient partials above have been reduced: stream order)
     const bool mask = L_in >= 0 && !defer;
     if (mask) {
         p.mask_y = A; p.ld_mask = lda; p.mask_scale = c.S.scale + oi; p.mask_shift = c.pf(kEncBnParam[L_in] + BN_B);

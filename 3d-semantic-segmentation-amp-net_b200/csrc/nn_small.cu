@@ -208,17 +208,18 @@ __global__ void __launch_bounds__(256) small_wgrad_kernel(const WgParams p) {
 // Narrow input (K <= 16: the 3 xyz / 9 raw feature columns, per-cloud or shared weights) over many rows, exact fp32:
 // memory bound on dy'. One CTA per (cloud, slab) partial of wgrad_reduce_kernel; thread == (output channel n, row phase),
 // the slab's input rows sit in shared memory, the row phases are added in a fixed order.
-constexpr int NW_MAXK = 16, NW_SLAB_MAX = 512;
-__global__ void __launch_bounds__(256) narrow_wgrad_kernel(const WgParams p, int slabs, int SLAB) {
+constexpr int NW_MAXK = 16, NW_SLAB_MAX = 512, NW_T = 512;   // 16 warps: the kernel is bound by the latency of its dy' loads
+__global__ void __launch_bounds__(NW_T) narrow_wgrad_kernel(const WgParams p, int slabs, int SLAB) {
     pdl_sync();
-    __shared__ float as[NW_SLAB_MAX * NW_MAXK];                  // input rows of the slab; reused for the phase partials
+    // input rows of the slab; reused for the phase partials (NW_T x (NW_MAXK + 1) floats)
+    __shared__ float as[(NW_SLAB_MAX * NW_MAXK > NW_T * (NW_MAXK + 1)) ? NW_SLAB_MAX * NW_MAXK : NW_T * (NW_MAXK + 1)];
     float* red = as;
     const int tid = threadIdx.x;
     const int K = p.K, N = p.Nout, rows = p.rows_per_cloud;
     const int unit = blockIdx.x, cloud = unit / slabs, slab = unit - cloud * slabs;
     const int r_begin = slab * SLAB, r_end = min(rows, r_begin + SLAB);
     const long long cloud_row = (long long)cloud * rows;
-    for (int e = tid; e < (r_end - r_begin) * K; e += 256) {
+    for (int e = tid; e < (r_end - r_begin) * K; e += NW_T) {
         const int r = e / K, k = e - r * K;
         float v = __ldg(p.A + (cloud_row + r_begin + r) * p.lda + k);
         if (p.a_a) v = fmaf(v - (p.a_m ? __ldg(p.a_m + k) : 0.f), __ldg(p.a_a + k), __ldg(p.a_b + k));
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(256) narrow_wgrad_kernel(const WgParams p, int
         as[e] = v;
     }
     __syncthreads();
-    const int phases = 256 / N, n = tid % N, ph = tid / N;       // N in {64, 128, 256}
+    const int phases = NW_T / N, n = tid % N, ph = tid / N;      // N in {64, 128, 256}
     float acc[NW_MAXK], bsum = 0.f;
 #pragma unroll
     for (int k = 0; k < NW_MAXK; ++k) acc[k] = 0.f;
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(256) narrow_wgrad_kernel(const WgParams p, int
     red[tid * (NW_MAXK + 1) + NW_MAXK] = bsum;
     __syncthreads();
     float* part = p.partials + (long long)unit * ((long long)N * K + N);
-    for (int e = tid; e < N * (K + 1); e += 256) {
+    for (int e = tid; e < N * (K + 1); e += NW_T) {
         const int nn = e / (K + 1), k = e - nn * (K + 1);
         float s = 0.f;
         for (int q = 0; q < phases; ++q) s += red[(q * N + nn) * (NW_MAXK + 1) + (k < K ? k : NW_MAXK)];
@@ -731,10 +732,60 @@ int narrow_wgrad_try(const WgParams& p, int slabs, int SLAB, cudaStream_t st) {
     if (path_disabled("narrow_wgrad")) return 0;
     if (p.K > NW_MAXK || SLAB > NW_SLAB_MAX || p.dy_transposed || p.a_drop_p != 0.f) return 0;
     if (p.Nout != 64 && p.Nout != 128 && p.Nout != 256) return 0;
-    launch_pdl(narrow_wgrad_kernel, dim3((unsigned)(p.n_clouds * slabs)), dim3(256), 0, st, p, slabs, SLAB);
+    launch_pdl(narrow_wgrad_kernel, dim3((unsigned)(p.n_clouds * slabs)), dim3(NW_T), 0, st, p, slabs, SLAB);
     count_launch();
     const int rc = check_launch("narrow_wgrad");
     return rc == AMP_OK ? 1 : rc;
+}
+
+// Split-K pair for few rows (<= 32) and a long reduction with transposed weights W[k][n] (input gradients of wide FC
+// layers: 32 x 4096 -> 128 took 78 us as eight serial 512-wide chunks on 16 CTAs): one CTA per 32-wide reduction slice
+// writes a partial [Nout][32 rows]; the second kernel adds the slices in a fixed order (deterministic) and runs the epilogue.
+constexpr int SK_KS = 32;
+__global__ void __launch_bounds__(128) small_splitk_kernel(const PwParams p, float* __restrict__ part) {
+    pdl_sync();
+    __shared__ __align__(16) float xs[32][SK_KS + 4];
+    const int tid = threadIdx.x, M = p.rows_per_cloud, N = p.Nout;
+    const int s = blockIdx.x, k0 = s * SK_KS;
+    for (int e = tid; e < 32 * SK_KS; e += 128) {
+        const int r = e / SK_KS, k = e - r * SK_KS;
+        xs[r][k] = r < M ? __ldg(p.X + (long long)r * p.ldx + k0 + k) : 0.f;
+    }
+    __syncthreads();
+    for (int n = tid; n < N; n += 128) {
+        float w[SK_KS];
+#pragma unroll
+        for (int k = 0; k < SK_KS; ++k) w[k] = __ldg(p.W + (long long)(k0 + k) * p.ldw + n);
+        float* dst = part + ((long long)s * N + n) * 32;
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k4 = 0; k4 < SK_KS / 4; ++k4) {
+                const float4 x = *reinterpret_cast<const float4*>(&xs[r][4 * k4]);
+                acc = fmaf(x.x, w[4 * k4], acc); acc = fmaf(x.y, w[4 * k4 + 1], acc);
+                acc = fmaf(x.z, w[4 * k4 + 2], acc); acc = fmaf(x.w, w[4 * k4 + 3], acc);
+            }
+            dst[r] = acc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) small_splitk_reduce_kernel(const PwParams p, const float* __restrict__ part, int n_slices) {
+    pdl_sync();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * 8 + warp, N = p.Nout;
+    if (n >= N) return;
+    float v = 0.f;
+    for (int s0 = 0; s0 < n_slices; s0 += 16) {                  // 16 loads in flight, added in slice order
+        float t[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) t[u] = s0 + u < n_slices ? part[((long long)(s0 + u) * N + n) * 32 + lane] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v += t[u];
+    }
+    const SmallEpi epi{p, p.rows_per_cloud, 0};
+    epi.run(v, lane, n);
 }
 
 int small_linear_try(const PwParams& p, cudaStream_t st) {
@@ -745,6 +796,15 @@ int small_linear_try(const PwParams& p, cudaStream_t st) {
     const bool stats = p.part_sum != nullptr;
     if ((stats || p.mask_y) && p.rows_per_cloud > SM_ROWS) return 0;      // the warp-level sums cover one 32-row tile
     const dim3 grid_rows((p.rows_per_cloud + SM_ROWS - 1) / SM_ROWS);
+    if (p.w_kn && !p.bias && p.K >= 1024 && p.K % SK_KS == 0 && p.rows_per_cloud <= 32 && !p.in_a && !p.X2 && !p.in_relu && p.splitk_ws &&
+        p.splitk_floats >= (size_t)(p.K / SK_KS) * p.Nout * 32 && !path_disabled("small_splitk")) {
+        const int n_slices = p.K / SK_KS;
+        launch_pdl(small_splitk_kernel, dim3((unsigned)n_slices), dim3(128), 0, st, p, p.splitk_ws);
+        launch_pdl(small_splitk_reduce_kernel, dim3((unsigned)((p.Nout + 7) / 8)), dim3(256), 0, st, p, (const float*)p.splitk_ws, n_slices);
+        count_launch(2);
+        const int rc = check_launch("small_splitk");
+        return rc == AMP_OK ? 1 : rc;
+    }
     {
         if (p.w_kn && p.bias) return 0;
         dim3 grid((p.Nout + SM_COLS - 1) / SM_COLS, grid_rows.x);
