@@ -16,4 +16,5 @@ from .assembly import assemble_windows, draw_augmentation  # noqa: F401
 from .blockstore import BlockStore, BlockStoreWriter, convert_kmeans_pt_files  # noqa: F401
 from .tensorcore import tc_linear, linear_wgrad  # noqa: F401
 from .graphstep import GraphedStep  # noqa: F401
+from .optim import FusedAdam  # noqa: F401
 

@@ -19,6 +19,8 @@ SIGNATURES = {
     "amp_launch_count": (_i64, []),
     "amp_path_count": (_i64, [_c.c_char_p]),
     "amp_set_dropout_offset": (_c.c_int, [_c.c_void_p]),
+    "amp_adam_chunk_elems": (_i32, []),
+    "amp_adam_step": (_c.c_int, [_vp, _i64, _vp, _f32, _f32, _f32, _f32, _vp]),
     "amp_debug_set_disabled": (_c.c_int, [_c.c_char_p]),
     "amp_fps_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "amp_fps_f32": (_c.c_int, [_vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),

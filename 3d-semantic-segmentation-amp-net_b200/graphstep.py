@@ -30,6 +30,7 @@ class GraphedStep:
             for _ in range(warmup):
                 self._one()
         torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)     # warm-up work is done: host-side staging buffers may be rewritten during capture
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._one()

@@ -157,8 +157,15 @@ def bench_train(dist, amp, steps, warmup, with_cpu):
         for p in params:
             torch.distributed.broadcast(p.data, 0)
     # the script's two Adam optimizers (train_pointnet-attention.py:141-142), torch's fused multi-tensor implementation
-    opt_e = torch.optim.Adam(enc.parameters(), lr=1e-3, fused=True, capturable=True)
-    opt_s = torch.optim.Adam(seg.parameters(), lr=1e-3, fused=True, capturable=True)
+    # the script's two Adam optimizers (train_pointnet-attention.py:141-142) as amp.FusedAdam: one launch per optimizer step
+    # (AMP_BENCH_TORCH_ADAM=1: torch's fused multi-tensor implementation instead)
+    torch_adam = os.environ.get("AMP_BENCH_TORCH_ADAM") == "1"
+    if torch_adam:
+        opt_e = torch.optim.Adam(enc.parameters(), lr=1e-3, fused=True, capturable=True)
+        opt_s = torch.optim.Adam(seg.parameters(), lr=1e-3, fused=True, capturable=True)
+    else:
+        opt_e = amp.FusedAdam(enc.parameters(), lr=1e-3)
+        opt_s = amp.FusedAdam(seg.parameters(), lr=1e-3)
     ce = torch.nn.CrossEntropyLoss(weight=torch.tensor([1., 2., 2., 1., 1.], device=dev), reduction="mean", ignore_index=-1)
     x_np, c_np, t_np = synthetic_blocks(dist.rank)
     x_host, c_host, t_host = (torch.from_numpy(a).pin_memory() for a in (x_np, c_np, t_np))
@@ -221,7 +228,7 @@ def bench_train(dist, amp, steps, warmup, with_cpu):
                      "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": src,
                      "model": "3 x 413 143 algorithmic FLOP per point (SURVEY 8d) x 65 536 points / step time"},
         "config": {"workload": "configs[2]: training step fwd+loss+bwd+2xAdam, batch %d x %d points per GPU" % (NN_BATCH, NN_POINTS)},
-        "notes": {"l2": "flushed between steps (256 MiB write)", "precision": "fp32", "dropout": 0.3, "adam": "torch fused",
+        "notes": {"l2": "flushed between steps (256 MiB write)", "precision": "fp32", "dropout": 0.3, "adam": "torch fused" if torch_adam else "amp.FusedAdam (one launch per optimizer)",
                   "launch": ("CUDA graph replay of the whole step (eager: %.3f ms per step)" % (eager_ms / steps)) if graphed is not None
                             else "eager",
                   "collective": "NCCL gradient all-reduce (AVG, one flat buffer)" if dist.pg else "none (1 GPU)"},
@@ -246,8 +253,8 @@ def bench_train_w9(dist, amp, steps, warmup, with_cpu):
     if dist.pg:
         for p in params:
             torch.distributed.broadcast(p.data, 0)
-    opt_e = torch.optim.Adam(enc.parameters(), lr=1e-3, fused=True)
-    opt_s = torch.optim.Adam(seg.parameters(), lr=1e-3, fused=True)
+    opt_e = amp.FusedAdam(enc.parameters(), lr=1e-3)
+    opt_s = amp.FusedAdam(seg.parameters(), lr=1e-3)
     ce = torch.nn.CrossEntropyLoss(weight=torch.tensor([1., 2., 2., 1., 1.], device=dev), reduction="mean", ignore_index=-1)
     rng = np.random.default_rng(5000 + dist.rank)
     pc = rng.random((B, N, NN_DIMS, W), dtype=np.float32)

@@ -268,6 +268,20 @@ size_t amp_wgrad_workspace_bytes(int64_t n_clouds, int64_t rows_per_cloud, int32
 int amp_wgrad_f32(const float* dy, const float* a, int64_t n_clouds, int64_t rows_per_cloud, int32_t N, int32_t K, float* dw,
                   float* db, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Adam step over a list of tensors in one launch.  Replaces `optimizer_pointnet.step()` / `optimizer_att.step()`
+ * (train_pointnet-attention.py:468-469; torch.optim.Adam built at :141-142 with lr only: betas (0.9, 0.999), eps 1e-8, no
+ * weight decay, no amsgrad) when the loop uses ampnet_b200.FusedAdam.
+ *   chunk_table  device array of n_chunks records {float* p; const float* g; float* m; float* v; int32 n; int32 tensor} (40 bytes):
+ *                consecutive pieces of at most amp_adam_chunk_elems() elements of tensor number `tensor` each
+ *   steps        device int64 per tensor: updates done so far; this one uses t = steps[tensor] + 1 (bias corrections
+ *                1 - beta^t, counted per parameter like torch: a tensor without a gradient is not stepped). The caller
+ *                increments the counters of the tensors it passed afterwards.
+ * ------------------------------------------------------------------------------------------ */
+int32_t amp_adam_chunk_elems(void);
+int amp_adam_step(const void* chunk_table, int64_t n_chunks, const int64_t* steps, float lr, float beta1, float beta2, float eps,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -540,3 +540,23 @@ def test_graphed_training_step_redraws_dropout_and_trains(amp, cuda):
     assert _rel(seen[0][1], seen[1][1]) > 1e-3               # consecutive replays: different dropout masks
     assert not torch.equal(w0, seg.conv_3.weight)            # the optimizers ran inside the graph
     assert seen[-1][0] < seen[0][0] * 1.5                    # and did not blow the loss up
+
+
+def test_fused_adam_matches_torch_adam(amp, cuda):
+    """amp.FusedAdam (one launch for all tensors) against torch.optim.Adam with the reference's settings (train_...:141-142)."""
+    torch.manual_seed(3)
+    shapes = [(64, 12, 1), (64,), (256, 128, 1), (4096, 128), (5,), (1,), (129, 3), (768, 256)]
+    pa = [torch.nn.Parameter(torch.randn(s, device=cuda)) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    oa = amp.FusedAdam(pa, lr=1e-3)
+    ob = torch.optim.Adam(pb, lr=1e-3)
+    for it in range(6):
+        for a, b in zip(pa, pb):
+            g = torch.randn_like(a) * (10.0 ** (it - 3))
+            a.grad = g.clone(); b.grad = g.clone()
+        if it == 3:
+            pa[2].grad = None; pb[2].grad = None            # a tensor without a gradient is skipped, as in torch
+        oa.step(); ob.step()
+        oa.zero_grad(set_to_none=True); ob.zero_grad(set_to_none=True)
+    for a, b in zip(pa, pb):
+        assert torch.allclose(a, b, rtol=2e-6, atol=1e-7), (a.shape, float((a - b).abs().max()))
