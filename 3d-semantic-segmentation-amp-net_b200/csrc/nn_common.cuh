@@ -100,6 +100,18 @@ struct WgParams {
     float* partials; size_t partial_floats;   // workspace from wgrad_workspace_floats()
 };
 size_t wgrad_workspace_floats(int n_clouds, int rows_per_cloud, int Nout, int K, int slab_rows = 0);
+// Deferred reduction of weight-gradient partials. While a scope is alive on the calling thread, wgrad() runs only the partial
+// pass of a PARAMETER gradient (per_cloud == 0, accumulate == 0, no dbg: nothing else in the backward reads the result) into its own
+// slice of `pool` and queues the fixed-order reduction; flush() reduces all queued jobs in ONE launch (a backward pass has
+// ~13 of them, each a few microseconds of pure launch latency). Jobs that do not fit are reduced at once as before.
+struct WgDeferScope {
+    WgDeferScope(float* pool, size_t pool_floats, cudaStream_t st);
+    ~WgDeferScope();                    // drops the scope; queued jobs must have been flushed (flush() returns the error code)
+    int flush();
+    WgDeferScope(const WgDeferScope&) = delete;
+    WgDeferScope& operator=(const WgDeferScope&) = delete;
+    float* pool; size_t pool_floats, used; cudaStream_t st; WgDeferScope* prev;
+};
 int wgrad_group_slab(const int* group_sizes, int n_groups);
 int wgrad(const WgParams& p, cudaStream_t st);
 int small_wgrad_try(const WgParams& p, cudaStream_t st);   // nn_small.cu

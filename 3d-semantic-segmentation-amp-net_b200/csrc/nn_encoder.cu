@@ -152,6 +152,7 @@ size_t fwd_ws_bytes(long long B, long long N, bool training) {
 
 struct BwdWs {
     float *gA, *gB, *g64, *dG, *dF, *dT, *dW1eff, *d_f2, *d_f1, *dpool, *colsum;
+    float* wg_pool; size_t wg_pool_floats;       // slices for the deferred weight-gradient reductions (WgDeferScope)
 };
 
 size_t wg_floats_needed(long long B, long long N) {
@@ -177,6 +178,10 @@ BwdWs bwd_carve(Arena& a, EncCtx* c, long long B, long long N) {
     w.dW1eff = a.take<float>(B * 576); w.d_f2 = a.take<float>(B * 128); w.d_f1 = a.take<float>(B * 256);
     w.dpool = a.take<float>(B * 256);
     w.colsum = a.take<float>(colsum_scratch_floats((int)B, (int)N, 256));
+    // every parameter gradient of one backward pass keeps its partials until the common reduction: sum over the layers
+    // of clouds x slabs x (Nout x K + Nout) = 4.7 x the largest layer (256 x 128)
+    w.wg_pool_floats = 5 * wgrad_workspace_floats((int)B, (int)N, 256, 128) + 64 * 32;
+    w.wg_pool = a.take<float>(w.wg_pool_floats);
     return w;
 }
 
@@ -707,6 +712,7 @@ int amp_encoder_bwd(const void* const* params, void* const* grads, const float* 
     const int Bi = c.B, Ni = c.N;
     const size_t M = (size_t)B * N;
     const float* local = out + 256;
+    WgDeferScope defer(w.wg_pool, w.wg_pool_floats, c.st);     // parameter-gradient reductions: one launch at the end
 
     // out = [G broadcast | local]: dG = column sums of d_out[:, :, :256]
     AMP_TRY(colsum_rows(d_out, 320, Bi, Ni, 256, w.dG, w.colsum, c.st));
@@ -753,8 +759,9 @@ int amp_encoder_bwd(const void* const* params, void* const* grads, const float* 
         AMP_TRY(fold_input_transform_bwd(w.dW1eff, c.pf(E_CONV1), S.T, Bi, c.gf(E_CONV1), w.dT, c.st));
     }
     // input T-Net (no input gradient: x is data)
-    return tnet_bwd(c, w, E_IT, L_IT1, 3, w.dT, S.it_y1, S.it_y2, S.it_y3, S.it_pool, S.it_arg, S.it_f1, S.it_f2, x, 9, 3, -1,
-                    nullptr, 0, w.gB, w.gA);
+    AMP_TRY(tnet_bwd(c, w, E_IT, L_IT1, 3, w.dT, S.it_y1, S.it_y2, S.it_y3, S.it_pool, S.it_arg, S.it_f1, S.it_f2, x, 9, 3, -1,
+                     nullptr, 0, w.gB, w.gA));
+    return defer.flush();
 }
 
 }  // extern "C"

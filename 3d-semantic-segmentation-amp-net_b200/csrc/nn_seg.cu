@@ -63,6 +63,7 @@ struct SegWs {
     unsigned char* tc_blob;                                     // bf16 tensor-core path: packed head weights + bias K groups
     unsigned char* pack32;                                      // fp32-class fused path without a caller-owned pack cache
     float *part_sum, *part_sq, *k1, *k2, *k3, *wg; size_t wg_floats;
+    float* wg_pool; size_t wg_pool_floats;
     float *dz3, *dz2, *dcb, *dg_w, *dattn_o, *dqkv, *dtokens, *dpre;
 };
 
@@ -89,6 +90,8 @@ SegWs seg_ws_carve(Arena& a, long long B, long long W, long long R, int E, int h
     w.k1 = a.take<float>(kSegBnTotal); w.k2 = a.take<float>(kSegBnTotal); w.k3 = a.take<float>(kSegBnTotal);
     w.wg_floats = seg_wg_floats(B, W, R, E, hid);
     w.wg = a.take<float>(w.wg_floats);
+    w.wg_pool_floats = 2 * w.wg_floats + 64 * 16;              // deferred parameter-gradient reductions (WgDeferScope)
+    w.wg_pool = a.take<float>(w.wg_pool_floats);
     w.dz3 = a.take<float>(M * 64); w.dz2 = a.take<float>(M * hid);
     w.dcb = a.take<float>(T * hid); w.dg_w = a.take<float>(T * E); w.dattn_o = a.take<float>(T * E);
     w.dqkv = a.take<float>(T * 3 * E); w.dtokens = a.take<float>(T * E); w.dpre = a.take<float>(T * 16);
@@ -367,6 +370,7 @@ int amp_seg_bwd(const void* const* params, void* const* grads, const float* lo_f
     SegWs ws = seg_ws_carve(wa, B, W, rows, E, hid, true);
     const int tiles = pw_tiles(Bi, Ri);
     const long long count = (long long)Bi * Ri;
+    WgDeferScope defer(ws.wg_pool, ws.wg_pool_floats, st);       // parameter-gradient reductions: one launch at the end
 
     // conv_4: dW4 / db4 from the [B, C, rows] logit gradients; d a3 -> dropout, relu mask, bn_3 sums
     {
@@ -462,8 +466,9 @@ int amp_seg_bwd(const void* const* params, void* const* grads, const float* lo_f
         AMP_TRY(pw_linear(p, st));
     }
     // positional encoding
-    return posenc_bwd(ws.dtokens, centroids, S.h_pre, pf(params, S_FC2W), Bi, Wi, E, d_gl_feats, ws.dpre, gf(grads, S_FC1W),
-                      gf(grads, S_FC1B), gf(grads, S_FC2W), gf(grads, S_FC2B), st);
+    AMP_TRY(posenc_bwd(ws.dtokens, centroids, S.h_pre, pf(params, S_FC2W), Bi, Wi, E, d_gl_feats, ws.dpre, gf(grads, S_FC1W),
+                      gf(grads, S_FC1B), gf(grads, S_FC2W), gf(grads, S_FC2B), st));
+    return defer.flush();
 }
 
 }  // extern "C"

@@ -136,9 +136,7 @@ __device__ __forceinline__ float chunk_sum(const float* __restrict__ src, long l
 // A block reduces 32 consecutive outputs: lanes = outputs (coalesced reads of every partial), the 8 warps take 8 consecutive
 // slices of the chunk list, so a thread's loads are all in flight at once and even a 64 x 64 layer fills the machine; the
 // slices are then added in a fixed order (deterministic).
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgParams p, int slabs, int SLAB) {
-    pdl_sync();
-    __shared__ float red[8][32];
+__device__ __forceinline__ void wgrad_reduce_body(const WgParams& p, int slabs, int SLAB, long long vblock, long long vgrid, float (*red)[32]) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long per = (long long)p.Nout * p.K + p.Nout;
     const int out_clouds = p.per_cloud ? p.n_clouds : 1;
@@ -147,7 +145,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgParams p, int
     const long long n_g = p.dbg ? (long long)p.n_clouds * p.n_groups * p.Nout : 0;
     const long long count = (long long)(p.per_cloud ? 1 : p.n_clouds) * slabs;       // chunks per output
     const long long cs = (count + 7) / 8, ch_lo = min(count, w * cs), ch_hi = min(count, ch_lo + cs);
-    for (long long base = (long long)blockIdx.x * 32; base < n_w + n_b; base += (long long)gridDim.x * 32) {
+    for (long long base = vblock * 32; base < n_w + n_b; base += vgrid * 32) {
         const long long i = base + lane;
         const float* src = nullptr;
         float* dst = nullptr;
@@ -172,7 +170,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgParams p, int
         __syncthreads();
     }
     // per-(cloud, block) bias gradients of the head: a handful of slabs each
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n_g; e += (long long)gridDim.x * blockDim.x) {
+    for (long long e = vblock * (long long)blockDim.x + threadIdx.x; e < n_g; e += vgrid * blockDim.x) {
         const int n = (int)(e % p.Nout), g = (int)((e / p.Nout) % p.n_groups), c = (int)(e / ((long long)p.Nout * p.n_groups));
         const int r_lo = p.group_rows[g], r_hi = (g + 1 < p.n_groups) ? p.group_rows[g + 1] : p.rows_per_cloud;
         float s = 0.f;
@@ -182,6 +180,28 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgParams p, int
     }
 }
 
+
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgParams p, int slabs, int SLAB) {
+    pdl_sync();
+    __shared__ float red[8][32];
+    wgrad_reduce_body(p, slabs, SLAB, blockIdx.x, gridDim.x, red);
+}
+
+// the queued reductions of a WgDeferScope in one launch: block -> (job, block within the job)
+constexpr int kWgMaxJobs = 24;
+struct WgJobs { int n; int block_end[kWgMaxJobs]; int slabs[kWgMaxJobs]; int SLAB[kWgMaxJobs]; WgParams p[kWgMaxJobs]; };
+__global__ void __launch_bounds__(256) wgrad_reduce_jobs_kernel(const __grid_constant__ WgJobs jobs) {
+    pdl_sync();
+    __shared__ float red[8][32];
+    int j = 0;
+    while (j + 1 < jobs.n && (int)blockIdx.x >= jobs.block_end[j]) ++j;       // block-uniform
+    const int b0 = j ? jobs.block_end[j - 1] : 0;
+    wgrad_reduce_body(jobs.p[j], jobs.slabs[j], jobs.SLAB[j], (int)blockIdx.x - b0, jobs.block_end[j] - b0, red);
+}
+
+thread_local WgDeferScope* t_defer = nullptr;
+thread_local WgJobs t_jobs;
+
 }  // namespace
 
 size_t wgrad_workspace_floats(int n_clouds, int rows_per_cloud, int Nout, int K, int slab_rows) {
@@ -190,8 +210,39 @@ size_t wgrad_workspace_floats(int n_clouds, int rows_per_cloud, int Nout, int K,
     return (size_t)n_clouds * slabs * ((size_t)Nout * K + Nout);
 }
 
-int wgrad(const WgParams& p, cudaStream_t st) {
-    if (!p.dY || !p.A || !p.dW || !p.partials) return fail(AMP_E_BADARG, "wgrad: null operand");
+WgDeferScope::WgDeferScope(float* pool_, size_t pool_floats_, cudaStream_t st_) : pool(pool_), pool_floats(pool_floats_), used(0), st(st_), prev(t_defer) {
+    t_defer = this;
+    t_jobs.n = 0;
+}
+WgDeferScope::~WgDeferScope() { t_defer = prev; }
+int WgDeferScope::flush() {
+    WgJobs& jb = t_jobs;
+    used = 0;
+    if (jb.n == 0) return AMP_OK;
+    const int blocks = jb.block_end[jb.n - 1];
+    launch_pdl(wgrad_reduce_jobs_kernel, dim3((unsigned)blocks), dim3(256), 0, st, jb);
+    jb.n = 0;
+    count_launch();
+    return check_launch("wgrad_reduce_jobs");
+}
+
+int wgrad(const WgParams& p_in, cudaStream_t st) {
+    if (!p_in.dY || !p_in.A || !p_in.dW || !p_in.partials) return fail(AMP_E_BADARG, "wgrad: null operand");
+    // a parameter gradient inside a WgDeferScope: partials into a slice of the scope's pool, reduction queued
+    WgParams p = p_in;
+    bool deferred = false;
+    if (t_defer && t_defer->st == st && !p.per_cloud && !p.accumulate && !p.dbg && p.n_clouds >= 1 && p.rows_per_cloud >= 1 && p.Nout >= 1 && p.K >= 1) {
+        const size_t need = (wgrad_workspace_floats(p.n_clouds, p.rows_per_cloud, p.Nout, p.K, p.slab_rows) + 63) & ~(size_t)63;
+        if (need <= t_defer->pool_floats) {
+            if (t_defer->used + need > t_defer->pool_floats || t_jobs.n == kWgMaxJobs) {
+                const int rc = t_defer->flush();
+                if (rc != AMP_OK) return rc;
+            }
+            p.partials = t_defer->pool + t_defer->used;
+            p.partial_floats = need;
+            deferred = true;
+        }
+    }
     if (p.K < 1 || p.Nout < 1 || p.n_clouds < 1 || p.rows_per_cloud < 1) return fail(AMP_E_BADARG, "wgrad: bad shape");
     if (p.n_clouds > 65535) return fail(AMP_E_BADARG, "wgrad: more than 65535 clouds in one launch");
     const int SLAB = p.slab_rows > 0 ? p.slab_rows : kDefaultSlab;
@@ -203,7 +254,7 @@ int wgrad(const WgParams& p, cudaStream_t st) {
     if (p.dbg && (!p.group_rows || p.n_groups < 1)) return fail(AMP_E_BADARG, "wgrad: dbg needs group_rows");
     const int slabs = (p.rows_per_cloud + SLAB - 1) / SLAB;
     const int n_tiles = (p.Nout + TNo - 1) / TNo, k_tiles = (p.K + TKo - 1) / TKo;
-    int rc = small_wgrad_try(p, st);                     // few rows: direct deterministic kernel, no partials (nn_small.cu)
+    int rc = small_wgrad_try(p_in, st);                  // few rows: direct deterministic kernel, no partials (nn_small.cu)
     if (rc != 0) return rc < 0 ? rc : AMP_OK;
     rc = narrow_wgrad_try(p, slabs, SLAB, st);           // K <= 16 over many rows: memory-bound exact fp32 partial pass
     if (rc == 0) rc = narrow_out_wgrad_try(p, slabs, SLAB, st);   // Nout <= 8 (class logits)
@@ -221,6 +272,14 @@ int wgrad(const WgParams& p, cudaStream_t st) {
                             (p.dbg ? (long long)p.n_clouds * p.n_groups * p.Nout : 0);
     long long blocks = (total + 31) / 32;                  // 32 outputs per block
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    if (deferred) {
+        WgJobs& jb = t_jobs;
+        const int j = jb.n++;
+        jb.p[j] = p; jb.slabs[j] = slabs; jb.SLAB[j] = SLAB;
+        jb.block_end[j] = (j ? jb.block_end[j - 1] : 0) + (int)blocks;
+        t_defer->used += p.partial_floats;
+        return AMP_OK;
+    }
     launch_pdl(wgrad_reduce_kernel, dim3((unsigned)((unsigned)blocks)), dim3(256), 0, st, p, slabs, SLAB);
     count_launch();
     return check_launch("wgrad_reduce");
