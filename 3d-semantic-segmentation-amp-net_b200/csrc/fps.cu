@@ -305,7 +305,7 @@ fps_cluster_kernel(const T* __restrict__ pc, int P, long long row_stride, int S,
         const T wd = warp_max(bd);
         if (lane == 0) s_wmax[par * NW + warp] = wd;
         __syncthreads();
-        const T wm = s_wmax[par * NW + lane];
+        const T wm = (NW == 32 || lane < NW) ? s_wmax[par * NW + (lane & (NW - 1))] : (T)-1;
         const T cm = warp_max(wm);
         const int n_tied = __popc(__ballot_sync(0xffffffffu, wm == cm));     // warps that carry the CTA maximum (uniform over the CTA)
         if (tid == 0) s_tie[par ^ 1] = kNoIdx;                               // the other parity's cell: nobody reads or writes it now
@@ -418,16 +418,19 @@ __global__ void gather_rows_kernel(const T* __restrict__ pc, long long P, long l
     }
 }
 
-constexpr int kThreads = 1024;
-constexpr int kRS = 2;
-template <typename T> struct MaxDS { static constexpr int v = 18; };
-template <> struct MaxDS<double> { static constexpr int v = 8; };
+// 512 threads per CTA (16 warps, 128 registers per thread): with 40 slots per thread instead of 20, twelve of them (not
+// two) keep their coordinates in registers, so a pick reads 28 x 512 x 12 B = 172 KB of shared memory per SM instead of
+// 221 KB (the shared-memory port is what bounds the slot loop), and the block barrier, the redux steps and the rescan of
+// a pick run in half as many warps. (RS, DS) variants keep small clouds from looping over absent slots.
+constexpr int kThreads = 512;
+template <typename T> struct MaxSlots { static constexpr int rs = 12, ds = 28; };     // 40 slots x 512 threads = 20 480 points per CTA
+template <> struct MaxSlots<double> { static constexpr int rs = 4, ds = 16; };         // 20 slots x 512 threads = 10 240 points per CTA
 
-template <typename T, int DS, int LC>
+template <typename T, int RS, int DS, int LC>
 int launch_kernel(const T* pc, int64_t B, int P, int64_t row_stride, int S, int start_idx,
                   int64_t* out_idx, int32_t* status, T* ovf, int ovf_slots, int log2C,
                   cudaStream_t st) {
-    auto kern = fps_cluster_kernel<T, kThreads, kRS, DS, LC>;
+    auto kern = fps_cluster_kernel<T, kThreads, RS, DS, LC>;
     const size_t n_cand = (size_t)(kThreads / 32) << log2C;
     size_t smem = (size_t)3 * DS * kThreads * sizeof(T) + 2 * n_cand * (4 * sizeof(T) + 4) + 8 + 16;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -454,24 +457,24 @@ int launch_kernel(const T* pc, int64_t B, int P, int64_t row_stride, int S, int 
     return AMP_OK;
 }
 
-template <typename T, int DS>
+template <typename T, int RS, int DS>
 int launch_variant(const T* pc, int64_t B, int P, int64_t row_stride, int S, int start_idx,
                    int64_t* out_idx, int32_t* status, T* ovf, int ovf_slots, int log2C,
                    cudaStream_t st) {
     if constexpr (sizeof(T) == 4) {
         switch (log2C) {
-            case 0: return launch_kernel<T, DS, 0>(pc, B, P, row_stride, S, start_idx, out_idx, status, ovf, ovf_slots, log2C, st);
-            case 1: return launch_kernel<T, DS, 1>(pc, B, P, row_stride, S, start_idx, out_idx, status, ovf, ovf_slots, log2C, st);
-            case 2: return launch_kernel<T, DS, 2>(pc, B, P, row_stride, S, start_idx, out_idx, status, ovf, ovf_slots, log2C, st);
-            default: return launch_kernel<T, DS, 3>(pc, B, P, row_stride, S, start_idx, out_idx, status, ovf, ovf_slots, log2C, st);
+            case 0: return launch_kernel<T, RS, DS, 0>(pc, B, P, row_stride, S, start_idx, out_idx, status, ovf, ovf_slots, log2C, st);
+            case 1: return launch_kernel<T, RS, DS, 1>(pc, B, P, row_stride, S, start_idx, out_idx, status, ovf, ovf_slots, log2C, st);
+            case 2: return launch_kernel<T, RS, DS, 2>(pc, B, P, row_stride, S, start_idx, out_idx, status, ovf, ovf_slots, log2C, st);
+            default: return launch_kernel<T, RS, DS, 3>(pc, B, P, row_stride, S, start_idx, out_idx, status, ovf, ovf_slots, log2C, st);
         }
     } else {
-        return launch_kernel<T, DS, -1>(pc, B, P, row_stride, S, start_idx, out_idx, status, ovf, ovf_slots, log2C, st);
+        return launch_kernel<T, RS, DS, -1>(pc, B, P, row_stride, S, start_idx, out_idx, status, ovf, ovf_slots, log2C, st);
     }
 }
 
 template <typename T>
-int64_t cap_per_cta(int ds) { return (int64_t)(kRS + ds) * kThreads; }
+int64_t cap_per_cta() { return (int64_t)(MaxSlots<T>::rs + MaxSlots<T>::ds) * kThreads; }
 
 // cluster size: fill the 148 SMs, then grow until the cloud fits on chip (max 8 CTAs)
 template <typename T>
@@ -479,7 +482,7 @@ int choose_log2C(int64_t B, int64_t P) {
     int lc = 0;
     while (lc < 3 && B * (2LL << lc) <= kNumSMs) ++lc;
     while (lc > 0 && P < ((int64_t)kThreads << lc)) --lc;
-    while (lc < 3 && (cap_per_cta<T>(MaxDS<T>::v) << lc) < P) ++lc;
+    while (lc < 3 && (cap_per_cta<T>() << lc) < P) ++lc;
     return lc;
 }
 
@@ -500,7 +503,7 @@ int fps_impl(const T* pc, int64_t B, int64_t P, int64_t row_stride, int32_t S, i
     const int64_t per_cta = (P + (1LL << lc) - 1) >> lc;
     int ovf_slots = 0;
     T* ovf = nullptr;
-    const int64_t cap = cap_per_cta<T>(MaxDS<T>::v);
+    const int64_t cap = cap_per_cta<T>();
     if (per_cta > cap) {
         ovf_slots = (int)((per_cta - cap + kThreads - 1) / kThreads);
         size_t need = (size_t)B * (1u << lc) * ovf_slots * 4 * kThreads * sizeof(T);
@@ -509,20 +512,26 @@ int fps_impl(const T* pc, int64_t B, int64_t P, int64_t row_stride, int32_t S, i
         ovf = reinterpret_cast<T*>(ws);
     }
     const int slots = (int)((per_cta + kThreads - 1) / kThreads);   // slots actually needed per thread
-#define AMP_FPS_VARIANT(DS_)                                                                     \
-    if (slots <= kRS + DS_ && DS_ <= MaxDS<T>::v)                                                \
-        return launch_variant<T, (DS_ <= MaxDS<T>::v ? DS_ : 0)>(pc, B, (int)P, row_stride, S,   \
-                                                                 start_idx, out_idx, status, ovf, \
-                                                                 ovf_slots, lc, st);
-    AMP_FPS_VARIANT(0)
-    AMP_FPS_VARIANT(2)
-    AMP_FPS_VARIANT(6)
-    AMP_FPS_VARIANT(8)
-    AMP_FPS_VARIANT(10)
-    AMP_FPS_VARIANT(18)
+#define AMP_FPS_VARIANT(RS_, DS_)                                                                \
+    if (slots <= RS_ + DS_)                                                                      \
+        return launch_variant<T, RS_, DS_>(pc, B, (int)P, row_stride, S, start_idx, out_idx, status, ovf, ovf_slots, lc, st);
+    if constexpr (sizeof(T) == 4) {
+        AMP_FPS_VARIANT(2, 0)
+        AMP_FPS_VARIANT(4, 0)
+        AMP_FPS_VARIANT(8, 0)
+        AMP_FPS_VARIANT(12, 0)
+        AMP_FPS_VARIANT(12, 4)
+        AMP_FPS_VARIANT(12, 8)
+        AMP_FPS_VARIANT(12, 16)
+    } else {
+        AMP_FPS_VARIANT(2, 0)
+        AMP_FPS_VARIANT(4, 0)
+        AMP_FPS_VARIANT(4, 4)
+        AMP_FPS_VARIANT(4, 8)
+    }
 #undef AMP_FPS_VARIANT
-    return launch_variant<T, MaxDS<T>::v>(pc, B, (int)P, row_stride, S, start_idx, out_idx, status,
-                                          ovf, ovf_slots, lc, st);
+    return launch_variant<T, MaxSlots<T>::rs, MaxSlots<T>::ds>(pc, B, (int)P, row_stride, S, start_idx, out_idx, status,
+                                                               ovf, ovf_slots, lc, st);
 }
 
 }  // namespace
@@ -537,8 +546,7 @@ extern "C" int amp_fps_prof_dump(long long* out) {
 extern "C" {
 
 size_t amp_fps_workspace_bytes(int64_t B, int64_t P, int32_t elem_bytes) {
-    const int64_t cap = (elem_bytes == 8 ? amp::cap_per_cta<double>(amp::MaxDS<double>::v)
-                                         : amp::cap_per_cta<float>(amp::MaxDS<float>::v));
+    const int64_t cap = (elem_bytes == 8 ? amp::cap_per_cta<double>() : amp::cap_per_cta<float>());
     if (P <= 8 * cap) return 0;
     const int64_t per_cta = (P + 7) / 8;
     const int64_t ovf_slots = (per_cta - cap + amp::kThreads - 1) / amp::kThreads;

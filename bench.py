@@ -39,8 +39,8 @@ PKG = "3d-semantic-segmentation-amp-net_b200"
 
 FPS_CLOUDS, FPS_POINTS, FPS_DIMS, FPS_SAMPLES = 64, 40000, 11, 2048
 # fps_cluster_kernel as built: thread instructions per (candidate, pick) and DRAM bytes per 64-cloud launch, from ncu
-FPS_WARP_INST_PER_UPDATE, FPS_DRAM_BYTES_PER_LAUNCH, FPS_NCU_SOURCE = 14.8, 122.3e6, "profiles/r02_fps_ncu_full.txt"
-FPS_SMEM_SLOT_FRACTION = 18.0 / 20.0        # configs[1]: 20 slots per thread, 18 of them in shared memory (2 in registers)
+FPS_WARP_INST_PER_UPDATE, FPS_DRAM_BYTES_PER_LAUNCH, FPS_NCU_SOURCE = 11.0, 119.6e6, "profiles/r02_fps_ncu_full.txt"
+FPS_SMEM_SLOT_FRACTION = 28.0 / 40.0        # configs[1]: 40 slots per thread, 28 of them in shared memory (12 in registers)
 NN_BATCH, NN_POINTS, NN_DIMS = 32, 2048, 9
 
 
@@ -216,8 +216,8 @@ def bench_fps(dist, amp, steps, warmup, with_cpu):
     clouds = FPS_CLOUDS * dist.world * steps
     # Roofline of fps_cluster_kernel: the whole cloud lives on chip (registers + shared memory; ncu: dram bytes = 0.2 % of the
     # HBM model's), so HBM bounds nothing. The binding resource is the shared-memory read port: every pick reads the 12-byte
-    # coordinates of every shared-memory-resident candidate once (ncu: the LSU shared pipe is 68 % busy over the active
-    # cycles, the issue slots 56 %). achieved = algorithmic shared-memory bytes / kernel time, peak = 128 B per clock per SM.
+    # coordinates of every shared-memory-resident candidate once (ncu: the LSU shared pipe is 57 % busy over the active
+    # cycles, the issue slots 50 %; the packed-FFMA2 pipe needs about as many cycles per pick). achieved = algorithmic shared-memory bytes / kernel time, peak = 128 B per clock per SM.
     sm_mhz = clock_mhz()
     smem_bytes = 12.0 * FPS_SMEM_SLOT_FRACTION * (FPS_SAMPLES - 1) * FPS_POINTS * FPS_CLOUDS
     ach = smem_bytes / (k_ms / steps * 1e-3) / 1e9
