@@ -462,6 +462,13 @@ def main():
             if name == args.workload:
                 continue
             try:
+                # every workload starts from an empty caching allocator: blocks cached by the previous one (hundreds of MB of
+                # training workspace) otherwise make the next one's first allocations fall back to cudaFree + cudaMalloc
+                # inside its timed steps
+                import gc
+                gc.collect()
+                torch.cuda.synchronize()
+                torch.cuda.empty_cache()
                 r = table[name](dist, amp, max(3, args.steps // 2), 3, with_cpu)
             except Exception as e:  # a secondary workload must not take the headline down
                 r = {"error": repr(e)[:160]}

@@ -420,7 +420,7 @@ def bench_tile(dist, amp, steps, warmup, with_cpu, precision="fp32"):
             out.setdefault("host", {})[k] = pr.to("cpu", non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    e_ms = _timed(dist, step_e2e, max(2, steps // 2), 1, flush)
+    e_ms = _timed(dist, step_e2e, max(2, steps // 2), 3, flush)
     es = max(2, steps // 2)
     n_pts = TILE_POINTS
     n_rows = int(sum(len(w) for w in wins))
