@@ -51,11 +51,29 @@ def gather_feats(pc, cols):
 N_INIT = 5        # the reference's KMeansConstrained(n_init=5) (3_kmeans.py:78-80, utils.py:500-503)
 
 
-def kmeans_constrained_windows(feats, offsets, ks, size_min=0, size_max=0, max_iter=10, tol=1e-2, n_init=1):
+_WINDOW_TABLES = {}
+
+
+def _window_tables(offsets, ks, dev):
+    """Device copies of the window offsets / cluster counts, cached by content: a tile is usually split with the same window
+    list call after call, and two small pageable host-to-device copies per call are two stream synchronisations."""
+    key = (offsets.tobytes(), ks.tobytes(), str(dev))
+    hit = _WINDOW_TABLES.get(key)
+    if hit is None:
+        if len(_WINDOW_TABLES) > 64:
+            _WINDOW_TABLES.clear()
+        hit = (torch.from_numpy(offsets.copy()).to(dev), torch.from_numpy(ks.copy()).to(dev))
+        _WINDOW_TABLES[key] = hit
+    return hit
+
+
+def kmeans_constrained_windows(feats, offsets, ks, size_min=0, size_max=0, max_iter=10, tol=1e-2, n_init=1, check_range=True):
     """Constrained k-means of W independent windows in one launch.
 
     feats [total,3] CUDA f32; offsets: W+1 ints (host list/array); ks: W ints (host).
-    Returns (labels int32 [total], centroids f32 [W,kmax,3], n_iter int32 [W]) on the device."""
+    Returns (labels int32 [total], centroids f32 [W,kmax,3], n_iter int32 [W]) on the device.
+    check_range=False skips the fixed-point range check of the features (one device-to-host read, i.e. a stream
+    synchronisation per call) for callers that know their columns are normalised."""
     _lib.require_cuda(feats, "feats", torch.float32)
     offsets = np.asarray(offsets, dtype=np.int64)
     ks = np.asarray(ks, dtype=np.int32)
@@ -78,13 +96,12 @@ def kmeans_constrained_windows(feats, offsets, ks, size_min=0, size_max=0, max_i
     dev = feats.device
     # fixed-point sums (rint(x * 2^32) in int64, csrc/kmeans.cu): sum |x| and sum x^2 of a window must stay below 2^31. The
     # reference clusters normalised columns ([-1, 1] coordinates, [0, 1] features); raw UTM coordinates would wrap silently.
-    amax = float(feats.abs().max()) if total else 0.0
+    amax = float(feats.abs().max()) if (total and check_range) else 0.0
     if not np.isfinite(amax) or amax * amax * float(sizes.max()) >= 2.0 ** 31 or amax * float(sizes.max()) >= 2.0 ** 31:
         raise ValueError("kmeans: clustering features must be finite and normalised (max |x| = %g over windows of up to %d points "
                          "overflows the fixed-point centroid sums); normalise the columns first as "
                          "data_proc/2_preprocessing_filter_norm.py does" % (amax, int(sizes.max())))
-    d_off = torch.from_numpy(offsets).to(dev)
-    d_ks = torch.from_numpy(ks).to(dev)
+    d_off, d_ks = _window_tables(offsets, ks, dev)
     labels = torch.empty((total,), dtype=torch.int32, device=dev)
     cent = torch.empty((W, kmax, 3), dtype=torch.float32, device=dev)
     n_iter = torch.empty((W,), dtype=torch.int32, device=dev)
@@ -106,8 +123,7 @@ def regroup_windows(labels, offsets, ks, pc=None):
     ks = np.asarray(ks, dtype=np.int32)
     W, kmax = len(ks), int(ks.max())
     dev = labels.device
-    d_off = torch.from_numpy(offsets).to(dev)
-    d_ks = torch.from_numpy(ks).to(dev)
+    d_off, d_ks = _window_tables(offsets, ks, dev)
     order = torch.empty((labels.shape[0],), dtype=torch.int64, device=dev)
     counts = torch.empty((W, kmax), dtype=torch.int32, device=dev)
     xy = None

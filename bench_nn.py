@@ -368,6 +368,10 @@ def bench_tile(dist, amp, steps, warmup, with_cpu, precision="fp32"):
     wins, ks, real = synthetic_tile()
     lo_w, hi_w = amp.shard_windows(ks, dist.world)[dist.rank]
     wins, ks, real = wins[lo_w:hi_w], ks[lo_w:hi_w], real[lo_w:hi_w]
+    # the rank walks its windows in order of block count (windows are independent): the blocks of every block-count group are
+    # then one contiguous range of the encoder output and the attention / head call reads them in place
+    by = sorted(range(len(ks)), key=lambda i: ks[i])
+    wins, ks, real = [wins[i] for i in by], [ks[i] for i in by], [real[i] for i in by]
     flush = _Flush(dev)
     out = {}
     if len(wins):
@@ -377,6 +381,10 @@ def bench_tile(dist, amp, steps, warmup, with_cpu, precision="fp32"):
         by_k = {}
         for i, k in enumerate(ks):
             by_k.setdefault(k, []).append(i)
+        # block / window index tensors of every block-count group: they depend on the window list only, not on the step
+        blk0 = np.concatenate([[0], np.cumsum(ks)])
+        rng_of = {k: (int(blk0[idx[0]]), int(blk0[idx[-1]] + k)) for k, idx in by_k.items()}      # block range of the group
+        win_of = {k: (idx[0], idx[-1] + 1) for k, idx in by_k.items()}                               # window range of the group
     ev = {}
 
     def step(pc_dev):
@@ -385,26 +393,21 @@ def bench_tile(dist, amp, steps, warmup, with_cpu, precision="fp32"):
         ev["a"] = torch.cuda.Event(enable_timing=True); ev["b"] = torch.cuda.Event(enable_timing=True)
         ev["a"].record()
         feats = amp.gather_feats(pc_dev, (0, 1, 9))                                   # 3_kmeans.py:81
-        labels, _, _ = amp.kmeans_constrained_windows(feats, offsets, ks, NN_POINTS, NN_POINTS)
+        labels, _, _ = amp.kmeans_constrained_windows(feats, offsets, ks, NN_POINTS, NN_POINTS, check_range=False)   # columns in [-1, 1] / [0, 1]
         order, _, xy = amp.regroup_windows(labels, offsets, ks, pc_dev)
         ev["b"].record()
         grouped = pc_dev.index_select(0, order)                                       # rows sorted by (window, block)
         x9 = torch.cat((grouped[:, 0:3], grouped[:, 4:10]), 1)                        # datasets.py:342 keeps cols 0:3, 4:10
         x9[:, :2] = x9[:, :2] * 2 - 1                                                 # datasets.py:378-379
         blocks = x9.view(-1, NN_POINTS, NN_DIMS)
-        feats_out = []
-        for b0 in range(0, blocks.shape[0], 256):                                     # encoder over all blocks, 256 per call
-            o, _ = enc(blocks[b0:b0 + 256])
-            feats_out.append(o)
-        enc_out = torch.cat(feats_out, 0)
-        blk0 = np.concatenate([[0], np.cumsum(ks)])
+        enc_out, _ = enc(blocks)                                                      # encoder over all blocks of the rank
         preds = {}
         for k, idx in by_k.items():                                                   # windows of equal block count together
-            sel = torch.as_tensor(np.concatenate([np.arange(blk0[i], blk0[i] + k) for i in idx]), device=dev)
-            e = enc_out.index_select(0, sel).view(len(idx), k, NN_POINTS, 320)
+            b_lo, b_hi = rng_of[k]
+            e = enc_out[b_lo:b_hi].view(len(idx), k, NN_POINTS, 320)                  # a view: no copy of the 320-wide rows
             gl = e[:, :, 0, :256].permute(1, 0, 2).contiguous()                       # [k, B, 256]
-            lo = e[:, :, :, 256:].reshape(len(idx), k * NN_POINTS, 64)
-            cent = xy[torch.as_tensor(idx, device=dev), :k, :]
+            lo = e.view(len(idx), k * NN_POINTS, 320)[:, :, 256:]                     # row-strided slice, read in place by seg
+            cent = xy[win_of[k][0]:win_of[k][1], :k, :]
             logits, _ = seg(gl, lo, cent, [NN_POINTS] * k, None)
             preds[k] = logits.argmax(1)
         out["preds"] = preds
