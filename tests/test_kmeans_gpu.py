@@ -202,3 +202,19 @@ def test_restarts_keep_the_lowest_inertia_and_match_the_oracle(amp, cuda):
         i5 = ko.inertia_fixed(xs, got, cent5[w, :ks[w]].cpu().numpy())
         i1 = ko.inertia_fixed(xs, lab1[offsets[w]:offsets[w + 1]].cpu().numpy(), cent1[w, :ks[w]].cpu().numpy())
         assert i5 <= i1
+
+
+def test_window_tables_are_cached_by_content_and_range_check_is_optional(amp, cuda):
+    """The device copies of (offsets, ks) are cached by content: the same window list twice, then a different one with the
+    same point count, must each give the oracle's labels; check_range=False skips only the host-side range check."""
+    rng = np.random.default_rng(31)
+    x = rng.random((2048 * 6, 3), dtype=np.float32); x[:, :2] = x[:, :2] * 2 - 1
+    d = torch.from_numpy(x).to(cuda)
+    for offs, ks in (([0, 2048 * 2, 2048 * 6], [2, 4]), ([0, 2048 * 2, 2048 * 6], [2, 4]), ([0, 2048 * 3, 2048 * 6], [3, 3])):
+        lab, _, _ = amp.kmeans_constrained_windows(d, offs, ks, 2048, 2048, check_range=False)
+        order, counts, _ = amp.regroup_windows(lab, offs, ks)
+        lab = lab.cpu().numpy()
+        for w, k in enumerate(ks):
+            e, _, _ = ko.kmeans_constrained(x[offs[w]:offs[w + 1]], k, 2048, 2048)
+            assert (lab[offs[w]:offs[w + 1]] == e).all(), (offs, ks, w)
+            assert (counts.cpu().numpy()[w, :k] == 2048).all()
