@@ -72,6 +72,21 @@ __global__ void __launch_bounds__(256) small_fwd_kernel(const PwParams p) {
     for (int k0 = 0; k0 < K; k0 += KC) {
         const int kc = min(KC, K - k0);
         if (k0) __syncthreads();
+        // the weight loads of this chunk (2 columns x up to 16 lane-strided elements) do not depend on the input rows: they are
+        // issued first, so that their latency overlaps the staging of the rows below (these layers are latency bound)
+        float wv[SM_CPW][SM_MAXK / 32];
+#pragma unroll
+        for (int j = 0; j < SM_CPW; ++j) {
+            const int n = blockIdx.x * SM_COLS + warp + 8 * j;
+            // w_kn == 0: W[n][k] (a contiguous row per output); w_kn == 1: W[k][n] (transposed weights of the backward)
+            const float* __restrict__ w = p.w_kn ? p.W + (long long)k0 * p.ldw + n : p.W + (long long)n * p.ldw + k0;
+            const long long ws = p.w_kn ? p.ldw : 1;
+#pragma unroll
+            for (int i = 0; i < SM_MAXK / 32; ++i) {
+                const int kk = lane + 32 * i;
+                wv[j][i] = (n < N && kk < kc) ? __ldg(w + kk * ws) : 0.f;
+            }
+        }
         for (int kk = tid; kk < kc; kk += 256) {  // thread == input channel: prologue constants once, 32 independent row loads
             const int k = k0 + kk;
             const float m = p.in_m ? __ldg(p.in_m + k) : 0.f, a = p.in_a ? __ldg(p.in_a + k) : 1.f, b = p.in_b ? __ldg(p.in_b + k) : 0.f;
@@ -93,21 +108,6 @@ __global__ void __launch_bounds__(256) small_fwd_kernel(const PwParams p) {
             }
         }
         __syncthreads();
-        // all weight loads of this chunk (2 columns x up to 16 lane-strided elements) are issued before the first FMA:
-        // these layers are latency bound, not bandwidth bound
-        float wv[SM_CPW][SM_MAXK / 32];
-#pragma unroll
-        for (int j = 0; j < SM_CPW; ++j) {
-            const int n = blockIdx.x * SM_COLS + warp + 8 * j;
-            // w_kn == 0: W[n][k] (a contiguous row per output); w_kn == 1: W[k][n] (transposed weights of the backward)
-            const float* __restrict__ w = p.w_kn ? p.W + (long long)k0 * p.ldw + n : p.W + (long long)n * p.ldw + k0;
-            const long long ws = p.w_kn ? p.ldw : 1;
-#pragma unroll
-            for (int i = 0; i < SM_MAXK / 32; ++i) {
-                const int kk = lane + 32 * i;
-                wv[j][i] = (n < N && kk < kc) ? __ldg(w + kk * ws) : 0.f;
-            }
-        }
 #pragma unroll
         for (int i = 0; i < SM_MAXK / 32; ++i) {
             const int kk = lane + 32 * i;
