@@ -1,6 +1,6 @@
 // Farthest-point sampling for sm_100a: one thread-block CLUSTER per cloud, the cloud resident
 // on chip for the whole run (coordinates in registers + shared memory, running min-distance in
-// registers), no block-wide or cluster-wide barrier inside a pick.
+// registers), no cluster-wide barrier inside a pick.
 //
 // Replaces utils/utils.py:889-933 `fps` (reference). Semantics are those pinned by
 // oracle/fps_oracle.py: start index given, picked points leave the candidate set, lowest index
@@ -11,19 +11,19 @@
 //   slots [0, RS)         x,y,z and min-dist in registers
 //   slots [RS, RS+DS)     x,y,z in shared memory (pairs of slots per 8-byte entry, conflict-free), min-dist in registers
 //   slots >= RS+DS        x,y,z,min-dist in a global workspace (only for P > 8 * capacity)
-// A pick, per thread: the subtract-square-add chain of TWO slots at a time on packed fp32 pairs (FFMA2, bit-identical
-// to the scalar operations), one min and one max per slot (FMNMX: the slot of the maximum is NOT tracked in the loop). Per warp: redux argmax of the value; the
-// lane(s) that hold it rescan their slots for the lowest one, a second redux takes the lowest
-// index; the winning lane posts (d, index, x, y, z) into the candidate table of EVERY CTA of the
-// cluster, its own included, with st.async -- a remote shared-memory store that completes
-// transaction bytes on the receiver's mbarrier. Every warp then waits on its CTA's mbarrier and
-// reduces the NW * C candidates itself (lanes = candidates, redux again). There is no
-// __syncthreads and no barrier.cluster in the loop (round 1 had one of each per pick; the cluster
-// barrier alone carried a MEMBAR.ALL.GPU). The candidate tables and mbarriers are double
-// buffered by pick parity: a CTA can only post pick s + 2 after it has seen all posts of pick
-// s + 1, which every warp of every peer sends after it has finished reading pick s.
-// The thread that owns the picked point retires it (d = -1) before the next pick, outside the
-// slot loop.
+// A pick:
+//   * per thread: the subtract-square-add chain of TWO slots at a time on packed fp32 pairs (FFMA2, bit-identical to the
+//     scalar operations), one min and one max per slot (FMNMX: the slot of the maximum is NOT tracked in the loop);
+//   * per CTA: warp maxima by redux -> shared memory -> ONE block barrier -> every warp reduces the NW values. Only the
+//     warp that carries the CTA maximum rescans its slots (lowest slot per lane, lowest index over the lanes by a second
+//     redux) and its winning lane posts ONE candidate (d, index, x, y, z) into the table of EVERY CTA of the cluster, its own
+//     included, with st.async -- a remote shared-memory store that completes transaction bytes on the receiver's
+//     mbarrier. Equal maxima in several warps (rare): a shared-memory atomicMin on the index and a second block barrier;
+//   * every thread waits on its CTA's mbarrier and picks the best of the C candidates itself.
+// There is no barrier.cluster in the loop (round 1 had one per pick, with its MEMBAR.ALL.GPU). The candidate tables and
+// mbarriers are double buffered by pick parity: a CTA can only post pick s + 2 after it has seen all posts of pick s + 1,
+// which every peer sends after all its threads have passed the block barrier of pick s + 1, i.e. after they have read the
+// candidates of pick s. The thread that owns the picked point retires it (d = -1) before the next pick, outside the loop.
 #include <cooperative_groups.h>
 
 #include "amp_common.cuh"
