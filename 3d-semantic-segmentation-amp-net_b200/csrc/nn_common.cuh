@@ -56,6 +56,10 @@ struct PwParams {
     // from the TILE mean (combined exactly by bn_finalize_train: no E[x^2] - mean^2 cancellation);
     // backward (mask_y given) = sum of dz and of dz * xhat
     float* part_sum; float* part_sq;
+    // optional: the tensor-core layer kernel also writes the split 16-bit operand it builds from X (after the prologue) to
+    // global memory, per 128-row tile: [tile][hi, lo][K / 8][128 rows] 16-byte pieces of 8 consecutive channels. The weight
+    // gradient of the same layer reads it back instead of redoing the prologue and the split (WgParams::dy_split).
+    void* split_dump;
     // optional scratch for the split-K path of the few-row kernels (long reductions, e.g. the 4096-wide gradient of the
     // 64 x 64 transform's fc_3): (K / 32) * Nout * 32 floats
     float* splitk_ws; size_t splitk_floats;
@@ -98,7 +102,12 @@ struct WgParams {
     const int* group_rows; int n_groups; float* dbg;
     int slab_rows;                      // rows per partial (0 = 512); must divide every group size when dbg is used
     float* partials; size_t partial_floats;   // workspace from wgrad_workspace_floats()
+    // optional: dy' already split into bf16 hi + lo by the input-gradient kernel of the same layer (PwParams::split_dump
+    // layout, tiles of 128 rows per cloud); dY / Y2 / y_* are then not read by the tensor-core kernel
+    const void* dy_split;
 };
+// did the last tensor-core layer launch of this thread write its PwParams::split_dump? (reset by the caller)
+bool& tc_layer_dumped();
 size_t wgrad_workspace_floats(int n_clouds, int rows_per_cloud, int Nout, int K, int slab_rows = 0);
 // Deferred reduction of weight-gradient partials. While a scope is alive on the calling thread, wgrad() runs only the partial
 // pass of a PARAMETER gradient (per_cloud == 0, accumulate == 0, no dbg: nothing else in the backward reads the result) into its own

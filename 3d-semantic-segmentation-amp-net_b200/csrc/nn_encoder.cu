@@ -32,6 +32,7 @@ struct EncCtx {
     // backward-only
     float *k1, *k2, *k3;        // BatchNorm-backward coefficient tables [kEncBnTotal]
     float* wg; size_t wg_floats;
+    void* split_dump;           // [tiles][hi, lo][<= 32 groups][128 rows] x 16 B: dy' of the layer being differentiated, split bf16
     const float* pf(int i) const { return reinterpret_cast<const float*>(P[i]); }
     float* gf(int i) const { return reinterpret_cast<float*>(Gd[i]); }
 };
@@ -182,6 +183,9 @@ BwdWs bwd_carve(Arena& a, EncCtx* c, long long B, long long N) {
     // of clouds x slabs x (Nout x K + Nout) = 4.7 x the largest layer (256 x 128)
     w.wg_pool_floats = 5 * wgrad_workspace_floats((int)B, (int)N, 256, 128) + 64 * 32;
     w.wg_pool = a.take<float>(w.wg_pool_floats);
+    // the input-gradient kernel leaves dy' (split bf16, up to 256 channels) here for the weight gradient of the same layer
+    void* dump = a.take<unsigned char>(tiles * (size_t)(2 * 32 * 128 * 16));
+    if (c) c->split_dump = dump;
     return w;
 }
 
@@ -209,8 +213,7 @@ int bwd_step(EncCtx& c, const float* dz, int Nout, int L_out, const float* y_out
     g.n_clouds = clouds; g.rows_per_cloud = rows;
     g.dW = dW; g.ldw = K; g.db = db;
     g.partials = c.wg; g.partial_floats = c.wg_floats;
-    AMP_TRY(wgrad(g, c.st));
-    if (!dA) return AMP_OK;
+    if (!dA) return wgrad(g, c.st);
     PwParams p{};
     p.X = dz; p.ldx = Nout; p.K = Nout;
     if (L_out >= 0) { p.in_a = c.k1 + oo; p.in_b = c.k3 + oo; p.in_c = c.k2 + oo; p.in_m = c.S.mean + oo; p.X2 = y_out; }
@@ -225,9 +228,16 @@ int bwd_step(EncCtx& c, const float* dz, int Nout, int L_out, const float* y_out
         p.mask_mean = c.S.mean + oi; p.mask_invstd = c.S.invstd + oi;
         p.part_sum = c.part_sum; p.part_sq = c.part_sq;
     }
+    // The input gradient runs first: its tensor-core kernel builds dy' = bn_backward(dz) split into bf16 hi + lo as its own
+    // operand and leaves a copy in c.split_dump, which the weight-gradient kernel of this layer then copies instead of
+    // reading dz and y_out again and redoing the prologue and the split (two thirds of its instructions for a 256-wide dy').
+    const bool want_dump = c.split_dump && Nout % 8 == 0 && Nout <= 256 && !path_disabled("wgrad_presplit");
+    if (want_dump) p.split_dump = c.split_dump;
+    tc_layer_dumped() = false;
     AMP_TRY(pw_linear(p, c.st));
+    if (want_dump && tc_layer_dumped()) g.dy_split = c.split_dump;
     if (mask) AMP_TRY(bwd_finalize(c, L_in, pw_tiles(clouds, rows), (long long)clouds * rows));
-    return AMP_OK;
+    return wgrad(g, c.st);
 }
 
 // backward of max-pool over the rows + ReLU + BatchNorm of the pooled layer L (raw output y [M, 256])

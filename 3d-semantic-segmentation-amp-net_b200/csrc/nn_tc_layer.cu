@@ -293,7 +293,15 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[j] = 0.f;
                         }
-                        split_store8<H16>(v, dhi + r, dlo + r);
+                        uint4 h4, l4;
+                        split_pair<H16>(v[0], v[1], h4.x, l4.x); split_pair<H16>(v[2], v[3], h4.y, l4.y);
+                        split_pair<H16>(v[4], v[5], h4.z, l4.z); split_pair<H16>(v[6], v[7], h4.w, l4.w);
+                        dhi[r] = h4; dlo[r] = l4;
+                        if (p.split_dump) {                    // [tile][hi, lo][K / 8][128 rows]: a warp writes 512 contiguous bytes
+                            uint4* g = reinterpret_cast<uint4*>(p.split_dump) + ((tile * 2) * (long long)(K >> 3) + (kc * ng + cg)) * TL_ROWS + r;
+                            g[0] = h4;
+                            g[(long long)(K >> 3) * TL_ROWS] = l4;
+                        }
                     }
                 }
             }
@@ -523,6 +531,11 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
 
 }  // namespace
 
+bool& tc_layer_dumped() {
+    static thread_local bool flag = false;
+    return flag;
+}
+
 // Large-row path of pw_linear(): returns 1 when the launch was taken, 0 when the shape is not eligible, < 0 on error.
 int tc_layer_try(const PwParams& p, cudaStream_t st) {
     if (path_disabled("tc_layer")) return 0;
@@ -590,6 +603,7 @@ int tc_layer_try(const PwParams& p, cudaStream_t st) {
     }
     count_launch();
     count_path("tc_layer");
+    if (p.split_dump) tc_layer_dumped() = true;
     if (mode & TL_MASK) count_path("tc_layer_dgrad");
     const int rc = check_launch("tc_layer_kernel");
     return rc == AMP_OK ? 1 : rc;

@@ -93,6 +93,17 @@ tc_wgrad_kernel(const __grid_constant__ WgParams p, const int Mpad, const int Kp
         s_bhi[g * 8 + (r >> 3) * (b_groups * 8) + (r & 7)] = make_uint4(half == 0 ? 0x00003f80u : 0u, 0u, 0u, 0u);   // bf16 1.0 at column K
         s_blo[g * 8 + (r >> 3) * (b_groups * 8) + (r & 7)] = make_uint4(0u, 0u, 0u, 0u);
     }
+    // dy' pre-split by the input-gradient kernel (WgParams::dy_split): the A operand of a block is copied, not computed.
+    // Its shared-memory layout is then [channel group][64 rows] 16-byte pieces (the dump's order): MN groups 1024 B apart,
+    // row groups 128 B apart. Groups past Nout / 8 (M is padded to 128) are zeroed once and never written again.
+    const bool pre_split = p.dy_split != nullptr;
+    const int a_real_groups = Nout >> 3;
+    if (pre_split) {
+        for (int e = wtid; e < (a_groups - a_real_groups) * TW_RB; e += 256) {
+            s_ahi[a_real_groups * TW_RB + e] = make_uint4(0u, 0u, 0u, 0u);
+            s_alo[a_real_groups * TW_RB + e] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -105,6 +116,7 @@ tc_wgrad_kernel(const __grid_constant__ WgParams p, const int Mpad, const int Kp
     const uint32_t a_lbo = (uint32_t)a_groups * 128u, b_lbo = (uint32_t)b_groups * 128u;
     const uint32_t idesc = umma_idesc_mn(128, Kext);
     const bool y_pro = p.y_a != nullptr, a_pro = p.a_a != nullptr;
+    const int tpc_dump = (rows + 127) >> 7;
     uint32_t phase = 0;
     const int n_units = p.n_clouds * slabs;
 
@@ -123,6 +135,20 @@ tc_wgrad_kernel(const __grid_constant__ WgParams p, const int Mpad, const int Kp
             const int rr = lane & 7, gq = lane >> 3, wq = warp & 7;
             const int blk_row0 = r_begin + blk * TW_RB;
             const int kgd = Kp >> 3;                                  // B groups that carry data
+            if (pre_split) {
+                // rows [blk_row0, blk_row0 + 64) of the cloud = one half of dump tile blk_row0 / 128, 1 KB contiguous per channel
+                // group; the copies run while the B operand is staged below
+                const int t = blk_row0 >> 7, hrow = blk_row0 & 64;
+                const uint4* __restrict__ src = reinterpret_cast<const uint4*>(p.dy_split) +
+                                                (((long long)cloud * tpc_dump + t) * 2) * ((long long)a_real_groups * 128) + hrow;
+                const long long lo_off = (long long)a_real_groups * 128;
+                for (int e = wtid; e < a_real_groups * TW_RB; e += 256) {
+                    const int g = e >> 6, rl = e & 63;
+                    cp_async16(ahi_addr + (uint32_t)e * 16u, src + g * 128 + rl, 16u);
+                    cp_async16(alo_addr + (uint32_t)e * 16u, src + lo_off + g * 128 + rl, 16u);
+                }
+                cp_async_commit();
+            }
 #pragma unroll 1
             for (int rg = wq; rg < TW_RB / 8; rg += 8) {
                 const int rl = rg * 8 + rr, r = blk_row0 + rl;
@@ -133,7 +159,7 @@ tc_wgrad_kernel(const __grid_constant__ WgParams p, const int Mpad, const int Kp
                 const float* __restrict__ arow = p.A + grow * p.lda;
                 // ---- A operand: dy'[r, n], pieces g = gq + 4 i ----
 #pragma unroll 1
-                for (int g0 = gq; g0 < a_groups; g0 += 16) {
+                for (int g0 = gq; g0 < (pre_split ? 0 : a_groups); g0 += 16) {
                     float4 xa[4][2], ya[4][2];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -220,6 +246,7 @@ tc_wgrad_kernel(const __grid_constant__ WgParams p, const int Mpad, const int Kp
                     }
                 }
             }
+            if (pre_split) cp_async_wait_all();
             fence_proxy_async();
             tc_fence_before();
             slot_bar_sync256(wg);
@@ -230,8 +257,10 @@ tc_wgrad_kernel(const __grid_constant__ WgParams p, const int Mpad, const int Kp
                     const uint32_t d = slot_col + (uint32_t)(mt * Kext);
 #pragma unroll
                     for (int ks = 0; ks < TW_RB / 16; ++ks) {
-                        const uint32_t aoff = (uint32_t)mt * 2048u + (uint32_t)ks * 2u * a_lbo, boff = (uint32_t)ks * 2u * b_lbo;
-                        const uint64_t a_hi = umma_desc(ahi_addr + aoff, a_lbo, 128u), a_lo = umma_desc(alo_addr + aoff, a_lbo, 128u);
+                        const uint32_t aoff = pre_split ? (uint32_t)mt * 16384u + (uint32_t)ks * 256u : (uint32_t)mt * 2048u + (uint32_t)ks * 2u * a_lbo;
+                        const uint32_t boff = (uint32_t)ks * 2u * b_lbo;
+                        const uint64_t a_hi = pre_split ? umma_desc(ahi_addr + aoff, 128u, 1024u) : umma_desc(ahi_addr + aoff, a_lbo, 128u);
+                        const uint64_t a_lo = pre_split ? umma_desc(alo_addr + aoff, 128u, 1024u) : umma_desc(alo_addr + aoff, a_lbo, 128u);
                         const uint64_t b_hi = umma_desc(bhi_addr + boff, b_lbo, 128u), b_lo = umma_desc(blo_addr + boff, b_lbo, 128u);
                         umma_bf16(d, a_lo, b_hi, idesc, (blk != blk_lo || ks != 0) ? 1u : 0u);
                         umma_bf16(d, a_hi, b_lo, idesc, 1u);
@@ -314,6 +343,7 @@ int tc_wgrad_try(const WgParams& p, int slabs, int SLAB, cudaStream_t st) {
     // 2^-17 split residual shows up as 1e-3 relative in the result
     if (p.K < 16 || p.K > 256 || p.Nout > 256 || Kext > 256 || (Mpad >> 7) * Kext > 256) return 0;
     if (SLAB % TW_RB) return 0;
+    if (p.dy_split && (SLAB % 128 || (reinterpret_cast<uintptr_t>(p.dy_split) & 15))) return fail(AMP_E_BADARG, "tc_wgrad: dy_split needs 128-row slabs");
     if (p.lddy % 4 || p.Nout % 8 || (reinterpret_cast<uintptr_t>(p.dY) & 15) || (p.Y2 && (reinterpret_cast<uintptr_t>(p.Y2) & 15))) return 0;
     const int a_vec = (p.lda % 4 == 0 && p.K % 8 == 0 && (reinterpret_cast<uintptr_t>(p.A) & 15) == 0) ? 1 : 0;
     const int out_vec = ((((long long)p.Nout * p.K + p.Nout) % 4) == 0 && p.K % 4 == 0 && (reinterpret_cast<uintptr_t>(p.partials) & 15) == 0) ? 1 : 0;
@@ -331,6 +361,7 @@ int tc_wgrad_try(const WgParams& p, int slabs, int SLAB, cudaStream_t st) {
     launch_pdl(tc_wgrad_kernel, dim3((unsigned)((int)grid)), dim3(TW_THREADS), smem_bytes, st, p, Mpad, Kp, Kext, slabs, SLAB, a_vec, out_vec);
     count_launch();
     count_path("tc_wgrad");
+    if (p.dy_split) count_path("tc_wgrad_presplit");
     const int rc = check_launch("tc_wgrad_kernel");
     return rc == AMP_OK ? 1 : rc;
 }

@@ -136,6 +136,8 @@ def bench_fwd(dist, amp, steps, warmup, with_cpu, precision="fp32"):
                      else "whole forward: tc_chain_kernel x 4 (tcgen05 bf16 chains) + fp32 per-cloud FC / attention kernels",
                      "achieved": ach, "peak": peak,
                      "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": src,
+                     # what the tensor pipe executes: three bf16 MMAs per product on the fp32-class path, one on the bf16 path
+                     "executed_frac": (3.0 if precision == "fp32" else 1.0) * ach / peak,
                      "model": "413 143 algorithmic FLOP per point (SURVEY 8d) x 65 536 points / step time; the fp32 path executes 3 MMAs per product"},
         "config": {"workload": "configs[0]: segmentation forward, batch %d x %d points, 9 channels, eval, random-init weights" % (NN_BATCH, NN_POINTS)},
         "notes": {"l2": "flushed between steps (256 MiB write)", "precision": precision,

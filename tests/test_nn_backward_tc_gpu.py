@@ -267,3 +267,23 @@ def test_tensor_core_training_step_vs_reference_golden(amp, cuda, name):
     assert checked >= 60
     assert _relnorm(ours["d_lo"][:, ::101, :], z[name + "__dlo"]) < 6 * env["d_lo"] + 1e-4
     assert _relnorm(ours["d_gl"], z[name + "__dgl"]) < 6 * env["d_gl"] + 1e-4
+
+
+def test_weight_gradient_from_the_input_gradient_kernels_split_operand_is_bit_identical(amp, cuda):
+    """bwd_step runs the input gradient first; its tensor-core kernel leaves dy' (BatchNorm-backward applied, split into bf16
+    hi + lo) in a scratch buffer and tc_wgrad_kernel copies it instead of recomputing it from dz and y. Same values, same
+    summation order: every gradient must be bit-identical to the path that recomputes (AMP_DISABLE=wgrad_presplit)."""
+    B, N, W, seed = 32, 2048, 1, 97
+    xs, cent = nn_params.conditioned_blocks(B, N, W, seed)
+    tg = torch.randint(-1, 5, (B, N * W), generator=torch.Generator().manual_seed(seed))
+    enc, seg, _, _ = _build(amp, seed, cuda)
+    n0 = amp._lib.path_count("tc_wgrad_presplit")
+    _, _, g_a, _, _ = _step(amp, enc, seg, xs, cent, tg, cuda)
+    used = amp._lib.path_count("tc_wgrad_presplit") - n0
+    assert used >= 8, used                                   # the encoder's wide layers
+    enc, seg, _, _ = _build(amp, seed, cuda)
+    n1 = amp._lib.path_count("tc_wgrad_presplit")
+    _, _, g_b, _, _ = _step(amp, enc, seg, xs, cent, tg, cuda, disable_for_backward=["wgrad_presplit"])
+    assert amp._lib.path_count("tc_wgrad_presplit") == n1
+    for k in g_a:
+        assert torch.equal(g_a[k], g_b[k]), k
