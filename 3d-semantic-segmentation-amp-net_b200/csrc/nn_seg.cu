@@ -64,6 +64,7 @@ struct SegWs {
     unsigned char* pack32;                                      // fp32-class fused path without a caller-owned pack cache
     float *part_sum, *part_sq, *k1, *k2, *k3, *wg; size_t wg_floats;
     float* wg_pool; size_t wg_pool_floats;
+    void* split_dump;                                           // dy' of the layer being differentiated, split bf16 (PwParams::split_dump)
     float *dz3, *dz2, *dcb, *dg_w, *dattn_o, *dqkv, *dtokens, *dpre;
 };
 
@@ -92,6 +93,7 @@ SegWs seg_ws_carve(Arena& a, long long B, long long W, long long R, int E, int h
     w.wg = a.take<float>(w.wg_floats);
     w.wg_pool_floats = 2 * w.wg_floats + 64 * 16;              // deferred parameter-gradient reductions (WgDeferScope)
     w.wg_pool = a.take<float>(w.wg_pool_floats);
+    w.split_dump = a.take<unsigned char>(tiles * (size_t)(2 * 16 * 128 * 16));          // up to 128 channels
     w.dz3 = a.take<float>(M * 64); w.dz2 = a.take<float>(M * hid);
     w.dcb = a.take<float>(T * hid); w.dg_w = a.take<float>(T * E); w.dattn_o = a.take<float>(T * E);
     w.dqkv = a.take<float>(T * 3 * E); w.dtokens = a.take<float>(T * E); w.dpre = a.take<float>(T * 16);
@@ -400,15 +402,20 @@ int amp_seg_bwd(const void* const* params, void* const* grads, const float* lo_f
         g.a_drop_p = dp; g.drop_off = dropout_offset(); g.a_drop_seed = seed + 2;
         g.n_clouds = Bi; g.rows_per_cloud = Ri; g.dW = gf(grads, S_C3W); g.ldw = hid; g.db = gf(grads, S_C3B);
         g.partials = ws.wg; g.partial_floats = ws.wg_floats;
-        AMP_TRY(wgrad(g, st));
+        // the input gradient first: its kernel leaves dy' split for the weight gradient (see bwd_step of nn_encoder.cu)
+        const bool want_dump = !path_disabled("wgrad_presplit");
         PwParams p{};
+        if (want_dump) p.split_dump = ws.split_dump;
         p.X = ws.dz3; p.ldx = 64; p.K = 64; p.in_a = ws.k1 + kSegBn3; p.in_b = ws.k3 + kSegBn3; p.in_c = ws.k2 + kSegBn3; p.in_m = S.mean + kSegBn3; p.X2 = S.y3;
         p.W = pf(params, S_C3W); p.ldw = hid; p.w_kn = 1; p.n_groups = 1;
         p.mask_y = S.y2; p.ld_mask = hid; p.mask_scale = S.scale + kSegBn2; p.mask_shift = pf(params, S_BN2 + BN_B);
         p.mask_mean = S.mean + kSegBn2; p.mask_invstd = S.invstd + kSegBn2; p.out_drop_p = dp; p.drop_off = dropout_offset(); p.out_drop_seed = seed + 2;
         p.part_sum = ws.part_sum; p.part_sq = ws.part_sq;
         p.Y = ws.dz2; p.ldy = hid; p.n_clouds = Bi; p.rows_per_cloud = Ri; p.Nout = hid;
+        tc_layer_dumped() = false;
         AMP_TRY(pw_linear(p, st));
+        if (want_dump && tc_layer_dumped()) g.dy_split = ws.split_dump;
+        AMP_TRY(wgrad(g, st));
         AMP_TRY(bn_backward_finalize(ws.part_sum, ws.part_sq, tiles, count, hid, pf(params, S_BN2 + BN_W), S.mean + kSegBn2,
                                      S.invstd + kSegBn2, gf(grads, S_BN2 + BN_W), gf(grads, S_BN2 + BN_B), 0, ws.k1 + kSegBn2,
                                      ws.k2 + kSegBn2, ws.k3 + kSegBn2, st));
@@ -421,12 +428,16 @@ int amp_seg_bwd(const void* const* params, void* const* grads, const float* lo_f
         g.n_clouds = Bi; g.rows_per_cloud = Ri; g.dW = gf(grads, S_C2W); g.ldw = 64 + E;
         g.group_rows = group_rows; g.n_groups = Wi; g.dbg = ws.dcb; g.slab_rows = gslab;
         g.partials = ws.wg; g.partial_floats = ws.wg_floats;
-        AMP_TRY(wgrad(g, st));
+        const bool want_dump = gslab % 128 == 0 && !path_disabled("wgrad_presplit");
         PwParams p{};
+        if (want_dump) p.split_dump = ws.split_dump;
         p.X = ws.dz2; p.ldx = hid; p.K = hid; p.in_a = ws.k1 + kSegBn2; p.in_b = ws.k3 + kSegBn2; p.in_c = ws.k2 + kSegBn2; p.in_m = S.mean + kSegBn2; p.X2 = S.y2;
         p.W = pf(params, S_C2W); p.ldw = 64 + E; p.w_kn = 1; p.n_groups = 1;
         p.Y = d_lo_feats; p.ldy = 64; p.n_clouds = Bi; p.rows_per_cloud = Ri; p.Nout = 64;
+        tc_layer_dumped() = false;
         AMP_TRY(pw_linear(p, st));
+        if (want_dump && tc_layer_dumped()) g.dy_split = ws.split_dump;
+        AMP_TRY(wgrad(g, st));
     }
     // conv_2, global half through the per-block bias: dW2[:, 64:], db2, d g_w
     {
