@@ -27,6 +27,7 @@
 
 #include "nn_common.cuh"
 #include "tc_ptx.cuh"
+#include "tc_ts.cuh"
 
 namespace amp {
 namespace {
@@ -40,9 +41,9 @@ constexpr int TL_MAX_SMEM = 232448, TL_MIN_SMEM = 120 * 1024;
 // prologue tables | exchange | barriers. `kcw` = input channels per chunk (64, 32 or 16: the widest that fits), `x2` = the
 // prologue reads a second tensor (BatchNorm backward), which gets its own raw buffer.
 struct TlPlan { int w_lo, b0, bhalf, raw0, rawsz, tab, exch, bar, total; };
-__host__ __device__ inline TlPlan tl_plan(int Mpad, int K, int kcw, int x2) {
+__host__ __device__ inline TlPlan tl_plan(int Mpad, int K, int kcw, int x2, int ts) {
     TlPlan s;
-    const int wbytes = Mpad * K * 2;
+    const int wbytes = ts ? 0 : Mpad * K * 2;  // ts: the weights live in tensor memory
     s.w_lo = wbytes;
     s.b0 = 2 * wbytes;
     s.bhalf = TL_ROWS * kcw * 2;                // bytes of the hi (or lo) half of one B chunk
@@ -96,14 +97,14 @@ __device__ __noinline__ float dropout_keep_ool(unsigned long long seed, unsigned
 enum { TL_STATS = 1, TL_POOL2 = 2, TL_AFFINE = 4, TL_POOL1 = 8, TL_MASK = 16, TL_DROP = 32, TL_ACC = 64, TL_FP16 = 128 };
 
 template <int MODE>
-__global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_constant__ PwParams p, const int Mpad, const int kcw, const int cloud_split, long long* prof_buf) {
+__global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_constant__ PwParams p, const int Mpad, const int kcw, const int cloud_split, const int ts, long long* prof_buf) {
     pdl_trigger();
     extern __shared__ __align__(1024) unsigned char smem[];
     // two slots of 256 threads (two warpgroups each): `wg` = slot, `sub` = which warpgroup of the slot, `wtid` = thread in slot
     const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31, wg = warp >> 3, sub = (warp >> 2) & 1, wtid = tid & (TL_SLOT - 1);
     const int K = p.K, Nout = p.Nout, rows = p.rows_per_cloud;
     const bool has_x2 = p.X2 != nullptr;
-    const TlPlan sp = tl_plan(Mpad, K, kcw, has_x2 ? 1 : 0);
+    const TlPlan sp = tl_plan(Mpad, K, kcw, has_x2 ? 1 : 0, ts);
     float* s_exch = reinterpret_cast<float*>(smem + sp.exch) + wg * (3 * 2 * 128);
     auto slot_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(wg + 1) : "memory"); };
     __nv_bfloat16* s_whi = reinterpret_cast<__nv_bfloat16*>(smem);
@@ -149,7 +150,48 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
     uint32_t phase = 0;
 
     // weights -> (hi, lo) core-matrix layout: one thread per (channel n, 8 consecutive k) = one 16-byte row of a core matrix
+    // ts (Mpad == 128, K <= 256): the weights (the A operand: M = output channels) live in TENSOR MEMORY, columns
+    // [128, 128 + K / 2) = hi and [384, 384 + K / 2) = lo of the allocation (the two slots' accumulators sit at [0, 128) and
+    // [256, 384)): lane = output channel, one 32-bit column = two consecutive input channels. The MMAs then read only the
+    // activation operand from shared memory -- in the SS form a 128 x 128 x 16 MMA reads 8 KB of operands per 67 cycles, i.e.
+    // the whole shared-memory bandwidth, and every copy / conversion of the other slot slowed it down (4-5 k cycles for the
+    // 12 MMAs of a 64-channel tile) -- and the weights' shared memory (up to 128 KB) goes to wider input chunks.
+    constexpr uint32_t kWHiCol = 128u, kWLoCol = 384u;
+    auto stage_weights_tmem = [&](int cloud) {
+        const float* __restrict__ W = p.W + (long long)cloud * p.w_cloud_stride;
+        const int n = (warp & 3) * 32 + lane;                     // this thread's TMEM lane = output channel
+        const int kq = K >> 2, k0 = (warp >> 2) * kq;             // the four warps of a lane quadrant split K
+        const bool n_ok = n < Nout;
+        const bool wvec = p.w_kn == 0 && (p.ldw & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kq; c0 += 16) {
+            float v[16];
+            const int k = k0 + c0;
+            if (!n_ok) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+            } else if (wvec) {
+                const float4* src = reinterpret_cast<const float4*>(W + (long long)n * p.ldw + k);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { const float4 a = __ldg(src + i); v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w; }
+            } else if (p.w_kn == 0) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __ldg(W + (long long)n * p.ldw + k + i);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __ldg(W + (long long)(k + i) * p.ldw + n);
+            }
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) split_pair<H16>(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+            tmem_st8(tmem_base + lane_addr + kWHiCol + (uint32_t)(k >> 1), hi);
+            tmem_st8(tmem_base + lane_addr + kWLoCol + (uint32_t)(k >> 1), lo);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+    };
     auto stage_weights = [&](int cloud) {
+        if (ts) { stage_weights_tmem(cloud); return; }
         const float* __restrict__ W = p.W + (long long)cloud * p.w_cloud_stride;
         const int k8n = K >> 3, total = Mpad * k8n;
         uint4* whi4 = reinterpret_cast<uint4*>(s_whi);
@@ -320,9 +362,16 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
                         const uint64_t a_hi = umma_desc(whi_addr + woff, w_lbo, 128u), a_lo = umma_desc(wlo_addr + woff, w_lbo, 128u);
                         const uint64_t b_hi = umma_desc(bhi_addr + (uint32_t)ks * 4096u, 2048u, 128u);
                         const uint64_t b_lo = umma_desc(blo_addr + (uint32_t)ks * 4096u, 2048u, 128u);
-                        umma_bf16(d, a_lo, b_hi, idesc, (kc | ks) != 0);
-                        umma_bf16(d, a_hi, b_lo, idesc, 1u);
-                        umma_bf16(d, a_hi, b_hi, idesc, 1u);
+                        if (ts) {
+                            const uint32_t t_hi = tmem_base + kWHiCol + kg * 8u, t_lo = tmem_base + kWLoCol + kg * 8u;
+                            umma_bf16_ts(d, t_lo, b_hi, idesc, (kc | ks) != 0);
+                            umma_bf16_ts(d, t_hi, b_lo, idesc, 1u);
+                            umma_bf16_ts(d, t_hi, b_hi, idesc, 1u);
+                        } else {
+                            umma_bf16(d, a_lo, b_hi, idesc, (kc | ks) != 0);
+                            umma_bf16(d, a_hi, b_lo, idesc, 1u);
+                            umma_bf16(d, a_hi, b_hi, idesc, 1u);
+                        }
                     }
                 }
                 umma_commit(mbar);
@@ -547,9 +596,10 @@ int tc_layer_try(const PwParams& p, cudaStream_t st) {
     if (p.X2 && (reinterpret_cast<uintptr_t>(p.X2) & 15)) return 0;
     if (p.group_rows && p.n_groups > 64) return 0;
     if (p.pool_mode && !p.pool_max) return 0;
+    const int ts = (Mpad == 128 && p.K <= 256 && !path_disabled("tc_layer_ts")) ? 1 : 0;   // weights in tensor memory (see the kernel)
     int kcw = 64;                              // widest input chunk whose buffers fit next to the weights
-    while (kcw > 16 && tl_plan(Mpad, p.K, kcw, p.X2 ? 1 : 0).total > TL_MAX_SMEM) kcw >>= 1;
-    const TlPlan sp = tl_plan(Mpad, p.K, kcw, p.X2 ? 1 : 0);
+    while (kcw > 16 && tl_plan(Mpad, p.K, kcw, p.X2 ? 1 : 0, ts).total > TL_MAX_SMEM) kcw >>= 1;
+    const TlPlan sp = tl_plan(Mpad, p.K, kcw, p.X2 ? 1 : 0, ts);
     if (sp.total > TL_MAX_SMEM) return 0;
     if (p.bias && p.group_rows && !p.groups_tile_aligned) return 0;
     int mode = 0;
@@ -585,7 +635,7 @@ int tc_layer_try(const PwParams& p, cudaStream_t st) {
             if (e != cudaSuccess) return fail(AMP_E_CUDA, "tc_layer: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); \
             attr_set = true; \
         } \
-        launch_pdl(tc_layer_kernel<M>, dim3((unsigned)((int)grid)), dim3(TL_THREADS), smem_bytes, st, q, Mpad, kcw, cloud_split, want_prof ? dprof : nullptr); \
+        launch_pdl(tc_layer_kernel<M>, dim3((unsigned)((int)grid)), dim3(TL_THREADS), smem_bytes, st, q, Mpad, kcw, cloud_split, ts, want_prof ? dprof : nullptr); \
         break; }
         TL_CASE(0) TL_CASE(TL_ACC) TL_CASE(TL_STATS) TL_CASE(TL_STATS | TL_POOL2) TL_CASE(TL_AFFINE) TL_CASE(TL_AFFINE | TL_POOL1)
         TL_CASE(TL_MASK) TL_CASE(TL_MASK | TL_ACC) TL_CASE(TL_MASK | TL_DROP)
@@ -603,6 +653,7 @@ int tc_layer_try(const PwParams& p, cudaStream_t st) {
     }
     count_launch();
     count_path("tc_layer");
+    if (ts) count_path("tc_layer_ts");
     if (p.split_dump) tc_layer_dumped() = true;
     if (mode & TL_MASK) count_path("tc_layer_dgrad");
     const int rc = check_launch("tc_layer_kernel");
