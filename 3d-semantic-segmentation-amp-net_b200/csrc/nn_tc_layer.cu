@@ -383,7 +383,13 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
             else if (have_next) issue_chunk(cn, tn, 0);
             TL_PROF();                                         // MMAs issued
             __syncwarp();
-            mbar_wait(mbar, phase);
+            // ONE thread of the slot polls the mbarrier, the other 255 block in the named barrier (a hardware wait): no
+            // try_wait traffic of 8 warps on the shared-memory pipe while the MMAs fetch their operand through it
+            if ((warp & 7) == 0) {
+                if (lane == 0) mbar_wait(mbar, phase);
+                __syncwarp();
+            }
+            slot_sync();
             phase ^= 1u;
             tc_fence_after();
             TL_PROF();                                         // MMAs complete
