@@ -96,6 +96,10 @@ __device__ __noinline__ float dropout_keep_ool(unsigned long long seed, unsigned
 // epilogue specialisations (bit mask): compile-time so that the per-element loop carries no dead branches
 enum { TL_STATS = 1, TL_POOL2 = 2, TL_AFFINE = 4, TL_POOL1 = 8, TL_MASK = 16, TL_DROP = 32, TL_ACC = 64, TL_FP16 = 128 };
 
+// Debug bisection of the phase timeline (AMP_TL_DBG, only read when AMP_LAYER_PROF passes a profile buffer; results are
+// garbage): 1 = no convert, 2 = no cp.async, 4 = no epilogue, 8 = slot 0 only. profiles/r02_tc_layer_phase_bisect.txt
+__device__ int g_tl_dbg = 0;
+
 template <int MODE>
 __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_constant__ PwParams p, const int Mpad, const int kcw, const int cloud_split, const int ts, long long* prof_buf) {
     pdl_trigger();
@@ -104,6 +108,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
     const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31, wg = warp >> 3, sub = (warp >> 2) & 1, wtid = tid & (TL_SLOT - 1);
     const int K = p.K, Nout = p.Nout, rows = p.rows_per_cloud;
     const bool has_x2 = p.X2 != nullptr;
+    const int dbg = prof_buf ? g_tl_dbg : 0;
     const TlPlan sp = tl_plan(Mpad, K, kcw, has_x2 ? 1 : 0, ts);
     float* s_exch = reinterpret_cast<float*>(smem + sp.exch) + wg * (3 * 2 * 128);
     auto slot_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(wg + 1) : "memory"); };
@@ -154,8 +159,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
     // [128, 128 + K / 2) = hi and [384, 384 + K / 2) = lo of the allocation (the two slots' accumulators sit at [0, 128) and
     // [256, 384)): lane = output channel, one 32-bit column = two consecutive input channels. The MMAs then read only the
     // activation operand from shared memory -- in the SS form a 128 x 128 x 16 MMA reads 8 KB of operands per 67 cycles, i.e.
-    // the whole shared-memory bandwidth, and every copy / conversion of the other slot slowed it down (4-5 k cycles for the
-    // 12 MMAs of a 64-channel tile) -- and the weights' shared memory (up to 128 KB) goes to wider input chunks.
+    // the whole shared-memory bandwidth, shared with every copy / conversion of the other slot -- and the weights' shared
+    // memory (up to 128 KB) goes to wider input chunks (64 instead of 32 channels at K = 256).
     constexpr uint32_t kWHiCol = 128u, kWLoCol = 384u;
     auto stage_weights_tmem = [&](int cloud) {
         const float* __restrict__ W = p.W + (long long)cloud * p.w_cloud_stride;
@@ -250,7 +255,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
     auto issue_chunk = [&](int cloud, int t, int kc) {
         const int row0 = t * TL_ROWS, valid = min(TL_ROWS, rows - row0);
         const int k = kc * kcw + q * 4;
-        if (k < K) {
+        if (k < K && !(dbg & 2)) {
             const long long row_base = (long long)cloud * rows + row0;
             const float* __restrict__ xb = p.X + row_base * p.ldx + k;
             const float* __restrict__ x2b = has_x2 ? p.X2 + row_base * p.ldx + k : nullptr;
@@ -296,7 +301,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
                 // a thread turns 8 consecutive channels of a row into one 16-byte K-group row of each operand half
                 cp_async_wait_all();
                 slot_sync();                                             // every thread's part of the raw chunk has landed
-                const bool g_ok = cg * 8 < kcur;
+                const bool g_ok = cg * 8 < kcur && !(dbg & 1);
                 const int k = kc * kcw + (g_ok ? cg * 8 : 0);
                 if (g_ok) {
                     float ca[8], cb[8], cm[8], cc[8];
@@ -399,7 +404,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
         int g_tile = 0;                                        // row group of the tile (groups are tile aligned)
         if (p.bias && p.group_rows)
             for (int q = 1; q < p.n_groups; ++q) g_tile += (row0 >= __ldg(p.group_rows + q)) ? 1 : 0;
-        for (int mt = 0; mt < n_mt; ++mt) {
+        for (int mt = 0; mt < ((dbg & 4) ? 0 : n_mt); ++mt) {
             const int n = mt * 128 + lrow;
             const bool n_ok = n < Nout;
             const int nn = n_ok ? n : 0;
@@ -557,12 +562,12 @@ __global__ void __launch_bounds__(TL_THREADS, 1) tc_layer_kernel(const __grid_co
             cloud = u / cloud_split;
             const int jj = (u - cloud * cloud_split) * tpu + j;
             t = jj * 2 + wg;
-            return u < n_units && jj < tps && t < tpc;
+            return u < n_units && jj < tps && t < tpc && !((dbg & 8) && wg);
         }
         const int tile = blockIdx.x * 2 + wg + it * gridDim.x * 2;
         cloud = tile / tpc;
         t = tile - cloud * tpc;
-        return tile < n_tiles;
+        return tile < n_tiles && !((dbg & 8) && wg);
     };
     bool pending = false;                     // the raw chunk 0 of this slot's tile of iteration `it` is already in flight
 #pragma unroll 1
@@ -633,6 +638,7 @@ int tc_layer_try(const PwParams& p, cudaStream_t st) {
     static long long* dprof = nullptr;
     if (want_prof && !dprof) cudaMalloc(&dprof, 256 * sizeof(long long));
     if (want_prof) cudaMemsetAsync(dprof, 0, 256 * sizeof(long long), st);
+    if (want_prof) { const int d = getenv("AMP_TL_DBG") ? atoi(getenv("AMP_TL_DBG")) : 0; cudaMemcpyToSymbolAsync(g_tl_dbg, &d, sizeof d, 0, cudaMemcpyHostToDevice, st); }
     switch (mode) {
 #define TL_CASE(M) case M: { \
         static bool attr_set = false; \
@@ -653,7 +659,7 @@ int tc_layer_try(const PwParams& p, cudaStream_t st) {
         long long h[256];
         cudaMemcpyAsync(h, dprof, sizeof h, cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
-        fprintf(stderr, "[tc_layer prof] mode=%d K=%d N=%d rows=%lld:", mode, p.K, p.Nout, (long long)p.n_clouds * p.rows_per_cloud);
+        fprintf(stderr, "[tc_layer prof] mode=%d K=%d N=%d rows=%lld kcw=%d ts=%d:", mode, p.K, p.Nout, (long long)p.n_clouds * p.rows_per_cloud, kcw, ts);
         for (int i = 1; i < (int)h[255] && i < 40; ++i) fprintf(stderr, " %lld", h[i] - h[i - 1]);
         fprintf(stderr, "\n");
     }

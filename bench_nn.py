@@ -47,6 +47,9 @@ def build_modules(amp, device, dropout=0.3):
     return enc, seg
 
 
+FWD_CHAIN32_DRAM_BYTES = 42.6e6
+
+
 def forward_pass(enc, seg, x, cent):
     """One window-block pass exactly as the scripts drive the modules (W = 1)."""
     out, ft = enc(x)
@@ -135,7 +138,10 @@ def bench_fwd(dist, amp, steps, warmup, with_cpu, precision="fp32"):
         "roofline": {"bound": "tensor", "kernel": "whole forward: tc_chain32_kernel x 5 (split-bf16 3-MMA tcgen05 chains, activations in TMEM) + fp32 per-cloud FC / attention kernels" if precision == "fp32"
                      else "whole forward: tc_chain_kernel x 4 (tcgen05 bf16 chains) + fp32 per-cloud FC / attention kernels",
                      "achieved": ach, "peak": peak,
-                     "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": src,
+                     "unit": "TFLOP/s", "frac": ach / peak,
+                     # dram__bytes_read + write summed over the five tc_chain32 launches of one forward, ncu --set full
+                     # (profiles/r02_tc_chain32_ncu.txt; the outputs stay in the 126 MB L2, so writes are ~0)
+                     "traffic": FWD_CHAIN32_DRAM_BYTES if precision == "fp32" else None, "peak_source": src,
                      # what the tensor pipe executes: three bf16 MMAs per product on the fp32-class path, one on the bf16 path
                      "executed_frac": (3.0 if precision == "fp32" else 1.0) * ach / peak,
                      "model": "413 143 algorithmic FLOP per point (SURVEY 8d) x 65 536 points / step time; the fp32 path executes 3 MMAs per product"},
