@@ -17,4 +17,5 @@ from .blockstore import BlockStore, BlockStoreWriter, convert_kmeans_pt_files  #
 from .tensorcore import tc_linear, linear_wgrad  # noqa: F401
 from .graphstep import GraphedStep  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
+from .streamed import StreamedForward  # noqa: F401
 

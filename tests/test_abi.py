@@ -75,6 +75,15 @@ def _ctype_class(c_arg):
     return table[base[0]]
 
 
+def test_streamed_forward_needs_a_gpu(amp):
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        amp.StreamedForward(lambda x: x, (torch.zeros(2, 3),))
+
+
 def test_binding_argument_types_match_header(amp):
     """Every ctypes argtypes list has the arity and the scalar / pointer kinds of the header's prototype (an ABI change that
     reaches only one of the two sides -- e.g. the gl_ld / lo_ld strides of amp_seg_fwd -- would otherwise show up on the GPU only)."""

@@ -560,3 +560,34 @@ def test_fused_adam_matches_torch_adam(amp, cuda):
         oa.zero_grad(set_to_none=True); ob.zero_grad(set_to_none=True)
     for a, b in zip(pa, pb):
         assert torch.allclose(a, b, rtol=2e-6, atol=1e-7), (a.shape, float((a - b).abs().max()))
+
+
+def test_streamed_forward_keeps_batches_in_flight_and_returns_each_batchs_logits(amp, cuda):
+    """amp.StreamedForward (copy-in / run / copy-out streams, one captured forward per slot): seven different batches through
+    three slots give, bit for bit, the logits of seven direct calls; slot reuse and bad inputs are refused."""
+    B, N, seed = 4, 1024, 91
+    enc, seg, _, _ = _build(amp, seed, cuda)
+    enc.eval(); seg.eval()
+    batches = []
+    for i in range(7):
+        xs, cent = nn_params.synthetic_blocks(B, N, 1, seed + i)
+        batches.append((xs[0].contiguous().pin_memory(), cent.contiguous().pin_memory()))
+    with torch.no_grad():
+        want = [_run(enc, seg, [x], c, None, cuda)[0].cpu() for x, c in batches]
+        assert not torch.equal(want[0], want[1])
+        pipe = amp.StreamedForward(lambda x, c: _run(enc, seg, [x], c, None, cuda)[0], batches[0], device=cuda, depth=3)
+        got = [lg.clone() for lg in pipe.run(batches)]
+    assert len(got) == 7
+    for g, w in zip(got, want):
+        assert torch.equal(g, w)
+    t = [pipe.submit(*batches[i]) for i in range(3)]
+    with pytest.raises(RuntimeError, match="must be collected"):
+        pipe.submit(*batches[3])
+    assert torch.equal(pipe.result(t[1]), want[1])
+    assert torch.equal(pipe.result(t[0]), want[0])
+    t3 = pipe.submit(*batches[3])                              # slot 0 is free again
+    with pytest.raises(KeyError):
+        pipe.result(t[0])
+    assert torch.equal(pipe.result(t[2]), want[2]) and torch.equal(pipe.result(t3), want[3])
+    with pytest.raises(ValueError):
+        pipe.submit(batches[0][0][:2], batches[0][1])
