@@ -16,7 +16,7 @@ constexpr int REPS = 20;
 
 // mode bit 0: A from TMEM; bit 1: B tiles distinct per K step; bit 2: other 3 warps write shared memory while the MMAs run
 template <int KSTEPS>
-__global__ void __launch_bounds__(128, 1) batch_kernel(int mode, long long* out) {
+__global__ void __launch_bounds__(128, 1) batch_kernel(int mode, long long* out, int n_cols = 128) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* s_a = smem;                       // 2 x 4 KB (hi, lo) per K step: 8 x 8 KB = 64 KB max
     unsigned char* s_b = smem + 65536;               // same
@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(128, 1) batch_kernel(int mode, long long* out)
       for (int c = 0; c < 256; c += 16) tmem_st16(tm + ((uint32_t)(warp * 32) << 16) + 256u + c, z);
       tmem_wait_st(); }
     tc_fence_before(); __syncthreads(); tc_fence_after();
-    const uint32_t idesc = umma_idesc(128, 128), barrier = smem_u32(&bar);
+    const uint32_t idesc = umma_idesc(128, n_cols), barrier = smem_u32(&bar);
+    const uint32_t lbo = (uint32_t)n_cols * 16u;       // B tile [K / 8][N][8] bf16: K-group stride
     uint32_t phase = 0;
     for (int rep = 0; rep < REPS; ++rep) {
         long long t0 = 0; bool elected = false;
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(128, 1) batch_kernel(int mode, long long* out)
                 t0 = clock64();
                 for (int ks = 0; ks < KSTEPS; ++ks) {
                     const uint32_t off = (mode & 2) ? (uint32_t)ks * 8192u : 0u;
-                    const uint64_t b_hi = umma_desc(smem_u32(s_b) + off, 2048u, 128u), b_lo = umma_desc(smem_u32(s_b) + off + 4096u, 2048u, 128u);
+                    const uint64_t b_hi = umma_desc(smem_u32(s_b) + off, lbo, 128u), b_lo = umma_desc(smem_u32(s_b) + off + 2u * lbo, lbo, 128u);
                     if (mode & 1) {
                         const uint32_t a_hi = tm + 256u + ks * 8u, a_lo = tm + 384u + ks * 8u;
                         umma_bf16_ts(tm, a_lo, b_hi, idesc, ks != 0); umma_bf16_ts(tm, a_hi, b_lo, idesc, 1u); umma_bf16_ts(tm, a_hi, b_hi, idesc, 1u);
@@ -76,10 +77,10 @@ __global__ void __launch_bounds__(128, 1) batch_kernel(int mode, long long* out)
 
 static int g_grid = 1;
 template <int KSTEPS>
-static double run(int mode, long long* d) {
+static double run(int mode, long long* d, int n_cols = 128) {
     std::vector<long long> h(REPS);
     cudaFuncSetAttribute(batch_kernel<KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 163840);
-    batch_kernel<KSTEPS><<<g_grid, 128, 163840>>>(mode, d);
+    batch_kernel<KSTEPS><<<g_grid, 128, 163840>>>(mode, d, n_cols);
     if (cudaDeviceSynchronize() != cudaSuccess) return -1;
     cudaMemcpy(h.data(), d, REPS * sizeof(long long), cudaMemcpyDeviceToHost);
     std::sort(h.begin() + 2, h.end());
@@ -96,5 +97,12 @@ int main(int argc, char** argv) {
     for (int mode = 0; mode < 8; ++mode) printf("%-44s %10.0f %10.0f %10.0f\n", names[mode], run<1>(mode, d), run<4>(mode, d), run<8>(mode, d));
     printf("the same with pseudo-random non-zero operands\n");
     for (int mode = 8; mode < 12; ++mode) printf("%-44s %10.0f %10.0f %10.0f\n", names[mode - 8], run<1>(mode, d), run<4>(mode, d), run<8>(mode, d));
+    // the width of the output block: does a narrow MMA cost less? (TS and SS, one B tile so that N = 256 fits)
+    printf("cycles per batch against N (M = 128, K = 16); per-MMA cost = (8 K steps - 4 K steps) / 12\n");
+    printf("%-44s %10s %10s %10s %10s\n", "N", "4 K steps", "8 K steps", "TS / MMA", "SS / MMA");
+    for (int n : {16, 32, 64, 128, 256}) {
+        const double t4 = run<4>(1, d, n), t8 = run<8>(1, d, n), s4 = run<4>(0, d, n), s8 = run<8>(0, d, n);
+        printf("%-44d %10.0f %10.0f %10.1f %10.1f\n", n, t4, t8, (t8 - t4) / 12.0, (s8 - s4) / 12.0);
+    }
     return 0;
 }
