@@ -186,9 +186,8 @@ def bench_fwd(dist, amp, steps, warmup, with_cpu, precision="fp32"):
         "notes": {"l2": "flushed between steps (256 MiB write)", "precision": precision,
                   "launch": "CUDA graph replay of the two module calls (eager: %.3f ms per step)" % (eager_ms / steps),
                   "e2e": ("serial loop: copy in, forward, copy out, synchronise; L2 flushed between steps" if serial else
-                          "amp.StreamedForward, 3 batches in flight, every step's H2D + D2H inside the timed region, host inputs "
-                          "rotate over a 151 MB pinned pool (> L2), no flush kernel; the serial loop (copy in, forward, copy "
-                          "out, synchronise; L2 flushed) gives %.0f points/s" % (pts / (serial_ms * 1e-3)))},
+                          "StreamedForward, 3 batches in flight, per-step H2D + D2H timed, 151 MB pinned input pool (> L2), no "
+                          "flush; serial loop (L2 flushed): %.0f points/s" % (pts / (serial_ms * 1e-3)))},
         "dtype": "f32" if precision == "fp32" else "bf16",
     }
     if with_cpu:
