@@ -6,7 +6,7 @@ shim `ampnet_b200.py`. Every op calls hand-written CUDA through the C ABI in
 include/ampnet_b200.h; there is no CPU / PyTorch fallback.
 """
 from . import _lib  # noqa: F401
-from .sampling import fps, fps_batch, fps_indices, gather_rows, fps_host_batch  # noqa: F401
+from .sampling import fps, fps_batch, fps_indices, gather_rows, fps_host_batch, fps_host_stream, FpsHostStream  # noqa: F401
 from .clustering import (kmeans_clustering, split_kmeans, split_kmeans_array, kmeans_assign,  # noqa: F401
                          kmeans_constrained_windows, regroup_windows, gather_feats, get_cluster_centroid)
 from .modules import BasePointNet, TransformationNet, SegmentationWithAttention, set_default_precision  # noqa: F401

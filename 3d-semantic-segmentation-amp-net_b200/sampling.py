@@ -35,6 +35,15 @@ def fps_indices(pc, n_samples, start_idx=0, check_finite=True):
     if n_samples > P:
         # the reference raises ValueError here too (np.argmax of an empty array, utils.py:927)
         raise ValueError("n_samples (%d) > number of points (%d)" % (n_samples, P))
+    out, status = _fps_launch(pc, n_samples, start_idx)
+    if check_finite and bool(status.any().item()):
+        raise ValueError("fps: non-finite coordinates in input")
+    return out[0] if squeeze else out
+
+
+def _fps_launch(pc, n_samples, start_idx=0):
+    """Enqueue amp_fps_* for a validated [B, P, D] CUDA tensor; returns (indices [B, S], status [B]) without synchronising."""
+    B, P, D = pc.shape
     lib = _lib.lib()
     elem = pc.element_size()
     out = torch.empty((B, n_samples), dtype=torch.int64, device=pc.device)
@@ -45,9 +54,7 @@ def fps_indices(pc, n_samples, start_idx=0, check_finite=True):
     with torch.cuda.device(pc.device):
         _lib.check(fn(pc.data_ptr(), B, P, D, int(n_samples), int(start_idx), out.data_ptr(),
                       status.data_ptr(), ws.data_ptr() if ws_bytes else None, ws_bytes, _lib.stream_ptr()))
-    if check_finite and bool(status.any().item()):
-        raise ValueError("fps: non-finite coordinates in input")
-    return out[0] if squeeze else out
+    return out, status
 
 
 def gather_rows(pc, idx):
@@ -86,6 +93,51 @@ def fps_host_batch(pc_host, n_samples, out=None, device=None):
     out.copy_(rows, non_blocking=True)
     torch.cuda.current_stream(dev).synchronize()
     return out
+
+
+class FpsHostStream:
+    """The sample_fps.py loop over MANY batches (data_proc/sample_fps.py:12-34 walks a directory of windows) with the copies
+    hidden: `run(batches)` takes an iterable of equally shaped host tensors / arrays [B, P, D] (pinned memory, or the copies
+    serialise) and yields the sampled rows [B, S, D] of each batch as pinned host tensors, in order. `depth` batches are in
+    flight (StreamedForward: copy-in / run / copy-out streams, one captured launch sequence per slot), so the host-to-device
+    copy of the next batch -- 2 ms for 64 x 40 000 x 3 floats, against 3.3 ms of sampling -- hides behind the kernel of the
+    current one. A yielded tensor is valid until `depth` more were requested. Non-finite coordinates raise ValueError when
+    the offending batch's result arrives."""
+
+    def __init__(self, example, n_samples, depth=3, device=None):
+        from .streamed import StreamedForward
+        self.n_samples = int(n_samples)
+        example = self._as_tensor(example)
+
+        def run(pc):
+            idx, status = _fps_launch(pc, self.n_samples, 0)
+            return gather_rows(pc, idx), status
+
+        self.pipe = StreamedForward(run, (example,), device=_device(device), depth=depth, warmup=1)
+
+    def _as_tensor(self, b):
+        t = torch.from_numpy(b) if isinstance(b, np.ndarray) else b
+        if t.dim() != 3 or t.dtype not in (torch.float32, torch.float64) or t.shape[2] < 3:
+            raise ValueError("batches must be [B, P, D >= 3] float32/float64")
+        if self.n_samples > t.shape[1]:
+            raise ValueError("n_samples (%d) > number of points (%d)" % (self.n_samples, t.shape[1]))
+        return t
+
+    def run(self, batches):
+        for rows, status in self.pipe.run((self._as_tensor(b),) for b in batches):
+            if bool(status.any()):
+                raise ValueError("fps: non-finite coordinates in input")
+            yield rows
+
+
+def fps_host_stream(batches, n_samples, depth=3, device=None):
+    """FpsHostStream for a one-off iterable: builds the pipeline from the first batch and runs all of them through it."""
+    import itertools
+    it = iter(batches)
+    first = next(it, None)
+    if first is None:
+        return
+    yield from FpsHostStream(first, n_samples, depth=depth, device=device).run(itertools.chain([first], it))
 
 
 def fps(pc, n_samples, device=None):

@@ -101,3 +101,27 @@ def test_full_size_properties(amp, cuda):
         assert (ih[b] == fps_oracle.fps_indices_c(pc[b].numpy(), 2048)).all()
     rows = amp.gather_rows(d, idx)
     assert (rows[5] == d[5, idx[5]]).all()
+
+
+def test_host_stream_matches_batch_calls_and_reports_bad_batches(amp, cuda):
+    """amp.FpsHostStream / fps_host_stream (three batches in flight, copies overlapped): the rows of every batch equal the
+    oracle's picks and the serial fps_host_batch call; a batch with a NaN raises when its result arrives."""
+    rng = np.random.default_rng(77)
+    B, P, S, D = 3, 3000, 200, 4
+    batches = [torch.from_numpy(rng.random((B, P, D), dtype=np.float32)).pin_memory() for _ in range(5)]
+    got = [r.clone() for r in amp.fps_host_stream(batches, S)]
+    assert len(got) == 5
+    for b, r in zip(batches, got):
+        assert torch.equal(r, amp.fps_host_batch(b, S))
+        for c in range(B):
+            want = fps_oracle.fps_indices_c(b[c].numpy(), S)
+            assert np.array_equal(r[c].numpy(), b[c].numpy()[want])
+    stream = amp.FpsHostStream(batches[0], S, depth=2)
+    assert sum(1 for _ in stream.run(batches[:3])) == 3          # reusable
+    bad = batches[1].clone().pin_memory()
+    bad[1, 17, 2] = float("nan")
+    with pytest.raises(ValueError, match="non-finite"):
+        list(stream.run([batches[0], bad, batches[2]]))
+    assert list(amp.fps_host_stream([], S)) == []
+    with pytest.raises(ValueError):
+        list(amp.fps_host_stream([batches[0]], P + 1))
