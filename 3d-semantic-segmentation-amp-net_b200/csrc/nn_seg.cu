@@ -183,35 +183,12 @@ int amp_seg_fwd(const void* const* params, const float* gl_feats, int64_t gl_ld,
     SegWs ws = seg_ws_carve(wa, B, W, rows, E, hid, false);
 
     const bool fused32 = !train && precision == AMP_PREC_FP32 && num_classes <= 32 && hid == 128 && !path_disabled("tc_chain32");
-    // positional encoding + token-major layout (:183-185)
-    AMP_TRY(posenc_add(gl_feats, gl_ld, centroids, pf(params, S_FC1W), pf(params, S_FC1B), pf(params, S_FC2W), pf(params, S_FC2B), Bi, Wi, E,
-                       S.tokens, S.h_pre, st));
-    // nn.MultiheadAttention (:187-190): in_proj, per-head softmax(QK^T)V, out_proj
-    {
-        PwParams p{};
-        p.X = S.tokens; p.ldx = E; p.K = E; p.W = pf(params, S_INW); p.ldw = E; p.bias = pf(params, S_INB); p.n_groups = 1;
-        p.Y = S.qkv; p.ldy = 3 * E; p.n_clouds = 1; p.rows_per_cloud = T; p.Nout = 3 * E;
-        AMP_TRY(pw_linear(p, st));
-    }
-    AMP_TRY(attention_core(S.qkv, key_padding_mask, dp, seed + 1, Bi, Wi, E, heads, S.attn_o, S.probs, st));
-    {
-        PwParams p{};
-        p.X = S.attn_o; p.ldx = E; p.K = E; p.W = pf(params, S_OUTW); p.ldw = E; p.bias = pf(params, S_OUTB); p.n_groups = 1;
-        p.Y = S.g_w; p.ldy = E; p.n_clouds = 1; p.rows_per_cloud = T; p.Nout = E;
-        AMP_TRY(pw_linear(p, st));
-    }
-    // per-block bias of conv_2: cb[b, w, :] = W2[:, 64:] g_w[b, w] + b2   (the repeat/cat of :192-200 folded away)
-    {
-        PwParams p{};
-        p.X = S.g_w; p.ldx = E; p.K = E; p.W = pf(params, S_C2W) + 64; p.ldw = 64 + E; p.bias = pf(params, S_C2B); p.n_groups = 1;
-        p.Y = S.cb; p.ldy = hid; p.n_clouds = 1; p.rows_per_cloud = T; p.Nout = hid;
-        if (precision != AMP_PREC_BF16 && !fused32) AMP_TRY(pw_linear(p, st));
-    }
+    const int Cp = (num_classes + 15) / 16 * 16;
+    SegPack k{};
+    bool tail_done = false;
     if (fused32) {
         // fused head on the tensor cores at fp32-class accuracy: bn_2 / bn_3 folded into the packed weights and the biases;
         // the per-block bias becomes cb' = scale2 * (W2[:, 64:] g_w + b2) + shift2
-        const int Cp = (num_classes + 15) / 16 * 16;
-        SegPack k;
         if (pack_cache) {
             if (pack_bytes < seg_pack_bytes(num_classes)) return fail(AMP_E_WORKSPACE, "seg_fwd: pack cache too small");
             Arena pa(pack_cache, pack_bytes);
@@ -234,12 +211,48 @@ int amp_seg_fwd(const void* const* params, const float* gl_feats, int64_t gl_ld,
             AMP_TRY(t32_affine_bias(pf(params, S_C3B), k.scale + kSegBn3, k.shift + kSegBn3, 64, 64, k.bias, st));
             AMP_TRY(t32_affine_bias(pf(params, S_C4B), nullptr, nullptr, num_classes, Cp, k.bias + 64, st));
         }
+        // positional encoding, attention and the per-block bias in one launch (nn_seg_tail.cu); the barrier words live in the
+        // h_pre slot of the saved buffer, which only the training backward reads
+        const int rc = seg_tail_eval(gl_feats, gl_ld, centroids, pf(params, S_FC1W), pf(params, S_FC1B), pf(params, S_FC2W), pf(params, S_FC2B),
+                                     pf(params, S_INW), pf(params, S_INB), pf(params, S_OUTW), pf(params, S_OUTB), pf(params, S_C2W) + 64, 64 + E,
+                                     pf(params, S_C2B), k.scale + kSegBn2, k.shift + kSegBn2, key_padding_mask, Bi, Wi, E, heads, hid, S.qkv,
+                                     S.attn_o, S.g_w, S.cb, reinterpret_cast<unsigned int*>(S.h_pre), st);
+        if (rc < 0) return rc;
+        tail_done = rc == 1;
+    }
+    if (!tail_done) {
+    // positional encoding + token-major layout (:183-185)
+    AMP_TRY(posenc_add(gl_feats, gl_ld, centroids, pf(params, S_FC1W), pf(params, S_FC1B), pf(params, S_FC2W), pf(params, S_FC2B), Bi, Wi, E,
+                       S.tokens, S.h_pre, st));
+    // nn.MultiheadAttention (:187-190): in_proj, per-head softmax(QK^T)V, out_proj
+    {
+        PwParams p{};
+        p.X = S.tokens; p.ldx = E; p.K = E; p.W = pf(params, S_INW); p.ldw = E; p.bias = pf(params, S_INB); p.n_groups = 1;
+        p.Y = S.qkv; p.ldy = 3 * E; p.n_clouds = 1; p.rows_per_cloud = T; p.Nout = 3 * E;
+        AMP_TRY(pw_linear(p, st));
+    }
+    AMP_TRY(attention_core(S.qkv, key_padding_mask, dp, seed + 1, Bi, Wi, E, heads, S.attn_o, S.probs, st));
+    {
+        PwParams p{};
+        p.X = S.attn_o; p.ldx = E; p.K = E; p.W = pf(params, S_OUTW); p.ldw = E; p.bias = pf(params, S_OUTB); p.n_groups = 1;
+        p.Y = S.g_w; p.ldy = E; p.n_clouds = 1; p.rows_per_cloud = T; p.Nout = E;
+        AMP_TRY(pw_linear(p, st));
+    }
+    }
+    // per-block bias of conv_2: cb[b, w, :] = W2[:, 64:] g_w[b, w] + b2   (the repeat/cat of :192-200 folded away)
+    {
+        PwParams p{};
+        p.X = S.g_w; p.ldx = E; p.K = E; p.W = pf(params, S_C2W) + 64; p.ldw = 64 + E; p.bias = pf(params, S_C2B); p.n_groups = 1;
+        p.Y = S.cb; p.ldy = hid; p.n_clouds = 1; p.rows_per_cloud = T; p.Nout = hid;
+        if (precision != AMP_PREC_BF16 && !fused32) AMP_TRY(pw_linear(p, st));
+    }
+    if (fused32) {
         {
             PwParams p{};
             p.X = S.g_w; p.ldx = E; p.K = E; p.W = pf(params, S_C2W) + 64; p.ldw = 64 + E; p.bias = pf(params, S_C2B); p.n_groups = 1;
             p.out_scale = k.scale + kSegBn2; p.out_shift = k.shift + kSegBn2;
             p.Y = S.cb; p.ldy = hid; p.n_clouds = 1; p.rows_per_cloud = T; p.Nout = hid;
-            AMP_TRY(pw_linear(p, st));
+            if (!tail_done) AMP_TRY(pw_linear(p, st));
         }
         T32Params p{};
         p.n_ops = 3;

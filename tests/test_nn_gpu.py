@@ -591,3 +591,31 @@ def test_streamed_forward_keeps_batches_in_flight_and_returns_each_batchs_logits
     assert torch.equal(pipe.result(t[2]), want[2]) and torch.equal(pipe.result(t3), want[3])
     with pytest.raises(ValueError):
         pipe.submit(batches[0][0][:2], batches[0][1])
+
+
+@pytest.mark.parametrize("B,W,masked", [(32, 1, False), (5, 3, True), (8, 9, True), (3, 20, False)])
+def test_fused_attention_tail_matches_the_separate_launches(amp, cuda, B, W, masked):
+    """Eval forward: positional encoding + attention + per-block bias in one launch (seg_tail_eval_kernel, grid barriers between
+    its phases) against the five separate launches (AMP_DISABLE=seg_tail), several row tiles and masked windows included."""
+    N, seed = 256, 300 + B + W
+    enc, seg, _, _ = _build(amp, seed, cuda)
+    enc.eval(); seg.eval()
+    xs, cent = nn_params.synthetic_blocks(B, N, W, seed)
+    mask = None
+    if masked:
+        mask = torch.zeros(B, W, dtype=torch.bool)
+        mask[0, W - 1] = True
+        mask[B - 1, 0] = True
+    with torch.no_grad():
+        n0 = amp._lib.path_count("seg_tail")
+        fused = _run(enc, seg, xs, cent, mask, cuda)[0].clone()
+        assert amp._lib.path_count("seg_tail") == n0 + 1
+        amp._lib.set_disabled(["seg_tail"])
+        try:
+            plain = _run(enc, seg, xs, cent, mask, cuda)[0].clone()
+            assert amp._lib.path_count("seg_tail") == n0 + 1
+        finally:
+            amp._lib.set_disabled(None)
+    assert torch.isfinite(fused).all()
+    assert _rel(fused, plain) < 2e-5
+    assert (fused.argmax(1) == plain.argmax(1)).float().mean().item() > 0.9995
