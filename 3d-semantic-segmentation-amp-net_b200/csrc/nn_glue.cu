@@ -2,6 +2,8 @@
 // value decode, T-Net identity and input-transform folding, the global-feature broadcast, the
 // positional encoding and the per-(cloud, head) attention core.
 // Reference: pointNet/model/pointnetAtt.py:28-47, 80-112, 176-209.
+#include <algorithm>
+
 #include "nn_common.cuh"
 
 namespace amp {
@@ -158,6 +160,18 @@ __global__ void broadcast_rows_kernel(const float* __restrict__ g, int rows_per_
         const long long b = row / rows_per_cloud;
         out[row * ldo4 + c] = reinterpret_cast<const float4*>(g)[b * C4 + c];
     }
+}
+
+// 256 % C4 == 0: a thread keeps ONE column piece of its cloud in a register and only stores (a pure write stream: the generic
+// kernel above spends three 64-bit divisions and a load per 16-byte store). grid = (row chunks, clouds).
+__global__ void __launch_bounds__(256) broadcast_rows_cols_kernel(const float* __restrict__ g, int rows_per_cloud, int C4,
+                                                                  float4* __restrict__ out, long long ldo4, int rows_per_cta) {
+    pdl_sync();
+    const int b = blockIdx.y, c = threadIdx.x % C4, rstep = 256 / C4;
+    const float4 v = reinterpret_cast<const float4*>(g)[(long long)b * C4 + c];
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows_per_cloud, r0 + rows_per_cta);
+    float4* o = out + ((long long)b * rows_per_cloud + r0 + threadIdx.x / C4) * ldo4 + c;
+    for (int r = r0 + threadIdx.x / C4; r < r1; r += rstep, o += (long long)rstep * ldo4) __stcs(o, v);
 }
 
 __global__ void posenc_add_kernel(const float* __restrict__ gl, long long gl_ld, const float* __restrict__ cent, const float* __restrict__ w1,
@@ -529,6 +543,17 @@ int broadcast_rows(const float* g, int n_clouds, int rows_per_cloud, int C, floa
     if ((C & 3) || (ldo & 3) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(g) & 15))
         return fail(AMP_E_BADARG, "broadcast_rows: needs 16-byte aligned rows");
     const long long total = (long long)n_clouds * rows_per_cloud * (C / 4);
+    if (C / 4 <= 256 && 256 % (C / 4) == 0 && n_clouds <= 65535) {
+        // ~8 CTAs per SM over the whole launch, at least 4 passes per thread
+        const int rstep = 256 / (C / 4);
+        int chunks = (int)std::min<long long>((rows_per_cloud + 4 * rstep - 1) / (4 * rstep), std::max<long long>(1, (long long)kNumSMs * 8 / n_clouds));
+        const int rows_per_cta = ((rows_per_cloud + chunks - 1) / chunks + rstep - 1) / rstep * rstep;
+        chunks = (rows_per_cloud + rows_per_cta - 1) / rows_per_cta;
+        launch_pdl(broadcast_rows_cols_kernel, dim3((unsigned)chunks, (unsigned)n_clouds), dim3(256), 0, st, g, rows_per_cloud, C / 4,
+                   reinterpret_cast<float4*>(out), ldo / 4, rows_per_cta);
+        count_launch();
+        return check_launch("broadcast_rows");
+    }
     long long blocks = (total + 255) / 256;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
     launch_pdl(broadcast_rows_kernel, dim3((unsigned)((unsigned)blocks)), dim3(256), 0, st, g, rows_per_cloud, C / 4, reinterpret_cast<float4*>(out), ldo / 4, total);
