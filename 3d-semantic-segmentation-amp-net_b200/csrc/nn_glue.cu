@@ -357,8 +357,18 @@ __global__ void colsum_stage1_kernel(const float* __restrict__ dout, long long l
     const int b = blockIdx.y, sl = blockIdx.x;
     const int r_lo = sl * 128, r_hi = min(rows, r_lo + 128);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        // 16 loads in flight, added in row order (the sum is the same as a plain loop's, bit for bit)
         float s = 0.f;
-        for (int r = r_lo; r < r_hi; ++r) s += dout[((long long)b * rows + r) * ldo + c];
+        const float* src = dout + ((long long)b * rows + r_lo) * ldo + c;
+        int r = r_lo;
+        for (; r + 16 <= r_hi; r += 16, src += 16 * ldo) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __ldg(src + j * ldo);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) s += v[j];
+        }
+        for (; r < r_hi; ++r, src += ldo) s += __ldg(src);
         scratch[((long long)b * slabs + sl) * C + c] = s;
     }
 }

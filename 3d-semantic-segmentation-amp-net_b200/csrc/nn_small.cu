@@ -279,7 +279,9 @@ __global__ void __launch_bounds__(NW_T) narrow_wgrad_kernel(const WgParams p, in
 // parity) keeps its 4 x K weights in registers and writes one 16-byte piece per row, so a warp store covers two whole rows.
 // Epilogue: raw value + per-tile BatchNorm sums (training; one pass with a shift, merged like tc_layer) or folded
 // BatchNorm + ReLU (eval).
-template <int KP>
+// MASK: the same shape as an INPUT-GRADIENT layer (dz = (dy W) masked by the ReLU of the saved activation, dropout of the
+// forward re-applied, per-tile sums for the BatchNorm backward): the 5-class logits layer's gradient, [B, C, rows] in.
+template <int KP, bool MASK>
 __global__ void __launch_bounds__(128) narrow_fwd_kernel(const PwParams p) {
     pdl_sync();
     __shared__ __align__(16) float xs[4][128 * KP];
@@ -291,6 +293,15 @@ __global__ void __launch_bounds__(128) narrow_fwd_kernel(const PwParams p) {
     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f), bs = sh;
     if (p.out_scale) { sc = __ldg(reinterpret_cast<const float4*>(p.out_scale) + q); sh = __ldg(reinterpret_cast<const float4*>(p.out_shift) + q); }
     if (p.bias) bs = __ldg(reinterpret_cast<const float4*>(p.bias) + q);
+    float msc[4] = {0.f, 0.f, 0.f, 0.f}, msh[4] = {0.f, 0.f, 0.f, 0.f}, mmu[4] = {0.f, 0.f, 0.f, 0.f}, mis[4] = {0.f, 0.f, 0.f, 0.f};
+    if (MASK) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            msc[j] = __ldg(p.mask_scale + q * 4 + j); msh[j] = __ldg(p.mask_shift + q * 4 + j);
+            mmu[j] = __ldg(p.mask_mean + q * 4 + j); mis[j] = __ldg(p.mask_invstd + q * 4 + j);
+        }
+    }
+    const unsigned long long dseed = MASK ? eff_seed(p.out_drop_seed, p.drop_off) : 0ull;
     int w_cloud = -1;
     float w[4][KP];
     for (int tile = blockIdx.x * 4 + warp; tile < n_tiles; tile += gridDim.x * 4) {
@@ -306,9 +317,16 @@ __global__ void __launch_bounds__(128) narrow_fwd_kernel(const PwParams p) {
                     w[j][k] = k < K ? __ldg(p.w_kn ? W + (long long)k * p.ldw + q * 4 + j : W + (long long)(q * 4 + j) * p.ldw + k) : 0.f;
         }
         __syncwarp();                                              // the previous tile's reads of xw are done
-        for (int e = lane; e < 128 * KP; e += 32) {
-            const int r = e / KP, k = e - r * KP;
-            xw[e] = (r < valid && k < K) ? __ldg(p.X + (row_base + r) * p.ldx + k) : 0.f;
+        if (MASK && p.x_transposed) {                              // [cloud][K][rows]: consecutive lanes read consecutive rows
+            for (int e = lane; e < 128 * KP; e += 32) {
+                const int k = e >> 7, r = e & 127;
+                xw[r * KP + k] = (r < valid && k < K) ? __ldg(p.X + ((long long)cloud * K + k) * rows + r0 + r) : 0.f;
+            }
+        } else {
+            for (int e = lane; e < 128 * KP; e += 32) {
+                const int r = e / KP, k = e - r * KP;
+                xw[e] = (r < valid && k < K) ? __ldg(p.X + (row_base + r) * p.ldx + k) : 0.f;
+            }
         }
         __syncwarp();
         float shift[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -327,7 +345,22 @@ __global__ void __launch_bounds__(128) narrow_fwd_kernel(const PwParams p) {
             for (int k = 0; k < KP; ++k)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) v[j] = fmaf(x[k], w[j][k], v[j]);
-            if (r < valid) {
+            if (MASK) {
+                if (r < valid) {
+                    const float4 ym4 = __ldg(reinterpret_cast<const float4*>(p.mask_y + (row_base + r) * p.ld_mask + q * 4));
+                    const float ym[4] = {ym4.x, ym4.y, ym4.z, ym4.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float dz = v[j];
+                        if (p.out_drop_p > 0.f) dz *= dropout_keep(dseed, (unsigned long long)(row_base + r) * 64 + q * 4 + j, p.out_drop_p);
+                        dz = fmaf(ym[j] - mmu[j], msc[j], msh[j]) > 0.f ? dz : 0.f;
+                        s1[j] += dz;
+                        s2[j] = fmaf(dz, (ym[j] - mmu[j]) * mis[j], s2[j]);
+                        v[j] = dz;
+                    }
+                    *reinterpret_cast<float4*>(yrow + (long long)r * p.ldy) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+            } else if (r < valid) {
                 if (stats) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -342,7 +375,16 @@ __global__ void __launch_bounds__(128) narrow_fwd_kernel(const PwParams p) {
                 *reinterpret_cast<float4*>(yrow + (long long)r * p.ldy) = make_float4(v[0], v[1], v[2], v[3]);
             }
         }
-        if (stats) {                                               // merge the even-row and the odd-row half (lanes q and q + 16)
+        if (MASK) {                                                // sum(dz) and sum(dz * xhat) of the tile: even rows + odd rows
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float o_s1 = __shfl_xor_sync(0xffffffffu, s1[j], 16), o_s2 = __shfl_xor_sync(0xffffffffu, s2[j], 16);
+                if (par == 0) {
+                    p.part_sum[(long long)tile * 64 + q * 4 + j] = s1[j] + o_s1;
+                    p.part_sq[(long long)tile * 64 + q * 4 + j] = s2[j] + o_s2;
+                }
+            }
+        } else if (stats) {                                        // merge the even-row and the odd-row half (lanes q and q + 16)
             const float na = (float)((valid + 1) >> 1), nb = (float)(valid >> 1);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -699,17 +741,28 @@ int narrow_out_fwd_try(const PwParams& p, cudaStream_t st) {
 // Forward of the narrow-input layers: 1 = launched, 0 = not eligible (the caller continues down the dispatch list).
 int narrow_fwd_try(const PwParams& p, cudaStream_t st) {
     if (path_disabled("narrow_fwd")) return 0;
-    if (p.K > 12 || p.Nout != 64 || !p.Y || p.x_transposed || p.y_transposed || p.X2 || p.in_a || p.in_relu || p.in_drop_p != 0.f ||
-        p.out_drop_p != 0.f || p.mask_y || p.pool_mode || p.accumulate || p.group_rows || p.n_groups > 1 || p.bias_group_stride != 0 || (p.out_relu && !p.out_scale))
+    if (p.K > 12 || p.Nout != 64 || !p.Y || p.y_transposed || p.X2 || p.in_a || p.in_relu || p.in_drop_p != 0.f ||
+        p.pool_mode || p.accumulate || p.group_rows || p.n_groups > 1 || p.bias_group_stride != 0 || (p.out_relu && !p.out_scale))
         return 0;
+    if (p.mask_y) {           // input-gradient form
+        if (!p.part_sum || !p.mask_invstd || p.bias || p.out_scale || p.out_relu || p.w_cloud_stride || p.ld_mask % 4 ||
+            (reinterpret_cast<uintptr_t>(p.mask_y) & 15))
+            return 0;
+    } else if (p.x_transposed || p.out_drop_p != 0.f) {
+        return 0;
+    }
     if ((long long)p.n_clouds * p.rows_per_cloud < 2048 || p.ldy % 4 || (reinterpret_cast<uintptr_t>(p.Y) & 15)) return 0;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     if ((p.bias && !al16(p.bias)) || (p.out_scale && (!al16(p.out_scale) || !al16(p.out_shift)))) return 0;
     const long long tiles = (long long)p.n_clouds * ((p.rows_per_cloud + 127) / 128);
     long long grid = (tiles + 3) / 4;
     if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-    if (p.K <= 4) launch_pdl(narrow_fwd_kernel<4>, dim3((unsigned)grid), dim3(128), 0, st, p);
-    else launch_pdl(narrow_fwd_kernel<12>, dim3((unsigned)grid), dim3(128), 0, st, p);
+    if (p.mask_y) {
+        if (p.K <= 8) launch_pdl(narrow_fwd_kernel<8, true>, dim3((unsigned)grid), dim3(128), 0, st, p);
+        else launch_pdl(narrow_fwd_kernel<12, true>, dim3((unsigned)grid), dim3(128), 0, st, p);
+        count_path("narrow_dgrad");
+    } else if (p.K <= 4) launch_pdl(narrow_fwd_kernel<4, false>, dim3((unsigned)grid), dim3(128), 0, st, p);
+    else launch_pdl(narrow_fwd_kernel<12, false>, dim3((unsigned)grid), dim3(128), 0, st, p);
     count_launch();
     const int rc = check_launch("narrow_fwd");
     return rc == AMP_OK ? 1 : rc;

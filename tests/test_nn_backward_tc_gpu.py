@@ -25,7 +25,7 @@ from oracle import make_golden_nn, nn_oracle, nn_params
 
 pytestmark = pytest.mark.gpu
 GOLDEN_TC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nn_reference_tc.npz")
-TC_PATHS = ("tc_layer", "tc_layer_dgrad", "tc_wgrad")
+TC_PATHS = ("tc_layer", "tc_layer_dgrad", "tc_wgrad", "narrow_dgrad")
 
 
 def _relnorm(a, b):
@@ -160,6 +160,7 @@ def test_tensor_core_backward_every_gradient_vs_oracle(amp, cuda, B, N, W, seed)
     logits, loss, ours, fwd, ran = _step(amp, enc, seg, xs, cent, tg, cuda)
     # the tensor-core kernels served this step (forward layers, input-gradient layers, weight gradients)
     assert fwd["tc_layer"] >= 9 * W and ran["tc_layer_dgrad"] >= 8 * W and ran["tc_wgrad"] >= 10 * W, (fwd, ran)
+    assert ran["narrow_dgrad"] == 1, ran          # the 5-class logits layer's input gradient: the narrow kernel's masked form
     t_logits, t_loss, truth = _oracle_grads(sd_e, sd_s, xs, cent, tg, torch.float64)
     o_logits, o_loss, _ = _oracle_grads(sd_e, sd_s, xs, cent, tg, torch.float32)
     assert _rel(logits, t_logits) < 1e-3
