@@ -199,11 +199,15 @@ int fold_input_transform_bwd(const float* dW1eff, const float* W1, const float* 
                              float* dT, cudaStream_t st);
 // out[b, r, 0:C] = g[b, 0:C] for every row r (the repeat + cat of :109-110)
 int broadcast_rows(const float* g, int n_clouds, int rows_per_cloud, int C, float* out, long long ldo, cudaStream_t st);
-// eval-mode attention tail of the segmentation head in one launch (nn_seg_tail.cu): 1 = launched, 0 = not eligible, < 0 = error
+// eval-mode attention tail of the segmentation head in one launch (nn_seg_tail.cu): 1 = launched, 0 = not eligible, < 0 = error;
+// wc / bc = out_proj folded into conv_2's global-feature columns (seg_fold_out, once per parameter version)
+bool seg_tail_eligible(int W, int E, int heads, int hid);
+int seg_fold_out(const float* c2w, long long c2_ld, const float* c2b, const float* outw, const float* outb, int E, int hid, float* wc,
+                 float* bc, cudaStream_t st);
 int seg_tail_eval(const float* gl, long long gl_ld, const float* cent, const float* fc1w, const float* fc1b, const float* fc2w,
-                  const float* fc2b, const float* inw, const float* inb, const float* outw, const float* outb, const float* c2w,
-                  long long c2_ld, const float* c2b, const float* s2, const float* t2, const unsigned char* key_mask, int B, int W,
-                  int E, int heads, int hid, float* qkv, float* attn_o, float* g_w, float* cb, unsigned int* bar, cudaStream_t st);
+                  const float* fc2b, const float* inw, const float* inb, const float* wc, const float* bc, const float* s2,
+                  const float* t2, const unsigned char* key_mask, int B, int W, int E, int heads, int hid, float* qkv, float* attn_o,
+                  float* cb, unsigned int* bar, cudaStream_t st);
 // dg[b, c] = sum_r dout[b, r, c]  (backward of the broadcast), deterministic two-stage column sum
 int colsum_rows(const float* dout, long long ldo, int n_clouds, int rows_per_cloud, int C, float* dg, float* scratch,
                 cudaStream_t st);

@@ -25,10 +25,11 @@ constexpr int kSegTcBlob = 16384 + (16384 + 1024) + (4096 + 512);
 // fp32-class fused head (tc_chain32): conv_2 local half (128 x 64), conv_3 (64 x 128), conv_4 (<= 32 x 64), hi + lo split;
 // bias table = [scale3 * b3 + shift3 (64) | b4 (Cp)]; kept in a caller-owned pack cache between calls
 constexpr int kSeg32W2 = 0, kSeg32W3 = 128 * 64 * 4, kSeg32W4 = kSeg32W3 + 64 * 128 * 4;
-struct SegPack { float *scale, *shift, *bias; unsigned char* blob; };
+struct SegPack { float *scale, *shift, *bias, *wc, *bc; unsigned char* blob; };   // wc / bc: seg_fold_out (E = 256, hid = 128)
 SegPack seg_pack_carve(Arena& a, int Cp) {
     SegPack k{};
     k.scale = a.take<float>(kSegBnTotal); k.shift = a.take<float>(kSegBnTotal); k.bias = a.take<float>(64 + Cp);
+    k.wc = a.take<float>(128 * 256); k.bc = a.take<float>(128);
     k.blob = a.take<unsigned char>(kSeg32W4 + Cp * 64 * 4);
     return k;
 }
@@ -210,13 +211,14 @@ int amp_seg_fwd(const void* const* params, const float* gl_feats, int64_t gl_ld,
             AMP_TRY(t32_pack_weights(pt, k.blob, st));
             AMP_TRY(t32_affine_bias(pf(params, S_C3B), k.scale + kSegBn3, k.shift + kSegBn3, 64, 64, k.bias, st));
             AMP_TRY(t32_affine_bias(pf(params, S_C4B), nullptr, nullptr, num_classes, Cp, k.bias + 64, st));
+            if (E == 256)      // whatever W and the debug switches of THIS call: the cache outlives it
+                AMP_TRY(seg_fold_out(pf(params, S_C2W) + 64, 64 + E, pf(params, S_C2B), pf(params, S_OUTW), pf(params, S_OUTB), E, hid, k.wc, k.bc, st));
         }
         // positional encoding, attention and the per-block bias in one launch (nn_seg_tail.cu); the barrier words live in the
         // h_pre slot of the saved buffer, which only the training backward reads
         const int rc = seg_tail_eval(gl_feats, gl_ld, centroids, pf(params, S_FC1W), pf(params, S_FC1B), pf(params, S_FC2W), pf(params, S_FC2B),
-                                     pf(params, S_INW), pf(params, S_INB), pf(params, S_OUTW), pf(params, S_OUTB), pf(params, S_C2W) + 64, 64 + E,
-                                     pf(params, S_C2B), k.scale + kSegBn2, k.shift + kSegBn2, key_padding_mask, Bi, Wi, E, heads, hid, S.qkv,
-                                     S.attn_o, S.g_w, S.cb, reinterpret_cast<unsigned int*>(S.h_pre), st);
+                                     pf(params, S_INW), pf(params, S_INB), k.wc, k.bc, k.scale + kSegBn2, k.shift + kSegBn2, key_padding_mask,
+                                     Bi, Wi, E, heads, hid, S.qkv, S.attn_o, S.cb, reinterpret_cast<unsigned int*>(S.h_pre), st);
         if (rc < 0) return rc;
         tail_done = rc == 1;
     }

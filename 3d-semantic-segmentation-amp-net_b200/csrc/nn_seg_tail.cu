@@ -1,9 +1,11 @@
 // Eval-mode attention tail of the segmentation head (pointNet/model/pointnetAtt.py:183-200) in ONE launch:
 //   tokens = global features + positional encoding of the window centroids   (fc_1 -> leaky_relu -> fc_2, :183-185)
-//   qkv = in_proj(tokens); per-head softmax(QK^T)V over the windows of a sample; g_w = out_proj(.)   (nn.MultiheadAttention, :187-190)
+//   qkv = in_proj(tokens); a = per-head softmax(QK^T)V over the windows of a sample; g_w = out_proj(a)   (nn.MultiheadAttention, :187-190)
 //   cb = scale_2 * (W2[:, 64:] g_w + b_2) + shift_2      (the per-block bias the fused head adds instead of the repeat / cat of :192-200)
+//      = scale_2 * (Wc a + bc) + shift_2 with Wc = W2[:, 64:] W_out, bc = W2[:, 64:] b_out + b_2 folded once per parameter
+//        version (seg_fold_out, kept in the pack cache): out_proj is not a phase of its own
 // These are five dependent launches of a few microseconds each (B x W = 32 tokens): 33 of the forward's 232 us on B200, all
-// of it launch + cold-cache latency. Here 96 CTAs (one in_proj output column per warp) stay resident across the four phases,
+// of it launch + cold-cache latency. Here 96 CTAs (one in_proj output column per warp) stay resident across the three phases,
 // separated by grid barriers (one 32-bit counter per barrier in a zeroed scratch word, release / acquire at gpu scope); the
 // weight rows of ALL phases are fetched before the first phase, so after a barrier a phase only waits for the few KB of
 // activations the other CTAs have just written (read with ld.global.cg: L1 is not coherent across SMs).
@@ -20,11 +22,11 @@ constexpr int ST_ROWS = 32, ST_THREADS = 256, ST_E = 256, ST_KI = ST_E / 32, ST_
 struct SegTailArgs {
     const float* gl; long long gl_ld; const float* cent;          // [W, B, gl_ld] view of the global features; [B, W, 2]
     const float *fc1w, *fc1b, *fc2w, *fc2b;                       // positional encoding: [16, 2], [16], [E, 16], [E]
-    const float *inw, *inb, *outw, *outb;                         // [3E, E], [3E], [E, E], [E]
-    const float* c2w; long long c2_ld; const float *c2b, *s2, *t2;   // W2[:, 64:] rows of c2_ld floats; bias, folded bn_2
+    const float *inw, *inb;                                       // [3E, E], [3E]
+    const float *wc, *bc, *s2, *t2;                               // folded out_proj + conv_2 global part [hid, E], [hid]; folded bn_2
     const unsigned char* key_mask;                                // [B, W] or null
-    float *qkv, *attn_o, *g_w, *cb;                               // [T, 3E], [T, E], [T, E], [T, hid]
-    unsigned int* bar;                                            // 3 zeroed counters
+    float *qkv, *attn_o, *cb;                                     // [T, 3E], [T, E], [T, hid]
+    unsigned int* bar;                                            // 2 zeroed counters
     int B, W, heads, hid;
 };
 
@@ -95,10 +97,9 @@ __global__ void __launch_bounds__(ST_THREADS) seg_tail_eval_kernel(const SegTail
     const int gw = blockIdx.x * (ST_THREADS / 32) + warp, n_warps = gridDim.x * (ST_THREADS / 32);
     const int T = a.B * a.W, E = ST_E;
     // the weight rows of every phase (parameters: never written by a kernel of this stream) before the predecessor is waited for
-    float w_in[ST_KI], w_out[ST_KI], w_cb[ST_KI];
+    float w_in[ST_KI], w_cb[ST_KI];
     load_row(w_in, a.inw + (long long)gw * E, gw < 3 * E);
-    load_row(w_out, a.outw + (long long)gw * E, gw < E);
-    load_row(w_cb, a.c2w + (long long)gw * a.c2_ld, gw < a.hid);
+    load_row(w_cb, a.wc + (long long)gw * E, gw < a.hid);
     pdl_wait();
 
     // ---- phase 1: tokens (every CTA builds the tile itself: 32 x 256 x 16 FMAs) -> qkv column gw ----
@@ -189,24 +190,12 @@ __global__ void __launch_bounds__(ST_THREADS) seg_tail_eval_kernel(const SegTail
     }
     grid_barrier(a.bar + 1, gridDim.x);
 
-    // ---- phase 3: g_w column gw = out_proj(attention output) (the CTAs that own a column) ----
-    if (blockIdx.x * (ST_THREADS / 32) < E) {
-        for (int r0 = 0; r0 < T; r0 += ST_ROWS) {
-            stage_rows(xs, a.attn_o, r0, T);
-            if (gw < E) {
-                const float v = tile_dot(xs, w_out) + __ldg(a.outb + gw);
-                if (r0 + lane < T) a.g_w[(long long)(r0 + lane) * E + gw] = v;
-            }
-        }
-    }
-    grid_barrier(a.bar + 2, gridDim.x);
-
-    // ---- phase 4: per-block bias of the fused head ----
+    // ---- phase 3: per-block bias of the fused head from the attention output (out_proj folded into Wc) ----
     if (blockIdx.x * (ST_THREADS / 32) < a.hid) {
         for (int r0 = 0; r0 < T; r0 += ST_ROWS) {
-            stage_rows(xs, a.g_w, r0, T);
+            stage_rows(xs, a.attn_o, r0, T);
             if (gw < a.hid) {
-                float v = tile_dot(xs, w_cb) + __ldg(a.c2b + gw);
+                float v = tile_dot(xs, w_cb) + __ldcg(a.bc + gw);
                 v = fmaf(v, __ldg(a.s2 + gw), __ldg(a.t2 + gw));
                 if (r0 + lane < T) a.cb[(long long)(r0 + lane) * a.hid + gw] = v;
             }
@@ -214,17 +203,47 @@ __global__ void __launch_bounds__(ST_THREADS) seg_tail_eval_kernel(const SegTail
     }
 }
 
+// Wc[n][k] = sum_j W2g[n][j] W_out[j][k], bc[n] = sum_j W2g[n][j] b_out[j] + b_2[n]  (W2g = conv_2's columns of the global
+// feature): one CTA per output channel n, thread = k; runs when the pack cache is (re)built
+__global__ void __launch_bounds__(ST_E) seg_fold_out_kernel(const float* __restrict__ c2w, long long c2_ld, const float* __restrict__ c2b,
+                                                            const float* __restrict__ outw, const float* __restrict__ outb, float* __restrict__ wc,
+                                                            float* __restrict__ bc) {
+    pdl_sync();
+    const int n = blockIdx.x, k = threadIdx.x;
+    const float* wrow = c2w + (long long)n * c2_ld;
+    float acc = 0.f;
+    for (int j = 0; j < ST_E; ++j) acc = fmaf(__ldg(wrow + j), __ldg(outw + (long long)j * ST_E + k), acc);
+    wc[(long long)n * ST_E + k] = acc;
+    if (k < 32) {
+        float b = 0.f;
+        for (int j = k; j < ST_E; j += 32) b = fmaf(__ldg(wrow + j), __ldg(outb + j), b);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+        if (k == 0) bc[n] = b + __ldg(c2b + n);
+    }
+}
+
 }  // namespace
+
+bool seg_tail_eligible(int W, int E, int heads, int hid) {
+    return !path_disabled("seg_tail") && E == ST_E && W >= 1 && W <= ST_MAXW && heads >= 1 && E % heads == 0 && hid <= ST_CTAS * 8;
+}
+
+int seg_fold_out(const float* c2w, long long c2_ld, const float* c2b, const float* outw, const float* outb, int E, int hid, float* wc,
+                 float* bc, cudaStream_t st) {
+    if (E != ST_E) return fail(AMP_E_BADARG, "seg_fold_out: embed_dim %d", E);
+    launch_pdl(seg_fold_out_kernel, dim3((unsigned)hid), dim3(ST_E), 0, st, c2w, c2_ld, c2b, outw, outb, wc, bc);
+    count_launch();
+    return check_launch("seg_fold_out");
+}
 
 // 1 = launched, 0 = shape not eligible (the caller runs the five separate launches)
 int seg_tail_eval(const float* gl, long long gl_ld, const float* cent, const float* fc1w, const float* fc1b, const float* fc2w,
-                  const float* fc2b, const float* inw, const float* inb, const float* outw, const float* outb, const float* c2w,
-                  long long c2_ld, const float* c2b, const float* s2, const float* t2, const unsigned char* key_mask, int B, int W,
-                  int E, int heads, int hid, float* qkv, float* attn_o, float* g_w, float* cb, unsigned int* bar, cudaStream_t st) {
-    if (path_disabled("seg_tail")) return 0;
-    if (E != ST_E || W < 1 || W > ST_MAXW || heads < 1 || E % heads || hid > ST_CTAS * 8 || (long long)B * W > (1 << 20)) return 0;
-    SegTailArgs a{gl, gl_ld, cent, fc1w, fc1b, fc2w, fc2b, inw, inb, outw, outb, c2w, c2_ld, c2b, s2, t2, key_mask,
-                  qkv, attn_o, g_w, cb, bar, B, W, heads, hid};
+                  const float* fc2b, const float* inw, const float* inb, const float* wc, const float* bc, const float* s2,
+                  const float* t2, const unsigned char* key_mask, int B, int W, int E, int heads, int hid, float* qkv, float* attn_o,
+                  float* cb, unsigned int* bar, cudaStream_t st) {
+    if (!seg_tail_eligible(W, E, heads, hid) || (long long)B * W > (1 << 20)) return 0;
+    SegTailArgs a{gl, gl_ld, cent, fc1w, fc1b, fc2w, fc2b, inw, inb, wc, bc, s2, t2, key_mask, qkv, attn_o, cb, bar, B, W, heads, hid};
     cudaError_t e = cudaMemsetAsync(bar, 0, 4 * sizeof(unsigned int), st);
     if (e != cudaSuccess) return fail(AMP_E_CUDA, "seg_tail_eval: cudaMemsetAsync: %s", cudaGetErrorString(e));
     const size_t smem = sizeof(float) * (ST_ROWS * ST_E + (ST_THREADS / 32) * ST_MAXW);
