@@ -243,10 +243,22 @@ int seg_tail_eval(const float* gl, long long gl_ld, const float* cent, const flo
                   const float* t2, const unsigned char* key_mask, int B, int W, int E, int heads, int hid, float* qkv, float* attn_o,
                   float* cb, unsigned int* bar, cudaStream_t st) {
     if (!seg_tail_eligible(W, E, heads, hid) || (long long)B * W > (1 << 20)) return 0;
+    const size_t smem = sizeof(float) * (ST_ROWS * ST_E + (ST_THREADS / 32) * ST_MAXW);
+    // the grid barriers need the whole grid resident at once: checked against the device, not assumed (a MIG slice or a smaller part
+    // falls back to the separate launches)
+    static int capacity = -1;
+    if (capacity < 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seg_tail_eval_kernel, ST_THREADS, smem) != cudaSuccess)
+            capacity = 0;
+        else
+            capacity = sms * per_sm;
+    }
+    if (capacity < ST_CTAS) return 0;
     SegTailArgs a{gl, gl_ld, cent, fc1w, fc1b, fc2w, fc2b, inw, inb, wc, bc, s2, t2, key_mask, qkv, attn_o, cb, bar, B, W, heads, hid};
     cudaError_t e = cudaMemsetAsync(bar, 0, 4 * sizeof(unsigned int), st);
     if (e != cudaSuccess) return fail(AMP_E_CUDA, "seg_tail_eval: cudaMemsetAsync: %s", cudaGetErrorString(e));
-    const size_t smem = sizeof(float) * (ST_ROWS * ST_E + (ST_THREADS / 32) * ST_MAXW);
     launch_pdl(seg_tail_eval_kernel, dim3(ST_CTAS), dim3(ST_THREADS), smem, st, a);
     count_launch();
     count_path("seg_tail");
