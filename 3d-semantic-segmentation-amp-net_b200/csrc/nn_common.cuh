@@ -72,6 +72,32 @@ int tnet_fc_eval(const float* pooled, int B, const float* fc1, const float* s4, 
                  cudaStream_t st);
 // fc_3 of the feature transform (+ bias + identity) -> out [B, 64, 64] and the packed split-bf16 per-cloud operand (nn_small.cu)
 int tnet_fc3_pack(const float* h2, const float* w, const float* b, int B, float* out, unsigned char* pk, long long pk_stride, cudaStream_t st);
+// the whole eval-mode FC stack of a T-Net (fc_1, fc_2, fc_3 + identity [+ the packed operand]) in ONE launch of 128 resident CTAs
+// with grid barriers between the layers (nn_small.cu): 1 = launched, 0 = not eligible; `bars` = 2 zeroed words
+int tnet_fc_grid(const float* pooled, int B, const float* fc1, const float* s4, const float* t4, const float* fc2, const float* s5,
+                 const float* t5, const float* fc3w, const float* fc3b, int d, float* h1, float* h2, float* out, unsigned char* pk,
+                 long long pk_stride, unsigned int* bars, cudaStream_t st);
+
+#ifdef __CUDACC__
+// Grid-wide barrier for kernels whose whole grid is resident (the launcher checks occupancy x SM count): every CTA has passed
+// this point and its global writes are visible (read them with ld.global.cg). One zeroed 32-bit counter per barrier. CTAs that
+// arrive first spin; a wait beyond ~10 s traps instead of hanging the device.
+__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int n_ctas) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        unsigned int v;
+        for (int spin = 0;; ++spin) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+            if (v >= n_ctas) break;
+            if (spin > (1 << 24)) __trap();
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+#endif
 // forward of the narrow-input (K <= 12) 64-channel layers over many rows, exact fp32 (nn_small.cu)
 int narrow_fwd_try(const PwParams& p, cudaStream_t st);
 // forward of the narrow-output (class logits, K = 64) layer over many rows, exact fp32 (nn_small.cu)

@@ -419,11 +419,12 @@ constexpr int kP32Stream = 256 * 128 * 4;                                       
 constexpr int kP32CloudW1 = 64 * 16 * 4, kP32CloudF = 64 * 64 * 4, kP32CloudStride = kP32CloudW1 + kP32CloudF;
 
 struct EncPack { float *scale, *shift; unsigned char *blob1, *blob2, *blob3a, *blob3b, *stream; };
-struct EncT32 { unsigned char* wcloud; float *pools, *f1, *f2, *T, *W1eff; };      // per-call buffers
+struct EncT32 { unsigned char* wcloud; float *pools, *f1, *f2, *T, *W1eff; unsigned int* bars; };      // per-call buffers
 EncT32 enc_t32_carve(Arena& a, long long B) {
     EncT32 t{};
     t.wcloud = a.take<unsigned char>((size_t)B * kP32CloudStride);
-    t.pools = a.take<float>((size_t)B * 256 * 3);
+    t.pools = a.take<float>((size_t)B * 256 * 3 + 16);    // + the grid-barrier words of the two T-Net FC launches (zeroed with the pools)
+    t.bars = reinterpret_cast<unsigned int*>(t.pools + (size_t)B * 256 * 3);
     t.f1 = a.take<float>(B * 256); t.f2 = a.take<float>(B * 128); t.T = a.take<float>(B * 9 + 7); t.W1eff = a.take<float>(B * 576);
     return t;
 }
@@ -514,7 +515,7 @@ int encoder_fwd_fp32_fused(EncCtx& c, const float* x, float* out, float* feat_t,
     if (!pack_valid) AMP_TRY(encoder_pack_fp32(c, k));
     c.S.scale = k.scale; c.S.shift = k.shift;            // tnet_fc_stack_eval reads the folded bn_4 / bn_5 from here
     auto sc = [&](int L) { return k.scale + enc_bn_offset(L); };
-    AMP_CUDA(cudaMemsetAsync(t.pools, 0, sizeof(float) * B * 256 * 3, c.st));
+    AMP_CUDA(cudaMemsetAsync(t.pools, 0, sizeof(float) * ((size_t)B * 256 * 3 + 16), c.st));
     float* it_pool = t.pools; float* ft_pool = t.pools + (size_t)B * 256; float* G = t.pools + (size_t)B * 512;
     T32Params base{};
     base.in_mode = 0; base.in_x = x; base.in_ld = 9; base.n_groups = 1; base.n_clouds = B; base.rows_per_cloud = N;
@@ -530,7 +531,13 @@ int encoder_fwd_fp32_fused(EncCtx& c, const float* x, float* out, float* feat_t,
         p.pool = reinterpret_cast<unsigned int*>(it_pool);
         AMP_TRY(tc_chain32_launch(p, c.st));
     }
-    AMP_TRY(tnet_fc_stack_eval(c, E_IT, L_IT1, 3, it_pool, t.f1, t.f2, t.T));
+    {
+        const int o4 = enc_bn_offset(L_IT1 + 3), o5 = enc_bn_offset(L_IT1 + 4);
+        const int rc = tnet_fc_grid(it_pool, B, c.pf(E_IT + T_FC1), k.scale + o4, k.shift + o4, c.pf(E_IT + T_FC2), k.scale + o5, k.shift + o5,
+                                    c.pf(E_IT + T_FC3W), c.pf(E_IT + T_FC3B), 3, t.f1, t.f2, t.T, nullptr, 0, t.bars, c.st);
+        if (rc < 0) return rc;
+        if (rc == 0) AMP_TRY(tnet_fc_stack_eval(c, E_IT, L_IT1, 3, it_pool, t.f1, t.f2, t.T));
+    }
     // bmm + cat + conv_1 (:85-90) as per-cloud conv_1 weights (bn_1 scale folded in), packed per cloud
     AMP_TRY(t32_fold_w1(c.pf(E_CONV1), t.T, sc(L_C1), B, t.wcloud, kP32CloudStride, c.st));
     // chain 2: conv_1, conv_2, feature T-Net convs + max-pool (:90-94)
@@ -549,9 +556,15 @@ int encoder_fwd_fp32_fused(EncCtx& c, const float* x, float* out, float* feat_t,
     }
     {   // fc_1, fc_2 in one cluster launch; fc_3 + identity + the packed operand of local = h @ F in a second one
         const int o4 = enc_bn_offset(L_FT1 + 3), o5 = enc_bn_offset(L_FT1 + 4);
-        AMP_TRY(tnet_fc_eval(ft_pool, B, c.pf(E_FT + T_FC1), k.scale + o4, k.shift + o4, c.pf(E_FT + T_FC2), k.scale + o5, k.shift + o5,
-                             c.pf(E_FT + T_FC3W), c.pf(E_FT + T_FC3B), 64, 0, t.f1, t.f2, feat_t, c.st));
-        AMP_TRY(tnet_fc3_pack(t.f2, c.pf(E_FT + T_FC3W), c.pf(E_FT + T_FC3B), B, feat_t, t.wcloud + kP32CloudW1, kP32CloudStride, c.st));
+        const int rc = tnet_fc_grid(ft_pool, B, c.pf(E_FT + T_FC1), k.scale + o4, k.shift + o4, c.pf(E_FT + T_FC2), k.scale + o5, k.shift + o5,
+                                    c.pf(E_FT + T_FC3W), c.pf(E_FT + T_FC3B), 64, t.f1, t.f2, feat_t, t.wcloud + kP32CloudW1, kP32CloudStride,
+                                    t.bars + 4, c.st);
+        if (rc < 0) return rc;
+        if (rc == 0) {
+            AMP_TRY(tnet_fc_eval(ft_pool, B, c.pf(E_FT + T_FC1), k.scale + o4, k.shift + o4, c.pf(E_FT + T_FC2), k.scale + o5, k.shift + o5,
+                                 c.pf(E_FT + T_FC3W), c.pf(E_FT + T_FC3B), 64, 0, t.f1, t.f2, feat_t, c.st));
+            AMP_TRY(tnet_fc3_pack(t.f2, c.pf(E_FT + T_FC3W), c.pf(E_FT + T_FC3B), B, feat_t, t.wcloud + kP32CloudW1, kP32CloudStride, c.st));
+        }
     }
     // chain 3a: conv_1, conv_2, bmm with the feature transform = local features (:96-97), stored into out[:, :, 256:320]
     {

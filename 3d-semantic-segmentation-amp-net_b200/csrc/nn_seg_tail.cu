@@ -30,27 +30,6 @@ struct SegTailArgs {
     int B, W, heads, hid;
 };
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// every CTA of the grid has passed this point and its writes are visible. The grid (96 CTAs) is smaller than the machine, so
-// all of it becomes resident as soon as earlier work drains; CTAs that arrive first spin. A wait beyond ~10 s (another stream
-// of the process holding every SM with kernels that in turn wait for this one) traps instead of hanging the device.
-__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned n_ctas) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1u);
-        for (int spin = 0; ld_acquire_u32(ctr) < n_ctas; ++spin)
-            if (spin > (1 << 24)) __trap();                        // far beyond any legitimate wait
-        __threadfence();
-    }
-    __syncthreads();
-}
-
 __device__ __forceinline__ void load_row(float (&wv)[ST_KI], const float* __restrict__ w_row, bool ok) {
     const int lane = threadIdx.x & 31;
 #pragma unroll

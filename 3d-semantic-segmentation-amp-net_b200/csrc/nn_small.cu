@@ -684,6 +684,35 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(256) tnet_fc_eval_ke
     tnet_fc_layer<1, 4>(xs, a.h2, r0, a.B, w3, rank * 8 + warp, nout, a.fc3b, nullptr, nullptr, false, a.d, a.out, nout);
 }
 
+// The same stack as ONE launch of 128 resident CTAs: one output column per warp for fc_1 / fc_2 (the first 32 / 16 CTAs), four
+// per warp for fc_3 (4096 columns of the 64 x 64 transform = every warp; 9 columns of the 3 x 3 one = three warps), grid
+// barriers between the layers, every layer's weight rows fetched before the predecessor kernel is waited for. Replaces the
+// cluster launch (8 CTAs pulling all weights, ~5 us per layer) plus, for the feature T-Net, the separate fc_3 launch.
+constexpr int TG_CTAS = 128;
+__global__ void __launch_bounds__(256) tnet_fc_grid_kernel(const TnetFcArgs a, unsigned char* __restrict__ pk, long long pk_stride,
+                                                           unsigned int* bars) {
+    pdl_trigger();
+    extern __shared__ float xs[];                          // [32][256]
+    const int warp = threadIdx.x >> 5, gw = blockIdx.x * 8 + warp;
+    const int nout = a.d * a.d;
+    float w1[1][8], w2[1][8], w3[4][4];
+    tnet_fc_load_w<1, 8>(w1, a.fc1, gw, 256);              // parameters: safe to read before the predecessor has finished
+    tnet_fc_load_w<1, 8>(w2, a.fc2, gw, 128);
+    tnet_fc_load_w<4, 4>(w3, a.fc3w, gw * 4, nout);
+    pdl_wait();
+    if (blockIdx.x * 8 < 256)
+        for (int r0 = 0; r0 < a.B; r0 += SM_ROWS)
+            tnet_fc_layer<1, 8>(xs, a.pooled, r0, a.B, w1, gw, 256, nullptr, a.s4, a.t4, true, 0, a.h1, 256);
+    grid_barrier(bars + 0, gridDim.x);
+    if (blockIdx.x * 8 < 128)
+        for (int r0 = 0; r0 < a.B; r0 += SM_ROWS)
+            tnet_fc_layer<1, 8>(xs, a.h1, r0, a.B, w2, gw, 128, nullptr, a.s5, a.t5, true, 0, a.h2, 128);
+    grid_barrier(bars + 1, gridDim.x);
+    if (blockIdx.x * 32 < nout)
+        for (int r0 = 0; r0 < a.B; r0 += SM_ROWS)
+            tnet_fc_layer<4, 4>(xs, a.h2, r0, a.B, w3, gw * 4, nout, a.fc3b, nullptr, nullptr, false, a.d, a.out, nout, pk, pk_stride);
+}
+
 // fc_3 of the 64 x 64 feature transform (4096 outputs, K = 128) + bias + identity, written as the module output [B, 64, 64]
 // AND as the packed per-cloud operand of the fused chains: 128 CTAs x 32 output columns, all rows of a 32-cloud tile per pass
 __global__ void __launch_bounds__(256) tnet_fc3_pack_kernel(const float* __restrict__ h2, const float* __restrict__ w, const float* __restrict__ b,
@@ -705,6 +734,31 @@ int tnet_fc3_pack(const float* h2, const float* w, const float* b, int B, float*
     launch_pdl(tnet_fc3_pack_kernel, dim3(128), dim3(256), sizeof(float) * SM_ROWS * 128, st, h2, w, b, B, out, pk, pk_stride);
     count_launch();
     return check_launch("tnet_fc3_pack");
+}
+
+int tnet_fc_grid(const float* pooled, int B, const float* fc1, const float* s4, const float* t4, const float* fc2, const float* s5,
+                 const float* t5, const float* fc3w, const float* fc3b, int d, float* h1, float* h2, float* out, unsigned char* pk,
+                 long long pk_stride, unsigned int* bars, cudaStream_t st) {
+    if (path_disabled("tnet_grid")) return 0;
+    if (!pooled || !fc1 || !fc2 || !fc3w || !fc3b || !h1 || !h2 || !out || !bars || B < 1) return fail(AMP_E_BADARG, "tnet_fc_grid: null pointer");
+    if (d * d > TG_CTAS * 32 || (pk && d != 64)) return 0;
+    const size_t smem = sizeof(float) * SM_ROWS * 256;
+    static int capacity = -1;                              // the grid barriers need the whole grid resident at once
+    if (capacity < 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tnet_fc_grid_kernel, 256, smem) != cudaSuccess)
+            capacity = 0;
+        else
+            capacity = sms * per_sm;
+    }
+    if (capacity < TG_CTAS) return 0;
+    TnetFcArgs a{pooled, fc1, s4, t4, fc2, s5, t5, fc3w, fc3b, h1, h2, out, B, d, 1};
+    launch_pdl(tnet_fc_grid_kernel, dim3(TG_CTAS), dim3(256), smem, st, a, pk, pk_stride, bars);
+    count_launch();
+    count_path("tnet_grid");
+    const int rc = check_launch("tnet_fc_grid");
+    return rc == AMP_OK ? 1 : rc;
 }
 
 // Eval-mode T-Net FC stack in one cluster launch; with fc3_inside == 0 the caller runs fc_3 (wide) itself on h2.
